@@ -1,0 +1,84 @@
+"""ctypes binding of libemphases_b200.so (the C ABI in include/emphases_b200.h).
+
+There is no CPU fallback: if the shared library is missing or fails to load,
+every call raises.  Build it with `python -m emphases_b200.build`.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libemphases_b200.so')
+
+# include/emphases_b200.h constants
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_LEAKY_RELU, ACT_SILU = 0, 1, 2, 3, 4
+POOL = {'average': 0, 'max': 1, 'sum': 2, 'center': 3}
+HEAD_LOGITS, HEAD_SIGMOID, HEAD_CLAMP = 0, 1, 2
+PREC_FP32, PREC_BF16_TC = 0, 1
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int32
+_F = ctypes.c_float
+
+# name -> argtypes; every function returns int.  Keep in sync with the header
+# (tests/test_abi.py checks that every declared symbol is exported).
+SIGNATURES = {
+    'emph_row_index': [_P, _P, _I, _P, _I, _P],
+    'emph_logmel_f32': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
+    'emph_logmel_i16': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
+    'emph_conv_stack': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    'emph_pack_conv_weights': [_P, _I, _I, _I, _P, _P],
+    'emph_pool_words': [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
+    'emph_output_head': [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _P],
+    'emph_pack_rows': [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+    'emph_unpack_rows': [_P, _P, _P, _I, _I, _I, _P, _P],
+}
+
+_lib = None
+
+
+class EmphasesB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise loudly when it is absent"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EmphasesB200Error(
+            f'{LIB_PATH} is missing: run `python -m emphases_b200.build`. '
+            'emphases_b200 has no CPU or PyTorch fallback path.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.emph_version.restype = ctypes.c_int
+    lib.emph_last_error.restype = ctypes.c_char_p
+    lib.emph_device_sm_count.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an entry point; non-zero status -> EmphasesB200Error"""
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        message = lib.emph_last_error().decode('utf-8', 'replace')
+        raise EmphasesB200Error(f'{name} failed ({status}): {message}')
+
+
+def ptr(tensor):
+    """Device pointer of a torch tensor (None -> NULL)"""
+    if tensor is None:
+        return None
+    return ctypes.c_void_p(tensor.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return ctypes.c_void_p(stream.cuda_stream)

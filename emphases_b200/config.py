@@ -1,0 +1,61 @@
+"""Configuration constants of the hot path, same names and defaults as the
+reference (emphases/config/defaults.py, emphases/config/static.py).
+
+Like the reference, code reads them at call time as `emphases_b200.NAME`, so
+`emphases_b200.configure(...)` (the stand-in for yapecs' `--config file.py`
+override, emphases/__init__.py:10-11) takes effect immediately.
+"""
+import torch
+
+# Metadata (defaults.py:14)
+CONFIG = 'emphases'
+
+# Audio parameters (defaults.py:53-74)
+HOPSIZE = 160
+NUM_FFT = 1024
+NUM_MELS = 80
+SAMPLE_RATE = 16000
+WINDOW_SIZE = 1024
+
+# Data parameters (defaults.py:89-116)
+MEL_FEATURE = True
+LOUDNESS_FEATURE = False
+PITCH_FEATURE = False
+PERIODICITY_FEATURE = False
+NORMALIZE = False
+RANDOM_SEED = 0
+
+# Model parameters (defaults.py:181-215)
+ACTIVATION_FUNCTION = torch.nn.ReLU
+ARCHITECTURE = 'convolution'
+CHANNELS = 80
+DECODER_KERNEL_SIZE = 3
+DROPOUT = None
+DOWNSAMPLE_LOCATION = 'intermediate'
+DOWNSAMPLE_METHOD = 'sum'
+ENCODER_KERNEL_SIZE = 3
+LAYERS = 6
+METHOD = 'neural'
+UPSAMPLE_METHOD = 'linear'
+
+# Training parameters (defaults.py:224-230)
+BUCKETS = 2
+LOSS = 'bce'
+MAX_TRAINING_FRAMES = 75000
+
+# emphases_b200 extensions (not in the reference)
+# 'fp32': CUDA-core FFMA conv stack, scores within 1e-5 of the reference's fp32
+# forward.  'bf16': tcgen05 tensor-core conv stack, within 2e-3.
+PRECISION = 'fp32'
+# Upper bound on packed frame rows per launch (memory: ~1 KB of HBM per row)
+MAX_ROWS_PER_LAUNCH = 1 << 22
+
+
+def static(namespace):
+    """Derived values (emphases/config/static.py:29-46)"""
+    namespace['HOPSIZE_SECONDS'] = namespace['HOPSIZE'] / namespace['SAMPLE_RATE']
+    namespace['NUM_FEATURES'] = (
+        namespace['MEL_FEATURE'] * namespace['NUM_MELS'] +
+        int(namespace['PITCH_FEATURE']) +
+        int(namespace['PERIODICITY_FEATURE']) +
+        int(namespace['LOUDNESS_FEATURE']))

@@ -1,0 +1,159 @@
+// C-ABI plumbing: error string, version, small utility kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace emph {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list args;
+    va_start(args, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, args);
+    va_end(args);
+}
+
+// row -> sequence map by binary search over the sorted row_start array
+__global__ void row_index_kernel(
+    const int32_t* __restrict__ row_start, const int32_t* __restrict__ n_rows,
+    int32_t n_seq, int32_t* __restrict__ row_seq, int32_t total_rows) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= total_rows) return;
+    int lo = 0, hi = n_seq;  // last u with row_start[u] <= r
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(row_start + mid) <= r) lo = mid + 1; else hi = mid;
+    }
+    int u = lo - 1;
+    int seq = -1;
+    if (u >= 0 && r < __ldg(row_start + u) + __ldg(n_rows + u)) seq = u;
+    row_seq[r] = seq;
+}
+
+// (out, in, k) -> [k][in][out]
+__global__ void pack_conv_weights_kernel(
+    const float* __restrict__ w, int co, int ci, int ks, float* __restrict__ packed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = co * ci * ks;
+    if (i >= total) return;
+    int o = i % co;
+    int c = (i / co) % ci;
+    int k = i / (co * ci);
+    packed[i] = w[(o * ci + c) * ks + k];
+}
+
+// (B, C, T) -> packed rows; 32x32 smem transpose tiles per sequence
+__global__ void pack_rows_kernel(
+    const float* __restrict__ bct, int channels, int frames,
+    const int32_t* __restrict__ row_start, const int32_t* __restrict__ n_rows,
+    float* __restrict__ rows) {
+    __shared__ float tile[32][33];
+    int b = blockIdx.z;
+    int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int n = n_rows[b];
+    if (t0 >= n) return;
+    const float* src = bct + (size_t)b * channels * frames;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < channels && t < n) ? src[(size_t)c * frames + t] : 0.f;
+    }
+    __syncthreads();
+    float* dst = rows + (size_t)row_start[b] * channels;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < n && c < channels) dst[(size_t)t * channels + c] = tile[threadIdx.x][i];
+    }
+}
+
+__global__ void zero_separator_rows_kernel(
+    const int32_t* __restrict__ row_seq, int total_rows, int channels,
+    float* __restrict__ rows) {
+    int r = blockIdx.x;
+    if (r >= total_rows || row_seq[r] >= 0) return;
+    for (int c = threadIdx.x; c < channels; c += blockDim.x)
+        rows[(size_t)r * channels + c] = 0.f;
+}
+
+__global__ void unpack_rows_kernel(
+    const float* __restrict__ rows, const int32_t* __restrict__ row_start,
+    const int32_t* __restrict__ n_rows, int channels, int frames,
+    float* __restrict__ bct) {
+    __shared__ float tile[32][33];
+    int b = blockIdx.z;
+    int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int n = n_rows[b];
+    const float* src = rows + (size_t)row_start[b] * channels;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (t < n && c < channels) ? src[(size_t)t * channels + c] : 0.f;
+    }
+    __syncthreads();
+    float* dst = bct + (size_t)b * channels * frames;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, t = t0 + threadIdx.x;
+        if (c < channels && t < frames) dst[(size_t)c * frames + t] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace emph
+
+extern "C" {
+
+int emph_version(void) { return 100; }
+
+const char* emph_last_error(void) { return emph::g_error; }
+
+int emph_device_sm_count(void) { return emph::sm_count(); }
+
+int emph_row_index(
+    const int32_t* row_start, const int32_t* n_rows, int32_t n_seq,
+    int32_t* row_seq, int32_t total_rows, void* stream) {
+    EMPH_REQUIRE(n_seq >= 0 && total_rows >= 0, "emph_row_index: negative size");
+    if (total_rows == 0) return EMPH_OK;
+    int threads = 256;
+    int blocks = (total_rows + threads - 1) / threads;
+    emph::row_index_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        row_start, n_rows, n_seq, row_seq, total_rows);
+    EMPH_CHECK_LAUNCH("emph_row_index");
+    return EMPH_OK;
+}
+
+int emph_pack_conv_weights(
+    const float* conv_weight, int32_t out_channels, int32_t in_channels,
+    int32_t kernel_size, float* packed, void* stream) {
+    int total = out_channels * in_channels * kernel_size;
+    EMPH_REQUIRE(total > 0, "emph_pack_conv_weights: empty weight");
+    emph::pack_conv_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        conv_weight, out_channels, in_channels, kernel_size, packed);
+    EMPH_CHECK_LAUNCH("emph_pack_conv_weights");
+    return EMPH_OK;
+}
+
+int emph_pack_rows(
+    const float* bct, int32_t batch, int32_t channels, int32_t frames,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* row_seq, int32_t total_rows, float* rows, void* stream) {
+    EMPH_REQUIRE(batch > 0 && channels > 0 && frames > 0, "emph_pack_rows: empty input");
+    dim3 grid((frames + 31) / 32, (channels + 31) / 32, batch), block(32, 8);
+    emph::pack_rows_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        bct, channels, frames, row_start, n_rows, rows);
+    EMPH_CHECK_LAUNCH("emph_pack_rows");
+    emph::zero_separator_rows_kernel<<<total_rows, 32, 0, (cudaStream_t)stream>>>(
+        row_seq, total_rows, channels, rows);
+    EMPH_CHECK_LAUNCH("emph_pack_rows(separators)");
+    return EMPH_OK;
+}
+
+int emph_unpack_rows(
+    const float* rows, const int32_t* row_start, const int32_t* n_rows,
+    int32_t batch, int32_t channels, int32_t frames, float* bct, void* stream) {
+    EMPH_REQUIRE(batch > 0 && channels > 0 && frames > 0, "emph_unpack_rows: empty input");
+    dim3 grid((frames + 31) / 32, (channels + 31) / 32, batch), block(32, 8);
+    emph::unpack_rows_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        rows, row_start, n_rows, channels, frames, bct);
+    EMPH_CHECK_LAUNCH("emph_unpack_rows");
+    return EMPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// Fused log-mel feature extraction for sm_100a.
+//
+// Replaces, in ONE kernel and with each audio sample read from HBM once
+// (overlapping frames are served from L1/L2), the reference call chain
+//   F.pad(zeros 432)            emphases/core.py:357-358
+//   audio[:, s:e] chunk slice   emphases/core.py:395-401
+//   F.pad(reflect 432)          emphases/data/preprocess/mels.py:32-36
+//   torch.stft(1024, hop 160, hann, center=False)      mels.py:39-48
+//   sqrt(re^2 + im^2 + 1e-6)    mels.py:51
+//   basis @ spectrogram, log(clamp(., 1e-5)), optional (x+10)/10
+//                               mels.py:94-109, 57-58
+//
+// One warp per frame.  The 1024-point real FFT is a 512-point complex FFT of
+// the even/odd packed signal (3 radix-8 Stockham passes, 2 butterflies per
+// lane per pass, exchanges through padded shared memory) followed by the
+// real-FFT unpacking, all in fp32.  Bound: FP32 pipe (about 25 kFLOP per frame
+// against 960 B of HBM traffic), see DESIGN.md.
+#include "common.cuh"
+
+namespace emph {
+
+constexpr int kFft = 1024;
+constexpr int kHop = 160;
+constexpr int kPad = (kFft - kHop) / 2;   // 432, both the zero and reflect pad
+constexpr int kBins = kFft / 2 + 1;       // 513
+constexpr int kHalf = kFft / 2;           // 512-point complex FFT
+constexpr int kWarps = 8;
+constexpr int kMaxNnz = 1536;             // mel CSR entries held in smem
+constexpr int kMaxMels = 128;
+
+// Exchange buffer index with one float2 of padding per 8 (bank spreading)
+__device__ __forceinline__ int xpad(int i) { return i + (i >> 3); }
+constexpr int kXchg = kHalf + kHalf / 8;  // 576 float2 per warp
+
+struct __align__(16) LogmelSmem {
+    float2 w512[kHalf];            // exp(-2 pi i m / 512)
+    float2 w1024[kHalf / 2 + 1];   // exp(-2 pi i k / 1024), k = 0..256
+    float hann[kFft];
+    float mel_val[kMaxNnz];
+    int16_t mel_col[kMaxNnz];
+    int32_t mel_ptr[kMaxMels + 1];
+    float2 xchg[kWarps][kXchg];
+    float mag[kWarps][kBins + 3];
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ void bfly2(float2& a, float2& b) {
+    float2 t = a;
+    a = make_float2(t.x + b.x, t.y + b.y);
+    b = make_float2(t.x - b.x, t.y - b.y);
+}
+// multiply by -i
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// 4-point DFT; outputs land as (X0, X2, X1, X3) in (a, b, c, d)
+__device__ __forceinline__ void fft4(float2& a, float2& b, float2& c, float2& d) {
+    bfly2(a, c);
+    bfly2(b, d);
+    d = mul_mi(d);
+    bfly2(a, b);
+    bfly2(c, d);
+}
+
+// 8-point DFT in place; v[] ends up in natural order
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+    const float s = 0.70710678118654752440f;
+    bfly2(v[0], v[4]);
+    bfly2(v[1], v[5]);
+    bfly2(v[2], v[6]);
+    bfly2(v[3], v[7]);
+    v[5] = make_float2(s * (v[5].x + v[5].y), s * (v[5].y - v[5].x));     // * (s, -s)
+    v[6] = mul_mi(v[6]);
+    v[7] = make_float2(s * (v[7].y - v[7].x), -s * (v[7].x + v[7].y));    // * (-s, -s)
+    fft4(v[0], v[1], v[2], v[3]);   // X0 X4 X2 X6
+    fft4(v[4], v[5], v[6], v[7]);   // X1 X5 X3 X7
+    float2 t1 = v[1], t3 = v[3], t4 = v[4], t6 = v[6];
+    v[1] = t4;      // X1
+    v[3] = t6;      // X3
+    v[4] = t1;      // X4
+    v[6] = t3;      // X6
+    // v[0]=X0 v[2]=X2 v[5]=X5 v[7]=X7 already in place
+}
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<int16_t>(int16_t v) {
+    return (float)v * (1.f / 32768.f);
+}
+
+// Sample q of the reflect-padded chunk, through the whole index map
+// (SURVEY.md A.2): chunk[j] = P[s + j], P = zeros(432) ++ audio ++ zeros(432)
+template <typename T>
+__device__ __forceinline__ float chunk_sample(
+    const T* __restrict__ audio, int T_len, int s, int L, int q) {
+    int j = q - kPad;
+    if (j < 0) j = -j;
+    if (j >= L) j = 2 * (L - 1) - j;
+    int a = s + j - kPad;
+    return (a >= 0 && a < T_len) ? to_float<T>(audio[a]) : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32)
+logmel_kernel(
+    const T* __restrict__ audio,
+    const int64_t* __restrict__ audio_off, const int32_t* __restrict__ audio_len,
+    const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_len,
+    const int32_t* __restrict__ row_start,
+    const int32_t* __restrict__ row_seq, int total_rows,
+    const int32_t* __restrict__ mel_ptr, const int16_t* __restrict__ mel_col,
+    const float* __restrict__ mel_val, int n_mels, int normalize,
+    float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LogmelSmem& sm = *reinterpret_cast<LogmelSmem*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // Tables (fp32 values of double-precision-accurate sincospi)
+    for (int i = tid; i < kHalf; i += blockDim.x) {
+        float sn, cs;
+        sincospif(-2.f * (float)i / (float)kHalf, &sn, &cs);
+        sm.w512[i] = make_float2(cs, sn);
+    }
+    for (int i = tid; i <= kHalf / 2; i += blockDim.x) {
+        float sn, cs;
+        sincospif(-2.f * (float)i / (float)kFft, &sn, &cs);
+        sm.w1024[i] = make_float2(cs, sn);
+    }
+    for (int i = tid; i < kFft; i += blockDim.x) {
+        // torch.hann_window(1024) (periodic): 0.5 - 0.5 cos(2 pi n / N)
+        sm.hann[i] = 0.5f - 0.5f * cospif(2.f * (float)i / (float)kFft);
+    }
+    const int nnz = mel_ptr[n_mels];
+    for (int i = tid; i < nnz; i += blockDim.x) {
+        sm.mel_val[i] = mel_val[i];
+        sm.mel_col[i] = mel_col[i];
+    }
+    for (int i = tid; i <= n_mels; i += blockDim.x) sm.mel_ptr[i] = mel_ptr[i];
+    __syncthreads();
+
+    float2* xw = sm.xchg[warp];
+    float* mag = sm.mag[warp];
+
+    for (int row = blockIdx.x * kWarps + warp; row < total_rows;
+         row += gridDim.x * kWarps) {
+        const int u = __ldg(row_seq + row);
+        float* dst = out + (size_t)row * n_mels;
+        if (u < 0) {   // separator row
+            for (int m = lane; m < n_mels; m += 32) dst[m] = 0.f;
+            continue;
+        }
+        const int frame = row - __ldg(row_start + u);
+        const int T_len = __ldg(audio_len + u);
+        const int s = __ldg(chunk_start + u);
+        const int L = __ldg(chunk_len + u);
+        const T* src = audio + __ldg(audio_off + u);
+        const int q0 = frame * kHop;            // first sample in reflect-padded coords
+
+        // ---- load 1024 samples as 512 complex, window, first radix-8 pass ----
+        // lane handles butterflies j = lane and j = lane + 32; inputs z[j + 64 r]
+        float2 v0[8], v1[8];
+        // interior: no reflect, no zero pad
+        const int a0 = s + q0 - 2 * kPad;       // audio index of sample q0
+        const bool interior = (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
+                              (a0 >= 0) && (a0 + kFft <= T_len);
+        if (interior) {
+            const T* p = src + a0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int n0 = lane + 64 * r, n1 = n0 + 32;
+                if constexpr (sizeof(T) == 4) {
+                    float2 x0 = *reinterpret_cast<const float2*>(p + 2 * n0);
+                    float2 x1 = *reinterpret_cast<const float2*>(p + 2 * n1);
+                    v0[r] = x0;
+                    v1[r] = x1;
+                } else {
+                    short2 x0 = *reinterpret_cast<const short2*>(p + 2 * n0);
+                    short2 x1 = *reinterpret_cast<const short2*>(p + 2 * n1);
+                    v0[r] = make_float2(to_float<int16_t>(x0.x), to_float<int16_t>(x0.y));
+                    v1[r] = make_float2(to_float<int16_t>(x1.x), to_float<int16_t>(x1.y));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int n0 = lane + 64 * r, n1 = n0 + 32;
+                v0[r] = make_float2(
+                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0),
+                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0 + 1));
+                v1[r] = make_float2(
+                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1),
+                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1 + 1));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int n0 = lane + 64 * r, n1 = n0 + 32;
+            float2 h0 = *reinterpret_cast<const float2*>(&sm.hann[2 * n0]);
+            float2 h1 = *reinterpret_cast<const float2*>(&sm.hann[2 * n1]);
+            v0[r].x *= h0.x; v0[r].y *= h0.y;
+            v1[r].x *= h1.x; v1[r].y *= h1.y;
+        }
+        // pass 1: Ns = 1, no twiddles, out[8 j + r]
+        fft8(v0);
+        fft8(v1);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            xw[xpad(8 * lane + r)] = v0[r];
+            xw[xpad(8 * (lane + 32) + r)] = v1[r];
+        }
+        __syncwarp();
+
+        // pass 2: Ns = 8; twiddle exp(-2 pi i r (j % 8) / 64) = w512[8 r (j%8)]
+        {
+            const int k0 = lane & 7;             // (lane + 32) % 8 is the same
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                v0[r] = xw[xpad(lane + 64 * r)];
+                v1[r] = xw[xpad(lane + 32 + 64 * r)];
+            }
+#pragma unroll
+            for (int r = 1; r < 8; ++r) {
+                float2 w = sm.w512[8 * r * k0];
+                v0[r] = cmul(v0[r], w);
+                v1[r] = cmul(v1[r], w);
+            }
+            fft8(v0);
+            fft8(v1);
+            __syncwarp();
+            const int b0 = (lane >> 3) * 64 + k0;
+            const int b1 = ((lane + 32) >> 3) * 64 + k0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                xw[xpad(b0 + 8 * r)] = v0[r];
+                xw[xpad(b1 + 8 * r)] = v1[r];
+            }
+            __syncwarp();
+        }
+
+        // pass 3: Ns = 64; twiddle exp(-2 pi i r j / 512); out[j + 64 r]
+        {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                v0[r] = xw[xpad(lane + 64 * r)];
+                v1[r] = xw[xpad(lane + 32 + 64 * r)];
+            }
+#pragma unroll
+            for (int r = 1; r < 8; ++r) {
+                v0[r] = cmul(v0[r], sm.w512[r * lane]);
+                v1[r] = cmul(v1[r], sm.w512[r * (lane + 32)]);
+            }
+            fft8(v0);
+            fft8(v1);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                xw[xpad(lane + 64 * r)] = v0[r];
+                xw[xpad(lane + 32 + 64 * r)] = v1[r];
+            }
+            __syncwarp();
+        }
+
+        // ---- real-FFT unpacking + magnitude: bins k and 512 - k, k = 0..256 ----
+        for (int k = lane; k <= kHalf / 2; k += 32) {
+            float2 a = xw[xpad(k)];
+            float2 bz = xw[xpad((kHalf - k) & (kHalf - 1))];
+            float2 b = make_float2(bz.x, -bz.y);                   // conj(Z[512-k])
+            float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+            float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+            float2 o = make_float2(d.y, -d.x);                     // -i * d
+            float2 w = sm.w1024[k];
+            float2 wo = cmul(w, o);
+            float xr = e.x + wo.x, xi = e.y + wo.y;                // X[k]
+            // X[512-k] = conj(e) - conj(w) conj(o) = conj(e - w o)
+            float yr = e.x - wo.x, yi = e.y - wo.y;
+            mag[k] = sqrtf(xr * xr + xi * xi + 1e-6f);
+            mag[kHalf - k] = sqrtf(yr * yr + yi * yi + 1e-6f);
+        }
+        __syncwarp();
+
+        // ---- sparse mel projection + log ----
+        for (int m = lane; m < n_mels; m += 32) {
+            float acc = 0.f;
+            const int e0 = sm.mel_ptr[m], e1 = sm.mel_ptr[m + 1];
+            for (int e = e0; e < e1; ++e)
+                acc = fmaf(sm.mel_val[e], mag[sm.mel_col[e]], acc);
+            float v = logf(fmaxf(acc, 1e-5f));
+            if (normalize) v = (v + 10.f) / 10.f;
+            dst[m] = v;
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T>
+int launch_logmel(
+    const T* audio,
+    const int64_t* audio_off, const int32_t* audio_len,
+    const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq,
+    const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize, float* out, void* stream) {
+    EMPH_REQUIRE(n_seq >= 0 && total_rows >= 0, "emph_logmel: negative size");
+    EMPH_REQUIRE(n_mels > 0 && n_mels <= kMaxMels, "emph_logmel: n_mels %d out of range", n_mels);
+    if (total_rows == 0) return EMPH_OK;
+    static bool configured = false;
+    const size_t smem = sizeof(LogmelSmem);
+    if (!configured) {
+        int s = check_cuda(
+            cudaFuncSetAttribute(
+                logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            "logmel smem attribute");
+        if (s != EMPH_OK) return s;
+        configured = true;
+    }
+    int per_sm = 3;
+    long want = ((long)total_rows + kWarps - 1) / kWarps;
+    long cap = (long)sm_count() * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    logmel_kernel<T><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
+        audio, audio_off, audio_len, chunk_start, chunk_len, row_start,
+        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out);
+    EMPH_CHECK_LAUNCH("emph_logmel");
+    return EMPH_OK;
+}
+
+}  // namespace emph
+
+extern "C" {
+
+int emph_logmel_f32(
+    const float* audio,
+    const int64_t* audio_off, const int32_t* audio_len,
+    const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq,
+    const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize, float* out, void* stream) {
+    return emph::launch_logmel<float>(
+        audio, audio_off, audio_len, chunk_start, chunk_len, row_start, n_seq,
+        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out, stream);
+}
+
+int emph_logmel_i16(
+    const int16_t* audio,
+    const int64_t* audio_off, const int32_t* audio_len,
+    const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq,
+    const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize, float* out, void* stream) {
+    return emph::launch_logmel<int16_t>(
+        audio, audio_off, audio_len, chunk_start, chunk_len, row_start, n_seq,
+        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out, stream);
+}
+
+}  // extern "C"

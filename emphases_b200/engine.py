@@ -1,0 +1,508 @@
+"""Packed-batch execution engine: host planning + kernel launches.
+
+Everything that computes runs in libemphases_b200.so (hand-written sm_100a
+kernels, include/emphases_b200.h).  PyTorch is used for device memory, streams
+and host<->device copies only.
+"""
+import dataclasses
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SAMPLE_RATE = 16000
+HOPSIZE = 160
+NUM_FFT = 1024
+WINDOW_SIZE = 1024
+PADDING = int((WINDOW_SIZE - HOPSIZE) / 2)   # 432, emphases/core.py:357
+
+ACTIVATIONS = {
+    'ReLU': _lib.ACT_RELU,
+    'GELU': _lib.ACT_GELU,
+    'LeakyReLU': _lib.ACT_LEAKY_RELU,
+    'SiLU': _lib.ACT_SILU,
+    'Identity': _lib.ACT_NONE,
+}
+
+
+###############################################################################
+# Mel basis (librosa.filters.mel restatement; reference call site
+# emphases/data/preprocess/mels.py:97-100)
+###############################################################################
+
+
+def _hz_to_mel(frequencies):
+    frequencies = np.atleast_1d(np.asarray(frequencies, dtype=np.float64))
+    f_sp = 200.0 / 3
+    mels = frequencies / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    log_t = frequencies >= min_log_hz
+    mels[log_t] = min_log_mel + np.log(frequencies[log_t] / min_log_hz) / logstep
+    return mels
+
+
+def _mel_to_hz(mels):
+    mels = np.atleast_1d(np.asarray(mels, dtype=np.float64))
+    f_sp = 200.0 / 3
+    freqs = f_sp * mels
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    log_t = mels >= min_log_mel
+    freqs[log_t] = min_log_hz * np.exp(logstep * (mels[log_t] - min_log_mel))
+    return freqs
+
+
+def mel_basis(sample_rate=SAMPLE_RATE, n_fft=NUM_FFT, n_mels=80):
+    """Slaney-scale, Slaney-normalised triangular filterbank (n_mels, 513)"""
+    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sample_rate)
+    edges = _mel_to_hz(np.linspace(
+        _hz_to_mel(0.0)[0], _hz_to_mel(sample_rate / 2.0)[0], n_mels + 2))
+    widths = np.diff(edges)
+    ramps = edges[:, None] - fftfreqs[None, :]
+    basis = np.zeros((n_mels, 1 + n_fft // 2), dtype=np.float32)
+    for i in range(n_mels):
+        basis[i] = np.maximum(
+            0, np.minimum(-ramps[i] / widths[i], ramps[i + 2] / widths[i + 1]))
+    basis *= (2.0 / (edges[2:] - edges[:-2]))[:, None]
+    return basis
+
+
+def basis_to_csr(basis):
+    """Dense (n_mels, 513) fp32 basis -> CSR arrays for emph_logmel_*"""
+    basis = np.asarray(basis, dtype=np.float32)
+    ptr = [0]
+    cols, vals = [], []
+    for row in basis:
+        nz = np.nonzero(row)[0]
+        cols.append(nz.astype(np.int16))
+        vals.append(row[nz])
+        ptr.append(ptr[-1] + len(nz))
+    return (
+        np.asarray(ptr, dtype=np.int32),
+        np.concatenate(cols).astype(np.int16),
+        np.concatenate(vals).astype(np.float32))
+
+
+###############################################################################
+# Host planning: chunker + packed layout (bit-exact integer logic)
+###############################################################################
+
+
+def seconds_to_frames(seconds):
+    """emphases/convert.py:19-31: float floor division"""
+    return (seconds * SAMPLE_RATE) // HOPSIZE
+
+
+def chunk_words(times: np.ndarray, num_samples: int, batch_size=None):
+    """Word-aligned chunking of emphases.preprocess (emphases/core.py:361-401)
+
+    times: (W, 2) float64 word (start, end) seconds.
+    Returns a list of (word_start, word_end, start_sample, length, bounds)
+    with bounds an (Wc, 2) int64 array relative to the chunk start; samples
+    are in zero-padded coordinates.  Chunks of <= 432 samples are dropped as
+    the reference silently does (core.py:413-415).
+    """
+    num_words = len(times)
+    padded = num_samples + 2 * PADDING
+    total_frames = int(padded / HOPSIZE)
+    batch_size = total_frames if batch_size is None else batch_size
+    durations = times[:, 1] - times[:, 0]
+    word_frames = (durations * SAMPLE_RATE) // HOPSIZE     # float, floor-div
+    chunks = []
+    start = 0
+    while start < num_words:
+        end = num_words
+        if start + 1 < num_words:
+            # frames accumulated after adding words start .. e-1, e = start+1..W-1
+            running = np.cumsum(word_frames[start:num_words - 1])
+            over = np.nonzero(running.astype(np.int64) > batch_size)[0]
+            if len(over):
+                end = start + int(over[0]) + 1
+        origin = times[start, 0]
+        chunk = times[start:end]
+        # pypar slice re-based to its first word, then int(t * sr / hop)
+        bounds = np.stack([
+            ((chunk[:, 0] - origin) * SAMPLE_RATE / HOPSIZE).astype(np.int64),
+            ((chunk[:, 1] - origin) * SAMPLE_RATE / HOPSIZE).astype(np.int64)],
+            axis=1)
+        start_sample = HOPSIZE * int(seconds_to_frames(float(times[start, 0])))
+        end_sample = HOPSIZE * int(seconds_to_frames(float(times[end - 1, 1])))
+        lo = min(max(start_sample, 0), padded)       # torch slice clipping
+        hi = min(max(end_sample, 0), padded)
+        length = max(hi - lo, 0)
+        if length > PADDING:
+            chunks.append((start, end, lo, length, bounds))
+        start = end
+    return chunks
+
+
+@dataclasses.dataclass
+class Plan:
+    """Host-side description of one packed launch"""
+    n_seq: int
+    total_rows: int
+    total_word_rows: int
+    utterance: np.ndarray        # (n_seq,) owning utterance of each chunk
+    word_first: np.ndarray       # (n_seq,) first word (in the utterance)
+    audio_off: np.ndarray        # int64 (n_seq,)
+    audio_len: np.ndarray        # int32 ...
+    chunk_start: np.ndarray
+    chunk_len: np.ndarray
+    row_start: np.ndarray
+    n_rows: np.ndarray
+    word_row_start: np.ndarray
+    n_words: np.ndarray
+    word_seq: np.ndarray         # (total_word_rows,)
+    word_lo: np.ndarray
+    word_hi: np.ndarray
+    audio_samples: int           # packed audio length (samples)
+    audio_offsets: np.ndarray    # int64 (n_utterances,) offset of each utterance
+
+    def int32_blob(self):
+        parts = [
+            self.audio_len, self.chunk_start, self.chunk_len, self.row_start,
+            self.n_rows, self.word_row_start, self.n_words, self.word_seq,
+            self.word_lo, self.word_hi]
+        return np.concatenate([p.astype(np.int32, copy=False) for p in parts])
+
+
+def packed_starts(lengths):
+    """Row layout with one separator row before, between and after sequences"""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    starts = 1 + np.concatenate([[0], np.cumsum(lengths[:-1] + 1)]) \
+        if len(lengths) else np.zeros(0, dtype=np.int64)
+    total = int(starts[-1] + lengths[-1] + 1) if len(lengths) else 1
+    return starts, total
+
+
+def make_plan(
+    utterances: Sequence,
+    batch_size: Optional[int] = None,
+    validate_method: Optional[str] = None
+) -> Plan:
+    """utterances: sequence of (times (W, 2) float64, num_samples)"""
+    utterance, word_first = [], []
+    audio_off, audio_len, chunk_start, chunk_len = [], [], [], []
+    bounds_list = []
+    offsets = np.zeros(len(utterances), dtype=np.int64)
+    cursor = 0
+    for index, (times, num_samples) in enumerate(utterances):
+        offsets[index] = cursor
+        for (w0, w1, start, length, bounds) in chunk_words(
+            np.asarray(times, dtype=np.float64).reshape(-1, 2),
+            int(num_samples),
+            batch_size
+        ):
+            utterance.append(index)
+            word_first.append(w0)
+            audio_off.append(cursor)
+            audio_len.append(num_samples)
+            chunk_start.append(start)
+            chunk_len.append(length)
+            bounds_list.append(bounds)
+        cursor += (int(num_samples) + 3) // 4 * 4        # keep offsets % 4 == 0
+    n_seq = len(utterance)
+    n_rows = np.asarray(chunk_len, dtype=np.int64) // HOPSIZE
+    n_words = np.asarray([len(b) for b in bounds_list], dtype=np.int64)
+    row_start, total_rows = packed_starts(n_rows)
+    word_row_start, total_word_rows = packed_starts(n_words)
+    if total_rows >= 2 ** 31 or cursor >= 2 ** 40:
+        raise ValueError('batch too large for one launch; split it')
+    word_seq = np.full(total_word_rows, -1, dtype=np.int32)
+    word_lo = np.zeros(total_word_rows, dtype=np.int32)
+    word_hi = np.zeros(total_word_rows, dtype=np.int32)
+    if n_seq:
+        all_bounds = np.concatenate(bounds_list, axis=0)
+        index = np.concatenate([
+            np.arange(s, s + n) for s, n in zip(word_row_start, n_words)])
+        word_seq[index] = np.repeat(np.arange(n_seq, dtype=np.int32), n_words)
+        word_lo[index] = all_bounds[:, 0]
+        word_hi[index] = all_bounds[:, 1]
+        if validate_method is not None:
+            validate_bounds(
+                all_bounds, np.repeat(n_rows, n_words), validate_method)
+    return Plan(
+        n_seq=n_seq,
+        total_rows=total_rows,
+        total_word_rows=total_word_rows,
+        utterance=np.asarray(utterance, dtype=np.int64),
+        word_first=np.asarray(word_first, dtype=np.int64),
+        audio_off=np.asarray(audio_off, dtype=np.int64),
+        audio_len=np.asarray(audio_len, dtype=np.int32),
+        chunk_start=np.asarray(chunk_start, dtype=np.int32),
+        chunk_len=np.asarray(chunk_len, dtype=np.int32),
+        row_start=row_start.astype(np.int32),
+        n_rows=n_rows.astype(np.int32),
+        word_row_start=word_row_start.astype(np.int32),
+        n_words=n_words.astype(np.int32),
+        word_seq=word_seq,
+        word_lo=word_lo,
+        word_hi=word_hi,
+        audio_samples=max(cursor, 4),
+        audio_offsets=offsets)
+
+
+def validate_bounds(bounds, frames, method):
+    """Raise where the reference raises (torch indexing)"""
+    lo = np.minimum(np.maximum(bounds[:, 0], 0), frames)
+    hi = np.minimum(np.maximum(bounds[:, 1], 0), frames)
+    if method == 'max' and np.any(hi <= lo):
+        raise IndexError(
+            'max(): Expected reduction dim 1 to have non-zero size '
+            '(a word spans zero frames)')
+    if method == 'center' and np.any((bounds[:, 0] + bounds[:, 1]) // 2 >= frames):
+        raise IndexError('center frame index out of range for a word')
+
+
+###############################################################################
+# Weights
+###############################################################################
+
+
+@dataclasses.dataclass
+class ConvStack:
+    weights: torch.Tensor        # [L][K][C][C] fp32 device
+    bias: torch.Tensor           # [L][C]
+    acts: np.ndarray             # int32 host
+    kernel_size: int
+    channels: int
+
+    @property
+    def n_layers(self):
+        return len(self.acts)
+
+
+@dataclasses.dataclass
+class ModelWeights:
+    frame: ConvStack
+    word: Optional[ConvStack]
+    head_weight: torch.Tensor    # [K][C]
+    head_bias: float
+    head_kernel: int
+    channels: int
+
+
+def _pack_conv(weight, device):
+    """Conv1d (out, in, k) -> [k][in][out] on device via the C ABI"""
+    weight = weight.detach().to(device=device, dtype=torch.float32).contiguous()
+    out_channels, in_channels, kernel = weight.shape
+    packed = torch.empty(
+        (kernel, in_channels, out_channels), dtype=torch.float32, device=device)
+    _lib.call(
+        'emph_pack_conv_weights', _lib.ptr(weight), out_channels, in_channels,
+        kernel, _lib.ptr(packed), _lib.stream_ptr())
+    return packed
+
+
+def pack_weights(state, device, layers, activation, dropout, has_decoder):
+    """Reference state_dict -> packed device buffers
+
+    `state` keys: input_layer, frame_encoder.{i}, word_decoder.{i},
+    output_layer; Sequential indices step by 2, or 3 with dropout
+    (emphases/model/layers/convolution.py:25-30).
+    """
+    step = 3 if dropout is not None else 2
+    act = ACTIVATIONS[activation]
+
+    def stack(first, prefix):
+        convs = list(first)
+        convs += [
+            (state[f'{prefix}.{i * step}.weight'],
+             state[f'{prefix}.{i * step}.bias']) for i in range(layers)]
+        channels = convs[-1][0].shape[0]
+        kernel = convs[-1][0].shape[2]
+        for weight, _ in convs:
+            if tuple(weight.shape) != (channels, channels, kernel):
+                raise NotImplementedError(
+                    'conv stack needs equal in/out channels and kernel sizes, '
+                    f'got {tuple(weight.shape)}')
+        weights = torch.stack([_pack_conv(w, device) for w, _ in convs])
+        bias = torch.stack([
+            b.detach().to(device=device, dtype=torch.float32) for _, b in convs])
+        acts = np.asarray(
+            [_lib.ACT_NONE] * len(first) + [act] * layers, dtype=np.int32)
+        return ConvStack(weights.contiguous(), bias.contiguous(), acts, kernel, channels)
+
+    frame = stack(
+        [(state['input_layer.weight'], state['input_layer.bias'])],
+        'frame_encoder')
+    word = stack([], 'word_decoder') if has_decoder else None
+    head = state['output_layer.weight'].detach().to(
+        device=device, dtype=torch.float32)           # (1, C, K)
+    head_weight = head[0].t().contiguous()            # [K][C]
+    return ModelWeights(
+        frame=frame,
+        word=word,
+        head_weight=head_weight,
+        head_bias=float(state['output_layer.bias'].detach().float().cpu()[0]),
+        head_kernel=head.shape[2],
+        channels=frame.channels)
+
+
+###############################################################################
+# Engine
+###############################################################################
+
+
+class Engine:
+    """Owns device-side constants and launches the kernels of one GPU"""
+
+    def __init__(self, device, n_mels=80):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.EmphasesB200Error(
+                'emphases_b200 runs on CUDA devices only (no CPU fallback)')
+        _lib.load()
+        self.n_mels = n_mels
+        with torch.cuda.device(self.device):
+            ptr, col, val = basis_to_csr(mel_basis(n_mels=n_mels))
+            self.mel_ptr = torch.from_numpy(ptr).to(self.device)
+            self.mel_col = torch.from_numpy(col).to(self.device)
+            self.mel_val = torch.from_numpy(val).to(self.device)
+        self._pinned = {}
+
+    # -- host staging ------------------------------------------------------
+
+    def pinned(self, key, numel, dtype):
+        """Grow-only pinned staging buffer"""
+        buffer = self._pinned.get(key)
+        if buffer is None or buffer.numel() < numel or buffer.dtype != dtype:
+            buffer = torch.empty(
+                max(numel, 1), dtype=dtype, pin_memory=True)
+            self._pinned[key] = buffer
+        return buffer[:numel]
+
+    def upload_plan(self, plan: Plan):
+        """One H2D copy for all int32 index arrays (+ one for int64 offsets)"""
+        blob = plan.int32_blob()
+        staging = self.pinned('plan32', len(blob), torch.int32)
+        staging.numpy()[:] = blob
+        device_blob = staging.to(self.device, non_blocking=True)
+        off_staging = self.pinned('plan64', max(plan.n_seq, 1), torch.int64)
+        off_staging.numpy()[:plan.n_seq] = plan.audio_off
+        audio_off = off_staging.to(self.device, non_blocking=True)
+        n, w = plan.n_seq, plan.total_word_rows
+        sizes = [n, n, n, n, n, n, n, w, w, w]
+        names = [
+            'audio_len', 'chunk_start', 'chunk_len', 'row_start', 'n_rows',
+            'word_row_start', 'n_words', 'word_seq', 'word_lo', 'word_hi']
+        views, cursor = {}, 0
+        for name, size in zip(names, sizes):
+            views[name] = device_blob[cursor:cursor + size]
+            cursor += size
+        views['audio_off'] = audio_off
+        return views
+
+    # -- kernels -----------------------------------------------------------
+
+    def row_index(self, row_start, n_rows, n_seq, total_rows):
+        row_seq = torch.empty(total_rows, dtype=torch.int32, device=self.device)
+        _lib.call(
+            'emph_row_index', _lib.ptr(row_start), _lib.ptr(n_rows), n_seq,
+            _lib.ptr(row_seq), total_rows, _lib.stream_ptr())
+        return row_seq
+
+    def logmel(self, audio, views, plan, row_seq, normalize=False):
+        out = torch.empty(
+            (plan.total_rows, self.n_mels), dtype=torch.float32,
+            device=self.device)
+        name = {torch.float32: 'emph_logmel_f32', torch.int16: 'emph_logmel_i16'}[
+            audio.dtype]
+        _lib.call(
+            name, _lib.ptr(audio), _lib.ptr(views['audio_off']),
+            _lib.ptr(views['audio_len']), _lib.ptr(views['chunk_start']),
+            _lib.ptr(views['chunk_len']), _lib.ptr(views['row_start']),
+            plan.n_seq, _lib.ptr(row_seq), plan.total_rows,
+            _lib.ptr(self.mel_ptr), _lib.ptr(self.mel_col),
+            _lib.ptr(self.mel_val), self.n_mels, int(bool(normalize)),
+            _lib.ptr(out), _lib.stream_ptr())
+        return out
+
+    def conv_stack(self, x, row_seq, stack: ConvStack, precision):
+        y = torch.empty_like(x)
+        import ctypes
+        acts = stack.acts.astype(np.int32)
+        _lib.call(
+            'emph_conv_stack', _lib.ptr(x), _lib.ptr(row_seq), x.shape[0],
+            _lib.ptr(stack.weights), _lib.ptr(stack.bias),
+            acts.ctypes.data_as(ctypes.c_void_p), stack.n_layers,
+            stack.channels, stack.kernel_size, precision, _lib.ptr(y),
+            _lib.stream_ptr())
+        return y
+
+    def pool(self, x, row_start, n_rows, word_seq, word_lo, word_hi, method):
+        total_word_rows = word_seq.shape[0]
+        y = torch.empty(
+            (total_word_rows, x.shape[1]), dtype=torch.float32,
+            device=self.device)
+        _lib.call(
+            'emph_pool_words', _lib.ptr(x), x.shape[1], _lib.ptr(row_start),
+            _lib.ptr(n_rows), _lib.ptr(word_seq), _lib.ptr(word_lo),
+            _lib.ptr(word_hi), total_word_rows, _lib.POOL[method], _lib.ptr(y),
+            _lib.stream_ptr())
+        return y
+
+    def head(self, x, row_seq, weights: ModelWeights, mode, want_logits=True,
+             want_scores=True):
+        rows = x.shape[0]
+        logits = torch.empty(rows, dtype=torch.float32, device=self.device) \
+            if want_logits else None
+        scores = torch.empty(rows, dtype=torch.float32, device=self.device) \
+            if want_scores else None
+        _lib.call(
+            'emph_output_head', _lib.ptr(x), _lib.ptr(row_seq), rows,
+            weights.channels, weights.head_kernel, _lib.ptr(weights.head_weight),
+            weights.head_bias, mode, _lib.ptr(logits), _lib.ptr(scores),
+            _lib.stream_ptr())
+        return logits, scores
+
+    # -- whole path --------------------------------------------------------
+
+    def forward_packed(
+        self,
+        audio,
+        plan: Plan,
+        weights: ModelWeights,
+        method='sum',
+        location='intermediate',
+        precision=_lib.PREC_FP32,
+        head_mode=_lib.HEAD_SIGMOID,
+        normalize=False,
+        views=None,
+        keep=False
+    ):
+        """audio: packed device tensor (fp32 or int16).  Returns dict with
+        `scores` and `logits` per packed word row (device tensors)."""
+        if location not in ('intermediate', 'loss', 'inference'):
+            raise ValueError(
+                f'Downsample location {location} not handled by the packed path')
+        if views is None:
+            views = self.upload_plan(plan)
+        row_seq = self.row_index(
+            views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+        word_row_seq = self.row_index(
+            views['word_row_start'], views['n_words'], plan.n_seq,
+            plan.total_word_rows)
+        features = self.logmel(audio, views, plan, row_seq, normalize)
+        frames = self.conv_stack(features, row_seq, weights.frame, precision)
+        pooled = self.pool(
+            frames, views['row_start'], views['n_rows'], views['word_seq'],
+            views['word_lo'], views['word_hi'], method)
+        if location == 'intermediate':
+            words = self.conv_stack(
+                pooled, word_row_seq, weights.word, _lib.PREC_FP32)
+        else:
+            words = pooled
+        logits, scores = self.head(words, word_row_seq, weights, head_mode)
+        result = {'scores': scores, 'logits': logits}
+        if keep:
+            result.update(
+                features=features, frames=frames, pooled=pooled,
+                row_seq=row_seq, word_row_seq=word_row_seq, views=views)
+        return result

@@ -1,0 +1,198 @@
+/*
+ * emphases_b200 -- C ABI of the B200-native (sm_100a) inference hot path of
+ * interactiveaudiolab/emphases:
+ *
+ *   waveform + word alignment -> log-mel -> framewise Conv1d/ReLU stack ->
+ *   word-bound segment pooling -> word decoder -> Conv1d(->1) -> sigmoid
+ *
+ * The reference has no FFI of its own (it is pure Python/PyTorch); every entry
+ * point below replaces one Python/PyTorch call site of the reference, cited as
+ * file:line relative to the reference root.  The host mirror of the reference's
+ * Python API (emphases_b200/) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it;
+ *   - every function returns 0 on success, a negative EMPH_E* code on failure,
+ *     never throws; emph_last_error() returns a thread-local message;
+ *   - nothing allocates: the caller owns all buffers;
+ *   - index arrays are int32 (int64 for sample offsets).
+ *
+ * Packed ("ragged, no padding FLOPs") layout
+ *   A launch processes n_seq sequences (utterance chunks).  All frame-resolution
+ *   tensors are [total_rows][channels] fp32, row-major (channel contiguous).
+ *   Sequence u owns rows [row_start[u], row_start[u] + n_rows[u]); between two
+ *   sequences, before the first and after the last there is at least ONE
+ *   separator row, whose content is forced to zero at every layer -- that
+ *   reproduces Conv1d(padding='same') zero padding per utterance
+ *   (emphases/model/layers/convolution.py:17-20) without per-utterance launches.
+ *   `row_seq[r]` = owning sequence of row r, or -1 for a separator.
+ *   The word-resolution tensors use the same layout over "word rows".
+ */
+#ifndef EMPHASES_B200_H
+#define EMPHASES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMPH_OK 0
+#define EMPH_EINVAL (-22)   /* bad argument */
+#define EMPH_ECUDA (-5)     /* CUDA runtime error, see emph_last_error() */
+#define EMPH_ENOSYS (-38)   /* configuration not compiled in */
+
+/* activation codes (emphases/config/defaults.py:181 ACTIVATION_FUNCTION and the
+ * config/hparam-search activations) */
+#define EMPH_ACT_NONE 0
+#define EMPH_ACT_RELU 1
+#define EMPH_ACT_GELU 2
+#define EMPH_ACT_LEAKY_RELU 3
+#define EMPH_ACT_SILU 4
+
+/* pooling methods (emphases/core.py:426-469 DOWNSAMPLE_METHOD) */
+#define EMPH_POOL_AVERAGE 0
+#define EMPH_POOL_MAX 1
+#define EMPH_POOL_SUM 2
+#define EMPH_POOL_CENTER 3
+
+/* head modes (emphases/core.py:335-342 postprocess) */
+#define EMPH_HEAD_LOGITS 0
+#define EMPH_HEAD_SIGMOID 1   /* LOSS == 'bce' */
+#define EMPH_HEAD_CLAMP 2     /* LOSS == 'mse' */
+
+/* precision modes of the conv stack */
+#define EMPH_PREC_FP32 0      /* CUDA-core FFMA, max-abs 1e-5 on scores */
+#define EMPH_PREC_BF16_TC 1   /* tcgen05 bf16 MMA, fp32 accumulate, 2e-3 */
+
+int emph_version(void);
+const char* emph_last_error(void);
+
+/* Number of SMs of the current device (for callers that size work lists). */
+int emph_device_sm_count(void);
+
+/*
+ * row_seq[r] = u if row_start[u] <= r < row_start[u] + n_rows[u] else -1.
+ * row_start must be strictly increasing.  Replaces the implicit batch
+ * dimension of the reference's padded tensors (emphases/data/collate.py:11-78).
+ */
+int emph_row_index(
+    const int32_t* row_start, const int32_t* n_rows, int32_t n_seq,
+    int32_t* row_seq, int32_t total_rows, void* stream);
+
+/*
+ * Log-mel features of every chunk, fused: zero pad (emphases/core.py:357-358),
+ * chunk slice (core.py:395-401), reflect pad (emphases/data/preprocess/
+ * mels.py:32-36), Hann window + 1024-point real FFT with hop 160
+ * (mels.py:39-48), sqrt(re^2+im^2+1e-6) (mels.py:51), mel projection and
+ * log(clamp(.,1e-5)) (mels.py:94-109), optional (x+10)/10 (mels.py:57-58).
+ *
+ *   audio          packed fp32 samples (channel 0 of each utterance)
+ *   audio_off[u]   first sample of the utterance chunk u is cut from
+ *                  (must be a multiple of 4)
+ *   audio_len[u]   T, that utterance's length in samples
+ *   chunk_start[u] first sample of the chunk in ZERO-PADDED coordinates
+ *                  (432 zeros before the utterance), = 160 * first frame
+ *   chunk_len[u]   L, chunk length in samples (> 432); frames = L / 160
+ *   row_start[u]   first packed row of the chunk; n_rows = L / 160
+ *   mel_ptr/col/val  CSR of the (n_mels x 513) mel basis (an input, as in
+ *                  the reference where librosa supplies it, mels.py:97-100)
+ *   out            [total_rows][n_mels] fp32; separator rows are zeroed
+ */
+int emph_logmel_f32(
+    const float* audio,
+    const int64_t* audio_off, const int32_t* audio_len,
+    const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq,
+    const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    float* out, void* stream);
+
+/* Same, int16 PCM input scaled by 1/32768 (what torchaudio.load returns for
+ * 16-bit wav files, emphases/load.py:11-17). */
+int emph_logmel_i16(
+    const int16_t* audio,
+    const int64_t* audio_off, const int32_t* audio_len,
+    const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq,
+    const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    float* out, void* stream);
+
+/*
+ * A stack of n_layers Conv1d(channels -> channels, kernel_size,
+ * padding='same') layers, each followed by its activation, over the packed row
+ * axis (emphases/model/core.py:17-20 input_layer + emphases/model/layers/
+ * convolution.py:13-37; also the word decoder, model/core.py:105-107).
+ *
+ *   x, y       [total_rows][channels] fp32 (may alias)
+ *   weights    [n_layers][kernel_size][channels(in)][channels(out)] fp32,
+ *              produced by emph_pack_conv_weights from Conv1d (out, in, k)
+ *   bias       [n_layers][channels]
+ *   acts       [n_layers] EMPH_ACT_* codes (host pointer)
+ *   precision  EMPH_PREC_*
+ */
+int emph_conv_stack(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const float* bias, const int32_t* acts_host,
+    int32_t n_layers, int32_t channels, int32_t kernel_size,
+    int32_t precision, float* y, void* stream);
+
+/* (out, in, k) Conv1d weight -> [k][in][out] (device to device). */
+int emph_pack_conv_weights(
+    const float* conv_weight, int32_t out_channels, int32_t in_channels,
+    int32_t kernel_size, float* packed, void* stream);
+
+/*
+ * Frame -> word segment pooling (emphases/core.py:426-469 `downsample`).
+ * One warp per word row, driven by integer offset arrays, no host round trip.
+ *
+ *   x              [total_rows][channels] fp32 frame-resolution activations
+ *   row_start[u], n_rows[u]  frame rows of sequence u
+ *   word_seq[w]    owning sequence of word row w, -1 for separator word rows
+ *   word_lo/hi[w]  word bounds [lo, hi) in frames relative to the sequence
+ *                  start, exactly the int64 bounds of core.py:384-392;
+ *                  hi is clipped to n_rows[u] like a torch slice.  lo = hi =
+ *                  -1 marks a padded word slot (j >= word_lengths[i]): zeros
+ *                  for average/max/sum, frame 0 for center (core.py:458-466).
+ *   y              [total_word_rows][channels]; separator rows zeroed
+ * Empty segments: sum -> 0, average -> NaN (as torch.mean of an empty slice),
+ * max -> -inf (the reference raises IndexError; the host mirror raises it
+ * before launching).
+ */
+int emph_pool_words(
+    const float* x, int32_t channels,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* word_seq, const int32_t* word_lo, const int32_t* word_hi,
+    int32_t total_word_rows, int32_t method, float* y, void* stream);
+
+/*
+ * Output projection Conv1d(channels -> 1, kernel_size, 'same') over packed rows
+ * (emphases/model/core.py:33-37,138) + postprocess (core.py:335-342).
+ *   weight [kernel_size][channels], bias_host scalar.
+ *   logits/scores [total_rows] (either may be NULL); separator rows get 0.
+ */
+int emph_output_head(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    int32_t channels, int32_t kernel_size, const float* weight, float bias_host,
+    int32_t mode, float* logits, float* scores, void* stream);
+
+/* (B, C, T) channel-major tensor (the reference's layout, model/core.py:39)
+ * <-> packed rows.  Sequence b occupies rows [row_start[b], +n_rows[b]) and
+ * columns [0, n_rows[b]) of its (C, T) plane with plane stride C * T. */
+int emph_pack_rows(
+    const float* bct, int32_t batch, int32_t channels, int32_t frames,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* row_seq, int32_t total_rows, float* rows, void* stream);
+int emph_unpack_rows(
+    const float* rows, const int32_t* row_start, const int32_t* n_rows,
+    int32_t batch, int32_t channels, int32_t frames, float* bct, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMPHASES_B200_H */

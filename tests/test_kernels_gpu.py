@@ -1,0 +1,329 @@
+"""GPU parity tests: each sm_100a kernel, called through the C ABI, against
+the CPU oracle and the golden vectors of the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import state_from_golden, times_list
+from oracle import emphases_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+METHODS = ['average', 'max', 'sum', 'center']
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from emphases_b200 import engine
+    return engine.Engine('cuda:0')
+
+
+def default_weights(state, has_decoder=True):
+    from emphases_b200 import engine
+    return engine.pack_weights(
+        state, torch.device('cuda:0'), layers=6, activation='ReLU',
+        dropout=None, has_decoder=has_decoder)
+
+
+def make_rows(lengths):
+    """Packed layout helpers on device"""
+    from emphases_b200 import engine
+    starts, total = engine.packed_starts(lengths)
+    row_start = torch.tensor(starts, dtype=torch.int32, device='cuda:0')
+    n_rows = torch.tensor(lengths, dtype=torch.int32, device='cuda:0')
+    return row_start, n_rows, total
+
+
+def test_row_index(eng):
+    lengths = [5, 1, 7, 3]
+    row_start, n_rows, total = make_rows(lengths)
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total).cpu().numpy()
+    expected = np.full(total, -1)
+    cursor = 1
+    for u, n in enumerate(lengths):
+        expected[cursor:cursor + n] = u
+        cursor += n + 1
+    np.testing.assert_array_equal(row_seq, expected)
+
+
+@pytest.mark.parametrize('tag,count', [('full', 1), ('bs300', 3)])
+@pytest.mark.parametrize('dtype', ['f32', 'i16'])
+def test_logmel_golden(eng, golden, tag, count, dtype):
+    """log-mel of every chunk of the C1 example vs the reference's features"""
+    from emphases_b200 import engine
+    data = golden('c1')
+    times = np.asarray(data['times'])
+    audio = torch.from_numpy(data['audio'])
+    if dtype == 'i16':
+        pcm = (audio * 32768.).round().clamp(-32768, 32767).to(torch.int16)
+        audio = pcm.float() / 32768.
+        device_audio = pcm[0].cuda()
+    else:
+        device_audio = audio[0].cuda()
+    batch_size = None if tag == 'full' else 300
+    plan = engine.make_plan([(times, audio.shape[-1])], batch_size)
+    assert plan.n_seq == count
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(
+        views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    out = eng.logmel(device_audio, views, plan, row_seq).cpu()
+    expected_chunks = list(oracle.preprocess(
+        times_list(times), audio, batch_size, data['mel_basis']))
+    for u in range(count):
+        rows = out[plan.row_start[u]:plan.row_start[u] + plan.n_rows[u]]
+        expected = expected_chunks[u][0][0].T
+        assert rows.shape == expected.shape
+        error = (rows - expected).abs().max().item()
+        assert error < 2e-5, f'chunk {u}: log-mel max-abs {error}'
+        if dtype == 'f32':
+            np.testing.assert_allclose(
+                rows.numpy(), data[f'{tag}.{u}.features'][0].T, atol=2e-5)
+        # separator rows are zero
+        assert out[plan.row_start[u] - 1].abs().max() == 0
+    assert out[-1].abs().max() == 0
+
+
+def test_logmel_ragged_edges(eng):
+    """clipped chunks (alignment past the audio end), odd lengths, tiny chunks"""
+    from emphases_b200 import engine
+    generator = torch.Generator().manual_seed(3)
+    utterances, audios = [], []
+    for samples, times in [
+        (16000, [[0.0, 0.5], [0.5, 1.2]]),          # alignment past the end
+        (7777, [[0.0, 0.2], [0.2, 0.45]]),          # odd length
+        (1600, [[0.03, 0.09]]),                     # tiny: 960 samples
+        (48000, [[0.5, 1.0], [1.0, 2.9]]),          # first word starts late
+    ]:
+        audio = 0.1 * torch.randn(1, samples, generator=generator)
+        utterances.append((np.asarray(times), samples))
+        audios.append(audio)
+    plan = engine.make_plan(utterances)
+    packed = torch.zeros(plan.audio_samples)
+    for offset, audio in zip(plan.audio_offsets, audios):
+        packed[offset:offset + audio.shape[-1]] = audio[0]
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(
+        views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    out = eng.logmel(packed.cuda(), views, plan, row_seq).cpu()
+    for u in range(plan.n_seq):
+        index = int(plan.utterance[u])
+        expected = list(oracle.preprocess(
+            times_list(utterances[index][0]), audios[index]))[0][0][0].T
+        rows = out[plan.row_start[u]:plan.row_start[u] + plan.n_rows[u]]
+        assert rows.shape == expected.shape
+        assert (rows - expected).abs().max().item() < 2e-5
+
+
+def oracle_conv_rows(state, prefix_layers, x_rows, lengths):
+    """Apply convs per sequence with the oracle, return packed rows"""
+    from emphases_b200 import engine
+    starts, total = engine.packed_starts(lengths)
+    out = torch.zeros(total, x_rows.shape[1])
+    for start, n in zip(starts, lengths):
+        x = x_rows[start:start + n].T[None]
+        with torch.no_grad():
+            for weight, bias, relu in prefix_layers:
+                x = oracle._conv(x, weight, bias)
+                if relu:
+                    x = torch.relu(x)
+        out[start:start + n] = x[0].T
+    return out
+
+
+@pytest.mark.parametrize('which', ['frame', 'word'])
+def test_conv_stack_f32(eng, golden, which):
+    from emphases_b200 import _lib
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    generator = torch.Generator().manual_seed(4)
+    lengths = [300, 1, 2, 131, 57, 640]
+    row_start, n_rows, total = make_rows(lengths)
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total)
+    x = torch.randn(total, 80, generator=generator)
+    x[(row_seq < 0).cpu()] = 0
+    if which == 'frame':
+        layers = [(state['input_layer.weight'], state['input_layer.bias'], False)]
+        layers += [
+            (state[f'frame_encoder.{2 * i}.weight'],
+             state[f'frame_encoder.{2 * i}.bias'], True) for i in range(6)]
+        stack = weights.frame
+    else:
+        layers = [
+            (state[f'word_decoder.{2 * i}.weight'],
+             state[f'word_decoder.{2 * i}.bias'], True) for i in range(6)]
+        stack = weights.word
+    y = eng.conv_stack(x.cuda(), row_seq, stack, _lib.PREC_FP32).cpu()
+    expected = oracle_conv_rows(state, layers, x, lengths)
+    scale = expected.abs().max().item()
+    error = (y - expected).abs().max().item()
+    assert error < 2e-6 * max(scale, 1.0), (error, scale)
+    assert y[(row_seq < 0).cpu()].abs().max() == 0
+
+
+@pytest.mark.parametrize('method', METHODS)
+def test_pool_clean(eng, golden, method):
+    data = golden('pool')
+    xs = torch.from_numpy(data['xs'])                     # (2, 80, 50)
+    bounds = data['clean_bounds']
+    lengths = data['clean_lengths']
+    pooled = run_pool(eng, xs, bounds, lengths, method)
+    np.testing.assert_allclose(
+        pooled, data[f'clean.{method}'], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('method', ['average', 'sum'])
+def test_pool_adversarial(eng, golden, method):
+    """zero-length words, single-frame words, bounds past T, late first word"""
+    data = golden('pool')
+    xs = torch.from_numpy(data['xs'])
+    pooled = run_pool(eng, xs, data['bounds'], data['lengths'], method)
+    expected = data[f'adversarial.{method}']
+    np.testing.assert_array_equal(np.isnan(pooled), np.isnan(expected))
+    np.testing.assert_allclose(
+        np.nan_to_num(pooled), np.nan_to_num(expected), rtol=1e-6, atol=1e-6)
+
+
+def run_pool(eng, xs, bounds, lengths, method):
+    """(B, C, T) + padded bounds -> (B, C, Wmax) through emph_pool_words"""
+    B, C, T = xs.shape
+    wmax = bounds.shape[2]
+    row_start, n_rows, total = make_rows([T] * B)
+    word_row_start, n_words, total_words = make_rows([wmax] * B)
+    rows = torch.zeros(total, C)
+    for b in range(B):
+        rows[int(row_start[b]):int(row_start[b]) + T] = xs[b].T
+    word_seq = torch.full((total_words,), -1, dtype=torch.int32)
+    word_lo = torch.zeros(total_words, dtype=torch.int32)
+    word_hi = torch.zeros(total_words, dtype=torch.int32)
+    for b in range(B):
+        s = int(word_row_start[b])
+        word_seq[s:s + wmax] = b
+        word_lo[s:s + wmax] = torch.from_numpy(bounds[b, 0]).int()
+        word_hi[s:s + wmax] = torch.from_numpy(bounds[b, 1]).int()
+        word_lo[s + int(lengths[b]):s + wmax] = -1     # padded word slots
+        word_hi[s + int(lengths[b]):s + wmax] = -1
+    y = eng.pool(
+        rows.cuda(), row_start, n_rows, word_seq.cuda(), word_lo.cuda(),
+        word_hi.cuda(), method).cpu()
+    out = np.zeros((B, C, wmax), dtype=np.float32)
+    for b in range(B):
+        s = int(word_row_start[b])
+        out[b] = y[s:s + wmax].T.numpy()
+        assert y[s - 1].abs().max() == 0
+    return out
+
+
+def test_pool_segment_assignment_bit_exact(eng):
+    """Integer check of segmentation: pool one-hot frame indicators with `sum`
+    so pooled[w][c] counts the frames of word w -> exact [lo, hi) recovery"""
+    from emphases_b200 import engine
+    utterances = []
+    for seed in range(6):
+        times, audio = oracle.synthetic_utterance(200 + seed)
+        utterances.append((np.asarray(times), audio.shape[-1]))
+    plan = engine.make_plan(utterances)
+    views = eng.upload_plan(plan)
+    # channel 0: 1.0, channel 1: frame index within the sequence, channel 2: idx^2
+    x = torch.zeros(plan.total_rows, 80)
+    for u in range(plan.n_seq):
+        s, n = int(plan.row_start[u]), int(plan.n_rows[u])
+        idx = torch.arange(n, dtype=torch.float32)
+        x[s:s + n, 0] = 1
+        x[s:s + n, 1] = idx
+    y = eng.pool(
+        x.cuda(), views['row_start'], views['n_rows'], views['word_seq'],
+        views['word_lo'], views['word_hi'], 'sum').cpu()
+    for u in range(plan.n_seq):
+        expected = oracle.word_bounds(
+            [tuple(t) for t in utterances[u][0].tolist()])
+        s = int(plan.word_row_start[u])
+        for j, (lo, hi) in enumerate(expected):
+            hi = min(hi, int(plan.n_rows[u]))
+            count = int(y[s + j, 0])
+            total = int(y[s + j, 1])
+            assert count == hi - lo
+            assert total == (lo + hi - 1) * (hi - lo) // 2
+
+
+def test_head(eng, golden):
+    from emphases_b200 import _lib
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    lengths = [25, 1, 9]
+    row_start, n_rows, total = make_rows(lengths)
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total)
+    generator = torch.Generator().manual_seed(8)
+    x = torch.randn(total, 80, generator=generator)
+    x[(row_seq < 0).cpu()] = 0
+    logits, scores = eng.head(x.cuda(), row_seq, weights, _lib.HEAD_SIGMOID)
+    layers = [(state['output_layer.weight'], state['output_layer.bias'], False)]
+    from emphases_b200 import engine
+    starts, _ = engine.packed_starts(lengths)
+    for start, n in zip(starts, lengths):
+        with torch.no_grad():
+            expected = oracle._conv(
+                x[start:start + n].T[None], *layers[0][:2])[0, 0]
+        np.testing.assert_allclose(
+            logits.cpu()[start:start + n].numpy(), expected.numpy(), atol=2e-6)
+        np.testing.assert_allclose(
+            scores.cpu()[start:start + n].numpy(),
+            torch.sigmoid(expected).numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize('batch_size', [None, 300, 100])
+def test_forward_packed_golden(eng, golden, batch_size):
+    """Whole path on the C1 example with the bundled checkpoint, fp32 mode:
+    scores within 1e-5 of the reference, intermediates compared too"""
+    from emphases_b200 import engine
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    times = np.asarray(data['times'])
+    plan = engine.make_plan([(times, 160000)], batch_size)
+    audio = torch.from_numpy(data['audio'])[0].cuda()
+    result = eng.forward_packed(audio, plan, weights, keep=True)
+    tag = 'full' if batch_size is None else f'bs{batch_size}'
+    scores = torch.cat([
+        result['scores'][s:s + n]
+        for s, n in zip(plan.word_row_start, plan.n_words)]).cpu().numpy()
+    expected = data[f'{tag}.scores'][0]
+    error = np.abs(scores - expected).max()
+    assert error < 1e-5, f'scores max-abs {error}'
+    if batch_size is None:
+        s, n = int(plan.row_start[0]), int(plan.n_rows[0])
+        frames = result['frames'][s:s + n].cpu().numpy()
+        np.testing.assert_allclose(
+            frames, data['full.frame_embeddings'][0].T, atol=2e-5)
+        ws, wn = int(plan.word_row_start[0]), int(plan.n_words[0])
+        pooled = result['pooled'][ws:ws + wn].cpu().numpy()
+        np.testing.assert_allclose(
+            pooled, data['full.word_embeddings'][0].T, rtol=2e-6, atol=2e-4)
+
+
+def test_forward_packed_ragged_batch(eng, golden):
+    """Many ragged utterances in ONE packed launch == per-utterance oracle"""
+    from emphases_b200 import engine
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    utterances, audios, all_times = [], [], []
+    for seed in range(12):
+        times, audio = oracle.synthetic_utterance(300 + seed)
+        utterances.append((np.asarray(times), audio.shape[-1]))
+        audios.append(audio)
+        all_times.append(times)
+    plan = engine.make_plan(utterances)
+    packed = torch.zeros(plan.audio_samples)
+    for offset, audio in zip(plan.audio_offsets, audios):
+        packed[offset:offset + audio.shape[-1]] = audio[0]
+    result = eng.forward_packed(packed.cuda(), plan, weights)
+    scores = result['scores'].cpu()
+    worst = 0.0
+    for u in range(plan.n_seq):
+        expected = oracle.from_alignment_and_audio(
+            all_times[u], audios[u], state)[0]
+        s, n = int(plan.word_row_start[u]), int(plan.n_words[u])
+        worst = max(worst, (scores[s:s + n] - expected).abs().max().item())
+    assert worst < 1e-5, worst
