@@ -124,7 +124,9 @@ def _fill_gaps(words, tolerance=1e-9):
     result = []
     cursor = 0.
     for word in words:
-        label = word.word if word.word.strip() else SILENCE
+        label = word.word
+        if label.strip() in ('', 'sp', 'sil'):
+            label = SILENCE
         if word.start() - cursor > tolerance:
             result.append(Word(SILENCE, cursor, word.start()))
         result.append(Word(label, word.start(), word.end()))
@@ -153,7 +155,12 @@ _NUMBER = r'[-+]?\d+(?:\.\d*)?(?:[eE][-+]?\d+)?'
 
 
 def _parse_tiers(text):
-    # Tokenise into quoted strings and numbers; works for long and short form
+    # Tokenise into quoted strings and numbers; works for long and short form.
+    # Quoted strings are matched first so digits inside labels survive; the
+    # bracketed indices of the long form ("intervals [3]:") are dropped.
+    text = re.sub(r'"(?:[^"]|"")*"|\[\s*\d*\s*\]',
+                  lambda m: m.group(0) if m.group(0).startswith('"') else ' ',
+                  text)
     tokens = re.findall(r'"((?:[^"]|"")*)"|(' + _NUMBER + r')', text)
     items = [
         ('s', s.replace('""', '"')) if n == '' else ('n', float(n))

@@ -96,9 +96,52 @@ __global__ void unpack_rows_kernel(
     }
 }
 
+// one warp per destination row
+__global__ void segment_rows_kernel(
+    const float* __restrict__ x, int channels,
+    const int32_t* __restrict__ src_row, const int32_t* __restrict__ count,
+    const int32_t* __restrict__ dst_row_start,
+    const int32_t* __restrict__ dst_row_seq, int total_dst_rows,
+    float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int groups = channels >> 2;
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+         r < total_dst_rows; r += gridDim.x * (blockDim.x >> 5)) {
+        const int q = __ldg(dst_row_seq + r);
+        const float* src = nullptr;
+        if (q >= 0) {
+            int i = r - __ldg(dst_row_start + q);
+            if (i < __ldg(count + q))
+                src = x + (size_t)(__ldg(src_row + q) + i) * channels;
+        }
+        for (int g = lane; g < groups; g += 32) {
+            float4 v = src ? *reinterpret_cast<const float4*>(src + 4 * g)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(y + (size_t)r * channels + 4 * g) = v;
+        }
+    }
+}
+
 }  // namespace emph
 
 extern "C" {
+
+int emph_segment_rows(
+    const float* x, int32_t channels,
+    const int32_t* src_row, const int32_t* count, const int32_t* dst_row_start,
+    int32_t n_seg, const int32_t* dst_row_seq, int32_t total_dst_rows,
+    float* y, void* stream) {
+    EMPH_REQUIRE(channels > 0 && channels % 4 == 0, "emph_segment_rows: channels %d not a multiple of 4", channels);
+    EMPH_REQUIRE(n_seg >= 0 && total_dst_rows >= 0, "emph_segment_rows: negative size");
+    if (total_dst_rows == 0) return EMPH_OK;
+    long want = ((long)total_dst_rows + 7) / 8;
+    long cap = (long)emph::sm_count() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    emph::segment_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, channels, src_row, count, dst_row_start, dst_row_seq, total_dst_rows, y);
+    EMPH_CHECK_LAUNCH("emph_segment_rows");
+    return EMPH_OK;
+}
 
 int emph_version(void) { return 100; }
 

@@ -42,7 +42,8 @@ pool_words_kernel(
         float* dst = y + (size_t)w * channels;
         const int lo = __ldg(word_lo + w), hi = __ldg(word_hi + w);
         const bool padded_slot = (lo == -1 && hi == -1);
-        if (u < 0 || (padded_slot && METHOD != EMPH_POOL_CENTER)) {
+        const bool masked_slot = (lo == -2 && hi == -2);
+        if (u < 0 || masked_slot || (padded_slot && METHOD != EMPH_POOL_CENTER)) {
             for (int g = lane; g < groups; g += 32)
                 *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
             continue;

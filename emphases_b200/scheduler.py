@@ -1,0 +1,268 @@
+"""Corpus scheduling: launch bucketing on one GPU, length-balanced sharding
+across GPUs.
+
+Utterances are independent (emphases/core.py:169-179 loops over files), so a
+corpus shards by utterance with no collective: each GPU runs its shard
+through the packed kernels and the host gathers the per-word scores.
+"""
+import threading
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+import emphases_b200 as emphases
+from . import _lib, engine
+from .alignment import as_times
+
+
+###############################################################################
+# Packed host audio
+###############################################################################
+
+
+class PackedAudio:
+    """A corpus of mono 16 kHz utterances in ONE pinned host buffer.
+
+    Utterance i occupies samples [offsets[i], offsets[i] + lengths[i]);
+    offsets are multiples of 4 samples (the kernels' vector-load alignment).
+    A launch covering utterances [a, b) needs a single host->device copy.
+    """
+
+    def __init__(self, buffer, offsets, lengths):
+        self.buffer = buffer
+        self.offsets = np.asarray(offsets, dtype=np.int64)
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.lengths)
+
+    def __getitem__(self, index):
+        start = int(self.offsets[index])
+        return self.buffer[start:start + int(self.lengths[index])][None]
+
+    @staticmethod
+    def layout(lengths):
+        lengths = np.asarray(lengths, dtype=np.int64)
+        padded = (lengths + 3) // 4 * 4
+        offsets = np.concatenate([[0], np.cumsum(padded[:-1])]) \
+            if len(lengths) else np.zeros(0, dtype=np.int64)
+        total = int(padded.sum())
+        return offsets.astype(np.int64), max(total, 4)
+
+
+def pack_audio(audios, dtype=torch.float32, pin=True):
+    """List of (C, T) tensors -> PackedAudio (channel 0, as mels.py:48)"""
+    lengths = [int(audio.shape[-1]) for audio in audios]
+    offsets, total = PackedAudio.layout(lengths)
+    buffer = torch.zeros(
+        total, dtype=dtype, pin_memory=pin and torch.cuda.is_available())
+    for offset, audio in zip(offsets, audios):
+        buffer[offset:offset + audio.shape[-1]] = audio[0]
+    return PackedAudio(buffer, offsets, lengths)
+
+
+###############################################################################
+# Length-balanced scheduling
+###############################################################################
+
+
+def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
+    """Longest-processing-time-first greedy assignment: sort by cost
+    descending, always give the next item to the least-loaded worker.
+    Returns, per worker, the item indices in their original order."""
+    import heapq
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    heap = [(0.0, worker) for worker in range(workers)]
+    shards = [[] for _ in range(workers)]
+    for index in order:
+        load, worker = heapq.heappop(heap)
+        shards[worker].append(index)
+        heapq.heappush(heap, (load + costs[index], worker))
+    return [sorted(shard) for shard in shards]
+
+
+def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
+    """Split utterances (kept in order) into launches of <= max_rows packed
+    rows; an utterance longer than max_rows gets a launch of its own."""
+    launches, current, rows = [], [], 1
+    for index, count in enumerate(frames):
+        need = int(count) + 1
+        if current and rows + need > max_rows:
+            launches.append(current)
+            current, rows = [], 1
+        current.append(index)
+        rows += need
+    if current:
+        launches.append(current)
+    return launches
+
+
+###############################################################################
+# Execution
+###############################################################################
+
+
+def _prepare(alignments, audios, sample_rate):
+    """Word-time arrays + a PackedAudio for a list of utterances"""
+    times = [as_times(alignment) for alignment in alignments]
+    if isinstance(audios, PackedAudio):
+        if sample_rate != emphases.SAMPLE_RATE:
+            raise ValueError('PackedAudio must already be at 16 kHz')
+        return times, audios
+    if sample_rate != emphases.SAMPLE_RATE:
+        audios = [emphases.resample(audio, sample_rate) for audio in audios]
+    cuda = [audio for audio in audios if audio.device.type == 'cuda']
+    if cuda:
+        audios = [audio.cpu() for audio in audios]
+    return times, pack_audio(audios, pin=len(audios) > 1)
+
+
+def run_on_device(
+    model, alignments, audios, sample_rate, batch_size, device, to_cpu=True
+):
+    """Run a list of utterances on one device; returns a list of (1, W_i)
+    score tensors (CPU when to_cpu, else on `device`)."""
+    if model.architecture == 'transformer' or model.location == 'input':
+        return _run_via_model(
+            model, alignments, audios, sample_rate, batch_size, device, to_cpu)
+    times, packed = _prepare(alignments, audios, sample_rate)
+    eng = emphases.get_engine(device)
+    weights = model.packed_weights()
+    method = emphases.DOWNSAMPLE_METHOD
+    if method not in _lib.POOL:
+        raise ValueError(f'Interpolation method {method} is not defined')
+    if emphases.LOSS == 'bce':
+        head_mode = _lib.HEAD_SIGMOID
+    elif emphases.LOSS == 'mse':
+        head_mode = _lib.HEAD_CLAMP
+    else:
+        head_mode = _lib.HEAD_LOGITS
+    precision = emphases.precision_code()
+
+    frames = (packed.lengths + 2 * engine.PADDING) // engine.HOPSIZE
+    launches = bucket_launches(frames, emphases.MAX_ROWS_PER_LAUNCH)
+    streams = [torch.cuda.current_stream(device)]
+    if len(launches) > 1:
+        streams = [torch.cuda.Stream(device) for _ in range(2)]
+        for stream in streams:
+            stream.wait_stream(torch.cuda.current_stream(device))
+    pending = []
+    for number, members in enumerate(launches):
+        first, last = members[0], members[-1]
+        plan = engine.make_plan(
+            [(times[i], int(packed.lengths[i])) for i in members],
+            batch_size,
+            validate_method=method)
+        base = int(packed.offsets[first])
+        end = int(packed.offsets[last] + (packed.lengths[last] + 3) // 4 * 4)
+        end = min(end, packed.buffer.numel())
+        stream = streams[number % len(streams)]
+        with torch.cuda.stream(stream):
+            device_audio = packed.buffer[base:end].to(
+                device, non_blocking=True)
+            result = eng.forward_packed(
+                device_audio, plan, weights, method=method,
+                location=model.location, precision=precision,
+                head_mode=head_mode, normalize=emphases.NORMALIZE)
+            scores = result['scores']
+            if to_cpu:
+                host = torch.empty(
+                    scores.shape, dtype=scores.dtype, pin_memory=True)
+                host.copy_(scores, non_blocking=True)
+                scores = host
+        pending.append((members, plan, scores))
+    for stream in streams:
+        torch.cuda.current_stream(device).wait_stream(stream)
+    if to_cpu:
+        torch.cuda.current_stream(device).synchronize()
+
+    outputs = [None] * len(times)
+    for members, plan, scores in pending:
+        pieces = [[] for _ in members]
+        for u in range(plan.n_seq):
+            s, n = int(plan.word_row_start[u]), int(plan.n_words[u])
+            pieces[int(plan.utterance[u])].append(scores[s:s + n])
+        for local, index in enumerate(members):
+            if pieces[local]:
+                outputs[index] = torch.cat(pieces[local])[None]
+            else:
+                outputs[index] = scores.new_zeros((1, 0))
+    return outputs
+
+
+def _run_via_model(
+    model, alignments, audios, sample_rate, batch_size, device, to_cpu
+):
+    """Chunk-at-a-time path through Model.forward (transformer variant and
+    the 'input' location), structured like the reference loop
+    (emphases/core.py:245-265)"""
+    outputs = []
+    for alignment, audio in zip(alignments, audios):
+        scores = []
+        for features, bounds in emphases.preprocess(
+            alignment, audio, sample_rate, batch_size, device.index
+        ):
+            logits = emphases.infer_with_model(model, features, bounds)[0]
+            scores.append(emphases.postprocess(logits))
+        result = torch.cat(scores, 1) if scores else torch.zeros(
+            (1, 0), device=device)
+        outputs.append(result.cpu() if to_cpu else result)
+    return outputs
+
+
+def run_sharded(alignments, audios, sample_rate, checkpoint, batch_size, gpus):
+    """One worker thread per GPU over an LPT-balanced split of the corpus.
+    Cost model: frames (conv) -- the transformer variant uses frames^2."""
+    lengths = np.array([
+        int(audios.lengths[i]) if isinstance(audios, PackedAudio)
+        else int(audios[i].shape[-1]) for i in range(len(alignments))])
+    rate = emphases.SAMPLE_RATE / float(sample_rate)
+    frames = lengths * rate / engine.HOPSIZE
+    costs = frames ** 2 if emphases.ARCHITECTURE == 'transformer' else frames
+    shards = lpt_assign(costs.tolist(), len(gpus))
+    outputs = [None] * len(alignments)
+    errors = []
+
+    def worker(gpu, shard):
+        try:
+            device = torch.device('cuda', gpu)
+            with torch.cuda.device(device):
+                # one model per device (load_model caches a single entry)
+                model = _model_for(checkpoint, device)
+                results = run_on_device(
+                    model,
+                    [alignments[i] for i in shard],
+                    [audios[i] for i in shard],
+                    sample_rate, batch_size, device, True)
+            for index, result in zip(shard, results):
+                outputs[index] = result
+        except Exception as error:   # surfaced after join
+            errors.append(error)
+
+    threads = [
+        threading.Thread(target=worker, args=(gpu, shard))
+        for gpu, shard in zip(gpus, shards) if shard]
+    for thread in threads:
+        thread.start()
+    for thread in threads:
+        thread.join()
+    if errors:
+        raise errors[0]
+    return outputs
+
+
+_models = {}
+_models_lock = threading.Lock()
+
+
+def _model_for(checkpoint, device):
+    with _models_lock:
+        key = (str(checkpoint), device)
+        if key not in _models:
+            state = torch.load(
+                checkpoint, map_location='cpu', weights_only=False)
+            model = emphases.Model()
+            model.load_state_dict(state['model'] if 'model' in state else state)
+            _models[key] = model.to(device).eval()
+        return _models[key]

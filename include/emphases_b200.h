@@ -129,7 +129,8 @@ int emph_logmel_i16(
  * axis (emphases/model/core.py:17-20 input_layer + emphases/model/layers/
  * convolution.py:13-37; also the word decoder, model/core.py:105-107).
  *
- *   x, y       [total_rows][channels] fp32 (may alias)
+ *   x, y       [total_rows][channels] fp32; must NOT alias (CTAs read halo
+ *              rows of x that neighbouring CTAs own in y)
  *   weights    [n_layers][kernel_size][channels(in)][channels(out)] fp32,
  *              produced by emph_pack_conv_weights from Conv1d (out, in, k)
  *   bias       [n_layers][channels]
@@ -159,6 +160,8 @@ int emph_pack_conv_weights(
  *                  hi is clipped to n_rows[u] like a torch slice.  lo = hi =
  *                  -1 marks a padded word slot (j >= word_lengths[i]): zeros
  *                  for average/max/sum, frame 0 for center (core.py:458-466).
+ *                  lo = hi = -2 forces zeros for every method (the word mask
+ *                  of the 'input' location, emphases/model/core.py:77-82).
  *   y              [total_word_rows][channels]; separator rows zeroed
  * Empty segments: sum -> 0, average -> NaN (as torch.mean of an empty slice),
  * max -> -inf (the reference raises IndexError; the host mirror raises it
@@ -191,6 +194,18 @@ int emph_pack_rows(
 int emph_unpack_rows(
     const float* rows, const int32_t* row_start, const int32_t* n_rows,
     int32_t batch, int32_t channels, int32_t frames, float* bct, void* stream);
+
+/*
+ * Word segmentation for the 'input' downsample location (emphases/core.py:
+ * 552-586 `segment`): segment q copies count[q] rows of x starting at absolute
+ * row src_row[q] into its own sequence of seg_len rows (zero-filled tail),
+ * dst rows [dst_row_start[q], +seg_len).  dst_row_seq maps dst rows to q / -1.
+ */
+int emph_segment_rows(
+    const float* x, int32_t channels,
+    const int32_t* src_row, const int32_t* count, const int32_t* dst_row_start,
+    int32_t n_seg, const int32_t* dst_row_seq, int32_t total_dst_rows,
+    float* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,231 @@
+"""GPU parity tests of the reference-facing Python API (emphases_b200.*),
+against goldens from the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import state_from_golden, times_list
+from oracle import emphases_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+METHODS = ['average', 'max', 'sum', 'center']
+LOCATIONS = ['input', 'intermediate', 'inference', 'loss']
+
+
+@pytest.fixture
+def emphases():
+    import emphases_b200
+    emphases_b200.reset_configuration()
+    yield emphases_b200
+    emphases_b200.reset_configuration()
+
+
+@pytest.fixture(scope='module')
+def c1_checkpoint(tmp_path_factory, golden):
+    path = tmp_path_factory.mktemp('ckpt') / 'checkpoint.pt'
+    torch.save({'model': state_from_golden(golden('c1'))}, path)
+    return path
+
+
+def build_model(emphases, state):
+    model = emphases.Model()
+    own = model.state_dict()
+    model.load_state_dict({k: v for k, v in state.items() if k in own})
+    return model.cuda().eval()
+
+
+@pytest.mark.parametrize('location', LOCATIONS)
+@pytest.mark.parametrize('method', METHODS)
+def test_model_forward_sweep(emphases, golden, location, method):
+    """Model.forward, B=1 and padded B=2, every method x location"""
+    data = golden('sweep')
+    emphases.configure(
+        DOWNSAMPLE_LOCATION=location, DOWNSAMPLE_METHOD=method)
+    model = build_model(emphases, state_from_golden(data))
+    tag = f'{location}.{method}'
+    with torch.no_grad():
+        features = torch.from_numpy(data['b1.features']).cuda()
+        bounds = torch.from_numpy(data['b1.bounds'])
+        logits = model(
+            features, torch.tensor([features.shape[-1]]), bounds,
+            torch.tensor([bounds.shape[-1]]))
+        expected = data[f'{tag}.b1.logits']
+        assert logits.shape == expected.shape
+        np.testing.assert_allclose(
+            logits.cpu().numpy(), expected, rtol=1e-5, atol=2e-5)
+        batch = [torch.from_numpy(data[f'b2.{name}']) for name in (
+            'features', 'frame_lengths', 'bounds', 'word_lengths')]
+        batch[0] = batch[0].cuda()
+        logits = model(*batch)
+        expected = data[f'{tag}.b2.logits']
+        assert logits.shape == expected.shape
+        np.testing.assert_allclose(
+            logits.cpu().numpy(), expected, rtol=1e-5, atol=2e-5)
+        if location == 'inference':
+            model.train()
+            frame_logits = model(*batch)
+            np.testing.assert_allclose(
+                frame_logits.cpu().numpy(), data[f'{tag}.b2.frame_logits'],
+                rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('batch_size', [None, 300, 100])
+def test_from_alignment_and_audio(emphases, golden, c1_checkpoint, batch_size):
+    data = golden('c1')
+    alignment = emphases.Alignment.from_times(times_list(data['times']))
+    audio = torch.from_numpy(data['audio'])
+    scores = emphases.from_alignment_and_audio(
+        alignment, audio, 16000, checkpoint=c1_checkpoint,
+        batch_size=batch_size, gpu=0)
+    tag = 'full' if batch_size is None else f'bs{batch_size}'
+    assert scores.shape == data[f'{tag}.scores'].shape
+    assert scores.dtype == torch.float32 and scores.device.type == 'cuda'
+    error = np.abs(scores.cpu().numpy() - data[f'{tag}.scores']).max()
+    assert error < 1e-5, error
+    # and against the reference's own public (bf16 autocast) answer
+    if batch_size is None:
+        np.testing.assert_allclose(
+            scores.cpu().numpy(), data['full.scores_autocast'], atol=4e-3)
+
+
+def test_preprocess_infer_postprocess_seams(emphases, golden, c1_checkpoint):
+    """The inner seams other reference code calls (evaluate/core.py:85-95)"""
+    data = golden('c1')
+    alignment = emphases.Alignment.from_times(times_list(data['times']))
+    audio = torch.from_numpy(data['audio'])
+    chunks = list(emphases.preprocess(alignment, audio, 16000, 300, 0))
+    assert len(chunks) == 3
+    scores = []
+    for i, (features, bounds) in enumerate(chunks):
+        np.testing.assert_array_equal(bounds.numpy(), data[f'bs300.{i}.bounds'])
+        np.testing.assert_allclose(
+            features.cpu().numpy(), data[f'bs300.{i}.features'], atol=2e-5)
+        logits = emphases.infer(features, bounds, c1_checkpoint)
+        assert logits.shape == (1, 1, bounds.shape[-1])
+        scores.append(emphases.postprocess(logits[0]))
+    scores = torch.cat(scores, 1).cpu().numpy()
+    assert np.abs(scores - data['bs300.scores']).max() < 1e-5
+    features = emphases.data.preprocess.from_audio(audio[:, :48000], 0)
+    expected = oracle.logmel(audio[:, :48000], data['mel_basis'])
+    assert features.shape == (1, 80, 300)
+    assert (features[0].cpu() - expected).abs().max() < 2e-5
+    with pytest.raises(RuntimeError):
+        emphases.data.preprocess.from_audio(audio[:, :400], 0)
+
+
+@pytest.mark.parametrize('method', METHODS)
+def test_downsample_api(emphases, golden, method):
+    data = golden('pool')
+    emphases.configure(DOWNSAMPLE_METHOD=method)
+    xs = torch.from_numpy(data['xs']).cuda()
+    result = emphases.downsample(
+        xs, torch.from_numpy(data['clean_bounds']),
+        torch.from_numpy(data['clean_lengths']))
+    np.testing.assert_allclose(
+        result.cpu().numpy(), data[f'clean.{method}'], rtol=1e-6, atol=1e-6)
+    error = str(data[f'adversarial.{method}.error'])
+    bounds = torch.from_numpy(data['bounds'])
+    lengths = torch.from_numpy(data['lengths'])
+    if error:
+        with pytest.raises(IndexError):
+            emphases.downsample(xs, bounds, lengths)
+    else:
+        result = emphases.downsample(xs, bounds, lengths).cpu().numpy()
+        expected = data[f'adversarial.{method}']
+        np.testing.assert_array_equal(np.isnan(result), np.isnan(expected))
+        np.testing.assert_allclose(
+            np.nan_to_num(result), np.nan_to_num(expected), rtol=1e-6, atol=1e-6)
+
+
+def test_downsample_unknown_method(emphases):
+    emphases.configure(DOWNSAMPLE_METHOD='median')
+    with pytest.raises(ValueError):
+        emphases.downsample(
+            torch.zeros(1, 80, 10).cuda(), torch.zeros(1, 2, 1).long(),
+            torch.ones(1).long())
+
+
+def test_segment_api(emphases, golden):
+    data = golden('pool')
+    segments, bounds, lengths = emphases.segment(
+        torch.from_numpy(data['xs']).cuda(),
+        torch.from_numpy(data['clean_bounds']),
+        torch.from_numpy(data['clean_lengths']))
+    np.testing.assert_array_equal(
+        segments.cpu().numpy(), data['segment.segments'])
+    np.testing.assert_array_equal(bounds.cpu().numpy(), data['segment.bounds'])
+    np.testing.assert_array_equal(lengths.cpu().numpy(), data['segment.lengths'])
+
+
+def test_files_roundtrip(emphases, golden, c1_checkpoint, tmp_path):
+    """from_file / from_file_to_file / from_files_to_files on wav + TextGrid"""
+    data = golden('c1')
+    state = state_from_golden(data)
+    os.chdir(tmp_path)
+    text_files, audio_files, expected = [], [], []
+    for seed in range(5):
+        times, audio = oracle.synthetic_utterance(700 + seed)
+        # 16-bit PCM on disk: the oracle sees the same quantised samples
+        wav = tmp_path / f'utt{seed}.wav'
+        emphases.load.save_wav(wav, audio)
+        loaded = emphases.load.audio(wav)
+        grid = tmp_path / f'utt{seed}.TextGrid'
+        emphases.Alignment.from_times(times).save(grid)
+        reread = emphases.Alignment(grid)
+        assert np.array_equal(reread.times(), np.asarray(times))
+        text_files.append(grid)
+        audio_files.append(wav)
+        expected.append(oracle.from_alignment_and_audio(times, loaded, state))
+    scores = emphases.from_file(
+        text_files[0], audio_files[0], checkpoint=c1_checkpoint, gpu=0)
+    assert (scores.cpu() - expected[0]).abs().max() < 1e-5
+    prefixes = [tmp_path / 'out' / f'utt{seed}' for seed in range(5)]
+    (tmp_path / 'out').mkdir()
+    emphases.from_files_to_files(
+        text_files, audio_files, prefixes, checkpoint=c1_checkpoint, gpu=0)
+    for prefix, want in zip(prefixes, expected):
+        got = torch.load(f'{prefix}.pt')
+        assert got.shape == want.shape
+        assert (got - want).abs().max() < 1e-5
+        assert os.path.exists(f'{prefix}.TextGrid')
+    emphases.from_file_to_file(
+        text_files[1], audio_files[1], tmp_path / 'single',
+        checkpoint=c1_checkpoint, gpu=0)
+    got = torch.load(tmp_path / 'single.pt')
+    assert (got - expected[1]).abs().max() < 1e-5
+
+
+def test_multiple_launches_match_single(emphases, golden, c1_checkpoint):
+    """Launch bucketing must not change results"""
+    alignments, audios = [], []
+    for seed in range(9):
+        times, audio = oracle.synthetic_utterance(800 + seed)
+        alignments.append(emphases.Alignment.from_times(times))
+        audios.append(audio)
+    single = emphases.from_alignments_and_audio(
+        alignments, audios, 16000, c1_checkpoint, gpu=0)
+    emphases.configure(MAX_ROWS_PER_LAUNCH=2500)
+    split = emphases.from_alignments_and_audio(
+        alignments, audios, 16000, c1_checkpoint, gpu=0)
+    for a, b in zip(single, split):
+        assert torch.equal(a, b)
+
+
+def test_errors(emphases, golden, c1_checkpoint):
+    data = golden('c1')
+    alignment = emphases.Alignment.from_times(times_list(data['times']))
+    audio = torch.from_numpy(data['audio'])
+    emphases.configure(METHOD='bogus')
+    with pytest.raises(ValueError):
+        emphases.from_alignment_and_audio(alignment, audio, 16000, c1_checkpoint)
+    emphases.reset_configuration()
+    emphases.configure(DOWNSAMPLE_LOCATION='nowhere')
+    with pytest.raises(ValueError):
+        emphases.Model()
+    emphases.reset_configuration()
+    emphases.configure(ARCHITECTURE='lstm')
+    with pytest.raises(ValueError):
+        emphases.Model()

@@ -130,3 +130,56 @@ def test_no_gpu_means_loud_failure():
         pytest.skip('GPU present')
     with pytest.raises(_lib.EmphasesB200Error):
         engine.Engine('cpu')
+
+
+def test_textgrid_roundtrip_and_formats(tmp_path):
+    from emphases_b200 import alignment
+    times = [(0.0, 0.31388501956), (0.31388501956, 1.25), (1.25, 2.0)]
+    labels = ['hello', 'wor"ld 2', alignment.SILENCE]
+    path = tmp_path / 'a.TextGrid'
+    alignment.Alignment.from_times(times, labels).save(path)
+    loaded = alignment.Alignment(path)
+    assert np.array_equal(loaded.times(), np.asarray(times))
+    assert [str(w) for w in loaded] == ['hello', 'wor"ld 2', alignment.SILENCE]
+    # short text format with a leading gap and an empty interval
+    short = tmp_path / 'short.TextGrid'
+    short.write_text(
+        'File type = "ooTextFile"\nObject class = "TextGrid"\n\n'
+        '0\n2.5\n<exists>\n1\n"IntervalTier"\n"words"\n0\n2.5\n3\n'
+        '0.5\n1.0\n"a"\n1.0\n1.5\n""\n1.5\n2.5\n"b"\n')
+    loaded = alignment.Alignment(short)
+    assert [str(w) for w in loaded] == [alignment.SILENCE, 'a', alignment.SILENCE, 'b']
+    assert loaded.times().tolist() == [[0, .5], [.5, 1.], [1., 1.5], [1.5, 2.5]]
+    # slicing re-bases to t = 0; word_bounds truncates like int()
+    part = loaded[1:3]
+    assert part.times().tolist() == [[0., .5], [.5, 1.]]
+    assert part.word_bounds(16000, 160, silences=True) == [(0, 50), (50, 100)]
+    assert len(loaded.word_bounds(16000, 160)) == 2
+
+
+def test_wav_roundtrip(tmp_path):
+    import torch
+    from emphases_b200 import load
+    generator = torch.Generator().manual_seed(0)
+    audio = (0.3 * torch.randn(1, 1234, generator=generator)).clamp(-1, 1)
+    path = tmp_path / 'a.wav'
+    load.save_wav(path, audio)
+    samples, rate = load.wav(path)
+    assert rate == 16000 and samples.shape == (1, 1234)
+    assert (samples - audio).abs().max() < 1e-4
+    pcm, _ = load.wav(path, normalize=False)
+    assert pcm.dtype == torch.int16
+    assert torch.equal(pcm.float() / 32768., samples)
+
+
+def test_scheduler_lpt_and_buckets():
+    from emphases_b200 import scheduler
+    costs = [9, 7, 6, 5, 4, 3, 2, 1, 1]
+    shards = scheduler.lpt_assign(costs, 3)
+    assert sorted(i for shard in shards for i in shard) == list(range(9))
+    loads = [sum(costs[i] for i in shard) for shard in shards]
+    assert max(loads) - min(loads) <= 2
+    launches = scheduler.bucket_launches([100, 200, 50, 1000, 20], 400)
+    assert launches == [[0, 1, 2], [3], [4]]
+    offsets, total = scheduler.PackedAudio.layout([5, 8, 3])
+    assert offsets.tolist() == [0, 8, 16] and total == 20
