@@ -1,0 +1,480 @@
+"""Benchmark of the emphases batched-inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision fp32|bf16] [--utterances U]
+
+Workload (BASELINE.json configs[1]): the default framewise conv model
+(80 mels, 6 layers, sum pooling at the intermediate location, random init)
+over a synthetic corpus of U = 3000 utterances of 2-20 s of 16 kHz audio with
+2.5 words/s synthetic alignments (about 9.2 h of audio, ragged, packed).
+A "step" is one pass of the whole path over the whole corpus:
+    log-mel -> 7 frame convs -> word pooling -> 6 word convs -> head+sigmoid.
+
+`value`  : audio-seconds per wall-second, inputs resident in HBM (kernel-only).
+`e2e`    : same metric through emphases_b200.from_alignments_and_audio with
+           HOST (pinned) audio: planning, H2D, kernels, D2H inside the timing.
+`roofline`: the dominant kernel (the frame conv stack) from CUDA events
+           recorded on the launch stream inside the timed region.
+`cpu_baseline`: the CPU oracle port of the reference path (its own bf16
+           autocast numerics) on a bounded sample, all host threads.
+
+With N > 1 (torchrun) every rank runs its own corpus of the same size (weak
+scaling, no data-path collective); times are the max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 16000
+HOPSIZE = 160
+# Algorithmic work
+CONV_FLOP_PER_FRAME = 7 * 2 * 80 * 80 * 3          # 268,800
+LOGMEL_BYTES_PER_FRAME = 640 + 320
+POOL_BYTES_PER_FRAME = 320
+
+
+def parse_args():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=10)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    parser.add_argument('--precision', default=None, choices=['fp32', 'bf16'])
+    parser.add_argument('--utterances', type=int, default=3000)
+    parser.add_argument('--cpu-seconds', type=float, default=15.)
+    return parser.parse_args()
+
+
+###############################################################################
+# Synthetic corpus
+###############################################################################
+
+
+def corpus_layout(utterances, seed):
+    """Durations U(2, 20) s (multiple of a hop), W = max(2, floor(2.5 dur))
+    words tiling the utterance, every word >= 2 frames"""
+    rng = np.random.default_rng(seed)
+    samples = (rng.uniform(2., 20., utterances) * SAMPLE_RATE).astype(np.int64)
+    samples = samples // HOPSIZE * HOPSIZE
+    times = []
+    for count in samples:
+        duration = count / SAMPLE_RATE
+        words = max(2, int(2.5 * duration))
+        frames = count // HOPSIZE
+        # cut points on a frame grid with >= 2 frames per word, jittered
+        # inside the frame so word times are not frame aligned
+        cuts = np.sort(rng.choice(
+            np.arange(1, frames // 2), size=words - 1, replace=False)) * 2
+        cuts = (cuts + rng.uniform(0.05, 0.95, words - 1)) * HOPSIZE / SAMPLE_RATE
+        edges = np.concatenate([[0.], cuts, [duration]])
+        times.append(np.stack([edges[:-1], edges[1:]], axis=1))
+    return samples, times
+
+
+def make_audio(lengths, seed, device=None, pin=False):
+    """0.1 * randn audio packed with 4-sample aligned offsets"""
+    from emphases_b200 import scheduler
+    offsets, total = scheduler.PackedAudio.layout(lengths)
+    if device is not None:
+        generator = torch.Generator(device=device).manual_seed(seed)
+        buffer = 0.1 * torch.randn(
+            total, generator=generator, device=device, dtype=torch.float32)
+        buffer.clamp_(-1, 1)
+        return buffer, offsets
+    generator = torch.Generator().manual_seed(seed)
+    buffer = torch.empty(total, dtype=torch.float32, pin_memory=pin)
+    torch.randn(total, generator=generator, out=buffer)
+    buffer.mul_(0.1).clamp_(-1, 1)
+    return buffer, offsets
+
+
+def random_state(seed=0):
+    """Random-init weights of the default architecture"""
+    import emphases_b200 as emphases
+    emphases.reset_configuration()
+    torch.manual_seed(seed)
+    return {k: v.detach().clone() for k, v in emphases.Model().state_dict().items()}
+
+
+###############################################################################
+# Clocks
+###############################################################################
+
+
+class ClockSampler:
+    QUERY = (
+        'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+        'clocks_event_reasons.hw_thermal_slowdown,'
+        'clocks_event_reasons.sw_thermal_slowdown,'
+        'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.samples = []
+        self.process = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.process = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', f'--id={self.index}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.process = None
+
+    def _read(self):
+        for line in self.process.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.process is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        self.process.terminate()
+        self.thread.join(timeout=2)
+        sm, sm_max, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for line in self.samples:
+            fields = [f.strip() for f in line.split(',')]
+            if len(fields) < 7:
+                continue
+            try:
+                sm.append(float(fields[0]))
+                sm_max.append(float(fields[1]))
+            except ValueError:
+                continue
+            for name, value in zip(names, fields[3:7]):
+                if value.lower().startswith('active'):
+                    reasons.add(name)
+        return {
+            'sm_mhz': statistics.median(sm) if sm else None,
+            'sm_max_mhz': max(sm_max) if sm_max else None,
+            'samples': len(sm),
+            'reasons': sorted(reasons)}
+
+
+###############################################################################
+# CPU baseline (oracle port of the reference path)
+###############################################################################
+
+
+def cpu_reference_pass(
+    state, lengths, times, seed, budget_seconds, max_items, packed=None
+):
+    """Time oracle.from_alignment_and_audio (reference numerics: bf16 autocast,
+    per-utterance serial loop, emphases/core.py:169-179) over the first
+    utterances of the corpus until `budget_seconds` of CPU work."""
+    from oracle import emphases_oracle as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    basis = oracle.mel_basis()
+    generator = torch.Generator().manual_seed(seed)
+    audios = []
+    for index, count in enumerate(lengths[:max_items]):
+        if packed is not None:
+            audios.append(packed[index].clone())
+        else:
+            audios.append((0.1 * torch.randn(
+                1, int(count), generator=generator)).clamp(-1, 1))
+    oracle.from_alignment_and_audio(                       # warm up
+        [tuple(t) for t in times[0].tolist()], audios[0], state, basis=basis,
+        autocast=True)
+    seconds = words = 0.
+    items = 0
+    start = time.perf_counter()
+    for audio, word_times in zip(audios, times):
+        oracle.from_alignment_and_audio(
+            [tuple(t) for t in word_times.tolist()], audio, state,
+            basis=basis, autocast=True)
+        seconds += audio.shape[-1] / SAMPLE_RATE
+        words += len(word_times)
+        items += 1
+        if time.perf_counter() - start > budget_seconds:
+            break
+    elapsed = time.perf_counter() - start
+    return seconds, words, items, elapsed
+
+
+###############################################################################
+# Main
+###############################################################################
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (the
+    oracle port; the Python reference cannot travel to the GPU box), all host
+    threads, each step a bounded sample of the workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    lengths, times = corpus_layout(args.utterances, seed=1234)
+    state = random_state()
+    per_step = 24
+    for _ in range(args.warmup):
+        cpu_reference_pass(state, lengths, times, 99, 1e9, per_step)
+    seconds = words = elapsed = 0.
+    for _ in range(args.steps):
+        s, w, _, e = cpu_reference_pass(state, lengths, times, 99, 1e9, per_step)
+        seconds += s
+        words += w
+        elapsed += e
+    value = seconds / elapsed
+    cores = torch.get_num_threads()
+    sample = (f'first {per_step} utterances of the corpus per step '
+              f'({seconds / args.steps:.0f} audio-s), serial per-utterance '
+              'loop, bf16 autocast')
+    print(json.dumps({
+        'impl': 'reference',
+        'metric': 'audio-sec/sec',
+        'value': value,
+        'unit': 'audio-s/s',
+        'words_per_s': words / elapsed,
+        'n_gpus': args.gpus,
+        'steps': args.steps,
+        'warmup': args.warmup,
+        'ms_per_step': 1e3 * elapsed / args.steps,
+        'higher_is_better': True,
+        'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'bf16-autocast(cpu)',
+        'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {
+            'value': value, 'unit': 'audio-s/s', 'cores': cores,
+            'kind': 'port', 'sample': sample},
+        'e2e': {
+            'value': value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0,
+            'd2h_bytes_per_step': 0}}))
+
+
+def workload_config(args):
+    return {
+        'workload': (
+            f'config2: default framewise conv model (80 mel, 6 layers, sum '
+            f'pooling @ intermediate, random init) over {args.utterances} '
+            'synthetic utterances U(2,20) s @16 kHz, 2.5 words/s, ragged, '
+            'one packed batch per GPU'),
+        'utterances_per_gpu': args.utterances,
+        'l2': 'inputs (packed audio + activations, >2 GB) exceed the 126 MB L2',
+        'parallelism': f'utterance-sharded x{args.gpus}, no collective'}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import emphases_b200 as emphases
+    from emphases_b200 import _lib, engine, scheduler
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+
+    precision = args.precision or default_precision()
+    emphases.reset_configuration()
+    emphases.configure(PRECISION=precision)
+
+    # ---- corpus: each rank owns its own shard of the same size (weak) ----
+    lengths, times = corpus_layout(args.utterances, seed=1234 + rank)
+    audio_seconds = float(lengths.sum()) / SAMPLE_RATE
+    n_words = int(sum(len(t) for t in times))
+    host_audio, offsets = make_audio(lengths, seed=99 + rank, pin=True)
+    packed = scheduler.PackedAudio(host_audio, offsets, lengths)
+    alignments = times                      # (W, 2) arrays are accepted as-is
+
+    state = random_state()
+    model = emphases.Model()
+    model.load_state_dict(state)
+    model = model.to(device).eval()
+    weights = model.packed_weights()
+    eng = emphases.get_engine(device)
+
+    # ---- kernel-only leg: everything resident in HBM ----
+    plan = engine.make_plan(
+        [(t, int(n)) for t, n in zip(times, lengths)], None, 'sum')
+    device_audio = host_audio.to(device)
+    views = eng.upload_plan(plan)
+    frames = int(plan.n_rows.sum())
+    prec_code = emphases.precision_code()
+
+    def step(timed=None):
+        return eng.forward_packed(
+            device_audio, plan, weights, method='sum',
+            location='intermediate', precision=prec_code, views=views,
+            timers=timed)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    timers = []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        timers.append({})
+        step(timers[-1])
+    end.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    clock_summary = clocks.stop()
+    launches_per_step = len(timers[0])
+    kernel_ms = {
+        name: statistics.mean(t[name][0].elapsed_time(t[name][1]) for t in timers)
+        for name in timers[0]}
+
+    # ---- end-to-end leg: host (pinned) audio through the public API ----
+    def e2e_step():
+        return emphases.from_alignments_and_audio(
+            alignments, packed, SAMPLE_RATE, model=model, gpu=local_rank)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        results = e2e_step()
+    torch.cuda.synchronize(device)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    assert sum(r.shape[-1] for r in results) == n_words
+    h2d_bytes = host_audio.numel() * 4 + plan.int32_blob().nbytes + plan.n_seq * 8
+    d2h_bytes = plan.total_word_rows * 4
+
+    # ---- reduce over ranks: max time, summed units ----
+    stats = torch.tensor(
+        [elapsed_ms, e2e_ms, audio_seconds, n_words, frames], dtype=torch.float64,
+        device=device)
+    if world > 1:
+        worst = stats.clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        total = stats.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_ms = worst[0].item(), worst[1].item()
+        audio_total, words_total, frames_total = (
+            total[2].item(), total[3].item(), total[4].item())
+    else:
+        audio_total, words_total, frames_total = audio_seconds, n_words, frames
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = elapsed_ms / args.steps
+    value = audio_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's events) ----
+    peaks = {}
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+    conv_ms = kernel_ms['conv_frames']
+    conv_tflops = frames * CONV_FLOP_PER_FRAME / (conv_ms * 1e-3) / 1e12
+    tensor_peak = peaks.get('bf16_tflops_sustained', 1400.0)
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    logmel_gbs = frames * LOGMEL_BYTES_PER_FRAME / (kernel_ms['logmel'] * 1e-3) / 1e9
+    pool_gbs = (frames * POOL_BYTES_PER_FRAME + n_words * 328) / (
+        kernel_ms['pool'] * 1e-3) / 1e9
+    roofline = {
+        'kernel': 'conv_stack(frame side, 7 fused layers)',
+        'bound': 'tensor',
+        'achieved': conv_tflops,
+        'peak': tensor_peak,
+        'unit': 'TFLOP/s',
+        'frac': conv_tflops / tensor_peak,
+        'traffic': None,
+        'peak_source': (
+            'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a '
+            'long step)' if peaks else 'fallback'),
+        'share_of_step': conv_ms / ms_per_step,
+        'others': {
+            'logmel': {
+                'bound': 'hbm (FP32-pipe limited, see DESIGN.md)',
+                'achieved': logmel_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': logmel_gbs / hbm_peak, 'ms': kernel_ms['logmel']},
+            'pool': {
+                'bound': 'hbm', 'achieved': pool_gbs, 'peak': hbm_peak,
+                'unit': 'GB/s', 'frac': pool_gbs / hbm_peak,
+                'ms': kernel_ms['pool']}},
+        'kernel_ms': kernel_ms}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and args.cpu_seconds > 0:
+        seconds, words, items, elapsed = cpu_reference_pass(
+            state, lengths, times, 99, args.cpu_seconds, 400, packed)
+        cpu = {
+            'value': seconds / elapsed,
+            'unit': 'audio-s/s',
+            'words_per_s': words / elapsed,
+            'cores': torch.get_num_threads(),
+            'kind': 'port',
+            'sample': (
+                f'first {items} utterances of the same corpus '
+                f'({seconds:.0f} audio-s, {elapsed:.1f} s of CPU work), oracle '
+                'port of the reference path with its bf16 autocast, serial '
+                'per-utterance loop like emphases/core.py:169-179')}
+
+    print(json.dumps({
+        'metric': 'audio-sec/sec',
+        'value': value,
+        'unit': 'audio-s/s',
+        'words_per_s': words_total / (ms_per_step * 1e-3),
+        'n_gpus': world,
+        'steps': args.steps,
+        'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step,
+        'higher_is_better': True,
+        'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f32' if precision == 'fp32' else 'bf16 (tcgen05, f32 accumulate)',
+        'data': 'synthetic',
+        'config': workload_config(args),
+        'clocks': clock_summary,
+        'e2e': {
+            'value': audio_total / (e2e_ms * 1e-3),
+            'unit': 'audio-s/s',
+            'words_per_s': words_total / (e2e_ms * 1e-3),
+            'ms_per_step': e2e_ms,
+            'h2d_bytes_per_step': int(h2d_bytes),
+            'd2h_bytes_per_step': int(d2h_bytes)},
+        'gpu_launches': launches_per_step * args.steps,
+        'roofline': roofline,
+        'cpu_baseline': cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def default_precision():
+    return os.environ.get('EMPHASES_B200_PRECISION', 'fp32')
+
+
+if __name__ == '__main__':
+    main()

@@ -156,7 +156,8 @@ def from_alignments_and_audio(
     checkpoint=None,
     batch_size=None,
     gpu=None,
-    to_cpu=True
+    to_cpu=True,
+    model=None
 ):
     """Batched form of from_alignment_and_audio (extension): lists in, list
     of (1, W_i) score tensors out.  `gpu` may be a list of device indices:
@@ -169,7 +170,8 @@ def from_alignments_and_audio(
     if isinstance(gpu, (list, tuple)):
         gpu = gpu[0] if gpu else None
     device = emphases.resolve_device(gpu)
-    model = load_model(checkpoint, device)
+    if model is None:
+        model = load_model(checkpoint, device)
     with torch.cuda.device(device):
         return scheduler.run_on_device(
             model, alignments, audios, sample_rate, batch_size, device, to_cpu)

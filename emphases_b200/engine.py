@@ -475,7 +475,8 @@ class Engine:
         head_mode=_lib.HEAD_SIGMOID,
         normalize=False,
         views=None,
-        keep=False
+        keep=False,
+        timers=None
     ):
         """audio: packed device tensor (fp32 or int16).  Returns dict with
         `scores` and `logits` per packed word row (device tensors)."""
@@ -484,22 +485,38 @@ class Engine:
                 f'Downsample location {location} not handled by the packed path')
         if views is None:
             views = self.upload_plan(plan)
-        row_seq = self.row_index(
-            views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
-        word_row_seq = self.row_index(
+
+        def timed(name, launch):
+            # CUDA events on the launch stream around one kernel (bench.py)
+            if timers is None:
+                return launch()
+            start = torch.cuda.Event(enable_timing=True)
+            end = torch.cuda.Event(enable_timing=True)
+            start.record()
+            output = launch()
+            end.record()
+            timers[name] = (start, end)
+            return output
+
+        row_seq = timed('row_index_frames', lambda: self.row_index(
+            views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows))
+        word_row_seq = timed('row_index_words', lambda: self.row_index(
             views['word_row_start'], views['n_words'], plan.n_seq,
-            plan.total_word_rows)
-        features = self.logmel(audio, views, plan, row_seq, normalize)
-        frames = self.conv_stack(features, row_seq, weights.frame, precision)
-        pooled = self.pool(
+            plan.total_word_rows))
+        features = timed('logmel', lambda: self.logmel(
+            audio, views, plan, row_seq, normalize))
+        frames = timed('conv_frames', lambda: self.conv_stack(
+            features, row_seq, weights.frame, precision))
+        pooled = timed('pool', lambda: self.pool(
             frames, views['row_start'], views['n_rows'], views['word_seq'],
-            views['word_lo'], views['word_hi'], method)
+            views['word_lo'], views['word_hi'], method))
         if location == 'intermediate':
-            words = self.conv_stack(
-                pooled, word_row_seq, weights.word, _lib.PREC_FP32)
+            words = timed('conv_words', lambda: self.conv_stack(
+                pooled, word_row_seq, weights.word, _lib.PREC_FP32))
         else:
             words = pooled
-        logits, scores = self.head(words, word_row_seq, weights, head_mode)
+        logits, scores = timed('head', lambda: self.head(
+            words, word_row_seq, weights, head_mode))
         result = {'scores': scores, 'logits': logits}
         if keep:
             result.update(
