@@ -47,7 +47,7 @@ POOL_BYTES_PER_FRAME = 320
 def parse_args():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=10)
+    parser.add_argument('--steps', type=int, default=20)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     parser.add_argument('--precision', default=None, choices=['fp32', 'bf16'])
@@ -128,7 +128,7 @@ class ClockSampler:
         try:
             self.process = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.QUERY}', f'--id={self.index}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -290,7 +290,7 @@ def main():
         dist.init_process_group('nccl', device_id=device)
 
     precision = args.precision or default_precision()
-    emphases.reset_configuration()
+    state = random_state()              # resets the configuration to defaults
     emphases.configure(PRECISION=precision)
 
     # ---- corpus: each rank owns its own shard of the same size (weak) ----
@@ -301,7 +301,6 @@ def main():
     packed = scheduler.PackedAudio(host_audio, offsets, lengths)
     alignments = times                      # (W, 2) arrays are accepted as-is
 
-    state = random_state()
     model = emphases.Model()
     model.load_state_dict(state)
     model = model.to(device).eval()
@@ -473,7 +472,7 @@ def main():
 
 
 def default_precision():
-    return os.environ.get('EMPHASES_B200_PRECISION', 'fp32')
+    return os.environ.get('EMPHASES_B200_PRECISION', 'bf16')
 
 
 if __name__ == '__main__':

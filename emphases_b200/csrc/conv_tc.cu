@@ -1,10 +1,471 @@
-// placeholder until the tcgen05 kernel lands
+// bf16 tensor-core fused Conv1d stack for sm_100a: implicit GEMM on tcgen05
+// with accumulators in TMEM and activations resident in shared memory across
+// all layers.
+//
+// Replaces input_layer + frame_encoder (emphases/model/core.py:92-94,
+// emphases/model/layers/convolution.py:13-37), i.e. the 7 frame-resolution
+// Conv1d(80 -> 80, k=3, 'same') layers that hold 99 % of the model FLOPs.
+//
+// GEMM view of one layer on a tile of 128 packed rows:
+//     D[128 rows][80 out] = sum_{tap} A_tap[128 rows][80 in] * W_tap[80 in][80 out]
+// A lives in smem as bf16 in the no-swizzle K-major "interleaved" UMMA layout
+// [k-group of 8 channels][row][8 channels] with all rows of a k-group
+// contiguous (SBO = 128 B), so the +-1 row shift of the three taps is just a
+// 16-byte offset of the descriptor start address: the same buffer feeds all
+// three taps.  B (weights) uses the same layout per tap, streamed per layer
+// from L2 into a 3-stage smem ring with cp.async.bulk + mbarrier.  D is a
+// 128-lane x 80-column fp32 accumulator in TMEM.
+//
+// Warp roles (persistent CTA, one per SM, kSlots tiles in flight):
+//   warps 4s .. 4s+3 : epilogue group of tile slot s (TMEM lane quadrant =
+//                      warp % 4): tcgen05.ld -> +bias -> activation ->
+//                      separator-row zeroing -> bf16 -> back into the slot's
+//                      A buffer (next layer's operand), fp32 to HBM after the
+//                      last layer
+//   warp 4*kSlots    : MMA issuer (one elected lane issues tcgen05.mma)
+//   warp 4*kSlots+1  : weight producer (cp.async.bulk)
+// While the tensor core works on slot s, the epilogue groups of the other
+// slots drain their accumulators, so MMA and epilogue overlap.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
 namespace emph {
-int conv_stack_bf16_tc(
-    const float*, const int32_t*, int32_t, const float*, const float*, const int32_t*,
-    int32_t, int32_t, int32_t, float*, cudaStream_t) {
-    set_error("emph_conv_stack: bf16 tensor-core mode not built yet");
-    return EMPH_ENOSYS;
+
+namespace tc {
+
+constexpr int C = 80;                 // channels (in = out)
+constexpr int KS = 3;                 // taps
+constexpr int KG = C / 8;             // k-groups of 8 channels
+constexpr int M = 128;                // rows per tile = UMMA M
+constexpr int RB = M + 2;             // buffer rows (one pad row each side)
+constexpr int kSlots = 4;             // tiles in flight per CTA
+constexpr int kStages = 3;            // weight ring
+constexpr int kMaxLayers = 16;
+constexpr int ACT_BYTES = KG * RB * 16;           // 20,800 per slot
+constexpr int W_TAP_BYTES = KG * C * 16;          // 12,800
+constexpr int W_LAYER_BYTES = KS * W_TAP_BYTES;   // 38,400
+constexpr int kEpilogueThreads = 128 * kSlots;
+constexpr int kThreads = kEpilogueThreads + 64;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 128;       // TMEM columns between slot accumulators
+
+struct __align__(128) Smem {
+    uint8_t act[kSlots][ACT_BYTES + 64];      // +64 keeps 128-B alignment of each slot
+    uint8_t w[kStages][W_LAYER_BYTES];
+    float bias[kMaxLayers][C];
+    uint64_t w_full[kStages];
+    uint64_t w_empty[kStages];
+    uint64_t act_ready[kSlots];
+    uint64_t mma_done[kSlots];
+    uint32_t tmem_base;
+};
+
+struct Acts {
+    int act[kMaxLayers];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b64 state;\n\t"
+        "mbarrier.arrive.shared::cta.b64 state, [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .b64 state;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 state, [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(
+    uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// No-swizzle K-major smem matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address [0,14), leading (K-chunk) byte offset [16,30), stride (8-row
+// group) byte offset [32,46), descriptor version 1 at [46,48), layout type 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// relu fused into the conversion: max(x, 0) -> bf16x2
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6) = 1,
+// A bf16 [7,10) = 1, B bf16 [10,13) = 1, A and B K-major, N >> 3 at [17,23),
+// M >> 4 at [24,29)
+constexpr uint32_t kInstrDesc =
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stack_tc_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
+    const uint8_t* __restrict__ weights,   // [L][tap][kg][n][8] bf16
+    const float* __restrict__ bias, Acts acts, int n_layers, int tile_rows, int n_tiles,
+    float* __restrict__ y) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int halo = n_layers * ((KS - 1) / 2);
+    const int rounds = (n_tiles + gridDim.x * kSlots - 1) / (gridDim.x * kSlots);
+
+    // ---- one-time setup ----
+    for (int i = tid; i < n_layers * C; i += kThreads) sm.bias[i / C][i % C] = bias[i];
+    // pad rows (buffer rows 0 and RB-1) of every k-group stay zero forever
+    for (int i = tid; i < kSlots * KG * 2 * 4; i += kThreads) {
+        int s = i / (KG * 8), rem = i % (KG * 8), kg = rem / 8, edge = (rem / 4) & 1, word = rem & 3;
+        reinterpret_cast<uint32_t*>(sm.act[s] + (kg * RB + (edge ? RB - 1 : 0)) * 16)[word] = 0u;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&sm.w_full[i], 1);
+            mbar_init(&sm.w_empty[i], 1);
+        }
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(&sm.act_ready[s], 128);
+            mbar_init(&sm.mma_done[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kSlots * 4) tmem_alloc(&sm.tmem_base, kTmemCols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp < kSlots * 4) {
+        // =========================== epilogue group ===========================
+        const int slot = warp >> 2;
+        const int quad = warp & 3;                  // TMEM lane quadrant of this warp
+        const int row = quad * 32 + lane;           // tile-local row == TMEM lane
+        const int gtid = tid & 127;                 // thread within the group
+        uint8_t* act = sm.act[slot];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * kAccStride;
+        uint32_t done_parity = 0;
+
+        for (int round = 0; round < rounds; ++round) {
+            const int tile = (round * gridDim.x + blockIdx.x) * kSlots + slot;
+            if (tile >= n_tiles) break;
+            const int row0 = tile * tile_rows - halo;   // global row of local row 0
+            const int g = row0 + row;
+            const bool in_range = g >= 0 && g < total_rows;
+            const bool valid = in_range && __ldg(row_seq + g) >= 0;
+
+            // fp32 rows -> bf16 A operand: coalesced float4 reads, 10 in flight
+            // per thread (M * C / 4 = 2560 float4 = 20 per thread)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 v[10];
+#pragma unroll
+                for (int it = 0; it < 10; ++it) {
+                    const int i = gtid + 128 * (half * 10 + it);
+                    const int gr = row0 + i / (C / 4);
+                    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gr >= 0 && gr < total_rows)
+                        v[it] = ld_stream4(x + (size_t)gr * C + 4 * (i % (C / 4)));
+                }
+#pragma unroll
+                for (int it = 0; it < 10; ++it) {
+                    const int i = gtid + 128 * (half * 10 + it);
+                    const int r = i / (C / 4), c4 = i % (C / 4);
+                    *reinterpret_cast<uint2*>(
+                        act + ((c4 >> 1) * RB + r + 1) * 16 + (c4 & 1) * 8) =
+                        make_uint2(pack_bf16(v[it].x, v[it].y), pack_bf16(v[it].z, v[it].w));
+                }
+            }
+            fence_proxy_async();        // generic-proxy writes -> visible to the tensor core
+            tc_fence_before();          // orders the previous round's TMEM reads too
+            mbar_arrive(&sm.act_ready[slot]);
+
+            // a warp whose 32 rows are all real frames (97 % of warps) skips
+            // the per-element separator masking
+            const bool all_valid = __all_sync(0xffffffffu, valid);
+
+            for (int layer = 0; layer < n_layers; ++layer) {
+                mbar_wait(&sm.mma_done[slot], done_parity);
+                done_parity ^= 1;
+                tc_fence_after();
+                const int a = acts.act[layer];
+                const bool last = layer + 1 == n_layers;
+                const float* b = sm.bias[layer];
+                const bool fast = !last && (a == EMPH_ACT_RELU || a == EMPH_ACT_NONE);
+                if (fast) {
+                    // whole accumulator row: 5 x 16 columns, one wait
+                    uint32_t raw[C];
+#pragma unroll
+                    for (int c0 = 0; c0 < C; c0 += 16)
+                        tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
+                    tmem_ld_wait();
+                    uint8_t* dst = act + (row + 1) * 16;
+                    const bool relu = a == EMPH_ACT_RELU;
+                    const bool zero = !all_valid && !valid;
+#pragma unroll
+                    for (int kg = 0; kg < KG; ++kg) {
+                        uint32_t p[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 bb = *reinterpret_cast<const float2*>(b + 8 * kg + 2 * j);
+                            const float lo = __uint_as_float(raw[8 * kg + 2 * j]) + bb.x;
+                            const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]) + bb.y;
+                            p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
+                        }
+                        if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
+                        *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
+                            make_uint4(p[0], p[1], p[2], p[3]);
+                    }
+                } else {
+                    // other activations and the fp32 output of the last layer
+                    const bool store = last && in_range && row >= halo && row < M - halo;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C; c0 += 16) {
+                        uint32_t raw[16];
+                        tmem_ld16(taddr + c0, raw);
+                        tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float t = __uint_as_float(raw[j]) + b[c0 + j];
+                            v[j] = valid ? apply_activation(t, a) : 0.f;
+                        }
+                        if (!last) {
+                            const int kg = c0 >> 3;
+                            *reinterpret_cast<uint4*>(act + (kg * RB + row + 1) * 16) =
+                                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            *reinterpret_cast<uint4*>(act + ((kg + 1) * RB + row + 1) * 16) =
+                                make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                        } else if (store) {
+                            float4* dst = reinterpret_cast<float4*>(y + (size_t)g * C + c0);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+                            dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+                        }
+                    }
+                }
+                if (!last) {
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(&sm.act_ready[slot]);
+                }
+            }
+        }
+    } else if (warp == kSlots * 4) {
+        // ============================ MMA issuer ============================
+        if (lane == 0) {
+            uint32_t ready_parity[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) ready_parity[s] = 0;
+            int stage = 0;
+            uint32_t full_parity = 0;
+            for (int round = 0; round < rounds; ++round) {
+                const int tile0 = (round * gridDim.x + blockIdx.x) * kSlots;
+                if (tile0 >= n_tiles) break;
+                const int active = min(kSlots, n_tiles - tile0);
+                for (int layer = 0; layer < n_layers; ++layer) {
+                    mbar_wait(&sm.w_full[stage], full_parity);
+                    const uint32_t w_base = smem_u32(sm.w[stage]);
+#pragma unroll
+                    for (int s = 0; s < kSlots; ++s) {
+                        if (s >= active) break;
+                        mbar_wait(&sm.act_ready[s], ready_parity[s]);
+                        ready_parity[s] ^= 1;
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(sm.act[s]);
+                        const uint32_t d = tmem_base + s * kAccStride;
+#pragma unroll
+                        for (int tap = 0; tap < KS; ++tap) {
+#pragma unroll
+                            for (int kk = 0; kk < C / 16; ++kk) {
+                                const uint64_t da = make_desc(
+                                    a_base + (2 * kk) * RB * 16 + tap * 16, RB * 16, 128);
+                                const uint64_t db = make_desc(
+                                    w_base + tap * W_TAP_BYTES + (2 * kk) * C * 16, C * 16, 128);
+                                umma_bf16(d, da, db, kInstrDesc, (tap | kk) != 0);
+                            }
+                        }
+                        umma_commit(&sm.mma_done[s]);
+                    }
+                    umma_commit(&sm.w_empty[stage]);     // weights of this layer consumed
+                    if (++stage == kStages) { stage = 0; full_parity ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ========================== weight producer ==========================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t empty_parity = 1;       // first pass over the ring never waits
+            for (int round = 0; round < rounds; ++round) {
+                const int tile0 = (round * gridDim.x + blockIdx.x) * kSlots;
+                if (tile0 >= n_tiles) break;
+                for (int layer = 0; layer < n_layers; ++layer) {
+                    mbar_wait(&sm.w_empty[stage], empty_parity);
+                    mbar_arrive_expect_tx(&sm.w_full[stage], W_LAYER_BYTES);
+                    bulk_load(sm.w[stage], weights + (size_t)layer * W_LAYER_BYTES,
+                              W_LAYER_BYTES, &sm.w_full[stage]);
+                    if (++stage == kStages) { stage = 0; empty_parity ^= 1; }
+                }
+            }
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kSlots * 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// fp32 [L][tap][in][out] -> bf16 [L][tap][kg][out][8 in]
+__global__ void pack_weights_tc_kernel(
+    const float* __restrict__ w, int n_layers, __nv_bfloat16* __restrict__ out) {
+    const int total = n_layers * KS * C * C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7;
+        int rest = i >> 3;
+        const int n = rest % C; rest /= C;
+        const int kg = rest % KG; rest /= KG;
+        const int tap = rest % KS;
+        const int layer = rest / KS;
+        const int ci = kg * 8 + e;
+        out[i] = __float2bfloat16_rn(w[((size_t)(layer * KS + tap) * C + ci) * C + n]);
+    }
+}
+
+}  // namespace tc
+
+int conv_stack_bf16_tc(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const float* bias, const int32_t* acts_host,
+    int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
+    cudaStream_t stream) {
+    if (channels != tc::C || kernel_size != tc::KS) {
+        set_error("emph_conv_stack(bf16 tc): channels=%d kernel_size=%d not compiled in",
+                  channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    EMPH_REQUIRE(n_layers <= tc::kMaxLayers, "emph_conv_stack(bf16 tc): too many layers");
+    const int halo = n_layers * ((tc::KS - 1) / 2);
+    const int tile_rows = tc::M - 2 * halo;
+    EMPH_REQUIRE(tile_rows >= 32, "emph_conv_stack(bf16 tc): %d layers leave no tile", n_layers);
+    tc::Acts acts;
+    for (int i = 0; i < tc::kMaxLayers; ++i) acts.act[i] = i < n_layers ? acts_host[i] : 0;
+    const size_t smem = sizeof(tc::Smem) + 128;
+    int s = check_cuda(
+        cudaFuncSetAttribute(tc::conv_stack_tc_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        "conv_tc smem attribute");
+    if (s != EMPH_OK) return s;
+    const int n_tiles = (total_rows + tile_rows - 1) / tile_rows;
+    const int want = (n_tiles + tc::kSlots - 1) / tc::kSlots;
+    const int grid = want < sm_count() ? want : sm_count();
+    tc::conv_stack_tc_kernel<<<grid, tc::kThreads, smem, stream>>>(
+        x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), bias, acts,
+        n_layers, tile_rows, n_tiles, y);
+    EMPH_CHECK_LAUNCH("emph_conv_stack(bf16 tc)");
+    return EMPH_OK;
+}
+
 }  // namespace emph
+
+extern "C" int emph_pack_conv_weights_tc(
+    const float* weights, int32_t n_layers, int32_t channels, int32_t kernel_size,
+    void* packed, void* stream) {
+    if (channels != emph::tc::C || kernel_size != emph::tc::KS) {
+        emph::set_error("emph_pack_conv_weights_tc: channels=%d kernel_size=%d not compiled in",
+                        channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    EMPH_REQUIRE(n_layers > 0, "emph_pack_conv_weights_tc: no layers");
+    emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
+        weights, n_layers, reinterpret_cast<__nv_bfloat16*>(packed));
+    EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");
+    return EMPH_OK;
+}

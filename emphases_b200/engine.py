@@ -272,6 +272,20 @@ class ConvStack:
     acts: np.ndarray             # int32 host
     kernel_size: int
     channels: int
+    weights_tc: Optional[torch.Tensor] = None    # bf16 UMMA-layout blob
+
+    def tensor_core_weights(self):
+        """bf16 operand-layout copy for the tcgen05 path, packed on demand"""
+        if self.weights_tc is None:
+            blob = torch.empty(
+                self.weights.numel(), dtype=torch.bfloat16,
+                device=self.weights.device)
+            _lib.call(
+                'emph_pack_conv_weights_tc', _lib.ptr(self.weights),
+                self.n_layers, self.channels, self.kernel_size, _lib.ptr(blob),
+                _lib.stream_ptr())
+            self.weights_tc = blob
+        return self.weights_tc
 
     @property
     def n_layers(self):
@@ -428,9 +442,11 @@ class Engine:
         y = torch.empty_like(x)
         import ctypes
         acts = stack.acts.astype(np.int32)
+        weights = stack.tensor_core_weights() \
+            if precision == _lib.PREC_BF16_TC else stack.weights
         _lib.call(
             'emph_conv_stack', _lib.ptr(x), _lib.ptr(row_seq), x.shape[0],
-            _lib.ptr(stack.weights), _lib.ptr(stack.bias),
+            _lib.ptr(weights), _lib.ptr(stack.bias),
             acts.ctypes.data_as(ctypes.c_void_p), stack.n_layers,
             stack.channels, stack.kernel_size, precision, _lib.ptr(y),
             _lib.stream_ptr())

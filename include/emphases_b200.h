@@ -131,8 +131,10 @@ int emph_logmel_i16(
  *
  *   x, y       [total_rows][channels] fp32; must NOT alias (CTAs read halo
  *              rows of x that neighbouring CTAs own in y)
- *   weights    [n_layers][kernel_size][channels(in)][channels(out)] fp32,
- *              produced by emph_pack_conv_weights from Conv1d (out, in, k)
+ *   weights    EMPH_PREC_FP32: [n_layers][kernel_size][channels(in)]
+ *              [channels(out)] fp32, produced by emph_pack_conv_weights from
+ *              Conv1d (out, in, k); EMPH_PREC_BF16_TC: the bf16 blob produced
+ *              by emph_pack_conv_weights_tc
  *   bias       [n_layers][channels]
  *   acts       [n_layers] EMPH_ACT_* codes (host pointer)
  *   precision  EMPH_PREC_*
@@ -142,6 +144,16 @@ int emph_conv_stack(
     const float* weights, const float* bias, const int32_t* acts_host,
     int32_t n_layers, int32_t channels, int32_t kernel_size,
     int32_t precision, float* y, void* stream);
+
+/*
+ * Weights for precision == EMPH_PREC_BF16_TC: fp32 [n_layers][k][in][out] (the
+ * layout above) -> bf16 in the UMMA shared-memory operand layout
+ * [n_layers][k][in / 8][out][8], 2 * n_layers * k * channels^2 bytes.  Pass the
+ * result as `weights` of emph_conv_stack.
+ */
+int emph_pack_conv_weights_tc(
+    const float* weights, int32_t n_layers, int32_t channels,
+    int32_t kernel_size, void* packed, void* stream);
 
 /* (out, in, k) Conv1d weight -> [k][in][out] (device to device). */
 int emph_pack_conv_weights(

@@ -327,3 +327,63 @@ def test_forward_packed_ragged_batch(eng, golden):
         s, n = int(plan.word_row_start[u]), int(plan.n_words[u])
         worst = max(worst, (scores[s:s + n] - expected).abs().max().item())
     assert worst < 1e-5, worst
+
+
+def test_conv_stack_bf16_tc(eng, golden):
+    """tcgen05 bf16 conv stack vs the fp32 oracle (trained checkpoint weights):
+    bf16 operands / fp32 accumulate -> relative error ~1e-2 on activations"""
+    from emphases_b200 import _lib
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    generator = torch.Generator().manual_seed(4)
+    lengths = [300, 1, 2, 131, 57, 640, 1000, 77]
+    row_start, n_rows, total = make_rows(lengths)
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total)
+    x = torch.randn(total, 80, generator=generator)
+    x[(row_seq < 0).cpu()] = 0
+    layers = [(state['input_layer.weight'], state['input_layer.bias'], False)]
+    layers += [
+        (state[f'frame_encoder.{2 * i}.weight'],
+         state[f'frame_encoder.{2 * i}.bias'], True) for i in range(6)]
+    y = eng.conv_stack(x.cuda(), row_seq, weights.frame, _lib.PREC_BF16_TC).cpu()
+    expected = oracle_conv_rows(state, layers, x, lengths)
+    scale = expected.abs().max().item()
+    error = (y - expected).abs().max().item()
+    assert error < 3e-2 * scale, (error, scale)
+    assert y[(row_seq < 0).cpu()].abs().max() == 0
+    # bf16-emulating oracle: quantise operands like the kernel does -> tight
+    emulated = torch.zeros_like(expected)
+    from emphases_b200 import engine
+    starts, _ = engine.packed_starts(lengths)
+    for start, n in zip(starts, lengths):
+        h = x[start:start + n].T[None]
+        for index, (weight, bias, relu) in enumerate(layers):
+            hq = h.to(torch.bfloat16).double()
+            wq = weight.to(torch.bfloat16).double()
+            h = (torch.nn.functional.conv1d(hq, wq, None, padding=1)
+                 + bias.double()[None, :, None]).float()
+            if relu:
+                h = torch.relu(h)
+        emulated[start:start + n] = h[0].T
+    tight = (y - emulated).abs().max().item()
+    # one bf16 rounding flip of an intermediate (ulp 2^-9 at 0.5) moves the output by ~3e-4
+    assert tight < 2e-3 * max(scale, 1.0), (tight, scale)
+
+
+def test_forward_packed_bf16_golden(eng, golden):
+    """Whole path in bf16 tensor-core mode: scores within 2e-3 of the
+    reference's fp32 forward (trained checkpoint, sum pooling)"""
+    from emphases_b200 import _lib, engine
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    times = np.asarray(data['times'])
+    plan = engine.make_plan([(times, 160000)], None)
+    audio = torch.from_numpy(data['audio'])[0].cuda()
+    result = eng.forward_packed(
+        audio, plan, weights, precision=_lib.PREC_BF16_TC)
+    s, n = int(plan.word_row_start[0]), int(plan.n_words[0])
+    scores = result['scores'][s:s + n].cpu().numpy()
+    error = np.abs(scores - data['full.scores'][0]).max()
+    assert error < 2e-3, f'bf16 scores max-abs {error}'
