@@ -7,7 +7,9 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libemphases_b200.so')
+# EMPHASES_B200_LIB selects an alternative build (kernel tuning experiments)
+LIB_PATH = os.environ.get(
+    'EMPHASES_B200_LIB', os.path.join(HERE, 'libemphases_b200.so'))
 
 # include/emphases_b200.h constants
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_LEAKY_RELU, ACT_SILU = 0, 1, 2, 3, 4
@@ -27,7 +29,7 @@ SIGNATURES = {
     'emph_logmel_i16': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
     'emph_conv_stack': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'emph_pack_conv_weights': [_P, _I, _I, _I, _P, _P],
-    'emph_pack_conv_weights_tc': [_P, _I, _I, _I, _P, _P],
+    'emph_pack_conv_weights_tc': [_P, _P, _I, _I, _I, _P, _P],
     'emph_pool_words': [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     'emph_output_head': [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _P],
     'emph_pack_rows': [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
@@ -59,6 +61,8 @@ def load():
     lib.emph_version.restype = ctypes.c_int
     lib.emph_last_error.restype = ctypes.c_char_p
     lib.emph_device_sm_count.restype = ctypes.c_int
+    lib.emph_conv_weights_tc_bytes.argtypes = [_I, _I, _I]
+    lib.emph_conv_weights_tc_bytes.restype = ctypes.c_int
     _lib = lib
     return lib
 

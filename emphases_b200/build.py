@@ -40,17 +40,19 @@ def stale():
     return any(os.path.getmtime(path) > built for path in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, output=None, extra_flags=()):
+    """`output` / `extra_flags` build a tuning variant next to the main lib"""
+    if output is None and not force and not stale():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    command = [nvcc] + NVCC_FLAGS + ['-o', LIB] + sources()
+    output = output or LIB
+    command = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-o', output] + sources()
     result = subprocess.run(command, capture_output=True, text=True)
     if verbose or result.returncode != 0:
         sys.stderr.write(result.stdout + result.stderr)
     if result.returncode != 0:
         raise RuntimeError('nvcc failed building libemphases_b200.so')
-    return LIB
+    return output
 
 
 if __name__ == '__main__':

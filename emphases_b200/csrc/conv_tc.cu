@@ -44,7 +44,9 @@ constexpr int kStages = 3;            // weight ring
 constexpr int kMaxLayers = 16;
 constexpr int ACT_BYTES = KG * RB * 16;           // 20,800 per slot
 constexpr int W_TAP_BYTES = KG * C * 16;          // 12,800
-constexpr int W_LAYER_BYTES = KS * W_TAP_BYTES;   // 38,400
+constexpr int W_BIAS_BYTES = 2 * C * 16;          // bias chunk: 2 k-groups, 2,560
+constexpr int W_CONV_BYTES = KS * W_TAP_BYTES;    // 38,400
+constexpr int W_LAYER_BYTES = W_CONV_BYTES + W_BIAS_BYTES;   // 40,960
 constexpr int kEpilogueThreads = 128 * kSlots;
 constexpr int kThreads = kEpilogueThreads + 64;
 constexpr int kTmemCols = 512;
@@ -53,6 +55,7 @@ constexpr int kAccStride = 128;       // TMEM columns between slot accumulators
 struct __align__(128) Smem {
     uint8_t act[kSlots][ACT_BYTES + 64];      // +64 keeps 128-B alignment of each slot
     uint8_t w[kStages][W_LAYER_BYTES];
+    uint8_t ones[2 * RB * 16 + 64];           // A operand of the bias MMA
     float bias[kMaxLayers][C];
     uint64_t w_full[kStages];
     uint64_t w_empty[kStages];
@@ -168,6 +171,15 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t elected;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(elected));
+    return elected != 0;
+}
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -178,12 +190,43 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 constexpr uint32_t kInstrDesc =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 
+// Rare path: activations other than ReLU / identity.  Out of line so the hot
+// loop stays small in the instruction cache.
+__device__ __noinline__ void epilogue_generic(
+    uint32_t taddr, uint8_t* act, int row, int a, bool valid, bool last, bool store,
+    float* yrow) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < C; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + c0, raw);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = valid ? apply_activation(__uint_as_float(raw[j]), a) : 0.f;
+        if (!last) {
+            const int kg = c0 >> 3;
+            *reinterpret_cast<uint4*>(act + (kg * RB + row + 1) * 16) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(act + ((kg + 1) * RB + row + 1) * 16) =
+                make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        } else if (store) {
+            float4* dst = reinterpret_cast<float4*>(yrow + c0);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+            dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stack_tc_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
-    const uint8_t* __restrict__ weights,   // [L][tap][kg][n][8] bf16
-    const float* __restrict__ bias, Acts acts, int n_layers, int tile_rows, int n_tiles,
-    float* __restrict__ y) {
+    const uint8_t* __restrict__ weights,   // per layer: [tap][kg][n][8] bf16 + bias chunk
+    Acts acts, int n_layers, int tile_rows, int n_tiles, float* __restrict__ y) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -192,11 +235,16 @@ conv_stack_tc_kernel(
     const int rounds = (n_tiles + gridDim.x * kSlots - 1) / (gridDim.x * kSlots);
 
     // ---- one-time setup ----
-    for (int i = tid; i < n_layers * C; i += kThreads) sm.bias[i / C][i % C] = bias[i];
     // pad rows (buffer rows 0 and RB-1) of every k-group stay zero forever
     for (int i = tid; i < kSlots * KG * 2 * 4; i += kThreads) {
         int s = i / (KG * 8), rem = i % (KG * 8), kg = rem / 8, edge = (rem / 4) & 1, word = rem & 3;
         reinterpret_cast<uint32_t*>(sm.act[s] + (kg * RB + (edge ? RB - 1 : 0)) * 16)[word] = 0u;
+    }
+    // bias chunk A operand: k-group 0 = {1, 1, 0, ...} for every row, k-group 1 = 0,
+    // so D = 1 * bias_hi + 1 * bias_lo (bf16 split of the fp32 bias) before the taps
+    for (int i = tid; i < 2 * RB * 4; i += kThreads) {
+        const int kg = i / (RB * 4), word = i & 3;
+        reinterpret_cast<uint32_t*>(sm.ones)[i] = (kg == 0 && word == 0) ? 0x3F803F80u : 0u;
     }
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -204,7 +252,7 @@ conv_stack_tc_kernel(
             mbar_init(&sm.w_empty[i], 1);
         }
         for (int s = 0; s < kSlots; ++s) {
-            mbar_init(&sm.act_ready[s], 128);
+            mbar_init(&sm.act_ready[s], 4);     // one elected lane per epilogue warp
             mbar_init(&sm.mma_done[s], 1);
         }
         fence_barrier_init();
@@ -258,121 +306,132 @@ conv_stack_tc_kernel(
             }
             fence_proxy_async();        // generic-proxy writes -> visible to the tensor core
             tc_fence_before();          // orders the previous round's TMEM reads too
-            mbar_arrive(&sm.act_ready[slot]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.act_ready[slot]);
+
+            // pull the next round's tile of this slot into L2 while this one computes
+            {
+                const int next = tile + gridDim.x * kSlots;
+                if (next < n_tiles) {
+                    const long lo = (long)max(next * tile_rows - halo, 0) * C * 4;
+                    const long hi = (long)min(next * tile_rows - halo + M, total_rows) * C * 4;
+                    const char* base = reinterpret_cast<const char*>(x);
+                    for (long off = lo + 128 * gtid; off < hi; off += 128 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+                }
+            }
 
             // a warp whose 32 rows are all real frames (97 % of warps) skips
-            // the per-element separator masking
-            const bool all_valid = __all_sync(0xffffffffu, valid);
+            // the separator masking
+            const bool zero = !__all_sync(0xffffffffu, valid) && !valid;
 
             for (int layer = 0; layer < n_layers; ++layer) {
+                const int a = acts.act[layer];
+                const bool last = layer + 1 == n_layers;
+                const bool simple = a == EMPH_ACT_RELU || a == EMPH_ACT_NONE;
+                const bool relu = a == EMPH_ACT_RELU;
                 mbar_wait(&sm.mma_done[slot], done_parity);
                 done_parity ^= 1;
                 tc_fence_after();
-                const int a = acts.act[layer];
-                const bool last = layer + 1 == n_layers;
-                const float* b = sm.bias[layer];
-                const bool fast = !last && (a == EMPH_ACT_RELU || a == EMPH_ACT_NONE);
-                if (fast) {
-                    // whole accumulator row: 5 x 16 columns, one wait
+                if (simple) {
+                    // whole accumulator row (bias already added by the bias MMA):
+                    // 5 x 16 columns, one wait
                     uint32_t raw[C];
 #pragma unroll
                     for (int c0 = 0; c0 < C; c0 += 16)
                         tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
                     tmem_ld_wait();
-                    uint8_t* dst = act + (row + 1) * 16;
-                    const bool relu = a == EMPH_ACT_RELU;
-                    const bool zero = !all_valid && !valid;
+                    if (!last) {
+                        uint8_t* dst = act + (row + 1) * 16;
 #pragma unroll
-                    for (int kg = 0; kg < KG; ++kg) {
-                        uint32_t p[4];
+                        for (int kg = 0; kg < KG; ++kg) {
+                            uint32_t p[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 bb = *reinterpret_cast<const float2*>(b + 8 * kg + 2 * j);
-                            const float lo = __uint_as_float(raw[8 * kg + 2 * j]) + bb.x;
-                            const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]) + bb.y;
-                            p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
+                            for (int j = 0; j < 4; ++j) {
+                                const float lo = __uint_as_float(raw[8 * kg + 2 * j]);
+                                const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]);
+                                p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
+                            }
+                            if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
+                            *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
+                                make_uint4(p[0], p[1], p[2], p[3]);
                         }
-                        if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
-                        *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
-                            make_uint4(p[0], p[1], p[2], p[3]);
+                    } else if (in_range && row >= halo && row < M - halo) {
+                        float4* dst = reinterpret_cast<float4*>(y + (size_t)g * C);
+#pragma unroll
+                        for (int c4 = 0; c4 < C / 4; ++c4) {
+                            float v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[j] = __uint_as_float(raw[4 * c4 + j]);
+                                if (relu) v[j] = fmaxf(v[j], 0.f);
+                                if (zero) v[j] = 0.f;
+                            }
+                            dst[c4] = make_float4(v[0], v[1], v[2], v[3]);
+                        }
                     }
                 } else {
-                    // other activations and the fp32 output of the last layer
-                    const bool store = last && in_range && row >= halo && row < M - halo;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < C; c0 += 16) {
-                        uint32_t raw[16];
-                        tmem_ld16(taddr + c0, raw);
-                        tmem_ld_wait();
-                        float v[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float t = __uint_as_float(raw[j]) + b[c0 + j];
-                            v[j] = valid ? apply_activation(t, a) : 0.f;
-                        }
-                        if (!last) {
-                            const int kg = c0 >> 3;
-                            *reinterpret_cast<uint4*>(act + (kg * RB + row + 1) * 16) =
-                                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                            *reinterpret_cast<uint4*>(act + ((kg + 1) * RB + row + 1) * 16) =
-                                make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-                        } else if (store) {
-                            float4* dst = reinterpret_cast<float4*>(y + (size_t)g * C + c0);
-                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-                            dst[3] = make_float4(v[12], v[13], v[14], v[15]);
-                        }
-                    }
+                    epilogue_generic(
+                        taddr, act, row, a, valid, last,
+                        last && in_range && row >= halo && row < M - halo,
+                        y + (size_t)(in_range ? g : 0) * C);
                 }
                 if (!last) {
                     fence_proxy_async();
                     tc_fence_before();
-                    mbar_arrive(&sm.act_ready[slot]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.act_ready[slot]);
                 }
             }
         }
     } else if (warp == kSlots * 4) {
         // ============================ MMA issuer ============================
-        if (lane == 0) {
-            uint32_t ready_parity[kSlots];
+        // The whole warp runs this loop (warp-uniform control flow keeps the
+        // descriptors in uniform registers); one elected lane issues.  A
+        // measured tcgen05.mma of this shape costs ~100 clk, so every
+        // instruction saved in the issue path counts.
+        uint32_t ready_parity = 0;                   // bit s = parity of slot s
+        int stage = 0;
+        uint32_t full_parity = 0;
+        const uint64_t d_ones = make_desc(smem_u32(sm.ones), RB * 16, 128);
+        uint64_t d_act[kSlots];
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s) ready_parity[s] = 0;
-            int stage = 0;
-            uint32_t full_parity = 0;
-            for (int round = 0; round < rounds; ++round) {
-                const int tile0 = (round * gridDim.x + blockIdx.x) * kSlots;
-                if (tile0 >= n_tiles) break;
-                const int active = min(kSlots, n_tiles - tile0);
-                for (int layer = 0; layer < n_layers; ++layer) {
-                    mbar_wait(&sm.w_full[stage], full_parity);
-                    const uint32_t w_base = smem_u32(sm.w[stage]);
+        for (int s = 0; s < kSlots; ++s) d_act[s] = make_desc(smem_u32(sm.act[s]), RB * 16, 128);
+        for (int round = 0; round < rounds; ++round) {
+            const int tile0 = (round * gridDim.x + blockIdx.x) * kSlots;
+            if (tile0 >= n_tiles) break;
+            const int active = min(kSlots, n_tiles - tile0);
+            for (int layer = 0; layer < n_layers; ++layer) {
+                mbar_wait(&sm.w_full[stage], full_parity);
+                const uint64_t d_w = make_desc(smem_u32(sm.w[stage]), C * 16, 128);
 #pragma unroll
-                    for (int s = 0; s < kSlots; ++s) {
-                        if (s >= active) break;
-                        mbar_wait(&sm.act_ready[s], ready_parity[s]);
-                        ready_parity[s] ^= 1;
+                for (int s = 0; s < kSlots; ++s) {
+                    if (s < active) {
+                        mbar_wait(&sm.act_ready[s], (ready_parity >> s) & 1);
+                        ready_parity ^= 1u << s;
                         tc_fence_after();
-                        const uint32_t a_base = smem_u32(sm.act[s]);
-                        const uint32_t d = tmem_base + s * kAccStride;
+                        if (elect_one()) {
+                            const uint32_t d = tmem_base + s * kAccStride;
+                            umma_bf16(d, d_ones, d_w + (W_CONV_BYTES >> 4), kInstrDesc, 0);   // D = bias
 #pragma unroll
-                        for (int tap = 0; tap < KS; ++tap) {
+                            for (int tap = 0; tap < KS; ++tap) {
 #pragma unroll
-                            for (int kk = 0; kk < C / 16; ++kk) {
-                                const uint64_t da = make_desc(
-                                    a_base + (2 * kk) * RB * 16 + tap * 16, RB * 16, 128);
-                                const uint64_t db = make_desc(
-                                    w_base + tap * W_TAP_BYTES + (2 * kk) * C * 16, C * 16, 128);
-                                umma_bf16(d, da, db, kInstrDesc, (tap | kk) != 0);
+                                for (int kk = 0; kk < C / 16; ++kk) {
+                                    umma_bf16(
+                                        d,
+                                        d_act[s] + (uint64_t)(((2 * kk) * RB * 16 + tap * 16) >> 4),
+                                        d_w + (uint64_t)((tap * W_TAP_BYTES + (2 * kk) * C * 16) >> 4),
+                                        kInstrDesc, 1);
+                                }
                             }
+                            umma_commit(&sm.mma_done[s]);
                         }
-                        umma_commit(&sm.mma_done[s]);
+                        __syncwarp();
                     }
-                    umma_commit(&sm.w_empty[stage]);     // weights of this layer consumed
-                    if (++stage == kStages) { stage = 0; full_parity ^= 1; }
                 }
+                if (elect_one()) umma_commit(&sm.w_empty[stage]);   // layer's weights consumed
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; full_parity ^= 1; }
             }
         }
     } else {
@@ -403,19 +462,36 @@ conv_stack_tc_kernel(
     }
 }
 
-// fp32 [L][tap][in][out] -> bf16 [L][tap][kg][out][8 in]
+// fp32 weights [L][tap][in][out] + bias [L][out] -> per layer
+//   bf16 [tap][kg][out][8 in]  followed by the bias chunk bf16 [2][out][8]:
+//   k-group 0 holds (bias_hi, bias_lo, 0, ...), k-group 1 is zero
 __global__ void pack_weights_tc_kernel(
-    const float* __restrict__ w, int n_layers, __nv_bfloat16* __restrict__ out) {
-    const int total = n_layers * KS * C * C;
+    const float* __restrict__ w, const float* __restrict__ bias, int n_layers,
+    __nv_bfloat16* __restrict__ out) {
+    const int per_layer = W_LAYER_BYTES / 2;
+    const int conv = W_CONV_BYTES / 2;
+    const int total = n_layers * per_layer;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int e = i & 7;
-        int rest = i >> 3;
-        const int n = rest % C; rest /= C;
-        const int kg = rest % KG; rest /= KG;
-        const int tap = rest % KS;
-        const int layer = rest / KS;
-        const int ci = kg * 8 + e;
-        out[i] = __float2bfloat16_rn(w[((size_t)(layer * KS + tap) * C + ci) * C + n]);
+        const int layer = i / per_layer, local = i % per_layer;
+        if (local < conv) {
+            const int e = local & 7;
+            int rest = local >> 3;
+            const int n = rest % C; rest /= C;
+            const int kg = rest % KG;
+            const int tap = rest / KG;
+            const int ci = kg * 8 + e;
+            out[i] = __float2bfloat16_rn(w[((size_t)(layer * KS + tap) * C + ci) * C + n]);
+        } else {
+            const int rem = local - conv;
+            const int e = rem & 7, n = (rem >> 3) % C, kg = (rem >> 3) / C;
+            float v = 0.f;
+            if (kg == 0 && e < 2) {
+                const float b = bias[layer * C + n];
+                const float hi = __bfloat162float(__float2bfloat16_rn(b));
+                v = e == 0 ? hi : b - hi;
+            }
+            out[i] = __float2bfloat16_rn(v);
+        }
     }
 }
 
@@ -447,7 +523,7 @@ int conv_stack_bf16_tc(
     const int want = (n_tiles + tc::kSlots - 1) / tc::kSlots;
     const int grid = want < sm_count() ? want : sm_count();
     tc::conv_stack_tc_kernel<<<grid, tc::kThreads, smem, stream>>>(
-        x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), bias, acts,
+        x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), acts,
         n_layers, tile_rows, n_tiles, y);
     EMPH_CHECK_LAUNCH("emph_conv_stack(bf16 tc)");
     return EMPH_OK;
@@ -455,9 +531,14 @@ int conv_stack_bf16_tc(
 
 }  // namespace emph
 
+extern "C" int emph_conv_weights_tc_bytes(int32_t n_layers, int32_t channels, int32_t kernel_size) {
+    if (channels != emph::tc::C || kernel_size != emph::tc::KS || n_layers <= 0) return 0;
+    return n_layers * emph::tc::W_LAYER_BYTES;
+}
+
 extern "C" int emph_pack_conv_weights_tc(
-    const float* weights, int32_t n_layers, int32_t channels, int32_t kernel_size,
-    void* packed, void* stream) {
+    const float* weights, const float* bias, int32_t n_layers, int32_t channels,
+    int32_t kernel_size, void* packed, void* stream) {
     if (channels != emph::tc::C || kernel_size != emph::tc::KS) {
         emph::set_error("emph_pack_conv_weights_tc: channels=%d kernel_size=%d not compiled in",
                         channels, kernel_size);
@@ -465,7 +546,7 @@ extern "C" int emph_pack_conv_weights_tc(
     }
     EMPH_REQUIRE(n_layers > 0, "emph_pack_conv_weights_tc: no layers");
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
-        weights, n_layers, reinterpret_cast<__nv_bfloat16*>(packed));
+        weights, bias, n_layers, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");
     return EMPH_OK;
 }

@@ -277,13 +277,18 @@ class ConvStack:
     def tensor_core_weights(self):
         """bf16 operand-layout copy for the tcgen05 path, packed on demand"""
         if self.weights_tc is None:
+            size = _lib.load().emph_conv_weights_tc_bytes(
+                self.n_layers, self.channels, self.kernel_size)
+            if size <= 0:
+                raise _lib.EmphasesB200Error(
+                    f'bf16 tensor-core conv stack is not compiled for '
+                    f'channels={self.channels} kernel_size={self.kernel_size}')
             blob = torch.empty(
-                self.weights.numel(), dtype=torch.bfloat16,
-                device=self.weights.device)
+                size, dtype=torch.uint8, device=self.weights.device)
             _lib.call(
                 'emph_pack_conv_weights_tc', _lib.ptr(self.weights),
-                self.n_layers, self.channels, self.kernel_size, _lib.ptr(blob),
-                _lib.stream_ptr())
+                _lib.ptr(self.bias), self.n_layers, self.channels,
+                self.kernel_size, _lib.ptr(blob), _lib.stream_ptr())
             self.weights_tc = blob
         return self.weights_tc
 

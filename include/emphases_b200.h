@@ -146,13 +146,18 @@ int emph_conv_stack(
     int32_t precision, float* y, void* stream);
 
 /*
- * Weights for precision == EMPH_PREC_BF16_TC: fp32 [n_layers][k][in][out] (the
- * layout above) -> bf16 in the UMMA shared-memory operand layout
- * [n_layers][k][in / 8][out][8], 2 * n_layers * k * channels^2 bytes.  Pass the
- * result as `weights` of emph_conv_stack.
+ * Weights for precision == EMPH_PREC_BF16_TC: fp32 weights [n_layers][k][in]
+ * [out] (the layout above) and bias [n_layers][out] -> per layer a bf16 blob in
+ * the UMMA shared-memory operand layout [k][in / 8][out][8] followed by a bias
+ * K-chunk (bias split into bf16 hi + lo, applied by one extra MMA against a
+ * constant ones operand).  emph_conv_weights_tc_bytes gives the blob size (0 if
+ * the configuration is not compiled in).  Pass the blob as `weights` of
+ * emph_conv_stack; `bias` is then unused.
  */
+int emph_conv_weights_tc_bytes(
+    int32_t n_layers, int32_t channels, int32_t kernel_size);
 int emph_pack_conv_weights_tc(
-    const float* weights, int32_t n_layers, int32_t channels,
+    const float* weights, const float* bias, int32_t n_layers, int32_t channels,
     int32_t kernel_size, void* packed, void* stream);
 
 /* (out, in, k) Conv1d weight -> [k][in][out] (device to device). */
