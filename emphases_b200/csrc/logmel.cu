@@ -10,11 +10,20 @@
 //   basis @ spectrogram, log(clamp(., 1e-5)), optional (x+10)/10
 //                               mels.py:94-109, 57-58
 //
-// One warp per frame.  The 1024-point real FFT is a 512-point complex FFT of
-// the even/odd packed signal (3 radix-8 Stockham passes, 2 butterflies per
-// lane per pass, exchanges through padded shared memory) followed by the
-// real-FFT unpacking, all in fp32.  Bound: FP32 pipe (about 25 kFLOP per frame
-// against 960 B of HBM traffic), see DESIGN.md.
+// A persistent CTA of 16 warps works on tiles of 32 consecutive packed rows:
+//   phase 1  one warp per frame: 1024-point real FFT as a 512-point complex
+//            FFT of the even/odd packed signal -- 3 radix-8 Stockham passes
+//            (2 butterflies per lane per pass, twiddles held in registers,
+//            two exchanges through bank-padded shared memory), then the
+//            real-FFT unpacking done in registers with warp shuffles and the
+//            magnitudes written to a [32 frames][513 bins] tile;
+//   phase 2  mel projection with lane = frame: the sparse basis entry is a
+//            warp-wide broadcast and the 32 magnitudes of one bin sit in 32
+//            different banks (row stride 513), so every nnz costs one
+//            conflict-free wavefront for 32 frames;
+//   phase 3  log / clamp and a fully coalesced store of the 32 x n_mels tile.
+// All fp32.  Bound: FP32 issue + shared-memory wavefronts (about 25 kFLOP per
+// frame against 960 B of HBM traffic), see DESIGN.md.
 #include "common.cuh"
 
 namespace emph {
@@ -24,7 +33,8 @@ constexpr int kHop = 160;
 constexpr int kPad = (kFft - kHop) / 2;   // 432, both the zero and reflect pad
 constexpr int kBins = kFft / 2 + 1;       // 513
 constexpr int kHalf = kFft / 2;           // 512-point complex FFT
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;
+constexpr int kTile = 32;                 // frames per CTA tile
 constexpr int kMaxNnz = 1536;             // mel CSR entries held in smem
 constexpr int kMaxMels = 128;
 
@@ -33,15 +43,18 @@ __device__ __forceinline__ int xpad(int i) { return i + (i >> 3); }
 constexpr int kXchg = kHalf + kHalf / 8;  // 576 float2 per warp
 
 struct __align__(16) LogmelSmem {
-    float2 w512[kHalf];            // exp(-2 pi i m / 512)
-    float2 w1024[kHalf / 2 + 1];   // exp(-2 pi i k / 1024), k = 0..256
+    float mag[kTile][kBins];       // stride 513 = 1 mod 32: lane = frame is conflict-free
+    float2 xchg[kWarps][kXchg];
     float hann[kFft];
+    float outs[kTile][kMaxMels + 1];
     float mel_val[kMaxNnz];
     int16_t mel_col[kMaxNnz];
     int32_t mel_ptr[kMaxMels + 1];
-    float2 xchg[kWarps][kXchg];
-    float mag[kWarps][kBins + 3];
 };
+
+// exp(-2 pi i r / 16), r = 0..7 and exp(-2 pi i q / 32), q = 0..15
+__device__ constexpr float kC16[8][2] = {{1.0f, 0.0f}, {0.9238795325112867f, -0.3826834323650898f}, {0.7071067811865476f, -0.7071067811865475f}, {0.38268343236508984f, -0.9238795325112867f}, {0.0f, -1.0f}, {-0.3826834323650897f, -0.9238795325112867f}, {-0.7071067811865475f, -0.7071067811865476f}, {-0.9238795325112867f, -0.3826834323650899f}};
+__device__ constexpr float kC32[16][2] = {{1.0f, 0.0f}, {0.9807852804032304f, -0.19509032201612825f}, {0.9238795325112867f, -0.3826834323650898f}, {0.8314696123025452f, -0.5555702330196022f}, {0.7071067811865476f, -0.7071067811865475f}, {0.5555702330196023f, -0.8314696123025452f}, {0.38268343236508984f, -0.9238795325112867f}, {0.19509032201612833f, -0.9807852804032304f}, {0.0f, -1.0f}, {-0.1950903220161282f, -0.9807852804032304f}, {-0.3826834323650897f, -0.9238795325112867f}, {-0.555570233019602f, -0.8314696123025455f}, {-0.7071067811865475f, -0.7071067811865476f}, {-0.8314696123025453f, -0.5555702330196022f}, {-0.9238795325112867f, -0.3826834323650899f}, {-0.9807852804032304f, -0.1950903220161286f}};
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -80,7 +93,6 @@ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
     v[3] = t6;      // X3
     v[4] = t1;      // X4
     v[6] = t3;      // X6
-    // v[0]=X0 v[2]=X2 v[5]=X5 v[7]=X7 already in place
 }
 
 template <typename T>
@@ -105,7 +117,7 @@ __device__ __forceinline__ float chunk_sample(
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 1)
 logmel_kernel(
     const T* __restrict__ audio,
     const int64_t* __restrict__ audio_off, const int32_t* __restrict__ audio_len,
@@ -120,17 +132,6 @@ logmel_kernel(
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // Tables (fp32 values of double-precision-accurate sincospi)
-    for (int i = tid; i < kHalf; i += blockDim.x) {
-        float sn, cs;
-        sincospif(-2.f * (float)i / (float)kHalf, &sn, &cs);
-        sm.w512[i] = make_float2(cs, sn);
-    }
-    for (int i = tid; i <= kHalf / 2; i += blockDim.x) {
-        float sn, cs;
-        sincospif(-2.f * (float)i / (float)kFft, &sn, &cs);
-        sm.w1024[i] = make_float2(cs, sn);
-    }
     for (int i = tid; i < kFft; i += blockDim.x) {
         // torch.hann_window(1024) (periodic): 0.5 - 0.5 cos(2 pi n / N)
         sm.hann[i] = 0.5f - 0.5f * cospif(2.f * (float)i / (float)kFft);
@@ -141,160 +142,200 @@ logmel_kernel(
         sm.mel_col[i] = mel_col[i];
     }
     for (int i = tid; i <= n_mels; i += blockDim.x) sm.mel_ptr[i] = mel_ptr[i];
+
+    // Per-lane twiddles, kept in registers for the whole kernel:
+    //   pass 2: exp(-2 pi i * 8 r (lane % 8) / 512), pass 3: exp(-2 pi i r lane / 512)
+    //   unpack: exp(-2 pi i lane / 1024)
+    float2 tw2[8], tw3[8];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        float sn, cs;
+        sincospif(-2.f * (float)(8 * r * (lane & 7)) / (float)kHalf, &sn, &cs);
+        tw2[r] = make_float2(cs, sn);
+        sincospif(-2.f * (float)(r * lane) / (float)kHalf, &sn, &cs);
+        tw3[r] = make_float2(cs, sn);
+    }
+    float2 wl;
+    sincospif(-2.f * (float)lane / (float)kFft, &wl.y, &wl.x);
     __syncthreads();
 
     float2* xw = sm.xchg[warp];
-    float* mag = sm.mag[warp];
+    const int n_tiles = (total_rows + kTile - 1) / kTile;
 
-    for (int row = blockIdx.x * kWarps + warp; row < total_rows;
-         row += gridDim.x * kWarps) {
-        const int u = __ldg(row_seq + row);
-        float* dst = out + (size_t)row * n_mels;
-        if (u < 0) {   // separator row
-            for (int m = lane; m < n_mels; m += 32) dst[m] = 0.f;
-            continue;
-        }
-        const int frame = row - __ldg(row_start + u);
-        const int T_len = __ldg(audio_len + u);
-        const int s = __ldg(chunk_start + u);
-        const int L = __ldg(chunk_len + u);
-        const T* src = audio + __ldg(audio_off + u);
-        const int q0 = frame * kHop;            // first sample in reflect-padded coords
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTile;
 
-        // ---- load 1024 samples as 512 complex, window, first radix-8 pass ----
-        // lane handles butterflies j = lane and j = lane + 32; inputs z[j + 64 r]
-        float2 v0[8], v1[8];
-        // interior: no reflect, no zero pad
-        const int a0 = s + q0 - 2 * kPad;       // audio index of sample q0
-        const bool interior = (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
-                              (a0 >= 0) && (a0 + kFft <= T_len);
-        if (interior) {
-            const T* p = src + a0;
+        // ======================= phase 1: FFT + magnitude =======================
+#pragma unroll 1
+        for (int f = warp; f < kTile; f += kWarps) {
+            const int row = row0 + f;
+            if (row >= total_rows) break;
+            const int u = __ldg(row_seq + row);
+            if (u < 0) continue;                    // separator row
+            const int frame = row - __ldg(row_start + u);
+            const int T_len = __ldg(audio_len + u);
+            const int s = __ldg(chunk_start + u);
+            const int L = __ldg(chunk_len + u);
+            const T* src = audio + __ldg(audio_off + u);
+            const int q0 = frame * kHop;            // first sample in reflect-padded coords
+
+            // ---- load 1024 samples as 512 complex, window, first radix-8 pass ----
+            // lane handles butterflies j = lane and j = lane + 32; inputs z[j + 64 r]
+            float2 v0[8], v1[8];
+            const int a0 = s + q0 - 2 * kPad;       // audio index of sample q0
+            const bool interior = (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
+                                  (a0 >= 0) && (a0 + kFft <= T_len);
+            if (interior) {
+                const T* p = src + a0;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                int n0 = lane + 64 * r, n1 = n0 + 32;
-                if constexpr (sizeof(T) == 4) {
-                    float2 x0 = *reinterpret_cast<const float2*>(p + 2 * n0);
-                    float2 x1 = *reinterpret_cast<const float2*>(p + 2 * n1);
-                    v0[r] = x0;
-                    v1[r] = x1;
-                } else {
-                    short2 x0 = *reinterpret_cast<const short2*>(p + 2 * n0);
-                    short2 x1 = *reinterpret_cast<const short2*>(p + 2 * n1);
-                    v0[r] = make_float2(to_float<int16_t>(x0.x), to_float<int16_t>(x0.y));
-                    v1[r] = make_float2(to_float<int16_t>(x1.x), to_float<int16_t>(x1.y));
+                for (int r = 0; r < 8; ++r) {
+                    int n0 = lane + 64 * r, n1 = n0 + 32;
+                    if constexpr (sizeof(T) == 4) {
+                        v0[r] = *reinterpret_cast<const float2*>(p + 2 * n0);
+                        v1[r] = *reinterpret_cast<const float2*>(p + 2 * n1);
+                    } else {
+                        short2 x0 = *reinterpret_cast<const short2*>(p + 2 * n0);
+                        short2 x1 = *reinterpret_cast<const short2*>(p + 2 * n1);
+                        v0[r] = make_float2(to_float<int16_t>(x0.x), to_float<int16_t>(x0.y));
+                        v1[r] = make_float2(to_float<int16_t>(x1.x), to_float<int16_t>(x1.y));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    int n0 = lane + 64 * r, n1 = n0 + 32;
+                    v0[r] = make_float2(
+                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0),
+                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0 + 1));
+                    v1[r] = make_float2(
+                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1),
+                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1 + 1));
                 }
             }
-        } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 int n0 = lane + 64 * r, n1 = n0 + 32;
-                v0[r] = make_float2(
-                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0),
-                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0 + 1));
-                v1[r] = make_float2(
-                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1),
-                    chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1 + 1));
+                float2 h0 = *reinterpret_cast<const float2*>(&sm.hann[2 * n0]);
+                float2 h1 = *reinterpret_cast<const float2*>(&sm.hann[2 * n1]);
+                v0[r].x *= h0.x; v0[r].y *= h0.y;
+                v1[r].x *= h1.x; v1[r].y *= h1.y;
             }
-        }
+            // pass 1: Ns = 1, no twiddles, out[8 j + r]
+            fft8(v0);
+            fft8(v1);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            int n0 = lane + 64 * r, n1 = n0 + 32;
-            float2 h0 = *reinterpret_cast<const float2*>(&sm.hann[2 * n0]);
-            float2 h1 = *reinterpret_cast<const float2*>(&sm.hann[2 * n1]);
-            v0[r].x *= h0.x; v0[r].y *= h0.y;
-            v1[r].x *= h1.x; v1[r].y *= h1.y;
-        }
-        // pass 1: Ns = 1, no twiddles, out[8 j + r]
-        fft8(v0);
-        fft8(v1);
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            xw[xpad(8 * lane + r)] = v0[r];
-            xw[xpad(8 * (lane + 32) + r)] = v1[r];
-        }
-        __syncwarp();
+            for (int r = 0; r < 8; ++r) {
+                xw[xpad(8 * lane + r)] = v0[r];
+                xw[xpad(8 * (lane + 32) + r)] = v1[r];
+            }
+            __syncwarp();
 
-        // pass 2: Ns = 8; twiddle exp(-2 pi i r (j % 8) / 64) = w512[8 r (j%8)]
-        {
-            const int k0 = lane & 7;             // (lane + 32) % 8 is the same
+            // pass 2: Ns = 8; twiddle exp(-2 pi i r (j % 8) / 64)
+            {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    v0[r] = xw[xpad(lane + 64 * r)];
+                    v1[r] = xw[xpad(lane + 32 + 64 * r)];
+                }
+#pragma unroll
+                for (int r = 1; r < 8; ++r) {
+                    v0[r] = cmul(v0[r], tw2[r]);
+                    v1[r] = cmul(v1[r], tw2[r]);
+                }
+                fft8(v0);
+                fft8(v1);
+                __syncwarp();
+                const int k0 = lane & 7;
+                const int b0 = (lane >> 3) * 64 + k0;
+                const int b1 = ((lane + 32) >> 3) * 64 + k0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    xw[xpad(b0 + 8 * r)] = v0[r];
+                    xw[xpad(b1 + 8 * r)] = v1[r];
+                }
+                __syncwarp();
+            }
+
+            // pass 3: Ns = 64; twiddle exp(-2 pi i r j / 512), results stay in
+            // registers: v0[r] = Z[lane + 64 r], v1[r] = Z[lane + 32 + 64 r]
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 v0[r] = xw[xpad(lane + 64 * r)];
                 v1[r] = xw[xpad(lane + 32 + 64 * r)];
             }
+            __syncwarp();                      // xw is free for the next frame
 #pragma unroll
             for (int r = 1; r < 8; ++r) {
-                float2 w = sm.w512[8 * r * k0];
-                v0[r] = cmul(v0[r], w);
-                v1[r] = cmul(v1[r], w);
+                v0[r] = cmul(v0[r], tw3[r]);
+                // exp(-2 pi i r (lane + 32) / 512) = tw3[r] * exp(-2 pi i r / 16)
+                v1[r] = cmul(v1[r], cmul(tw3[r], make_float2(kC16[r][0], kC16[r][1])));
             }
             fft8(v0);
             fft8(v1);
-            __syncwarp();
-            const int b0 = (lane >> 3) * 64 + k0;
-            const int b1 = ((lane + 32) >> 3) * 64 + k0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                xw[xpad(b0 + 8 * r)] = v0[r];
-                xw[xpad(b1 + 8 * r)] = v1[r];
-            }
-            __syncwarp();
-        }
 
-        // pass 3: Ns = 64; twiddle exp(-2 pi i r j / 512); out[j + 64 r]
+            // ---- real-FFT unpacking in registers ----
+            // Z_q = Z[lane + 32 q]: q even -> v0[q / 2], q odd -> v1[q / 2].
+            // X[k] = e + w^k o,  e = (Z[k] + conj Z[512-k]) / 2,
+            //                    o = -i (Z[k] - conj Z[512-k]) / 2,  w = exp(-2 pi i / 1024).
+            // Z[512 - k] for k = lane + 32 q lives in lane (32 - lane) % 32 as
+            // Z_{15-q} (lane 0: own Z_{(16-q) % 16}).
+            float* mag = sm.mag[f];
+            const int partner = (32 - lane) & 31;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float2 a = (q & 1) ? v1[q >> 1] : v0[q >> 1];
+                const float2 zs = ((15 - q) & 1) ? v1[(15 - q) >> 1] : v0[(15 - q) >> 1];
+                const float2 zo = (((16 - q) & 15) & 1) ? v1[((16 - q) & 15) >> 1]
+                                                       : v0[((16 - q) & 15) >> 1];
+                float2 pz = make_float2(__shfl_sync(0xffffffffu, zs.x, partner),
+                                        __shfl_sync(0xffffffffu, zs.y, partner));
+                if (lane == 0) pz = zo;
+                const float2 e = make_float2(0.5f * (a.x + pz.x), 0.5f * (a.y - pz.y));
+                const float2 d = make_float2(0.5f * (a.x - pz.x), 0.5f * (a.y + pz.y));
+                const float2 o = make_float2(d.y, -d.x);                    // -i * d
+                const float2 w = cmul(wl, make_float2(kC32[q][0], kC32[q][1]));
+                const float2 wo = cmul(w, o);
+                const float xr = e.x + wo.x, xi = e.y + wo.y;
+                mag[lane + 32 * q] = sqrtf(xr * xr + xi * xi + 1e-6f);
+                if (q == 0 && lane == 0) {
+                    // X[512] = conj(e - w o) at k = 0
+                    const float yr = e.x - wo.x, yi = e.y - wo.y;
+                    mag[kHalf] = sqrtf(yr * yr + yi * yi + 1e-6f);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase 2: sparse mel projection, lane = frame =================
         {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                v0[r] = xw[xpad(lane + 64 * r)];
-                v1[r] = xw[xpad(lane + 32 + 64 * r)];
+            const int row = row0 + lane;
+            const bool live = row < total_rows && __ldg(row_seq + row) >= 0;
+            const float* mag = sm.mag[lane];
+            // rows are dealt to warps in a snake so long (high-frequency) and
+            // short (low-frequency) filters balance across warps
+            for (int j = 0; j * kWarps < n_mels; ++j) {
+                const int m = j * kWarps + ((j & 1) ? kWarps - 1 - warp : warp);
+                if (m >= n_mels) continue;
+                float acc = 0.f;
+                const int e0 = sm.mel_ptr[m], e1 = sm.mel_ptr[m + 1];
+                for (int e = e0; e < e1; ++e)
+                    acc = fmaf(sm.mel_val[e], mag[sm.mel_col[e]], acc);
+                float v = logf(fmaxf(acc, 1e-5f));
+                if (normalize) v = (v + 10.f) / 10.f;
+                sm.outs[lane][m] = live ? v : 0.f;
             }
-#pragma unroll
-            for (int r = 1; r < 8; ++r) {
-                v0[r] = cmul(v0[r], sm.w512[r * lane]);
-                v1[r] = cmul(v1[r], sm.w512[r * (lane + 32)]);
-            }
-            fft8(v0);
-            fft8(v1);
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                xw[xpad(lane + 64 * r)] = v0[r];
-                xw[xpad(lane + 32 + 64 * r)] = v1[r];
-            }
-            __syncwarp();
         }
+        __syncthreads();
 
-        // ---- real-FFT unpacking + magnitude: bins k and 512 - k, k = 0..256 ----
-        for (int k = lane; k <= kHalf / 2; k += 32) {
-            float2 a = xw[xpad(k)];
-            float2 bz = xw[xpad((kHalf - k) & (kHalf - 1))];
-            float2 b = make_float2(bz.x, -bz.y);                   // conj(Z[512-k])
-            float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
-            float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
-            float2 o = make_float2(d.y, -d.x);                     // -i * d
-            float2 w = sm.w1024[k];
-            float2 wo = cmul(w, o);
-            float xr = e.x + wo.x, xi = e.y + wo.y;                // X[k]
-            // X[512-k] = conj(e) - conj(w) conj(o) = conj(e - w o)
-            float yr = e.x - wo.x, yi = e.y - wo.y;
-            mag[k] = sqrtf(xr * xr + xi * xi + 1e-6f);
-            mag[kHalf - k] = sqrtf(yr * yr + yi * yi + 1e-6f);
+        // ========================= phase 3: coalesced store =========================
+        {
+            const int rows = min(kTile, total_rows - row0);
+            float* dst = out + (size_t)row0 * n_mels;
+            for (int i = tid; i < rows * n_mels; i += blockDim.x)
+                dst[i] = sm.outs[i / n_mels][i % n_mels];
         }
-        __syncwarp();
-
-        // ---- sparse mel projection + log ----
-        for (int m = lane; m < n_mels; m += 32) {
-            float acc = 0.f;
-            const int e0 = sm.mel_ptr[m], e1 = sm.mel_ptr[m + 1];
-            for (int e = e0; e < e1; ++e)
-                acc = fmaf(sm.mel_val[e], mag[sm.mel_col[e]], acc);
-            float v = logf(fmaxf(acc, 1e-5f));
-            if (normalize) v = (v + 10.f) / 10.f;
-            dst[m] = v;
-        }
-        __syncwarp();
+        // the next tile's phase 1 only touches mag / xchg; outs is rewritten
+        // after the next __syncthreads
     }
 }
 
@@ -310,20 +351,14 @@ int launch_logmel(
     EMPH_REQUIRE(n_seq >= 0 && total_rows >= 0, "emph_logmel: negative size");
     EMPH_REQUIRE(n_mels > 0 && n_mels <= kMaxMels, "emph_logmel: n_mels %d out of range", n_mels);
     if (total_rows == 0) return EMPH_OK;
-    static bool configured = false;
     const size_t smem = sizeof(LogmelSmem);
-    if (!configured) {
-        int s = check_cuda(
-            cudaFuncSetAttribute(
-                logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-            "logmel smem attribute");
-        if (s != EMPH_OK) return s;
-        configured = true;
-    }
-    int per_sm = 3;
-    long want = ((long)total_rows + kWarps - 1) / kWarps;
-    long cap = (long)sm_count() * per_sm;
-    int grid = (int)(want < cap ? want : cap);
+    int s = check_cuda(
+        cudaFuncSetAttribute(
+            logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        "logmel smem attribute");
+    if (s != EMPH_OK) return s;
+    const int n_tiles = (total_rows + kTile - 1) / kTile;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     logmel_kernel<T><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
         audio, audio_off, audio_len, chunk_start, chunk_len, row_start,
         row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out);
