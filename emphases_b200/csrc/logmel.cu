@@ -47,8 +47,7 @@ struct __align__(16) LogmelSmem {
     float2 xchg[kWarps][kXchg];
     float hann[kFft];
     float outs[kTile][kMaxMels + 1];
-    float mel_val[kMaxNnz];
-    int16_t mel_col[kMaxNnz];
+    float2 mel_entry[kMaxNnz];     // (weight, byte offset of the bin within a mag row)
     int32_t mel_ptr[kMaxMels + 1];
 };
 
@@ -63,6 +62,13 @@ __device__ __forceinline__ void bfly2(float2& a, float2& b) {
     float2 t = a;
     a = make_float2(t.x + b.x, t.y + b.y);
     b = make_float2(t.x - b.x, t.y - b.y);
+}
+// sqrt of a strictly positive normal number (x >= 1e-6 here): rsqrt seed + one
+// Newton step, ~1 ulp, no special-case branches
+__device__ __forceinline__ float sqrt_pos(float x) {
+    const float y = rsqrtf(x);
+    const float s = x * y;
+    return fmaf(fmaf(-s, s, x), 0.5f * y, s);
 }
 // multiply by -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -137,10 +143,8 @@ logmel_kernel(
         sm.hann[i] = 0.5f - 0.5f * cospif(2.f * (float)i / (float)kFft);
     }
     const int nnz = mel_ptr[n_mels];
-    for (int i = tid; i < nnz; i += blockDim.x) {
-        sm.mel_val[i] = mel_val[i];
-        sm.mel_col[i] = mel_col[i];
-    }
+    for (int i = tid; i < nnz; i += blockDim.x)
+        sm.mel_entry[i] = make_float2(mel_val[i], __int_as_float(4 * (int)mel_col[i]));
     for (int i = tid; i <= n_mels; i += blockDim.x) sm.mel_ptr[i] = mel_ptr[i];
 
     // Per-lane twiddles, kept in registers for the whole kernel:
@@ -159,7 +163,14 @@ logmel_kernel(
     sincospif(-2.f * (float)lane / (float)kFft, &wl.y, &wl.x);
     __syncthreads();
 
-    float2* xw = sm.xchg[warp];
+    // xpad(lane + 64 r) = px0 + 72 r, xpad(lane + 32 + 64 r) = px0 + 36 + 72 r,
+    // xpad(8 lane + r) = px1 + r, xpad(8 (lane + 32) + r) = px1 + 288 + r,
+    // xpad(b0 + 8 r) = px2 + 9 r with b0 = (lane / 8) 64 + lane % 8, (+256 -> +288)
+    float2* const xw = sm.xchg[warp];
+    float2* const px0 = xw + lane + (lane >> 3);
+    float2* const px1 = xw + 9 * lane;
+    float2* const px2 = xw + (lane >> 3) * 72 + (lane & 7);
+    const float2* const ph = reinterpret_cast<const float2*>(sm.hann) + lane;
     const int n_tiles = (total_rows + kTile - 1) / kTile;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -214,9 +225,7 @@ logmel_kernel(
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                int n0 = lane + 64 * r, n1 = n0 + 32;
-                float2 h0 = *reinterpret_cast<const float2*>(&sm.hann[2 * n0]);
-                float2 h1 = *reinterpret_cast<const float2*>(&sm.hann[2 * n1]);
+                const float2 h0 = ph[64 * r], h1 = ph[64 * r + 32];
                 v0[r].x *= h0.x; v0[r].y *= h0.y;
                 v1[r].x *= h1.x; v1[r].y *= h1.y;
             }
@@ -225,8 +234,8 @@ logmel_kernel(
             fft8(v1);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                xw[xpad(8 * lane + r)] = v0[r];
-                xw[xpad(8 * (lane + 32) + r)] = v1[r];
+                px1[r] = v0[r];
+                px1[288 + r] = v1[r];
             }
             __syncwarp();
 
@@ -234,8 +243,8 @@ logmel_kernel(
             {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    v0[r] = xw[xpad(lane + 64 * r)];
-                    v1[r] = xw[xpad(lane + 32 + 64 * r)];
+                    v0[r] = px0[72 * r];
+                    v1[r] = px0[36 + 72 * r];
                 }
 #pragma unroll
                 for (int r = 1; r < 8; ++r) {
@@ -245,13 +254,10 @@ logmel_kernel(
                 fft8(v0);
                 fft8(v1);
                 __syncwarp();
-                const int k0 = lane & 7;
-                const int b0 = (lane >> 3) * 64 + k0;
-                const int b1 = ((lane + 32) >> 3) * 64 + k0;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    xw[xpad(b0 + 8 * r)] = v0[r];
-                    xw[xpad(b1 + 8 * r)] = v1[r];
+                    px2[9 * r] = v0[r];
+                    px2[288 + 9 * r] = v1[r];
                 }
                 __syncwarp();
             }
@@ -260,8 +266,8 @@ logmel_kernel(
             // registers: v0[r] = Z[lane + 64 r], v1[r] = Z[lane + 32 + 64 r]
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                v0[r] = xw[xpad(lane + 64 * r)];
-                v1[r] = xw[xpad(lane + 32 + 64 * r)];
+                v0[r] = px0[72 * r];
+                v1[r] = px0[36 + 72 * r];
             }
             __syncwarp();                      // xw is free for the next frame
 #pragma unroll
@@ -279,8 +285,10 @@ logmel_kernel(
             //                    o = -i (Z[k] - conj Z[512-k]) / 2,  w = exp(-2 pi i / 1024).
             // Z[512 - k] for k = lane + 32 q lives in lane (32 - lane) % 32 as
             // Z_{15-q} (lane 0: own Z_{(16-q) % 16}).
-            float* mag = sm.mag[f];
+            float* const mag = sm.mag[f] + lane;
             const int partner = (32 - lane) & 31;
+            const bool lane0 = lane == 0;
+            float nyquist = 0.f;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const float2 a = (q & 1) ? v1[q >> 1] : v0[q >> 1];
@@ -289,20 +297,22 @@ logmel_kernel(
                                                        : v0[((16 - q) & 15) >> 1];
                 float2 pz = make_float2(__shfl_sync(0xffffffffu, zs.x, partner),
                                         __shfl_sync(0xffffffffu, zs.y, partner));
-                if (lane == 0) pz = zo;
+                pz.x = lane0 ? zo.x : pz.x;
+                pz.y = lane0 ? zo.y : pz.y;
                 const float2 e = make_float2(0.5f * (a.x + pz.x), 0.5f * (a.y - pz.y));
                 const float2 d = make_float2(0.5f * (a.x - pz.x), 0.5f * (a.y + pz.y));
                 const float2 o = make_float2(d.y, -d.x);                    // -i * d
                 const float2 w = cmul(wl, make_float2(kC32[q][0], kC32[q][1]));
                 const float2 wo = cmul(w, o);
                 const float xr = e.x + wo.x, xi = e.y + wo.y;
-                mag[lane + 32 * q] = sqrtf(xr * xr + xi * xi + 1e-6f);
-                if (q == 0 && lane == 0) {
-                    // X[512] = conj(e - w o) at k = 0
+                mag[32 * q] = sqrt_pos(fmaf(xr, xr, fmaf(xi, xi, 1e-6f)));
+                if (q == 0) {
+                    // X[512] = conj(e - w o) at k = 0 (only lane 0's value is used)
                     const float yr = e.x - wo.x, yi = e.y - wo.y;
-                    mag[kHalf] = sqrtf(yr * yr + yi * yi + 1e-6f);
+                    nyquist = sqrt_pos(fmaf(yr, yr, fmaf(yi, yi, 1e-6f)));
                 }
             }
+            if (lane0) mag[kHalf] = nyquist;
         }
         __syncthreads();
 
@@ -313,13 +323,26 @@ logmel_kernel(
             const float* mag = sm.mag[lane];
             // rows are dealt to warps in a snake so long (high-frequency) and
             // short (low-frequency) filters balance across warps
+            const char* const magb = reinterpret_cast<const char*>(mag);
             for (int j = 0; j * kWarps < n_mels; ++j) {
                 const int m = j * kWarps + ((j & 1) ? kWarps - 1 - warp : warp);
                 if (m >= n_mels) continue;
-                float acc = 0.f;
-                const int e0 = sm.mel_ptr[m], e1 = sm.mel_ptr[m + 1];
-                for (int e = e0; e < e1; ++e)
-                    acc = fmaf(sm.mel_val[e], mag[sm.mel_col[e]], acc);
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                int e = sm.mel_ptr[m];
+                const int e1 = sm.mel_ptr[m + 1];
+                for (; e + 4 <= e1; e += 4) {
+                    const float2 w0 = sm.mel_entry[e], w1 = sm.mel_entry[e + 1];
+                    const float2 w2 = sm.mel_entry[e + 2], w3 = sm.mel_entry[e + 3];
+                    acc0 = fmaf(w0.x, *reinterpret_cast<const float*>(magb + __float_as_int(w0.y)), acc0);
+                    acc1 = fmaf(w1.x, *reinterpret_cast<const float*>(magb + __float_as_int(w1.y)), acc1);
+                    acc2 = fmaf(w2.x, *reinterpret_cast<const float*>(magb + __float_as_int(w2.y)), acc2);
+                    acc3 = fmaf(w3.x, *reinterpret_cast<const float*>(magb + __float_as_int(w3.y)), acc3);
+                }
+                for (; e < e1; ++e) {
+                    const float2 w0 = sm.mel_entry[e];
+                    acc0 = fmaf(w0.x, *reinterpret_cast<const float*>(magb + __float_as_int(w0.y)), acc0);
+                }
+                const float acc = (acc0 + acc1) + (acc2 + acc3);
                 float v = logf(fmaxf(acc, 1e-5f));
                 if (normalize) v = (v + 10.f) / 10.f;
                 sm.outs[lane][m] = live ? v : 0.f;
