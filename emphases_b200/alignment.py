@@ -86,10 +86,14 @@ class Alignment:
         return self.end() - self.start()
 
     def times(self):
-        """(W, 2) float64 array of (start, end) seconds"""
-        return np.array(
-            [(word.start(), word.end()) for word in self._words],
-            dtype=np.float64).reshape(-1, 2)
+        """(W, 2) float64 array of (start, end) seconds (cached)"""
+        cached = getattr(self, '_times', None)
+        if cached is None or len(cached) != len(self._words):
+            cached = np.array(
+                [(word.start(), word.end()) for word in self._words],
+                dtype=np.float64).reshape(-1, 2)
+            self._times = cached
+        return cached
 
     def word_bounds(self, sample_rate, hopsize=1, silences=False):
         return [

@@ -47,8 +47,10 @@ MAX_TRAINING_FRAMES = 75000
 # 'fp32': CUDA-core FFMA conv stack, scores within 1e-5 of the reference's fp32
 # forward.  'bf16': tcgen05 tensor-core conv stack, within 2e-3.
 PRECISION = 'fp32'
-# Upper bound on packed frame rows per launch (memory: ~1 KB of HBM per row)
-MAX_ROWS_PER_LAUNCH = 1 << 22
+# Upper bound on packed frame rows per launch (~1 KB of HBM per row).  A corpus
+# larger than this runs as several launches on two alternating streams so the
+# host->device copy of launch i+1 overlaps the kernels of launch i.
+MAX_ROWS_PER_LAUNCH = 1 << 19
 
 
 def static(namespace):

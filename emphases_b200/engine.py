@@ -186,7 +186,16 @@ def make_plan(
     batch_size: Optional[int] = None,
     validate_method: Optional[str] = None
 ) -> Plan:
-    """utterances: sequence of (times (W, 2) float64, num_samples)"""
+    """utterances: sequence of (times (W, 2) float64, num_samples).
+
+    With batch_size=None every utterance is normally ONE chunk; that case is
+    planned for the whole corpus with vectorised numpy (same float64
+    operations, element-wise, as the scalar chunker).  Anything else goes
+    through `chunk_words` utterance by utterance."""
+    if batch_size is None and len(utterances) > 1:
+        plan = _make_plan_single_chunk(utterances, validate_method)
+        if plan is not None:
+            return plan
     utterance, word_first = [], []
     audio_off, audio_len, chunk_start, chunk_len = [], [], [], []
     bounds_list = []
@@ -207,9 +216,73 @@ def make_plan(
             chunk_len.append(length)
             bounds_list.append(bounds)
         cursor += (int(num_samples) + 3) // 4 * 4        # keep offsets % 4 == 0
+    all_bounds = np.concatenate(bounds_list, axis=0) if bounds_list \
+        else np.zeros((0, 2), dtype=np.int64)
+    return _assemble_plan(
+        np.asarray(utterance, dtype=np.int64),
+        np.asarray(word_first, dtype=np.int64),
+        np.asarray(audio_off, dtype=np.int64),
+        np.asarray(audio_len, dtype=np.int64),
+        np.asarray(chunk_start, dtype=np.int64),
+        np.asarray(chunk_len, dtype=np.int64),
+        np.asarray([len(b) for b in bounds_list], dtype=np.int64),
+        all_bounds, offsets, cursor, validate_method)
+
+
+def _make_plan_single_chunk(utterances, validate_method):
+    """Whole-corpus plan when every utterance is exactly one chunk
+    (emphases/core.py:361-401 with batch_size = total_frames); returns None
+    when any utterance needs the general chunker."""
+    counts = np.fromiter(
+        (len(times) for times, _ in utterances), dtype=np.int64,
+        count=len(utterances))
+    if np.any(counts == 0):
+        return None
+    samples = np.fromiter(
+        (int(n) for _, n in utterances), dtype=np.int64, count=len(utterances))
+    times = np.concatenate([
+        np.asarray(t, dtype=np.float64).reshape(-1, 2) for t, _ in utterances])
+    first = np.concatenate([[0], np.cumsum(counts[:-1])])
+    last = first + counts - 1
+    padded = samples + 2 * PADDING
+    total_frames = (padded / HOPSIZE).astype(np.int64)        # int(len / hop)
+    word_frames = ((times[:, 1] - times[:, 0]) * SAMPLE_RATE) // HOPSIZE
+    if np.any(word_frames < 0):
+        return None
+    # the chunk loop accumulates the frames of words 0 .. W-2 (integer-valued
+    # floats: any summation order is exact) and breaks when int(sum) > limit
+    running = np.add.reduceat(word_frames, first) - word_frames[last]
+    if np.any(running.astype(np.int64) > total_frames):
+        return None
+    origin = np.repeat(times[first, 0], counts)
+    bounds = np.stack([
+        ((times[:, 0] - origin) * SAMPLE_RATE / HOPSIZE).astype(np.int64),
+        ((times[:, 1] - origin) * SAMPLE_RATE / HOPSIZE).astype(np.int64)],
+        axis=1)
+    start_sample = HOPSIZE * (
+        (times[first, 0] * SAMPLE_RATE) // HOPSIZE).astype(np.int64)
+    end_sample = HOPSIZE * (
+        (times[last, 1] * SAMPLE_RATE) // HOPSIZE).astype(np.int64)
+    lo = np.minimum(np.maximum(start_sample, 0), padded)
+    hi = np.minimum(np.maximum(end_sample, 0), padded)
+    length = np.maximum(hi - lo, 0)
+    if np.any(length <= PADDING):
+        return None                       # dropped chunks: general path
+    aligned = (samples + 3) // 4 * 4
+    offsets = np.concatenate([[0], np.cumsum(aligned[:-1])])
+    return _assemble_plan(
+        np.arange(len(utterances), dtype=np.int64),
+        np.zeros(len(utterances), dtype=np.int64),
+        offsets, samples, lo, length, counts, bounds, offsets,
+        int(aligned.sum()), validate_method)
+
+
+def _assemble_plan(
+    utterance, word_first, audio_off, audio_len, chunk_start, chunk_len,
+    n_words, all_bounds, offsets, cursor, validate_method
+):
     n_seq = len(utterance)
-    n_rows = np.asarray(chunk_len, dtype=np.int64) // HOPSIZE
-    n_words = np.asarray([len(b) for b in bounds_list], dtype=np.int64)
+    n_rows = chunk_len // HOPSIZE
     row_start, total_rows = packed_starts(n_rows)
     word_row_start, total_word_rows = packed_starts(n_words)
     if total_rows >= 2 ** 31 or cursor >= 2 ** 40:
@@ -218,25 +291,26 @@ def make_plan(
     word_lo = np.zeros(total_word_rows, dtype=np.int32)
     word_hi = np.zeros(total_word_rows, dtype=np.int32)
     if n_seq:
-        all_bounds = np.concatenate(bounds_list, axis=0)
-        index = np.concatenate([
-            np.arange(s, s + n) for s, n in zip(word_row_start, n_words)])
-        word_seq[index] = np.repeat(np.arange(n_seq, dtype=np.int32), n_words)
+        # word rows of sequence u: word_row_start[u] + (0 .. n_words[u])
+        sequence = np.repeat(np.arange(n_seq, dtype=np.int64), n_words)
+        within = np.arange(len(sequence), dtype=np.int64) - np.repeat(
+            np.concatenate([[0], np.cumsum(n_words[:-1])]), n_words)
+        index = word_row_start[sequence] + within
+        word_seq[index] = sequence
         word_lo[index] = all_bounds[:, 0]
         word_hi[index] = all_bounds[:, 1]
         if validate_method is not None:
-            validate_bounds(
-                all_bounds, np.repeat(n_rows, n_words), validate_method)
+            validate_bounds(all_bounds, n_rows[sequence], validate_method)
     return Plan(
         n_seq=n_seq,
         total_rows=total_rows,
         total_word_rows=total_word_rows,
-        utterance=np.asarray(utterance, dtype=np.int64),
-        word_first=np.asarray(word_first, dtype=np.int64),
-        audio_off=np.asarray(audio_off, dtype=np.int64),
-        audio_len=np.asarray(audio_len, dtype=np.int32),
-        chunk_start=np.asarray(chunk_start, dtype=np.int32),
-        chunk_len=np.asarray(chunk_len, dtype=np.int32),
+        utterance=utterance,
+        word_first=word_first,
+        audio_off=audio_off.astype(np.int64),
+        audio_len=audio_len.astype(np.int32),
+        chunk_start=chunk_start.astype(np.int32),
+        chunk_len=chunk_len.astype(np.int32),
         row_start=row_start.astype(np.int32),
         n_rows=n_rows.astype(np.int32),
         word_row_start=word_row_start.astype(np.int32),
@@ -244,8 +318,8 @@ def make_plan(
         word_seq=word_seq,
         word_lo=word_lo,
         word_hi=word_hi,
-        audio_samples=max(cursor, 4),
-        audio_offsets=offsets)
+        audio_samples=max(int(cursor), 4),
+        audio_offsets=np.asarray(offsets, dtype=np.int64))
 
 
 def validate_bounds(bounds, frames, method):
@@ -397,13 +471,16 @@ class Engine:
             self._pinned[key] = buffer
         return buffer[:numel]
 
-    def upload_plan(self, plan: Plan):
-        """One H2D copy for all int32 index arrays (+ one for int64 offsets)"""
+    def upload_plan(self, plan: Plan, slot=0):
+        """One H2D copy for all int32 index arrays (+ one for int64 offsets).
+        `slot` selects the pinned staging buffer: launches whose copies may
+        still be in flight must not share one."""
         blob = plan.int32_blob()
-        staging = self.pinned('plan32', len(blob), torch.int32)
+        staging = self.pinned(('plan32', slot), len(blob), torch.int32)
         staging.numpy()[:] = blob
         device_blob = staging.to(self.device, non_blocking=True)
-        off_staging = self.pinned('plan64', max(plan.n_seq, 1), torch.int64)
+        off_staging = self.pinned(
+            ('plan64', slot), max(plan.n_seq, 1), torch.int64)
         off_staging.numpy()[:plan.n_seq] = plan.audio_off
         audio_off = off_staging.to(self.device, non_blocking=True)
         n, w = plan.n_seq, plan.total_word_rows

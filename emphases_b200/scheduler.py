@@ -164,11 +164,12 @@ def run_on_device(
             result = eng.forward_packed(
                 device_audio, plan, weights, method=method,
                 location=model.location, precision=precision,
-                head_mode=head_mode, normalize=emphases.NORMALIZE)
+                head_mode=head_mode, normalize=emphases.NORMALIZE,
+                views=eng.upload_plan(plan, slot=number))
             scores = result['scores']
             if to_cpu:
-                host = torch.empty(
-                    scores.shape, dtype=scores.dtype, pin_memory=True)
+                host = eng.pinned(
+                    ('scores', number), scores.numel(), scores.dtype)
                 host.copy_(scores, non_blocking=True)
                 scores = host
         pending.append((members, plan, scores))
@@ -179,15 +180,16 @@ def run_on_device(
 
     outputs = [None] * len(times)
     for members, plan, scores in pending:
-        pieces = [[] for _ in members]
-        for u in range(plan.n_seq):
-            s, n = int(plan.word_row_start[u]), int(plan.n_words[u])
-            pieces[int(plan.utterance[u])].append(scores[s:s + n])
-        for local, index in enumerate(members):
-            if pieces[local]:
-                outputs[index] = torch.cat(pieces[local])[None]
-            else:
-                outputs[index] = scores.new_zeros((1, 0))
+        # word rows without separators are all words of all utterances in order
+        keep = torch.from_numpy(np.nonzero(plan.word_seq >= 0)[0])
+        # (indexing copies, so the pinned staging buffer can be reused)
+        flat = scores[keep.to(scores.device)] if len(keep) else scores[:0].clone()
+        per_utterance = np.bincount(
+            plan.utterance, weights=plan.n_words, minlength=len(members)
+        ).astype(np.int64)
+        pieces = torch.split(flat, per_utterance.tolist())
+        for index, piece in zip(members, pieces):
+            outputs[index] = piece[None]
     return outputs
 
 

@@ -183,3 +183,39 @@ def test_scheduler_lpt_and_buckets():
     assert launches == [[0, 1, 2], [3], [4]]
     offsets, total = scheduler.PackedAudio.layout([5, 8, 3])
     assert offsets.tolist() == [0, 8, 16] and total == 20
+
+
+def test_vectorised_plan_matches_scalar_chunker():
+    """The whole-corpus fast path must equal the per-utterance chunker"""
+    import bench
+    lengths, times = bench.corpus_layout(64, 5)
+    utterances = [(t, int(n)) for t, n in zip(times, lengths)]
+    for seed in range(8):
+        t, audio = oracle.synthetic_utterance(2000 + seed)
+        utterances.append((np.asarray(t), audio.shape[-1]))
+    fast = engine._make_plan_single_chunk(utterances, 'sum')
+    assert fast is not None
+    slow = engine.make_plan(utterances[:1], None)           # warm path check
+    assert slow.n_seq == 1
+    # force the scalar path by planning one utterance at a time
+    cursor = 0
+    for index, (t, n) in enumerate(utterances):
+        chunks = engine.chunk_words(np.asarray(t, dtype=np.float64), n, None)
+        assert len(chunks) == 1
+        w0, w1, start, length, bounds = chunks[0]
+        assert fast.chunk_start[index] == start
+        assert fast.chunk_len[index] == length
+        assert fast.n_rows[index] == length // 160
+        assert fast.audio_off[index] == cursor
+        s, c = fast.word_row_start[index], fast.n_words[index]
+        assert c == len(bounds)
+        np.testing.assert_array_equal(fast.word_lo[s:s + c], bounds[:, 0])
+        np.testing.assert_array_equal(fast.word_hi[s:s + c], bounds[:, 1])
+        assert (fast.word_seq[s:s + c] == index).all()
+        cursor += (n + 3) // 4 * 4
+    # utterances that need the general chunker make the fast path bow out
+    long_alignment = (np.array([[0.0, 5.0], [5.0, 30.0], [30.0, 31.0]]), 16000)
+    assert engine._make_plan_single_chunk(
+        utterances[:3] + [long_alignment], None) is None
+    plan = engine.make_plan(utterances[:3] + [long_alignment], None)
+    assert plan.n_seq >= 4
