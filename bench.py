@@ -220,7 +220,7 @@ def run_reference(args, rank, world):
         return
     lengths, times = corpus_layout(args.utterances, seed=1234)
     state = random_state()
-    per_step = 24
+    per_step = min(300, args.utterances)
     for _ in range(args.warmup):
         cpu_reference_pass(state, lengths, times, 99, 1e9, per_step)
     seconds = words = elapsed = 0.
@@ -428,7 +428,7 @@ def main():
     cpu = None
     if world == 1 and args.cpu_seconds > 0:
         seconds, words, items, elapsed = cpu_reference_pass(
-            state, lengths, times, 99, args.cpu_seconds, 400, packed)
+            state, lengths, times, 99, args.cpu_seconds, len(lengths), packed)
         cpu = {
             'value': seconds / elapsed,
             'unit': 'audio-s/s',
