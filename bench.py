@@ -285,6 +285,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    numa_cpus = scheduler.bind_to_gpu_numa_node(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
@@ -356,12 +357,13 @@ def main():
     for _ in range(2):
         e2e_step()
     barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         results = e2e_step()
     torch.cuda.synchronize(device)
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    e2e_ms_rank0 = e2e_ms
     assert sum(r.shape[-1] for r in results) == n_words
     h2d_bytes = host_audio.numel() * 4 + plan.int32_blob().nbytes + plan.n_seq * 8
     d2h_bytes = plan.total_word_rows * 4
@@ -394,35 +396,46 @@ def main():
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peaks = json.load(open(peaks_path))
-    conv_ms = kernel_ms['conv_frames']
-    conv_tflops = frames * CONV_FLOP_PER_FRAME / (conv_ms * 1e-3) / 1e12
     tensor_peak = peaks.get('bf16_tflops_sustained', 1400.0)
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    source = ('MEASURED_PEAKS.json (hbm_gbs; bf16_tflops_sustained: kernels '
+              'timed inside a long step)' if peaks else 'fallback')
+    conv_tflops = frames * CONV_FLOP_PER_FRAME / (kernel_ms['conv_frames'] * 1e-3) / 1e12
     logmel_gbs = frames * LOGMEL_BYTES_PER_FRAME / (kernel_ms['logmel'] * 1e-3) / 1e9
     pool_gbs = (frames * POOL_BYTES_PER_FRAME + n_words * 328) / (
         kernel_ms['pool'] * 1e-3) / 1e9
-    roofline = {
-        'kernel': 'conv_stack(frame side, 7 fused layers)',
-        'bound': 'tensor',
-        'achieved': conv_tflops,
-        'peak': tensor_peak,
-        'unit': 'TFLOP/s',
-        'frac': conv_tflops / tensor_peak,
-        'traffic': None,
-        'peak_source': (
-            'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a '
-            'long step)' if peaks else 'fallback'),
-        'share_of_step': conv_ms / ms_per_step,
-        'others': {
-            'logmel': {
-                'bound': 'hbm (FP32-pipe limited, see DESIGN.md)',
-                'achieved': logmel_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': logmel_gbs / hbm_peak, 'ms': kernel_ms['logmel']},
-            'pool': {
-                'bound': 'hbm', 'achieved': pool_gbs, 'peak': hbm_peak,
-                'unit': 'GB/s', 'frac': pool_gbs / hbm_peak,
-                'ms': kernel_ms['pool']}},
-        'kernel_ms': kernel_ms}
+    conv_bound = 'tensor' if precision == 'bf16' else 'tensor (fp32 FFMA mode)'
+    candidates = {
+        'logmel': {
+            'kernel': 'logmel_kernel (framing + 1024-pt rFFT + mel + log)',
+            'bound': 'hbm',
+            'achieved': logmel_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': logmel_gbs / hbm_peak,
+            # dram read+write per frame from the ncu --set full capture in
+            # profiles/r01e_logmel.md, scaled to this launch
+            'traffic': 915.0 * frames,
+            'note': ('fp32 FFT: FP32-issue/latency bound, not HBM bound '
+                     '(960 algorithmic B/frame vs ~30 kFLOP/frame), DESIGN.md 4.1')},
+        'conv_frames': {
+            'kernel': 'conv_stack (7 fused frame layers)',
+            'bound': conv_bound,
+            'achieved': conv_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s',
+            'frac': conv_tflops / tensor_peak,
+            'traffic': None},
+        'pool': {
+            'kernel': 'pool_words_kernel',
+            'bound': 'hbm',
+            'achieved': pool_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': pool_gbs / hbm_peak, 'traffic': None}}
+    for name, entry in candidates.items():
+        entry['ms'] = kernel_ms[name]
+        entry['share_of_step'] = kernel_ms[name] / ms_per_step
+    dominant = max(candidates, key=lambda name: kernel_ms[name])
+    roofline = dict(candidates[dominant])
+    roofline['peak_source'] = source
+    roofline['others'] = {
+        name: entry for name, entry in candidates.items() if name != dominant}
+    roofline['kernel_ms'] = kernel_ms
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
     cpu = None
@@ -463,7 +476,11 @@ def main():
             'words_per_s': words_total / (e2e_ms * 1e-3),
             'ms_per_step': e2e_ms,
             'h2d_bytes_per_step': int(h2d_bytes),
-            'd2h_bytes_per_step': int(d2h_bytes)},
+            'd2h_bytes_per_step': int(d2h_bytes),
+            'h2d_gbs_effective': h2d_bytes / (e2e_ms_rank0 * 1e-3) / 1e9,
+            'gpu_local_cpus': numa_cpus,
+            'note': ('PCIe-bound: one pinned H2D of the fp32 audio per '
+                     'launch, kernels overlap the next launch copy')},
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,
         'cpu_baseline': cpu}))

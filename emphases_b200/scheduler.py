@@ -17,6 +17,40 @@ from .alignment import as_times
 
 
 ###############################################################################
+# Host placement
+###############################################################################
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin the calling thread to the CPUs local to GPU `index` so that pinned
+    staging buffers (first-touch) and the copy-issuing thread sit on the
+    GPU's NUMA node; host->device bandwidth halves from the wrong socket.
+    Returns the cpulist string, or None when it cannot be determined."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        domain = torch.cuda.get_device_properties(index).pci_domain_id
+        device = torch.cuda.get_device_properties(index).pci_device_id
+        path = f'/sys/bus/pci/devices/{domain:04x}:{bus:02x}:{device:02x}.0/local_cpulist'
+        with open(path) as stream:
+            cpulist = stream.read().strip()
+        cpus = set()
+        for part in cpulist.split(','):
+            if '-' in part:
+                lo, hi = part.split('-')
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        return cpulist
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        return None
+
+
+###############################################################################
 # Packed host audio
 ###############################################################################
 
