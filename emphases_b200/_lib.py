@@ -35,6 +35,9 @@ SIGNATURES = {
     'emph_pack_rows': [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     'emph_unpack_rows': [_P, _P, _P, _I, _I, _I, _P, _P],
     'emph_segment_rows': [_P, _I, _P, _P, _P, _I, _P, _I, _P, _P],
+    'emph_add_positional': [_P, _P, _P, _I, _I, _P, _I, _P, _P],
+    'emph_attention_rows': [_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _I, _F, _P, _P],
+    'emph_add_layernorm': [_P, _P, _P, _P, _F, _P, _I, _I, _P, _P],
 }
 
 _lib = None

@@ -603,12 +603,26 @@ class Engine:
             plan.total_word_rows))
         features = timed('logmel', lambda: self.logmel(
             audio, views, plan, row_seq, normalize))
-        frames = timed('conv_frames', lambda: self.conv_stack(
-            features, row_seq, weights.frame, precision))
+        transformer_variant = hasattr(weights, 'input_layer')
+        if transformer_variant:
+            from . import transformer
+            embedded = self.conv_stack(
+                features, row_seq, weights.input_layer, _lib.PREC_FP32)
+            frames = timed('conv_frames', lambda: transformer.run_stack(
+                self, weights.frame, embedded, views['row_start'], plan.n_rows,
+                plan.n_rows, row_seq, self.device))
+        else:
+            frames = timed('conv_frames', lambda: self.conv_stack(
+                features, row_seq, weights.frame, precision))
         pooled = timed('pool', lambda: self.pool(
             frames, views['row_start'], views['n_rows'], views['word_seq'],
             views['word_lo'], views['word_hi'], method))
-        if location == 'intermediate':
+        if location == 'intermediate' and transformer_variant:
+            from . import transformer
+            words = timed('conv_words', lambda: transformer.run_stack(
+                self, weights.word, pooled, views['word_row_start'],
+                plan.n_words, plan.n_words, word_row_seq, self.device))
+        elif location == 'intermediate':
             words = timed('conv_words', lambda: self.conv_stack(
                 pooled, word_row_seq, weights.word, _lib.PREC_FP32))
         else:

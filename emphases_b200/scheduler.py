@@ -157,7 +157,7 @@ def run_on_device(
 ):
     """Run a list of utterances on one device; returns a list of (1, W_i)
     score tensors (CPU when to_cpu, else on `device`)."""
-    if model.architecture == 'transformer' or model.location == 'input':
+    if model.location == 'input':
         return _run_via_model(
             model, alignments, audios, sample_rate, batch_size, device, to_cpu)
     times, packed = _prepare(alignments, audios, sample_rate)

@@ -1,0 +1,281 @@
+"""Transformer variant (`ARCHITECTURE = 'transformer'`), mirroring
+emphases/model/layers/transformer.py:13-52 on packed rows.
+
+The modules below are parameter containers with the reference's state_dict
+keys (`position.encoding`, `model.layers.{i}.self_attn.in_proj_weight`, ...,
+SURVEY.md A.7); the math runs in libemphases_b200.so: per-row linear maps
+through the fused fp32 conv stack with kernel size 1 (the feed-forward block
+is ONE fused two-layer launch), attention / LayerNorm / positional add through
+csrc/attention.cu.
+"""
+import dataclasses
+import math
+from typing import List
+
+import numpy as np
+import torch
+
+import emphases_b200 as emphases
+from . import _lib, engine
+
+HEADS = 2                      # transformer.py:20
+MAX_LENGTH = 5000              # transformer.py:38
+
+
+class PositionalEncoding(torch.nn.Module):
+    """transformer.py:36-52 (buffer only; dropout is identity in eval)"""
+
+    def __init__(self, channels, dropout=.1, max_len=MAX_LENGTH):
+        super().__init__()
+        self.dropout = torch.nn.Dropout(p=dropout)
+        index = torch.arange(max_len).unsqueeze(1)
+        frequency = torch.exp(
+            torch.arange(0, channels, 2) * (-math.log(10000.0) / channels))
+        encoding = torch.zeros(max_len, 1, channels)
+        encoding[:, 0, 0::2] = torch.sin(index * frequency)
+        encoding[:, 0, 1::2] = torch.cos(index * frequency)
+        self.register_buffer('encoding', encoding)
+
+
+class Transformer(torch.nn.Module):
+    """transformer.py:13-30"""
+
+    def __init__(self):
+        super().__init__()
+        channels = emphases.CHANNELS
+        self.position = PositionalEncoding(channels, .1)
+        self.model = torch.nn.TransformerEncoder(
+            torch.nn.TransformerEncoderLayer(
+                channels, HEADS, dim_feedforward=emphases.CHANNELS),
+            emphases.LAYERS,
+            enable_nested_tensor=False)
+
+    def forward(self, x, lengths):
+        raise _lib.EmphasesB200Error(
+            'submodules are parameter containers; call Model.forward')
+
+
+###############################################################################
+# Packed weights
+###############################################################################
+
+
+@dataclasses.dataclass
+class EncoderLayer:
+    qkv: List[engine.ConvStack]          # three 1-layer, kernel-1 stacks
+    out_proj: engine.ConvStack
+    feedforward: engine.ConvStack        # linear1 + ReLU + linear2, fused
+    norm1: tuple
+    norm2: tuple
+
+
+@dataclasses.dataclass
+class TransformerStack:
+    table: torch.Tensor                  # (max_len, channels) positional table
+    layers: List[EncoderLayer]
+    channels: int
+
+
+def _linear_stack(pairs, acts, device):
+    """[(weight (out, in), bias)] -> ConvStack with kernel size 1"""
+    weights = torch.stack([
+        engine._pack_conv(weight[:, :, None], device) for weight, _ in pairs])
+    bias = torch.stack([
+        b.detach().to(device=device, dtype=torch.float32) for _, b in pairs])
+    return engine.ConvStack(
+        weights.contiguous(), bias.contiguous(),
+        np.asarray(acts, dtype=np.int32), 1, pairs[0][0].shape[0])
+
+
+def pack_stack(state, prefix, layers, channels, device):
+    encoder_layers = []
+    for index in range(layers):
+        p = f'{prefix}.model.layers.{index}'
+        w = state[f'{p}.self_attn.in_proj_weight']
+        b = state[f'{p}.self_attn.in_proj_bias']
+        qkv = [
+            _linear_stack(
+                [(w[i * channels:(i + 1) * channels],
+                  b[i * channels:(i + 1) * channels])],
+                [_lib.ACT_NONE], device)
+            for i in range(3)]
+        out_proj = _linear_stack(
+            [(state[f'{p}.self_attn.out_proj.weight'],
+              state[f'{p}.self_attn.out_proj.bias'])], [_lib.ACT_NONE], device)
+        if state[f'{p}.linear1.weight'].shape != (channels, channels):
+            raise NotImplementedError('dim_feedforward must equal CHANNELS')
+        feedforward = _linear_stack(
+            [(state[f'{p}.linear1.weight'], state[f'{p}.linear1.bias']),
+             (state[f'{p}.linear2.weight'], state[f'{p}.linear2.bias'])],
+            [_lib.ACT_RELU, _lib.ACT_NONE], device)
+
+        def norm(name):
+            return (
+                state[f'{p}.{name}.weight'].detach().to(device, torch.float32).contiguous(),
+                state[f'{p}.{name}.bias'].detach().to(device, torch.float32).contiguous())
+        encoder_layers.append(EncoderLayer(
+            qkv, out_proj, feedforward, norm('norm1'), norm('norm2')))
+    table = state[f'{prefix}.position.encoding'].detach().to(
+        device, torch.float32)[:, 0, :].contiguous()
+    return TransformerStack(table, encoder_layers, channels)
+
+
+@dataclasses.dataclass
+class TransformerWeights:
+    input_layer: engine.ConvStack
+    frame: TransformerStack
+    word: TransformerStack
+    head_weight: torch.Tensor
+    head_bias: float
+    head_kernel: int
+    channels: int
+
+
+def pack_weights(model, device):
+    state = model.state_dict()
+    channels = state['input_layer.weight'].shape[0]
+    if state['input_layer.weight'].shape[1] != channels:
+        raise NotImplementedError('input layer needs equal in/out channels')
+    kernel = state['input_layer.weight'].shape[2]
+    input_layer = engine.ConvStack(
+        engine._pack_conv(state['input_layer.weight'], device)[None].contiguous(),
+        state['input_layer.bias'].detach().to(device, torch.float32)[None].contiguous(),
+        np.asarray([_lib.ACT_NONE], dtype=np.int32), kernel, channels)
+    head = state['output_layer.weight'].detach().to(device, torch.float32)
+    return TransformerWeights(
+        input_layer=input_layer,
+        frame=pack_stack(state, 'frame_encoder', model.layers, channels, device),
+        word=pack_stack(state, 'word_decoder', model.layers, channels, device)
+        if hasattr(model, 'word_decoder') else None,
+        head_weight=head[0].t().contiguous(),
+        head_bias=float(state['output_layer.bias'].detach().float().cpu()[0]),
+        head_kernel=head.shape[2],
+        channels=channels)
+
+
+###############################################################################
+# Execution on packed rows
+###############################################################################
+
+
+def query_blocks(n_keys, block=64):
+    """(block_seq, block_q0): 64-query blocks that never cross a sequence"""
+    n_keys = np.asarray(n_keys, dtype=np.int64)
+    counts = (n_keys + block - 1) // block
+    sequence = np.repeat(np.arange(len(n_keys)), counts)
+    first = np.concatenate([[0], np.cumsum(counts[:-1])]) if len(counts) else counts
+    within = np.arange(int(counts.sum())) - np.repeat(first, counts)
+    return sequence.astype(np.int32), (within * block).astype(np.int32)
+
+
+def run_stack(
+    eng, stack, x, row_start, n_rows_host, n_keys_host, row_seq, device
+):
+    """x: packed rows (total_rows, C); sequence u has n_rows[u] rows (all are
+    queries) of which the first n_keys[u] are valid keys"""
+    if int(np.max(n_rows_host, initial=0)) > stack.table.shape[0]:
+        raise RuntimeError(
+            f'The size of tensor a ({int(np.max(n_rows_host))}) must match the '
+            f'size of tensor b ({stack.table.shape[0]}) at non-singleton '
+            'dimension 0 (positional encoding table, transformer.py:52)')
+    total_rows, channels = x.shape
+    block_seq, block_q0 = query_blocks(n_rows_host)
+    meta = torch.from_numpy(np.concatenate([
+        np.asarray(n_rows_host, dtype=np.int32),
+        np.asarray(n_keys_host, dtype=np.int32), block_seq, block_q0])).to(device)
+    n_seq = len(n_keys_host)
+    n_queries, n_keys = meta[:n_seq], meta[n_seq:2 * n_seq]
+    d_block_seq = meta[2 * n_seq:2 * n_seq + len(block_seq)]
+    d_block_q0 = meta[2 * n_seq + len(block_seq):]
+    scale = 1.0 / math.sqrt(channels // HEADS)
+
+    h = torch.empty_like(x)
+    _lib.call(
+        'emph_add_positional', _lib.ptr(x), _lib.ptr(row_start),
+        _lib.ptr(row_seq), total_rows, channels, _lib.ptr(stack.table),
+        stack.table.shape[0], _lib.ptr(h), _lib.stream_ptr())
+    for layer in stack.layers:
+        q, k, v = (
+            eng.conv_stack(h, row_seq, part, _lib.PREC_FP32) for part in layer.qkv)
+        context = torch.empty_like(h)
+        _lib.call(
+            'emph_attention_rows', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v),
+            channels, HEADS, _lib.ptr(row_start), _lib.ptr(n_queries),
+            _lib.ptr(n_keys), _lib.ptr(row_seq), total_rows, _lib.ptr(d_block_seq),
+            _lib.ptr(d_block_q0), len(block_seq), scale, _lib.ptr(context),
+            _lib.stream_ptr())
+        attended = eng.conv_stack(context, row_seq, layer.out_proj, _lib.PREC_FP32)
+        normed = torch.empty_like(h)
+        _lib.call(
+            'emph_add_layernorm', _lib.ptr(h), _lib.ptr(attended),
+            _lib.ptr(layer.norm1[0]), _lib.ptr(layer.norm1[1]), 1e-5,
+            _lib.ptr(row_seq), total_rows, channels, _lib.ptr(normed),
+            _lib.stream_ptr())
+        forward = eng.conv_stack(normed, row_seq, layer.feedforward, _lib.PREC_FP32)
+        h = torch.empty_like(normed)
+        _lib.call(
+            'emph_add_layernorm', _lib.ptr(normed), _lib.ptr(forward),
+            _lib.ptr(layer.norm2[0]), _lib.ptr(layer.norm2[1]), 1e-5,
+            _lib.ptr(row_seq), total_rows, channels, _lib.ptr(h),
+            _lib.stream_ptr())
+    return h
+
+
+def run_forward(
+    model, eng, weights, features, frame_lengths, word_bounds, word_lengths
+):
+    """Model.forward for the transformer variant (padded (B, C, T) batch)"""
+    from . import model as model_module
+    if model.location == 'input':
+        raise NotImplementedError(
+            "the transformer variant at DOWNSAMPLE_LOCATION='input' is not built")
+    method = emphases.DOWNSAMPLE_METHOD
+    device = features.device
+    batch, channels, frames = features.shape
+    frame_keys = frame_lengths.detach().to('cpu', torch.int64).numpy()
+    starts, total = engine.packed_starts([frames] * batch)
+    rows_meta = torch.from_numpy(np.concatenate([
+        starts.astype(np.int32), np.full(batch, frames, dtype=np.int32)])
+    ).to(device)
+    row_start, n_rows = rows_meta[:batch], rows_meta[batch:]
+    row_seq = eng.row_index(row_start, n_rows, batch, total)
+    rows = torch.empty((total, channels), dtype=torch.float32, device=device)
+    features = features.detach().to(torch.float32).contiguous()
+    _lib.call(
+        'emph_pack_rows', _lib.ptr(features), batch, channels, frames,
+        _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
+        _lib.ptr(rows), _lib.stream_ptr())
+    # input_layer is a Conv1d over ALL T columns, padding included
+    embedded = eng.conv_stack(rows, row_seq, weights.input_layer, _lib.PREC_FP32)
+    frame_rows = run_stack(
+        eng, weights.frame, embedded, row_start, np.full(batch, frames),
+        frame_keys, row_seq, device)
+
+    if model.location == 'inference' and model.training:
+        logits, _ = eng.head(
+            frame_rows, row_seq, weights, _lib.HEAD_LOGITS, want_scores=False)
+        index = torch.from_numpy(
+            (starts[:, None] + np.arange(frames)[None]).astype(np.int64)).to(device)
+        return logits[index][:, None, :]
+
+    views, word_starts, total_words, bounds, lengths = model_module.word_rows(
+        word_bounds, word_lengths, device)
+    wmax = word_bounds.shape[2]
+    valid = np.arange(wmax)[None] < lengths[:, None]
+    engine.validate_bounds(
+        np.stack([bounds[:, 0][valid], bounds[:, 1][valid]], axis=1),
+        np.full(int(valid.sum()), frames), method)
+    pooled = eng.pool(
+        frame_rows, row_start, n_rows, views['word_seq'], views['word_lo'],
+        views['word_hi'], method)
+    word_row_seq = eng.row_index(
+        views['word_row_start'], views['n_words'], batch, total_words)
+    if model.location == 'intermediate':
+        pooled = run_stack(
+            eng, weights.word, pooled, views['word_row_start'],
+            np.full(batch, wmax), lengths, word_row_seq, device)
+    logits, _ = eng.head(
+        pooled, word_row_seq, weights, _lib.HEAD_LOGITS, want_scores=False)
+    index = torch.from_numpy(
+        (word_starts[:, None] + np.arange(wmax)[None]).astype(np.int64)).to(device)
+    return logits[index][:, None, :]

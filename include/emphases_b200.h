@@ -224,6 +224,39 @@ int emph_segment_rows(
     int32_t n_seg, const int32_t* dst_row_seq, int32_t total_dst_rows,
     float* y, void* stream);
 
+/*
+ * Transformer variant (emphases/model/layers/transformer.py:13-52), fp32.
+ * Per-row linear maps (in_proj, out_proj, linear1/2) run through
+ * emph_conv_stack with kernel_size 1; these cover the rest.
+ *
+ * emph_add_positional: y = x + table[t] with t the row's index inside its
+ *   sequence (transformer.py:50-52; `table` is the module's (max_len, channels)
+ *   `position.encoding` buffer).
+ * emph_attention_rows: out = softmax(q k^T * scale + key mask) v per head over
+ *   the rows of each sequence; keys with index >= n_keys[u] are the padded
+ *   positions of the reference's src_key_padding_mask (transformer.py:26-29).
+ *   All n_queries[u] rows are computed as queries, padded ones included, as
+ *   nn.TransformerEncoder does (their values reach valid words through the
+ *   k=3 output conv).  The caller supplies the query blocks (block_seq[b],
+ *   block_q0[b]): 64 queries each, never crossing a sequence.
+ * emph_add_layernorm: y = LayerNorm(x + residual; gamma, beta, eps).
+ */
+int emph_add_positional(
+    const float* x, const int32_t* row_start, const int32_t* row_seq,
+    int32_t total_rows, int32_t channels, const float* table,
+    int32_t table_rows, float* y, void* stream);
+int emph_attention_rows(
+    const float* q, const float* k, const float* v, int32_t channels,
+    int32_t heads, const int32_t* row_start, const int32_t* n_queries,
+    const int32_t* n_keys, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* block_seq,
+    const int32_t* block_q0, int32_t n_blocks, float scale, float* out,
+    void* stream);
+int emph_add_layernorm(
+    const float* x, const float* residual, const float* gamma,
+    const float* beta, float eps, const int32_t* row_seq, int32_t total_rows,
+    int32_t channels, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,3 +229,76 @@ def test_errors(emphases, golden, c1_checkpoint):
     emphases.configure(ARCHITECTURE='lstm')
     with pytest.raises(ValueError):
         emphases.Model()
+
+
+def test_transformer_variant(emphases, golden):
+    """ARCHITECTURE='transformer' Model.forward vs the reference (B=1 and a
+    padded B=2 batch whose key-padding mask matters)"""
+    data = golden('transformer')
+    emphases.configure(ARCHITECTURE='transformer')
+    model = emphases.Model()
+    state = state_from_golden(data)
+    missing = model.load_state_dict(state, strict=False)
+    assert all('position.encoding' in key for key in missing.missing_keys)
+    assert not missing.unexpected_keys
+    model = model.cuda().eval()
+    with torch.no_grad():
+        features = torch.from_numpy(data['b1.features']).cuda()
+        bounds = torch.from_numpy(data['b1.bounds'])
+        logits = model(
+            features, torch.tensor([features.shape[-1]]), bounds,
+            torch.tensor([bounds.shape[-1]]))
+        np.testing.assert_allclose(
+            logits.cpu().numpy(), data['b1.logits'], rtol=0, atol=3e-5)
+        batch = [torch.from_numpy(data[f'b2.{name}']) for name in (
+            'features', 'frame_lengths', 'bounds', 'word_lengths')]
+        batch[0] = batch[0].cuda()
+        logits = model(*batch).cpu().numpy()
+        for i, words in enumerate(batch[3].tolist()):
+            np.testing.assert_allclose(
+                logits[i, :, :words], data['b2.logits'][i, :, :words],
+                rtol=0, atol=3e-5)
+
+
+def test_transformer_end_to_end(emphases, golden, tmp_path):
+    """from_alignment_and_audio with the transformer variant vs the oracle"""
+    data = golden('transformer')
+    emphases.configure(ARCHITECTURE='transformer')
+    state = state_from_golden(data)
+    encoding = oracle.positional_encoding(80)
+    state['frame_encoder.position.encoding'] = encoding
+    state['word_decoder.position.encoding'] = encoding
+    path = tmp_path / 'transformer.pt'
+    torch.save({'model': state}, path)
+    times, audio = oracle.synthetic_utterance(31, duration=4.0, words=9)
+    scores = emphases.from_alignment_and_audio(
+        emphases.Alignment.from_times(times), audio, 16000, checkpoint=path,
+        gpu=0)
+    expected = oracle.from_alignment_and_audio(
+        times, audio, state, config={'ARCHITECTURE': 'transformer'})
+    assert scores.shape == expected.shape
+    assert (scores.cpu() - expected).abs().max() < 2e-5
+
+
+def test_transformer_packed_corpus(emphases, golden, tmp_path):
+    """Several ragged utterances through the packed transformer path"""
+    data = golden('transformer')
+    emphases.configure(ARCHITECTURE='transformer')
+    state = state_from_golden(data)
+    encoding = oracle.positional_encoding(80)
+    state['frame_encoder.position.encoding'] = encoding
+    state['word_decoder.position.encoding'] = encoding
+    path = tmp_path / 'transformer.pt'
+    torch.save({'model': state}, path)
+    alignments, audios, expected = [], [], []
+    for seed in range(4):
+        times, audio = oracle.synthetic_utterance(900 + seed, duration=2.0 + seed)
+        alignments.append(emphases.Alignment.from_times(times))
+        audios.append(audio)
+        expected.append(oracle.from_alignment_and_audio(
+            times, audio, state, config={'ARCHITECTURE': 'transformer'}))
+    scores = emphases.from_alignments_and_audio(
+        alignments, audios, 16000, checkpoint=path, gpu=0)
+    for got, want in zip(scores, expected):
+        assert got.shape == want.shape
+        assert (got - want).abs().max() < 2e-5
