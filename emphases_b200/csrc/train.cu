@@ -1,0 +1,312 @@
+// Backward kernels of the conv model for the data-parallel training step
+// (BASELINE config 5; reference single-device step: emphases/train/core.py:
+// 86-142, loss: emphases/train/core.py:315-353), fp32, sm_100a.
+//
+// Forward in training keeps every layer's activations (one emph_conv_stack
+// launch per layer); backward per Conv1d(C -> C, k, 'same') + activation:
+//   dpre = dY * act'(Y)                       emph_activation_backward
+//   dX   = conv(dpre, W flipped/transposed)   emph_conv_stack (existing kernel)
+//   dW[tap][ci][co] = sum_r X[r + tap - half][ci] dpre[r][co],  db = sum_r dpre
+//                                             emph_conv_weight_grad
+// plus the backward of word pooling, of the output projection and the masked
+// BCE / MSE loss with its gradient.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace emph {
+
+// dpre = dy * act'(y) (y is the POST-activation output; ReLU/identity only
+// need y), separator rows zeroed
+__global__ void activation_backward_kernel(
+    const float* __restrict__ dy, const float* __restrict__ y,
+    const int32_t* __restrict__ row_seq, int total_rows, int channels, int act,
+    float* __restrict__ dpre) {
+    const size_t n = (size_t)total_rows * channels;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / channels);
+        float g = dy[i];
+        if (act == EMPH_ACT_RELU) g = y[i] > 0.f ? g : 0.f;
+        dpre[i] = row_seq[r] >= 0 ? g : 0.f;
+    }
+}
+
+// Weight / bias gradient of one conv layer.  256 threads: thread (gi, go) owns
+// a 5 x 5 block of (ci, co) for all taps (C = 80: 16 x 16 blocks).
+template <int C, int KS>
+__global__ void __launch_bounds__(256)
+conv_weight_grad_kernel(
+    const float* __restrict__ x, const float* __restrict__ dpre, int total_rows,
+    float* __restrict__ dw, float* __restrict__ db) {
+    constexpr int R = 64;                  // rows per smem tile
+    constexpr int HALF = (KS - 1) / 2;
+    constexpr int B = C / 16;              // block edge (5 for C = 80)
+    __shared__ float xs[R + 2 * HALF][C + 1];
+    __shared__ float ds[R][C + 1];
+    const int tid = threadIdx.x;
+    const int gi = tid >> 4, go = tid & 15;
+    float acc[KS][B][B];
+    float bias_acc[B];
+#pragma unroll
+    for (int t = 0; t < KS; ++t)
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+#pragma unroll
+            for (int o = 0; o < B; ++o) acc[t][i][o] = 0.f;
+#pragma unroll
+    for (int o = 0; o < B; ++o) bias_acc[o] = 0.f;
+
+    for (int r0 = blockIdx.x * R; r0 < total_rows; r0 += gridDim.x * R) {
+        __syncthreads();
+        for (int i = tid; i < (R + 2 * HALF) * C; i += 256) {
+            const int r = i / C, c = i % C;
+            const int g = r0 + r - HALF;
+            xs[r][c] = (g >= 0 && g < total_rows) ? x[(size_t)g * C + c] : 0.f;
+        }
+        for (int i = tid; i < R * C; i += 256) {
+            const int r = i / C, c = i % C;
+            const int g = r0 + r;
+            ds[r][c] = g < total_rows ? dpre[(size_t)g * C + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int r = 0; r < R; ++r) {
+            float d[B];
+#pragma unroll
+            for (int o = 0; o < B; ++o) d[o] = ds[r][go * B + o];
+            if (gi == 0) {
+#pragma unroll
+                for (int o = 0; o < B; ++o) bias_acc[o] += d[o];
+            }
+#pragma unroll
+            for (int t = 0; t < KS; ++t) {
+#pragma unroll
+                for (int i = 0; i < B; ++i) {
+                    const float xv = xs[r + t][gi * B + i];
+#pragma unroll
+                    for (int o = 0; o < B; ++o) acc[t][i][o] = fmaf(xv, d[o], acc[t][i][o]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < KS; ++t)
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+#pragma unroll
+            for (int o = 0; o < B; ++o)
+                atomicAdd(dw + ((size_t)t * C + gi * B + i) * C + go * B + o, acc[t][i][o]);
+    if (gi == 0) {
+#pragma unroll
+        for (int o = 0; o < B; ++o) atomicAdd(db + go * B + o, bias_acc[o]);
+    }
+}
+
+// Backward of emph_pool_words: one warp per word row, adds into dx (pre-zeroed)
+__global__ void __launch_bounds__(256)
+pool_backward_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, int channels,
+    const int32_t* __restrict__ row_start, const int32_t* __restrict__ n_rows,
+    const int32_t* __restrict__ word_seq, const int32_t* __restrict__ word_lo,
+    const int32_t* __restrict__ word_hi, int total_word_rows, int method,
+    float* __restrict__ dx) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= total_word_rows) return;
+    const int u = word_seq[w];
+    if (u < 0) return;
+    const int lo = word_lo[w], hi = word_hi[w];
+    const bool padded_slot = lo == -1 && hi == -1;
+    // masked slots never reach the input; padded slots only through `center`,
+    // which gathers frame 0 for them (emphases/core.py:458-466)
+    if (lo < 0 && !(padded_slot && method == EMPH_POOL_CENTER)) return;
+    const int n = n_rows[u];
+    const size_t base = (size_t)row_start[u] * channels;
+    const float* g = dy + (size_t)w * channels;
+    if (method == EMPH_POOL_CENTER) {
+        const int idx = padded_slot ? 0 : (lo + hi) >> 1;
+        if (idx < n)
+            for (int c = lane; c < channels; c += 32)
+                atomicAdd(dx + base + (size_t)idx * channels + c, g[c]);
+        return;
+    }
+    const int s = min(max(lo, 0), n), e = min(max(hi, 0), n);
+    if (e <= s) return;
+    for (int c = lane; c < channels; c += 32) {
+        if (method == EMPH_POOL_MAX) {
+            int arg = s;
+            float best = x[base + (size_t)s * channels + c];
+            for (int f = s + 1; f < e; ++f) {
+                const float v = x[base + (size_t)f * channels + c];
+                if (v > best) { best = v; arg = f; }
+            }
+            atomicAdd(dx + base + (size_t)arg * channels + c, g[c]);
+        } else {
+            const float value = method == EMPH_POOL_AVERAGE ? g[c] / (float)(e - s) : g[c];
+            for (int f = s; f < e; ++f)
+                atomicAdd(dx + base + (size_t)f * channels + c, value);
+        }
+    }
+}
+
+// Backward of emph_output_head (logits only): single CTA, rows are few
+__global__ void __launch_bounds__(256)
+head_backward_kernel(
+    const float* __restrict__ x, const float* __restrict__ dz,
+    const int32_t* __restrict__ row_seq, int total_rows, int channels, int kernel_size,
+    const float* __restrict__ weight, float* __restrict__ dx, float* __restrict__ dw,
+    float* __restrict__ db) {
+    const int half = (kernel_size - 1) / 2;
+    // dx[r][c] = sum_tap w[tap][c] dz[r + half - tap]
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+         i < (size_t)total_rows * channels; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / channels), c = (int)(i % channels);
+        float acc = 0.f;
+        for (int tap = 0; tap < kernel_size; ++tap) {
+            const int g = r + half - tap;
+            if (g >= 0 && g < total_rows && row_seq[g] >= 0) acc = fmaf(weight[tap * channels + c], dz[g], acc);
+        }
+        dx[i] = row_seq[r] >= 0 ? acc : 0.f;
+    }
+    if (blockIdx.x == 0) {
+        // dw[tap][c] = sum_r x[r + tap - half][c] dz[r];  db = sum_r dz[r]
+        for (int i = threadIdx.x; i < kernel_size * channels; i += blockDim.x) {
+            const int tap = i / channels, c = i % channels;
+            float acc = 0.f;
+            for (int r = 0; r < total_rows; ++r) {
+                const int g = r + tap - half;
+                if (row_seq[r] >= 0 && g >= 0 && g < total_rows)
+                    acc = fmaf(x[(size_t)g * channels + c], dz[r], acc);
+            }
+            dw[i] = acc;
+        }
+        if (threadIdx.x == 0) {
+            float acc = 0.f;
+            for (int r = 0; r < total_rows; ++r)
+                if (row_seq[r] >= 0) acc += dz[r];
+            db[0] = acc;
+        }
+    }
+}
+
+// Masked loss over packed word rows (emphases/train/core.py:340-353):
+// mean over rows with valid[r] != 0 of BCE-with-logits (mode 0) or squared
+// error (mode 1); writes the scalar loss and d loss / d logits.  Single CTA.
+__global__ void __launch_bounds__(256)
+masked_loss_kernel(
+    const float* __restrict__ logits, const float* __restrict__ targets,
+    const uint8_t* __restrict__ valid, int total_rows, int mode,
+    float* __restrict__ loss, float* __restrict__ dlogits) {
+    __shared__ float partial[256];
+    __shared__ int counts[256];
+    float sum = 0.f;
+    int count = 0;
+    for (int r = threadIdx.x; r < total_rows; r += 256) {
+        if (!valid[r]) continue;
+        const float z = logits[r], t = targets[r];
+        if (mode == 0) sum += fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
+        else sum += (z - t) * (z - t);
+        ++count;
+    }
+    partial[threadIdx.x] = sum;
+    counts[threadIdx.x] = count;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            partial[threadIdx.x] += partial[threadIdx.x + o];
+            counts[threadIdx.x] += counts[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const float n = (float)counts[0];
+    if (threadIdx.x == 0) loss[0] = partial[0] / n;
+    for (int r = threadIdx.x; r < total_rows; r += 256) {
+        float g = 0.f;
+        if (valid[r]) {
+            const float z = logits[r], t = targets[r];
+            g = mode == 0 ? (1.f / (1.f + expf(-z)) - t) / n : 2.f * (z - t) / n;
+        }
+        dlogits[r] = g;
+    }
+}
+
+}  // namespace emph
+
+extern "C" {
+
+int emph_activation_backward(
+    const float* dy, const float* y, const int32_t* row_seq, int32_t total_rows,
+    int32_t channels, int32_t act, float* dpre, void* stream) {
+    EMPH_REQUIRE(act == EMPH_ACT_RELU || act == EMPH_ACT_NONE,
+                 "emph_activation_backward: only ReLU / identity are built");
+    if (total_rows == 0) return EMPH_OK;
+    emph::activation_backward_kernel<<<emph::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(
+        dy, y, row_seq, total_rows, channels, act, dpre);
+    EMPH_CHECK_LAUNCH("emph_activation_backward");
+    return EMPH_OK;
+}
+
+int emph_conv_weight_grad(
+    const float* x, const float* dpre, int32_t total_rows, int32_t channels,
+    int32_t kernel_size, float* dw, float* db, void* stream) {
+    if (!(channels == 80 && kernel_size == 3)) {
+        emph::set_error("emph_conv_weight_grad: channels=%d kernel_size=%d not compiled in",
+                        channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int s = emph::check_cuda(
+        cudaMemsetAsync(dw, 0, sizeof(float) * kernel_size * channels * channels, st), "memset dw");
+    if (s != EMPH_OK) return s;
+    s = emph::check_cuda(cudaMemsetAsync(db, 0, sizeof(float) * channels, st), "memset db");
+    if (s != EMPH_OK) return s;
+    if (total_rows == 0) return EMPH_OK;
+    int grid = (total_rows + 63) / 64;
+    if (grid > emph::sm_count() * 2) grid = emph::sm_count() * 2;
+    emph::conv_weight_grad_kernel<80, 3><<<grid, 256, 0, st>>>(x, dpre, total_rows, dw, db);
+    EMPH_CHECK_LAUNCH("emph_conv_weight_grad");
+    return EMPH_OK;
+}
+
+int emph_pool_words_backward(
+    const float* dy, const float* x, int32_t channels,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* word_seq, const int32_t* word_lo, const int32_t* word_hi,
+    int32_t total_word_rows, int32_t method, int32_t total_rows, float* dx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int s = emph::check_cuda(
+        cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)total_rows * channels, st), "memset dx");
+    if (s != EMPH_OK) return s;
+    if (total_word_rows == 0) return EMPH_OK;
+    emph::pool_backward_kernel<<<(total_word_rows + 7) / 8, 256, 0, st>>>(
+        dy, x, channels, row_start, n_rows, word_seq, word_lo, word_hi, total_word_rows,
+        method, dx);
+    EMPH_CHECK_LAUNCH("emph_pool_words_backward");
+    return EMPH_OK;
+}
+
+int emph_output_head_backward(
+    const float* x, const float* dz, const int32_t* row_seq, int32_t total_rows,
+    int32_t channels, int32_t kernel_size, const float* weight,
+    float* dx, float* dw, float* db, void* stream) {
+    if (total_rows == 0) return EMPH_OK;
+    int grid = (int)(((size_t)total_rows * channels + 255) / 256);
+    if (grid > emph::sm_count() * 4) grid = emph::sm_count() * 4;
+    emph::head_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, dz, row_seq, total_rows, channels, kernel_size, weight, dx, dw, db);
+    EMPH_CHECK_LAUNCH("emph_output_head_backward");
+    return EMPH_OK;
+}
+
+int emph_masked_loss(
+    const float* logits, const float* targets, const uint8_t* valid, int32_t total_rows,
+    int32_t mode, float* loss, float* dlogits, void* stream) {
+    EMPH_REQUIRE(mode == 0 || mode == 1, "emph_masked_loss: mode must be 0 (bce) or 1 (mse)");
+    emph::masked_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
+        logits, targets, valid, total_rows, mode, loss, dlogits);
+    EMPH_CHECK_LAUNCH("emph_masked_loss");
+    return EMPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+"""Training step of the conv model on device: forward with saved
+activations, hand-written backward kernels (csrc/train.cu), masked loss, and
+a flat-bucket gradient all-reduce for data parallelism.
+
+The reference trains on one device (emphases/train/core.py:86-142) with
+torch autograd; it has no data-parallel code.  Here `Model.forward` in
+training mode goes through `forward_with_grad`: a torch.autograd.Function
+whose backward fills the `.grad` of the Model's own torch parameters, so any
+torch optimizer (the reference uses Adam, train/core.py:69-75) can step.
+"""
+import numpy as np
+import torch
+
+import emphases_b200 as emphases
+from . import _lib, engine
+
+
+def _layer_list(model):
+    """[(weight, bias, act)] per conv layer, frame side then word side"""
+    step = 3 if model.dropout is not None else 2
+    act = engine.ACTIVATIONS[model.activation]
+    frame = [(model.input_layer.weight, model.input_layer.bias, _lib.ACT_NONE)]
+    frame += [
+        (model.frame_encoder[i * step].weight,
+         model.frame_encoder[i * step].bias, act)
+        for i in range(model.layers)]
+    word = []
+    if hasattr(model, 'word_decoder'):
+        word = [
+            (model.word_decoder[i * step].weight,
+             model.word_decoder[i * step].bias, act)
+            for i in range(model.layers)]
+    return frame, word
+
+
+def _stack(weight, bias, act, device, backward=False):
+    """One-layer ConvStack; backward=True packs the adjoint (taps flipped,
+    channel matrix transposed) with zero bias and no activation"""
+    packed = engine._pack_conv(weight, device)          # [k][in][out]
+    if backward:
+        packed = packed.flip(0).transpose(1, 2).contiguous()
+        bias = torch.zeros_like(bias)
+        act = _lib.ACT_NONE
+    return engine.ConvStack(
+        packed[None].contiguous(),
+        bias.detach().to(device, torch.float32)[None].contiguous(),
+        np.asarray([act], dtype=np.int32), weight.shape[2], weight.shape[0])
+
+
+class _ConvModelFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, model, features, word_bounds, word_lengths, *parameters):
+        from . import model as model_module
+        device = features.device
+        eng = emphases.get_engine(device)
+        method = emphases.DOWNSAMPLE_METHOD
+        if method not in _lib.POOL:
+            raise ValueError(f'Interpolation method {method} is not defined')
+        if model.architecture != 'convolution' or model.location != 'intermediate':
+            raise NotImplementedError(
+                'the training step is built for the convolution architecture '
+                "at DOWNSAMPLE_LOCATION='intermediate'")
+        if model.activation not in ('ReLU', 'Identity'):
+            raise NotImplementedError('training backward supports ReLU only')
+        batch, channels, frames = features.shape
+        wmax = word_bounds.shape[2]
+        with torch.cuda.device(device):
+            starts, total = engine.packed_starts([frames] * batch)
+            meta = torch.from_numpy(np.concatenate([
+                starts.astype(np.int32), np.full(batch, frames, dtype=np.int32)])
+            ).to(device)
+            row_start, n_rows = meta[:batch], meta[batch:]
+            row_seq = eng.row_index(row_start, n_rows, batch, total)
+            rows = torch.empty((total, channels), dtype=torch.float32, device=device)
+            features32 = features.detach().to(torch.float32).contiguous()
+            _lib.call(
+                'emph_pack_rows', _lib.ptr(features32), batch, channels, frames,
+                _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
+                _lib.ptr(rows), _lib.stream_ptr())
+            frame_layers, word_layers = _layer_list(model)
+            frame_acts = [rows]
+            for weight, bias, act in frame_layers:
+                frame_acts.append(eng.conv_stack(
+                    frame_acts[-1], row_seq, _stack(weight, bias, act, device),
+                    _lib.PREC_FP32))
+            views, word_starts, total_words, bounds, lengths = \
+                model_module.word_rows(word_bounds, word_lengths, device)
+            pooled = eng.pool(
+                frame_acts[-1], row_start, n_rows, views['word_seq'],
+                views['word_lo'], views['word_hi'], method)
+            word_row_seq = eng.row_index(
+                views['word_row_start'], views['n_words'], batch, total_words)
+            word_acts = [pooled]
+            for weight, bias, act in word_layers:
+                word_acts.append(eng.conv_stack(
+                    word_acts[-1], word_row_seq, _stack(weight, bias, act, device),
+                    _lib.PREC_FP32))
+            weights = model.packed_weights()
+            logits, _ = eng.head(
+                word_acts[-1], word_row_seq, weights, _lib.HEAD_LOGITS,
+                want_scores=False)
+            index = torch.from_numpy(
+                (word_starts[:, None] + np.arange(wmax)[None]).astype(np.int64)
+            ).to(device)
+        ctx.model = model
+        ctx.saved = dict(
+            frame_acts=frame_acts, word_acts=word_acts, row_seq=row_seq,
+            word_row_seq=word_row_seq, row_start=row_start, n_rows=n_rows,
+            views=views, index=index, total=total, total_words=total_words,
+            method=method, head_weight=weights.head_weight,
+            head_kernel=weights.head_kernel)
+        return logits[index][:, None, :]
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        model, s = ctx.model, ctx.saved
+        device = grad_logits.device
+        eng = emphases.get_engine(device)
+        channels = s['frame_acts'][0].shape[1]
+        with torch.cuda.device(device):
+            dz = torch.zeros(s['total_words'], dtype=torch.float32, device=device)
+            dz[s['index'].reshape(-1)] = grad_logits.reshape(-1).to(torch.float32)
+            frame_layers, word_layers = _layer_list(model)
+            grads = {}
+
+            # output projection
+            x = s['word_acts'][-1]
+            dx = torch.empty_like(x)
+            dw = torch.empty_like(s['head_weight'])
+            db = torch.empty(1, dtype=torch.float32, device=device)
+            _lib.call(
+                'emph_output_head_backward', _lib.ptr(x), _lib.ptr(dz),
+                _lib.ptr(s['word_row_seq']), s['total_words'], channels,
+                s['head_kernel'], _lib.ptr(s['head_weight']), _lib.ptr(dx),
+                _lib.ptr(dw), _lib.ptr(db), _lib.stream_ptr())
+            grads[model.output_layer.weight] = dw.t()[None].contiguous()
+            grads[model.output_layer.bias] = db
+
+            def conv_backward(layers, acts, row_seq, dy):
+                for position in range(len(layers) - 1, -1, -1):
+                    weight, bias, act = layers[position]
+                    x_in, y_out = acts[position], acts[position + 1]
+                    dpre = torch.empty_like(dy)
+                    _lib.call(
+                        'emph_activation_backward', _lib.ptr(dy), _lib.ptr(y_out),
+                        _lib.ptr(row_seq), dy.shape[0], channels, act,
+                        _lib.ptr(dpre), _lib.stream_ptr())
+                    kernel = weight.shape[2]
+                    dw = torch.empty(
+                        (kernel, channels, channels), dtype=torch.float32,
+                        device=device)
+                    db = torch.empty(channels, dtype=torch.float32, device=device)
+                    _lib.call(
+                        'emph_conv_weight_grad', _lib.ptr(x_in), _lib.ptr(dpre),
+                        dy.shape[0], channels, kernel, _lib.ptr(dw), _lib.ptr(db),
+                        _lib.stream_ptr())
+                    grads[weight] = dw.permute(2, 1, 0).contiguous()
+                    grads[bias] = db
+                    dy = eng.conv_stack(
+                        dpre, row_seq,
+                        _stack(weight, bias, act, device, backward=True),
+                        _lib.PREC_FP32)
+                return dy
+
+            d_pooled = conv_backward(
+                word_layers, s['word_acts'], s['word_row_seq'], dx)
+            d_frames = torch.empty_like(s['frame_acts'][-1])
+            views = s['views']
+            _lib.call(
+                'emph_pool_words_backward', _lib.ptr(d_pooled),
+                _lib.ptr(s['frame_acts'][-1]), channels, _lib.ptr(s['row_start']),
+                _lib.ptr(s['n_rows']), _lib.ptr(views['word_seq']),
+                _lib.ptr(views['word_lo']), _lib.ptr(views['word_hi']),
+                s['total_words'], _lib.POOL[s['method']], s['total'],
+                _lib.ptr(d_frames), _lib.stream_ptr())
+            conv_backward(frame_layers, s['frame_acts'], s['row_seq'], d_frames)
+        ordered = [
+            grads[p].to(p.dtype) if p in grads else None
+            for p in model.parameters()]
+        return (None, None, None, None, *ordered)
+
+
+def forward_with_grad(model, features, frame_lengths, word_bounds, word_lengths):
+    """Model.forward in training mode (gradients flow to model.parameters())"""
+    return _ConvModelFunction.apply(
+        model, features, word_bounds, word_lengths, *model.parameters())
+
+
+class _MaskedLoss(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, scores, targets, mask, mode):
+        device = scores.device
+        flat = scores.detach().reshape(-1).to(torch.float32).contiguous()
+        target = targets.detach().reshape(-1).to(device, torch.float32).contiguous()
+        valid = mask.reshape(-1).to(device, torch.uint8).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=device)
+        grad = torch.empty_like(flat)
+        with torch.cuda.device(device):
+            _lib.call(
+                'emph_masked_loss', _lib.ptr(flat), _lib.ptr(target),
+                _lib.ptr(valid), flat.numel(), mode, _lib.ptr(loss),
+                _lib.ptr(grad), _lib.stream_ptr())
+        ctx.save_for_backward(grad)
+        ctx.shape = scores.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        return (grad.reshape(ctx.shape) * grad_output, None, None, None)
+
+
+def loss(
+    scores, targets, frame_lengths, word_bounds, word_lengths, training=False,
+    loss_fn=None
+):
+    """Masked loss, mirroring emphases.loss (emphases/train/core.py:315-353)
+    for the word-resolution branch"""
+    from . import model as model_module
+    if loss_fn is None:
+        loss_fn = emphases.LOSS
+    if training and emphases.DOWNSAMPLE_LOCATION == 'inference':
+        raise NotImplementedError(
+            'frame-resolution loss (upsample, emphases/core.py:472-544) is a '
+            'next-row item')
+    if loss_fn not in ('bce', 'mse'):
+        raise ValueError(f'Loss {loss_fn} is not recognized')
+    mask = model_module.mask_from_lengths(word_lengths.to(scores.device))
+    return _MaskedLoss.apply(scores, targets, mask, 0 if loss_fn == 'bce' else 1)
+
+
+###############################################################################
+# Data parallelism
+###############################################################################
+
+
+def allreduce_gradients(model, average=True):
+    """One all-reduce over a flat fp32 bucket holding every gradient
+    (250,881 floats ~ 1 MB for the default model: latency bound, so a single
+    NCCL call beats per-tensor calls).  No-op without a process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size()
+    if world == 1:
+        return
+    parameters = [p for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in parameters])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat.div_(world)
+    cursor = 0
+    for p in parameters:
+        count = p.grad.numel()
+        p.grad.copy_(flat[cursor:cursor + count].reshape(p.grad.shape))
+        cursor += count
+
+
+def train_step(model, optimizer, batch):
+    """One data-parallel step: forward, masked loss, backward, gradient
+    all-reduce (mean over ranks), optimizer step.  `batch` follows the
+    reference collate order (emphases/data/collate.py:72-78):
+    (features, frame_lengths, word_bounds, word_lengths, targets)."""
+    features, frame_lengths, word_bounds, word_lengths, targets = batch[:5]
+    model.train()
+    optimizer.zero_grad(set_to_none=True)
+    scores = model(features, frame_lengths, word_bounds, word_lengths)
+    value = loss(
+        scores, targets, frame_lengths, word_bounds, word_lengths, training=True)
+    value.backward()
+    allreduce_gradients(model)
+    optimizer.step()
+    return value.detach()

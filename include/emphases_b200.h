@@ -257,6 +257,38 @@ int emph_add_layernorm(
     const float* beta, float eps, const int32_t* row_seq, int32_t total_rows,
     int32_t channels, float* y, void* stream);
 
+/*
+ * Training step (BASELINE config 5; the reference's single-device step is
+ * emphases/train/core.py:86-142, its loss :315-353), fp32.  Forward keeps each
+ * layer's output (one emph_conv_stack launch per layer); per layer backward:
+ *   emph_activation_backward  dpre = dy * act'(y), separators zeroed
+ *   emph_conv_stack           dx = conv(dpre, W flipped and transposed)
+ *   emph_conv_weight_grad     dw [k][in][out], db [out] (zeroed, then summed)
+ * emph_pool_words_backward / emph_output_head_backward are the adjoints of
+ * emph_pool_words / emph_output_head (logits).  emph_masked_loss: mean BCE-with-
+ * logits (mode 0) or squared error (mode 1) over word rows with valid != 0, and
+ * its gradient with respect to the logits.
+ */
+int emph_activation_backward(
+    const float* dy, const float* y, const int32_t* row_seq, int32_t total_rows,
+    int32_t channels, int32_t act, float* dpre, void* stream);
+int emph_conv_weight_grad(
+    const float* x, const float* dpre, int32_t total_rows, int32_t channels,
+    int32_t kernel_size, float* dw, float* db, void* stream);
+int emph_pool_words_backward(
+    const float* dy, const float* x, int32_t channels,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* word_seq, const int32_t* word_lo, const int32_t* word_hi,
+    int32_t total_word_rows, int32_t method, int32_t total_rows, float* dx,
+    void* stream);
+int emph_output_head_backward(
+    const float* x, const float* dz, const int32_t* row_seq, int32_t total_rows,
+    int32_t channels, int32_t kernel_size, const float* weight,
+    float* dx, float* dw, float* db, void* stream);
+int emph_masked_loss(
+    const float* logits, const float* targets, const uint8_t* valid,
+    int32_t total_rows, int32_t mode, float* loss, float* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,3 +44,32 @@ def test_two_rank_sharding_and_gather(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+def _grad_worker(rank, world, port, tmpdir):
+    os.environ.update(
+        MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+        WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from emphases_b200 import training
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(
+            torch.nn.Conv1d(4, 4, 3), torch.nn.ReLU(), torch.nn.Conv1d(4, 1, 3))
+        for index, parameter in enumerate(model.parameters()):
+            parameter.grad = torch.full_like(parameter, float(rank + 1) * (index + 1))
+        training.allreduce_gradients(model)
+        for index, parameter in enumerate(model.parameters()):
+            expected = (index + 1) * sum(range(1, world + 1)) / world
+            assert torch.allclose(parameter.grad, torch.full_like(parameter, expected))
+        with open(os.path.join(tmpdir, f'grad{rank}'), 'w') as stream:
+            stream.write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_gradient_allreduce(tmp_path):
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_grad_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f'grad{r}').exists() for r in range(world))
