@@ -281,16 +281,20 @@ logmel_kernel(
 
             // ---- real-FFT unpacking in registers ----
             // Z_q = Z[lane + 32 q]: q even -> v0[q / 2], q odd -> v1[q / 2].
-            // X[k] = e + w^k o,  e = (Z[k] + conj Z[512-k]) / 2,
-            //                    o = -i (Z[k] - conj Z[512-k]) / 2,  w = exp(-2 pi i / 1024).
-            // Z[512 - k] for k = lane + 32 q lives in lane (32 - lane) % 32 as
-            // Z_{15-q} (lane 0: own Z_{(16-q) % 16}).
-            float* const mag = sm.mag[f] + lane;
+            // With e = (Z[k] + conj Z[512-k]) / 2, o = -i (Z[k] - conj Z[512-k]) / 2
+            // and w = exp(-2 pi i k / 1024):  X[k] = e + w o,  X[512-k] = conj(e - w o),
+            // so one (e, w o) serves both bins of a pair.  (The magnitudes are taken
+            // from the complex sums, not as |e|^2 + |o|^2 +- 2 Re(e conj(w o)):
+            // bins k and 512-k of speech differ by up to 60 dB and subtracting
+            // powers would wipe out the weak one.)
+            // A lane handles the 8 pairs k = lane + 32 q, q = 0..7;
+            // Z[512 - k] lives in lane (32 - lane) % 32 as Z_{15-q}
+            // (lane 0: its own Z_{(16-q) % 16}).
+            float* const mag = sm.mag[f];
             const int partner = (32 - lane) & 31;
             const bool lane0 = lane == 0;
-            float nyquist = 0.f;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 const float2 a = (q & 1) ? v1[q >> 1] : v0[q >> 1];
                 const float2 zs = ((15 - q) & 1) ? v1[(15 - q) >> 1] : v0[(15 - q) >> 1];
                 const float2 zo = (((16 - q) & 15) & 1) ? v1[((16 - q) & 15) >> 1]
@@ -305,14 +309,12 @@ logmel_kernel(
                 const float2 w = cmul(wl, make_float2(kC32[q][0], kC32[q][1]));
                 const float2 wo = cmul(w, o);
                 const float xr = e.x + wo.x, xi = e.y + wo.y;
-                mag[32 * q] = sqrt_pos(fmaf(xr, xr, fmaf(xi, xi, 1e-6f)));
-                if (q == 0) {
-                    // X[512] = conj(e - w o) at k = 0 (only lane 0's value is used)
-                    const float yr = e.x - wo.x, yi = e.y - wo.y;
-                    nyquist = sqrt_pos(fmaf(yr, yr, fmaf(yi, yi, 1e-6f)));
-                }
+                const float yr = e.x - wo.x, yi = e.y - wo.y;
+                mag[lane + 32 * q] = sqrt_pos(fmaf(xr, xr, fmaf(xi, xi, 1e-6f)));
+                mag[kHalf - lane - 32 * q] = sqrt_pos(fmaf(yr, yr, fmaf(yi, yi, 1e-6f)));
             }
-            if (lane0) mag[kHalf] = nyquist;
+            // k = 256 pairs with itself: X[256] = conj(Z[256]); Z[256] = Z_8 of lane 0
+            if (lane0) mag[kHalf / 2] = sqrt_pos(fmaf(v0[4].x, v0[4].x, fmaf(v0[4].y, v0[4].y, 1e-6f)));
         }
         __syncthreads();
 

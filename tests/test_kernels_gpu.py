@@ -387,3 +387,43 @@ def test_forward_packed_bf16_golden(eng, golden):
     scores = result['scores'][s:s + n].cpu().numpy()
     error = np.abs(scores - data['full.scores'][0]).max()
     assert error < 2e-3, f'bf16 scores max-abs {error}'
+
+
+def test_logmel_spectral_tilt_precision(eng):
+    """Speech-like audio (strong low-frequency tilt): bins k and 512-k share a
+    butterfly in the packed real FFT, so check the weak high-frequency bands
+    against an fp64 reference -- our error must stay in the class of
+    torch.stft's own fp32 error"""
+    from emphases_b200 import engine
+    generator = torch.Generator().manual_seed(7)
+    noise = torch.randn(1, 48000, generator=generator, dtype=torch.float64)
+    audio = torch.zeros_like(noise)
+    state = 0.0
+    values = noise[0].tolist()
+    out = []
+    for v in values:                       # one-pole low-pass, ~45 dB tilt
+        state = 0.985 * state + v
+        out.append(state)
+    audio[0] = torch.tensor(out, dtype=torch.float64)
+    audio = (0.5 * audio / audio.abs().max()).float()
+    times = [(0.0, 1.5), (1.5, 3.0)]
+    # fp64 reference of the same pipeline
+    padded = torch.nn.functional.pad(audio.double(), (432, 432))
+    chunk = torch.nn.functional.pad(padded, (432, 432), mode='reflect')
+    stft = torch.stft(
+        chunk, 1024, hop_length=160, window=torch.hann_window(1024, dtype=torch.float64),
+        center=False, return_complex=True)[0]
+    spectrogram = torch.sqrt(stft.real ** 2 + stft.imag ** 2 + 1e-6)
+    basis = torch.from_numpy(engine.mel_basis()).double()
+    exact = torch.log(torch.clamp(basis @ spectrogram, min=1e-5)).T
+    reference = list(oracle.preprocess(times, audio))[0][0][0].T.double()
+    plan = engine.make_plan([(np.asarray(times), 48000)])
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(
+        views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    ours = eng.logmel(audio[0].cuda(), views, plan, row_seq).cpu()[1:-1].double()
+    frames = min(len(exact), len(ours))
+    torch_error = (reference[:frames] - exact[:frames]).abs().max().item()
+    our_error = (ours[:frames] - exact[:frames]).abs().max().item()
+    assert exact.max() - exact.min() > 6          # a real dynamic range
+    assert our_error < 4 * torch_error + 2e-5, (our_error, torch_error)
