@@ -69,6 +69,18 @@ def load():
     lib.emph_version.restype = ctypes.c_int
     lib.emph_last_error.restype = ctypes.c_char_p
     lib.emph_device_sm_count.restype = ctypes.c_int
+    lib.emph_corpus_open.argtypes = [_P, _P, _I, _I]
+    lib.emph_corpus_open.restype = ctypes.c_void_p
+    lib.emph_corpus_info.argtypes = [_P, _P, _P, _P, _P, _P]
+    lib.emph_corpus_info.restype = ctypes.c_int
+    lib.emph_corpus_error.argtypes = [_P, _I]
+    lib.emph_corpus_error.restype = ctypes.c_char_p
+    lib.emph_corpus_fill.argtypes = [_P, _P, _P, _P, _P, _I]
+    lib.emph_corpus_fill.restype = ctypes.c_int
+    lib.emph_corpus_write_textgrids.argtypes = [_P, _P, _I]
+    lib.emph_corpus_write_textgrids.restype = ctypes.c_int
+    lib.emph_corpus_close.argtypes = [_P]
+    lib.emph_corpus_close.restype = None
     lib.emph_conv_weights_tc_bytes.argtypes = [_I, _I, _I]
     lib.emph_conv_weights_tc_bytes.restype = ctypes.c_int
     _lib = lib

@@ -87,25 +87,35 @@ def from_files_to_files(
             '(emphases/core.py:138-166), which is outside this build; pass '
             '.TextGrid alignments')
 
-    def load(pair):
-        text_file, audio_file = pair
-        return Alignment(text_file), emphases.load.audio(audio_file)
-
+    from . import corpus
     workers = min(32, (os.cpu_count() or 1))
-    with ThreadPoolExecutor(workers) as pool:
-        loaded = list(pool.map(load, zip(text_files, audio_files)))
-    alignments = [item[0] for item in loaded]
-    audios = [item[1] for item in loaded]
-    scores = from_alignments_and_audio(
-        alignments, audios, emphases.SAMPLE_RATE, checkpoint, batch_size, gpu)
+    with corpus.Corpus(text_files, audio_files, workers) as parsed:
+        # Fast path: 16-bit PCM wav at the model rate + a parsable TextGrid go
+        # through the native reader into pinned int16 / float64 buffers
+        usable = parsed.usable(emphases.SAMPLE_RATE)
+        indices, times, packed = parsed.load(usable)
+        scores = [None] * len(text_files)
+        if len(indices):
+            results = from_alignments_and_audio(
+                times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size, gpu)
+            for index, result in zip(indices, results):
+                scores[index] = result
+            parsed.write_textgrids(
+                [f'{prefix}.TextGrid' for prefix in output_prefixes], usable)
 
-    def save(item):
-        alignment, result, prefix = item
-        alignment.save(f'{prefix}.TextGrid')
-        torch.save(result, f'{prefix}.pt')
+    def save(index):
+        torch.save(scores[index], f'{output_prefixes[index]}.pt')
 
     with ThreadPoolExecutor(workers) as pool:
-        list(pool.map(save, zip(alignments, scores, output_prefixes)))
+        list(pool.map(save, [int(i) for i in indices]))
+
+    # Everything else (other encodings / sample rates) goes file by file
+    first_gpu = gpu[0] if isinstance(gpu, (list, tuple)) and gpu else gpu
+    for index in range(len(text_files)):
+        if scores[index] is None:
+            from_file_to_file(
+                text_files[index], audio_files[index], output_prefixes[index],
+                checkpoint, batch_size, first_gpu)
 
 
 def from_text_and_audio(

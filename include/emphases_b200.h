@@ -289,6 +289,34 @@ int emph_masked_loss(
     const float* logits, const float* targets, const uint8_t* valid,
     int32_t total_rows, int32_t mode, float* loss, float* dlogits, void* stream);
 
+/*
+ * Host-side corpus ingest / egress for from_files_to_files (HOST pointers, no
+ * CUDA): reads n_files (TextGrid, 16-bit PCM wav) pairs on a thread pool,
+ * replacing per file emphases.load.audio (emphases/load.py:11-17),
+ * pypar.Alignment(file) (emphases/core.py:49) and alignment.save
+ * (emphases/core.py:111).  emph_corpus_open parses headers and alignments;
+ * emph_corpus_info reports per file: status (0 = ok, otherwise the Python path
+ * must handle the file), sample rate, channels, samples per channel, words
+ * (gaps filled with silences); emph_corpus_fill writes channel 0 as int16 at
+ * audio_dst + sample_offsets[i] (e.g. a pinned buffer) and (start, end) word
+ * times as float64 pairs at times_dst + 2 * word_offsets[i];
+ * emph_corpus_write_textgrids re-serialises the parsed alignments.
+ */
+typedef struct emph_corpus emph_corpus;
+emph_corpus* emph_corpus_open(
+    const char* const* text_paths, const char* const* audio_paths,
+    int32_t n_files, int32_t n_threads);
+int emph_corpus_info(
+    const emph_corpus* corpus, int32_t* status, int32_t* sample_rate,
+    int32_t* channels, int64_t* n_samples, int32_t* n_words);
+const char* emph_corpus_error(const emph_corpus* corpus, int32_t index);
+int emph_corpus_fill(
+    emph_corpus* corpus, int16_t* audio_dst, const int64_t* sample_offsets,
+    double* times_dst, const int64_t* word_offsets, int32_t n_threads);
+int emph_corpus_write_textgrids(
+    const emph_corpus* corpus, const char* const* output_paths, int32_t n_threads);
+void emph_corpus_close(emph_corpus* corpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,3 +219,52 @@ def test_vectorised_plan_matches_scalar_chunker():
         utterances[:3] + [long_alignment], None) is None
     plan = engine.make_plan(utterances[:3] + [long_alignment], None)
     assert plan.n_seq >= 4
+
+
+def test_native_corpus_reader_matches_python(tmp_path):
+    """csrc/corpus_io.cu (wav + TextGrid on a thread pool) vs the Python
+    loaders: identical word times, identical samples, TextGrid round trip"""
+    import torch
+    from emphases_b200 import alignment, corpus, load
+    generator = torch.Generator().manual_seed(3)
+    text_files, audio_files = [], []
+    for index in range(7):
+        times, audio = oracle.synthetic_utterance(400 + index, duration=1.0 + index / 4)
+        if index == 2:                                     # leading gap + empty label
+            times = [(0.25, 0.5), (0.5, 0.9), (0.9, times[-1][1])]
+        labels = [f'w"{j}' if j == 1 else f'w{j}' for j in range(len(times))]
+        if index == 2:
+            labels[1] = ''
+        if index == 3:                                     # stereo: channel 0 is kept
+            audio = torch.cat([audio, -audio])
+        load.save_wav(tmp_path / f'{index}.wav', audio, 22050 if index == 4 else 16000)
+        alignment.Alignment.from_times(times, labels).save(tmp_path / f'{index}.TextGrid')
+        text_files.append(tmp_path / f'{index}.TextGrid')
+        audio_files.append(tmp_path / f'{index}.wav')
+    # a float wav the native reader must hand to the Python path
+    import struct
+    body = np.zeros(800, dtype='<f4').tobytes()
+    (tmp_path / '5.wav').write_bytes(
+        b'RIFF' + struct.pack('<I', 36 + len(body)) + b'WAVEfmt ' +
+        struct.pack('<IHHIIHH', 16, 3, 1, 16000, 64000, 4, 32) + b'data' +
+        struct.pack('<I', len(body)) + body)
+    with corpus.Corpus(text_files, audio_files, threads=4) as parsed:
+        usable = parsed.usable(16000)
+        assert usable.tolist() == [True, True, True, True, False, False, True]
+        assert parsed.sample_rate[4] == 22050 and parsed.status[5] != 0
+        assert 'PCM' in parsed.error(5)
+        indices, times, packed = parsed.load(usable, pin=False)
+        assert indices.tolist() == [0, 1, 2, 3, 6]
+        for j, index in enumerate(indices):
+            expected = alignment.Alignment(text_files[index])
+            np.testing.assert_array_equal(times[j], expected.times())
+            pcm, rate = load.wav(audio_files[index], normalize=False)
+            assert torch.equal(packed[j][0], pcm[0])
+        outputs = [tmp_path / f'out{index}.TextGrid' for index in range(7)]
+        parsed.write_textgrids(outputs, usable)
+        for index in indices:
+            original = alignment.Alignment(text_files[index])
+            rewritten = alignment.Alignment(outputs[index])
+            np.testing.assert_array_equal(rewritten.times(), original.times())
+            assert [str(w) for w in rewritten] == [str(w) for w in original]
+        assert not outputs[4].exists()
