@@ -53,6 +53,7 @@ def parse_args():
     parser.add_argument('--precision', default=None, choices=['fp32', 'bf16'])
     parser.add_argument('--utterances', type=int, default=3000)
     parser.add_argument('--cpu-seconds', type=float, default=15.)
+    parser.add_argument('--file-utterances', type=int, default=500)
     return parser.parse_args()
 
 
@@ -258,6 +259,47 @@ def run_reference(args, rank, world):
             'd2h_bytes_per_step': 0}}))
 
 
+def time_files_path(emphases, count, state, gpu):
+    """emphases_b200.from_files_to_files on an on-disk corpus of `count`
+    16-bit wav + TextGrid pairs (tmpfs when available): native threaded
+    ingest -> int16 H2D -> kernels -> .pt / .TextGrid outputs"""
+    import shutil
+    import tempfile
+    from pathlib import Path
+    lengths, times = corpus_layout(count, seed=4321)
+    base = '/dev/shm' if os.path.isdir('/dev/shm') else None
+    root = Path(tempfile.mkdtemp(dir=base))
+    try:
+        generator = torch.Generator().manual_seed(5)
+        text_files, audio_files, prefixes = [], [], []
+        (root / 'out').mkdir()
+        for i, (n, t) in enumerate(zip(lengths, times)):
+            audio = (0.1 * torch.randn(1, int(n), generator=generator)).clamp(-1, 1)
+            emphases.load.save_wav(root / f'u{i}.wav', audio)
+            emphases.Alignment.from_times(
+                [tuple(x) for x in t.tolist()]).save(root / f'u{i}.TextGrid')
+            text_files.append(root / f'u{i}.TextGrid')
+            audio_files.append(root / f'u{i}.wav')
+            prefixes.append(root / 'out' / f'u{i}')
+        checkpoint = root / 'checkpoint.pt'
+        torch.save({'model': state}, checkpoint)
+        emphases.from_files_to_files(
+            text_files, audio_files, prefixes, checkpoint=checkpoint, gpu=gpu)
+        repeats = 3
+        start = time.perf_counter()
+        for _ in range(repeats):
+            emphases.from_files_to_files(
+                text_files, audio_files, prefixes, checkpoint=checkpoint, gpu=gpu)
+        elapsed = (time.perf_counter() - start) / repeats
+        seconds = float(lengths.sum()) / SAMPLE_RATE
+        return {
+            'value': seconds / elapsed, 'unit': 'audio-s/s',
+            'files': count, 'ms_per_file': 1e3 * elapsed / count,
+            'note': 'wav + TextGrid read, inference, .pt + .TextGrid written'}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def workload_config(args):
     return {
         'workload': (
@@ -367,6 +409,11 @@ def main():
     assert sum(r.shape[-1] for r in results) == n_words
     h2d_bytes = host_audio.numel() * 4 + plan.int32_blob().nbytes + plan.n_seq * 8
     d2h_bytes = plan.total_word_rows * 4
+
+    # ---- the same API through files on disk (from_files_to_files), rank 0 ----
+    files_leg = None
+    if rank == 0 and args.file_utterances > 0:
+        files_leg = time_files_path(emphases, args.file_utterances, state, local_rank)
 
     # ---- reduce over ranks: max time, summed units ----
     stats = torch.tensor(
@@ -481,6 +528,7 @@ def main():
             'gpu_local_cpus': numa_cpus,
             'note': ('PCIe-bound: one pinned H2D of the fp32 audio per '
                      'launch, kernels overlap the next launch copy')},
+        'files_e2e': files_leg,
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,
         'cpu_baseline': cpu}))
