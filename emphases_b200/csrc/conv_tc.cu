@@ -27,6 +27,8 @@
 // While the tensor core works on slot s, the epilogue groups of the other
 // slots drain their accumulators, so MMA and epilogue overlap.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -497,6 +499,28 @@ __global__ void pack_weights_tc_kernel(
 
 }  // namespace tc
 
+// conv_tc240.cu: the wide-N formulation (three taps as output columns)
+int conv_stack_bf16_tc240(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host, int32_t n_layers, float* y,
+    cudaStream_t stream);
+int conv_weights_tc240_bytes(int n_layers);
+int pack_conv_weights_tc240(
+    const float* weights, const float* bias, int n_layers, void* packed, cudaStream_t stream);
+
+// EMPHASES_B200_TC=wide selects the experimental wide-N kernel (conv_tc240.cu:
+// numerically identical, currently epilogue-bound and slower);
+// the default is the N=80 / 16-MMA kernel in this file.  The weight blob layout
+// follows the choice, so it must not change within a process.
+static bool use_wide() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* value = getenv("EMPHASES_B200_TC");
+        cached = (value && !strcmp(value, "wide")) ? 1 : 0;
+    }
+    return cached == 1;
+}
+
 int conv_stack_bf16_tc(
     const float* x, const int32_t* row_seq, int32_t total_rows,
     const float* weights, const float* bias, const int32_t* acts_host,
@@ -507,6 +531,8 @@ int conv_stack_bf16_tc(
                   channels, kernel_size);
         return EMPH_ENOSYS;
     }
+    if (use_wide())
+        return conv_stack_bf16_tc240(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
     EMPH_REQUIRE(n_layers <= tc::kMaxLayers, "emph_conv_stack(bf16 tc): too many layers");
     const int halo = n_layers * ((tc::KS - 1) / 2);
     const int tile_rows = tc::M - 2 * halo;
@@ -533,6 +559,7 @@ int conv_stack_bf16_tc(
 
 extern "C" int emph_conv_weights_tc_bytes(int32_t n_layers, int32_t channels, int32_t kernel_size) {
     if (channels != emph::tc::C || kernel_size != emph::tc::KS || n_layers <= 0) return 0;
+    if (emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
     return n_layers * emph::tc::W_LAYER_BYTES;
 }
 
@@ -545,6 +572,8 @@ extern "C" int emph_pack_conv_weights_tc(
         return EMPH_ENOSYS;
     }
     EMPH_REQUIRE(n_layers > 0, "emph_pack_conv_weights_tc: no layers");
+    if (emph::use_wide())
+        return emph::pack_conv_weights_tc240(weights, bias, n_layers, packed, (cudaStream_t)stream);
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
         weights, bias, n_layers, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");

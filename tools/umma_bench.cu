@@ -129,6 +129,8 @@ int main() {
         q = base; q.n = 128; q.b_lbo = 128 * 16; run("none  N=128 aligned 1acc", q, grid);
         q = base; q.n = 160; q.b_lbo = 160 * 16; run("none  N=160 aligned 1acc", q, grid);
         q = base; q.n = 16; run("none  N=16 aligned 1acc", q, grid);
+        q = base; q.n = 240; q.b_lbo = 240 * 16; q.n_acc = 2; run("none  N=240 2acc", q, grid);
+        q = base; q.n = 240; q.b_lbo = 240 * 16; q.n_acc = 2; q.a_lbo = 128 * 16; q.a_stride = 2 * 128 * 16; q.b_stride = 2 * 240 * 16; run("none  N=240 2acc k-advance", q, grid);
         q = base; q.layout = 2; q.a_lbo = 16; q.a_sbo = 1024; q.b_lbo = 16; q.b_sbo = 1024; run("sw128 N=80 1acc", q, grid);
         q.n = 256; run("sw128 N=256 1acc", q, grid);
         q = base; q.layout = 6; q.a_lbo = 16; q.a_sbo = 256; q.b_lbo = 16; q.b_sbo = 256; run("sw32  N=80 1acc", q, grid);
