@@ -407,6 +407,30 @@ def main():
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
     e2e_ms_rank0 = e2e_ms
     assert sum(r.shape[-1] for r in results) == n_words
+    # raw pinned host->device bandwidth of this box right now (context for e2e)
+    probe = host_audio[:min(host_audio.numel(), 1 << 28)]
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        probe.to(device, non_blocking=True)
+    torch.cuda.synchronize(device)
+    pcie_gbs = 3 * probe.numel() * 4 / (time.perf_counter() - t0) / 1e9
+
+    # the same with 16-bit PCM on the host (what wav files hold): half the bytes
+    pcm = scheduler.PackedAudio(
+        (host_audio * 32768.).round_().clamp_(-32768, 32767).to(torch.int16).pin_memory(),
+        offsets, lengths)
+    for _ in range(2):
+        emphases.from_alignments_and_audio(
+            alignments, pcm, SAMPLE_RATE, model=model, gpu=local_rank)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        emphases.from_alignments_and_audio(
+            alignments, pcm, SAMPLE_RATE, model=model, gpu=local_rank)
+    torch.cuda.synchronize(device)
+    e2e_pcm_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    del pcm
     h2d_bytes = host_audio.numel() * 4 + plan.int32_blob().nbytes + plan.n_seq * 8
     d2h_bytes = plan.total_word_rows * 4
 
@@ -525,7 +549,11 @@ def main():
             'h2d_bytes_per_step': int(h2d_bytes),
             'd2h_bytes_per_step': int(d2h_bytes),
             'h2d_gbs_effective': h2d_bytes / (e2e_ms_rank0 * 1e-3) / 1e9,
+            'pinned_h2d_gbs_probe': pcie_gbs,
             'gpu_local_cpus': numa_cpus,
+            'int16_pcm_upload': {
+                'value': audio_seconds / (e2e_pcm_ms * 1e-3), 'unit': 'audio-s/s',
+                'ms_per_step': e2e_pcm_ms, 'note': 'rank 0, same call, int16 host audio'},
             'note': ('PCIe-bound: one pinned H2D of the fp32 audio per '
                      'launch, kernels overlap the next launch copy')},
         'files_e2e': files_leg,
