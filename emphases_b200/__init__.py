@@ -90,4 +90,5 @@ from . import data  # noqa: E402,F401
 from . import load  # noqa: E402,F401
 from . import model  # noqa: E402,F401
 from . import training  # noqa: E402,F401
+from .scheduler import PackedAudio, pack_audio  # noqa: E402,F401
 from .training import loss  # noqa: E402,F401
