@@ -22,7 +22,9 @@ struct ConvActs {
     int act[kConvMaxLayers];
 };
 
-template <int C, int KS>
+// DB: double-buffer the layer weights (prefetch layer l+1 during layer l);
+// kernel sizes 5 and 7 only fit shared memory single-buffered
+template <int C, int KS, bool DB = true>
 struct ConvF32 {
     static constexpr int R = 128;                 // rows per CTA per layer
     static constexpr int HALF = (KS - 1) / 2;
@@ -31,8 +33,9 @@ struct ConvF32 {
     static constexpr int CT = C / 8;              // output channels per thread
     static constexpr int WFLOATS = KS * C * C;    // one layer's weights
     static constexpr int ACT_FLOATS = (R + 2 * HALF) * LD;
+    static constexpr int WBUFS = DB ? 2 : 1;
     static constexpr size_t SMEM =
-        (size_t)(ACT_FLOATS + 2 * WFLOATS) * sizeof(float) + R * sizeof(int);
+        (size_t)(ACT_FLOATS + WBUFS * WFLOATS) * sizeof(float) + R * sizeof(int);
     static_assert(C % 8 == 0 && CT % 2 == 0, "channels must be a multiple of 16");
 };
 
@@ -48,18 +51,18 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-template <int C, int KS>
-__global__ void __launch_bounds__(ConvF32<C, KS>::THREADS, 1)
+template <int C, int KS, bool DB>
+__global__ void __launch_bounds__(ConvF32<C, KS, DB>::THREADS, 1)
 conv_stack_f32_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
     const float* __restrict__ weights, const float* __restrict__ bias,
     ConvActs acts, int n_layers, int tile_rows, float* __restrict__ y) {
-    using Cfg = ConvF32<C, KS>;
+    using Cfg = ConvF32<C, KS, DB>;
     constexpr int R = Cfg::R, HALF = Cfg::HALF, LD = Cfg::LD, CT = Cfg::CT;
     extern __shared__ __align__(16) float smem[];
     float* act = smem;                              // [(R + 2 HALF)][LD]
-    float* wbuf = smem + Cfg::ACT_FLOATS;           // [2][KS*C][C]
-    int* valid = reinterpret_cast<int*>(wbuf + 2 * Cfg::WFLOATS);   // [R]
+    float* wbuf = smem + Cfg::ACT_FLOATS;           // [WBUFS][KS*C][C]
+    int* valid = reinterpret_cast<int*>(wbuf + Cfg::WBUFS * Cfg::WFLOATS);   // [R]
 
     const int tid = threadIdx.x;
     const int halo = n_layers * HALF;
@@ -92,8 +95,8 @@ conv_stack_f32_kernel(
     const int ty = tid >> 3;       // rows ty + 32 i, i = 0..3
 
     for (int layer = 0; layer < n_layers; ++layer) {
-        float* w = wbuf + (layer & 1) * Cfg::WFLOATS;
-        if (layer + 1 < n_layers) {
+        float* w = wbuf + (DB ? (layer & 1) : 0) * Cfg::WFLOATS;
+        if (DB && layer + 1 < n_layers) {
             float* wn = wbuf + ((layer + 1) & 1) * Cfg::WFLOATS;
             const float* src = weights + (size_t)(layer + 1) * Cfg::WFLOATS;
             for (int i = tid; i < Cfg::WFLOATS / 4; i += Cfg::THREADS)
@@ -139,7 +142,15 @@ conv_stack_f32_kernel(
                 }
             }
         }
-        __syncthreads();   // every read of this layer's input is done
+        __syncthreads();   // every read of this layer's input (and weights) is done
+        if (!DB && layer + 1 < n_layers) {
+            // single weight buffer: the next layer's weights load while the
+            // epilogue below runs
+            const float* src = weights + (size_t)(layer + 1) * Cfg::WFLOATS;
+            for (int i = tid; i < Cfg::WFLOATS / 4; i += Cfg::THREADS)
+                cp_async16(wbuf + 4 * i, src + 4 * i);
+            cp_async_commit();
+        }
 
         const int a = acts.act[layer];
         const float* b = bias + layer * C + tx * CT;
@@ -171,12 +182,12 @@ conv_stack_f32_kernel(
     }
 }
 
-template <int C, int KS>
+template <int C, int KS, bool DB = true>
 int launch_conv_f32(
     const float* x, const int32_t* row_seq, int32_t total_rows,
     const float* weights, const float* bias, const int32_t* acts_host,
     int32_t n_layers, float* y, cudaStream_t stream) {
-    using Cfg = ConvF32<C, KS>;
+    using Cfg = ConvF32<C, KS, DB>;
     const int halo = n_layers * Cfg::HALF;
     const int tile_rows = Cfg::R - 2 * halo;
     EMPH_REQUIRE(tile_rows >= 32, "emph_conv_stack: %d layers of kernel %d leave no tile", n_layers, KS);
@@ -184,12 +195,12 @@ int launch_conv_f32(
     for (int i = 0; i < kConvMaxLayers; ++i) acts.act[i] = i < n_layers ? acts_host[i] : 0;
     int s = check_cuda(
         cudaFuncSetAttribute(
-            conv_stack_f32_kernel<C, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            conv_stack_f32_kernel<C, KS, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int)Cfg::SMEM),
         "conv_f32 smem attribute");
     if (s != EMPH_OK) return s;
     int grid = (total_rows + tile_rows - 1) / tile_rows;
-    conv_stack_f32_kernel<C, KS><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(
+    conv_stack_f32_kernel<C, KS, DB><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(
         x, row_seq, total_rows, weights, bias, acts, n_layers, tile_rows, y);
     EMPH_CHECK_LAUNCH("emph_conv_stack(fp32)");
     return EMPH_OK;
@@ -204,10 +215,10 @@ int conv_stack_f32(
         return launch_conv_f32<80, 3>(x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
     if (channels == 80 && kernel_size == 1)
         return launch_conv_f32<80, 1>(x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
-    if (channels == 64 && kernel_size == 3)
-        return launch_conv_f32<64, 3>(x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
-    if (channels == 64 && kernel_size == 5)
-        return launch_conv_f32<64, 5>(x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
+    if (channels == 80 && kernel_size == 5)
+        return launch_conv_f32<80, 5, false>(x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
+    if (channels == 80 && kernel_size == 7)
+        return launch_conv_f32<80, 7, false>(x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
     set_error("emph_conv_stack(fp32): channels=%d kernel_size=%d not compiled in", channels, kernel_size);
     return EMPH_ENOSYS;
 }

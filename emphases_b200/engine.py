@@ -18,6 +18,7 @@ HOPSIZE = 160
 NUM_FFT = 1024
 WINDOW_SIZE = 1024
 PADDING = int((WINDOW_SIZE - HOPSIZE) / 2)   # 432, emphases/core.py:357
+KERNEL_CHANNELS = 80      # channel width the conv / tensor-core kernels are compiled for
 
 ACTIVATIONS = {
     'ReLU': _lib.ACT_RELU,
@@ -172,12 +173,24 @@ class Plan:
         return np.concatenate([p.astype(np.int32, copy=False) for p in parts])
 
 
-def packed_starts(lengths):
-    """Row layout with one separator row before, between and after sequences"""
+def separator_rows():
+    """Separator rows needed between packed sequences: a Conv1d with kernel k
+    reaches (k - 1) / 2 rows across a boundary, so that many zero rows
+    reproduce its per-utterance 'same' padding (1 for the default k = 3)."""
+    import emphases_b200 as emphases
+    kernel = max(emphases.ENCODER_KERNEL_SIZE, emphases.DECODER_KERNEL_SIZE)
+    return max(1, (int(kernel) - 1) // 2)
+
+
+def packed_starts(lengths, gap=None):
+    """Row layout with `gap` separator rows before, between and after
+    sequences (default: what the configured kernel sizes need)"""
+    if gap is None:
+        gap = separator_rows()
     lengths = np.asarray(lengths, dtype=np.int64)
-    starts = 1 + np.concatenate([[0], np.cumsum(lengths[:-1] + 1)]) \
+    starts = gap + np.concatenate([[0], np.cumsum(lengths[:-1] + gap)]) \
         if len(lengths) else np.zeros(0, dtype=np.int64)
-    total = int(starts[-1] + lengths[-1] + 1) if len(lengths) else 1
+    total = int(starts[-1] + lengths[-1] + gap) if len(lengths) else gap
     return starts, total
 
 
@@ -402,33 +415,50 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
     """
     step = 3 if dropout is not None else 2
     act = ACTIVATIONS[activation]
+    width = KERNEL_CHANNELS            # channel count the kernels are built for
+
+    def pad(tensor, shape):
+        """Zero-pad a weight/bias to the kernels' channel count.  Padded
+        output channels compute act(0) = 0 for every supported activation and
+        padded input channels multiply zeros, so the embedding is exact."""
+        tensor = tensor.detach().to(torch.float32)
+        if tuple(tensor.shape) == tuple(shape):
+            return tensor
+        padded = torch.zeros(shape, dtype=torch.float32, device=tensor.device)
+        padded[tuple(slice(0, n) for n in tensor.shape)] = tensor
+        return padded
 
     def stack(first, prefix):
         convs = list(first)
         convs += [
             (state[f'{prefix}.{i * step}.weight'],
              state[f'{prefix}.{i * step}.bias']) for i in range(layers)]
-        channels = convs[-1][0].shape[0]
         kernel = convs[-1][0].shape[2]
+        if (kernel - 1) // 2 > separator_rows():
+            raise ValueError(
+                f'kernel size {kernel} needs {(kernel - 1) // 2} separator rows; '
+                'set ENCODER_KERNEL_SIZE / DECODER_KERNEL_SIZE with '
+                'emphases_b200.configure before running this model')
         for weight, _ in convs:
-            if tuple(weight.shape) != (channels, channels, kernel):
+            if max(weight.shape[0], weight.shape[1]) > width or weight.shape[2] != kernel:
                 raise NotImplementedError(
-                    'conv stack needs equal in/out channels and kernel sizes, '
-                    f'got {tuple(weight.shape)}')
-        weights = torch.stack([_pack_conv(w, device) for w, _ in convs])
-        bias = torch.stack([
-            b.detach().to(device=device, dtype=torch.float32) for _, b in convs])
+                    f'conv stack shape {tuple(weight.shape)} is not built: the '
+                    f'kernels cover up to {width} channels (smaller models are '
+                    'zero-padded) with one kernel size per stack')
+        weights = torch.stack([
+            _pack_conv(pad(w, (width, width, kernel)), device) for w, _ in convs])
+        bias = torch.stack([pad(b, (width,)).to(device) for _, b in convs])
         acts = np.asarray(
             [_lib.ACT_NONE] * len(first) + [act] * layers, dtype=np.int32)
-        return ConvStack(weights.contiguous(), bias.contiguous(), acts, kernel, channels)
+        return ConvStack(weights.contiguous(), bias.contiguous(), acts, kernel, width)
 
     frame = stack(
         [(state['input_layer.weight'], state['input_layer.bias'])],
         'frame_encoder')
     word = stack([], 'word_decoder') if has_decoder else None
-    head = state['output_layer.weight'].detach().to(
-        device=device, dtype=torch.float32)           # (1, C, K)
-    head_weight = head[0].t().contiguous()            # [K][C]
+    head = state['output_layer.weight']                  # (1, C, K)
+    head = pad(head, (1, width, head.shape[2])).to(device)
+    head_weight = head[0].t().contiguous()               # [K][C]
     return ModelWeights(
         frame=frame,
         word=word,

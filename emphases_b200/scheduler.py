@@ -119,12 +119,13 @@ def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
 def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
     """Split utterances (kept in order) into launches of <= max_rows packed
     rows; an utterance longer than max_rows gets a launch of its own."""
-    launches, current, rows = [], [], 1
+    gap = engine.separator_rows()
+    launches, current, rows = [], [], gap
     for index, count in enumerate(frames):
-        need = int(count) + 1
+        need = int(count) + gap
         if current and rows + need > max_rows:
             launches.append(current)
-            current, rows = [], 1
+            current, rows = [], gap
         current.append(index)
         rows += need
     if current:

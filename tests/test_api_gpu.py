@@ -302,3 +302,56 @@ def test_transformer_packed_corpus(emphases, golden, tmp_path):
     for got, want in zip(scores, expected):
         assert got.shape == want.shape
         assert (got - want).abs().max() < 2e-5
+
+
+HPARAMS = [
+    # the reference's config/hparam-search space
+    dict(CHANNELS=64),
+    dict(LAYERS=5),
+    dict(LAYERS=7),
+    dict(ENCODER_KERNEL_SIZE=5, DECODER_KERNEL_SIZE=7),
+    dict(ENCODER_KERNEL_SIZE=7, DECODER_KERNEL_SIZE=1),
+    dict(ACTIVATION_FUNCTION=torch.nn.GELU),
+    dict(ACTIVATION_FUNCTION=torch.nn.LeakyReLU),
+    dict(ACTIVATION_FUNCTION=torch.nn.SiLU),
+    dict(DROPOUT=.1),
+    dict(LOSS='mse'),
+]
+
+
+@pytest.mark.parametrize('overrides', HPARAMS, ids=lambda d: '-'.join(map(str, d)))
+def test_hyperparameter_shapes(emphases, overrides):
+    """Model shapes of the reference's hyper-parameter sweep, random init,
+    against the oracle (fp32 mode, end to end from audio)"""
+    emphases.configure(**overrides)
+    torch.manual_seed(3)
+    model = emphases.Model()
+    for parameter in model.parameters():
+        if parameter.dim() > 1:
+            parameter.data.mul_(1.5)
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    activation = emphases.ACTIVATION_FUNCTION.__name__
+    config = dict(
+        CHANNELS=emphases.CHANNELS, LAYERS=emphases.LAYERS,
+        DROPOUT=emphases.DROPOUT, LOSS=emphases.LOSS,
+        ACTIVATION={'ReLU': 'relu', 'GELU': 'gelu', 'LeakyReLU': 'leaky_relu',
+                    'SiLU': 'silu'}[activation])
+    alignments, audios, expected = [], [], []
+    for seed in range(3):
+        times, audio = oracle.synthetic_utterance(1200 + seed, duration=2.5 + seed)
+        alignments.append(emphases.Alignment.from_times(times))
+        audios.append(audio)
+        expected.append(oracle.from_alignment_and_audio(times, audio, state, config))
+    scores = emphases.from_alignments_and_audio(
+        alignments, audios, 16000, model=model, gpu=0)
+    for got, want in zip(scores, expected):
+        assert got.shape == want.shape
+        assert (got - want).abs().max() < 1e-5
+
+
+def test_wide_model_is_rejected_loudly(emphases):
+    emphases.configure(CHANNELS=128)
+    model = emphases.Model().cuda().eval()
+    with pytest.raises(NotImplementedError):
+        model.packed_weights()
