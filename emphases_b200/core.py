@@ -360,12 +360,15 @@ def inference_context(model):
 
 
 def resample(audio, sample_rate, target_rate=None):
-    """emphases/core.py:613-619 (torchaudio sinc resampler)"""
+    """emphases/core.py:613-619: windowed-sinc resampling with torchaudio's
+    default filter, computed by csrc/resample.cu.  The result lives on the
+    device of `audio` like in the reference (a CPU tensor makes a round trip
+    through the current CUDA device)."""
     if target_rate is None:
         target_rate = emphases.SAMPLE_RATE
     if sample_rate == target_rate:
         return audio
-    import torchaudio
-    resampler = torchaudio.transforms.Resample(sample_rate, target_rate)
-    resampler = resampler.to(audio.device)
-    return resampler(audio)
+    from . import resampling
+    device = emphases.resolve_device(None, audio)
+    result = resampling.resample(audio, sample_rate, target_rate, device)
+    return result if audio.device.type == 'cuda' else result.cpu()

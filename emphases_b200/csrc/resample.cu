@@ -1,0 +1,45 @@
+// Polyphase windowed-sinc resampler, sm_100a.  Replaces emphases.resample
+// (emphases/core.py:613-619 -> torchaudio.transforms.Resample, i.e. a strided
+// conv1d with `new_freq` filters of 2 * width + orig_freq taps):
+//   y[q * new + p] = sum_k kernel[p][k] * xpad[q * orig + k],
+//   xpad = zeros(width) ++ x ++ zeros(width + orig)
+// The filter bank is built on the host exactly as torchaudio builds it
+// (emphases_b200/resampling.py) and passed in.  One thread per output sample;
+// a block's outputs share their input window through L1.
+#include "common.cuh"
+
+namespace emph {
+
+__global__ void __launch_bounds__(256)
+resample_kernel(
+    const float* __restrict__ x, long long length, const float* __restrict__ kernel,
+    int orig, int fresh, int width, int taps, float* __restrict__ y, long long target) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= target) return;
+    const long long q = n / fresh;
+    const int p = (int)(n - q * fresh);
+    const float* w = kernel + (size_t)p * taps;
+    const long long first = q * orig - width;          // x index of tap 0
+    float acc = 0.f;
+    int k0 = first < 0 ? (int)(-first) : 0;
+    long long k1 = length - first;                      // taps with x index < length
+    if (k1 > taps) k1 = taps;
+    for (int k = k0; k < (int)k1; ++k) acc = fmaf(__ldg(w + k), __ldg(x + first + k), acc);
+    y[n] = acc;
+}
+
+}  // namespace emph
+
+extern "C" int emph_resample_f32(
+    const float* x, int64_t length, const float* kernel, int32_t orig_freq,
+    int32_t new_freq, int32_t width, float* y, int64_t target_length, void* stream) {
+    EMPH_REQUIRE(orig_freq > 0 && new_freq > 0 && width >= 0, "emph_resample_f32: bad filter");
+    EMPH_REQUIRE(length >= 0 && target_length >= 0, "emph_resample_f32: negative length");
+    if (target_length == 0) return EMPH_OK;
+    const int taps = 2 * width + orig_freq;
+    const long long blocks = (target_length + 255) / 256;
+    emph::resample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        x, length, kernel, orig_freq, new_freq, width, taps, y, target_length);
+    EMPH_CHECK_LAUNCH("emph_resample_f32");
+    return EMPH_OK;
+}

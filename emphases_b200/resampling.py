@@ -1,0 +1,64 @@
+"""Sample-rate conversion (`emphases.resample`, emphases/core.py:613-619).
+
+The reference delegates to torchaudio.transforms.Resample (windowed-sinc
+interpolation, Hann window, lowpass_filter_width 6, rolloff 0.99).  The filter
+bank below restates torchaudio's construction (torchaudio/functional/
+functional.py `_get_sinc_resample_kernel`, a third-party dependency) in numpy
+with the same dtypes; the convolution runs in csrc/resample.cu.
+"""
+import functools
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LOWPASS_FILTER_WIDTH = 6
+ROLLOFF = 0.99
+
+
+@functools.lru_cache(maxsize=16)
+def filter_bank(orig_freq, new_freq):
+    """(kernels float32 (new, 2 * width + orig), width, orig, new) after
+    dividing both rates by their gcd"""
+    gcd = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // gcd, int(new_freq) // gcd
+    base_freq = min(orig, new) * ROLLOFF
+    width = math.ceil(LOWPASS_FILTER_WIDTH * orig / base_freq)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    # torch: int64 arange / int -> float32 division, then promoted to float64
+    phase = (np.arange(0, -new, -1).astype(np.float32) / np.float32(new)).astype(np.float64)
+    t = phase[:, None] + idx
+    t *= base_freq
+    np.clip(t, -LOWPASS_FILTER_WIDTH, LOWPASS_FILTER_WIDTH, out=t)
+    window = np.cos(t * math.pi / LOWPASS_FILTER_WIDTH / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    with np.errstate(invalid='ignore', divide='ignore'):
+        kernels = np.where(t == 0, 1.0, np.sin(t) / t)
+    kernels = kernels * window * scale
+    return kernels.astype(np.float32), width, orig, new
+
+
+_device_banks = {}
+
+
+def resample(audio, sample_rate, target_rate, device):
+    """(C, T) float tensor -> (C, ceil(T * target / source)) on `device`"""
+    kernels, width, orig, new = filter_bank(int(sample_rate), int(target_rate))
+    key = (int(sample_rate), int(target_rate), device)
+    if key not in _device_banks:
+        _device_banks[key] = torch.from_numpy(kernels).to(device)
+    bank = _device_banks[key]
+    audio = audio.detach().to(device, torch.float32).contiguous()
+    channels, length = audio.shape
+    target = int(math.ceil(new * length / orig))
+    out = torch.empty((channels, target), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        for channel in range(channels):
+            _lib.call(
+                'emph_resample_f32', _lib.ptr(audio[channel]), length,
+                _lib.ptr(bank), orig, new, width, _lib.ptr(out[channel]), target,
+                _lib.stream_ptr())
+    return out

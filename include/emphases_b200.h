@@ -290,6 +290,17 @@ int emph_masked_loss(
     int32_t total_rows, int32_t mode, float* loss, float* dlogits, void* stream);
 
 /*
+ * Polyphase windowed-sinc resampling (emphases/core.py:613-619 `resample`, which
+ * is torchaudio.transforms.Resample): y[q * new + p] = sum_k kernel[p][k] *
+ * xpad[q * orig + k], xpad = zeros(width) ++ x ++ zeros(width + orig).
+ * `kernel` is the (new_freq, 2 * width + orig_freq) filter bank (rates already
+ * divided by their gcd), built on the host like torchaudio builds it.
+ */
+int emph_resample_f32(
+    const float* x, int64_t length, const float* kernel, int32_t orig_freq,
+    int32_t new_freq, int32_t width, float* y, int64_t target_length, void* stream);
+
+/*
  * Host-side corpus ingest / egress for from_files_to_files (HOST pointers, no
  * CUDA): reads n_files (TextGrid, 16-bit PCM wav) pairs on a thread pool,
  * replacing per file emphases.load.audio (emphases/load.py:11-17),

@@ -355,3 +355,33 @@ def test_wide_model_is_rejected_loudly(emphases):
     model = emphases.Model().cuda().eval()
     with pytest.raises(NotImplementedError):
         model.packed_weights()
+
+
+@pytest.mark.parametrize('rate', [24000, 44100, 8000])
+def test_resample_matches_torchaudio(emphases, rate):
+    """emphases.resample vs torchaudio.transforms.Resample on CPU"""
+    import torchaudio
+    generator = torch.Generator().manual_seed(rate)
+    audio = 0.3 * torch.randn(2, rate + 37, generator=generator)
+    expected = torchaudio.transforms.Resample(rate, 16000)(audio)
+    got = emphases.resample(audio.cuda(), rate)
+    assert got.shape == expected.shape and got.device.type == 'cuda'
+    assert (got.cpu() - expected).abs().max() < 2e-6
+    assert emphases.resample(audio, rate).device.type == 'cpu'
+    assert emphases.resample(audio, 16000) is audio
+
+
+def test_non_16k_audio_end_to_end(emphases, golden, c1_checkpoint):
+    """from_alignment_and_audio resamples like the reference (core.py:353-354)"""
+    import torchaudio
+    data = golden('c1')
+    state = state_from_golden(data)
+    generator = torch.Generator().manual_seed(4)
+    audio = 0.1 * torch.randn(1, 72000, generator=generator)          # 3 s at 24 kHz
+    times = oracle.synthetic_alignment(3.0, 8, generator)
+    expected = oracle.from_alignment_and_audio(
+        times, torchaudio.transforms.Resample(24000, 16000)(audio), state)
+    scores = emphases.from_alignment_and_audio(
+        emphases.Alignment.from_times(times), audio, 24000,
+        checkpoint=c1_checkpoint, gpu=0)
+    assert (scores.cpu() - expected).abs().max() < 1e-5

@@ -268,3 +268,17 @@ def test_native_corpus_reader_matches_python(tmp_path):
             np.testing.assert_array_equal(rewritten.times(), original.times())
             assert [str(w) for w in rewritten] == [str(w) for w in original]
         assert not outputs[4].exists()
+
+
+@pytest.mark.parametrize('rates', [(24000, 16000), (44100, 16000), (8000, 16000), (22050, 16000)])
+def test_resample_filter_bank_matches_torchaudio(rates):
+    """The host-built polyphase filter bank is bit-identical to torchaudio's"""
+    import math
+    import torchaudio.functional.functional as F
+    from emphases_b200 import resampling
+    orig, new = rates
+    gcd = math.gcd(orig, new)
+    expected, width = F._get_sinc_resample_kernel(orig, new, gcd)
+    kernels, our_width, o, n = resampling.filter_bank(orig, new)
+    assert our_width == width and (o, n) == (orig // gcd, new // gcd)
+    np.testing.assert_array_equal(kernels, expected[:, 0].numpy())
