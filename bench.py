@@ -323,7 +323,7 @@ def main():
         return
 
     import emphases_b200 as emphases
-    from emphases_b200 import _lib, engine, scheduler
+    from emphases_b200 import engine, scheduler
 
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)

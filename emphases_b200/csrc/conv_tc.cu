@@ -182,9 +182,6 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(elected));
     return elected != 0;
 }
-__device__ __forceinline__ void named_barrier(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6) = 1,
 // A bf16 [7,10) = 1, B bf16 [10,13) = 1, A and B K-major, N >> 3 at [17,23),

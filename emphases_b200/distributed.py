@@ -8,7 +8,6 @@ agree on the shards and, optionally, to gather scores on rank 0.
 """
 import os
 
-import numpy as np
 import torch
 
 import emphases_b200 as emphases

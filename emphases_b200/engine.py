@@ -5,8 +5,9 @@ kernels, include/emphases_b200.h).  PyTorch is used for device memory, streams
 and host<->device copies only.
 """
 import dataclasses
-import math
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
+
+import ctypes
 
 import numpy as np
 import torch
@@ -552,7 +553,6 @@ class Engine:
 
     def conv_stack(self, x, row_seq, stack: ConvStack, precision):
         y = torch.empty_like(x)
-        import ctypes
         acts = stack.acts.astype(np.int32)
         weights = stack.tensor_core_weights() \
             if precision == _lib.PREC_BF16_TC else stack.weights
