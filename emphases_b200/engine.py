@@ -474,6 +474,37 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
 ###############################################################################
 
 
+class Workspace:
+    """Grow-only device buffers reused across launches.  Launch sizes vary, so
+    fresh torch allocations make the caching allocator fragment and fall back
+    to cudaMalloc (50-200 ms stalls); a workspace per stream slot makes the
+    steady state allocation-free.  Buffers are handed out as views, valid
+    until the next launch that uses the same workspace."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buffers = {}
+
+    def get(self, name, shape, dtype):
+        numel = 1
+        for extent in shape:
+            numel *= int(extent)
+        buffer = self.buffers.get(name)
+        if buffer is None or buffer.numel() < numel or buffer.dtype != dtype:
+            # 10 % headroom: launches of one corpus have similar sizes
+            buffer = torch.empty(
+                max(int(numel * 1.1) + 16, 16), dtype=dtype, device=self.device)
+            self.buffers[name] = buffer
+        return buffer[:numel].view(*shape)
+
+
+def _empty(ws, name, shape, dtype, device):
+    if ws is None:
+        return torch.empty(shape, dtype=dtype, device=device)
+    return ws.get(name, shape, dtype)
+
+
+
 class Engine:
     """Owns device-side constants and launches the kernels of one GPU"""
 
@@ -490,6 +521,12 @@ class Engine:
             self.mel_col = torch.from_numpy(col).to(self.device)
             self.mel_val = torch.from_numpy(val).to(self.device)
         self._pinned = {}
+        self._workspaces = {}
+
+    def workspace(self, slot):
+        if slot not in self._workspaces:
+            self._workspaces[slot] = Workspace(self.device)
+        return self._workspaces[slot]
 
     # -- host staging ------------------------------------------------------
 
@@ -502,18 +539,21 @@ class Engine:
             self._pinned[key] = buffer
         return buffer[:numel]
 
-    def upload_plan(self, plan: Plan, slot=0):
+    def upload_plan(self, plan: Plan, slot=0, ws=None):
         """One H2D copy for all int32 index arrays (+ one for int64 offsets).
         `slot` selects the pinned staging buffer: launches whose copies may
         still be in flight must not share one."""
         blob = plan.int32_blob()
         staging = self.pinned(('plan32', slot), len(blob), torch.int32)
         staging.numpy()[:] = blob
-        device_blob = staging.to(self.device, non_blocking=True)
+        device_blob = _empty(ws, 'plan32', (len(blob),), torch.int32, self.device)
+        device_blob.copy_(staging, non_blocking=True)
         off_staging = self.pinned(
             ('plan64', slot), max(plan.n_seq, 1), torch.int64)
         off_staging.numpy()[:plan.n_seq] = plan.audio_off
-        audio_off = off_staging.to(self.device, non_blocking=True)
+        audio_off = _empty(
+            ws, 'plan64', (off_staging.numel(),), torch.int64, self.device)
+        audio_off.copy_(off_staging, non_blocking=True)
         n, w = plan.n_seq, plan.total_word_rows
         sizes = [n, n, n, n, n, n, n, w, w, w]
         names = [
@@ -528,17 +568,17 @@ class Engine:
 
     # -- kernels -----------------------------------------------------------
 
-    def row_index(self, row_start, n_rows, n_seq, total_rows):
-        row_seq = torch.empty(total_rows, dtype=torch.int32, device=self.device)
+    def row_index(self, row_start, n_rows, n_seq, total_rows, ws=None, name='row_seq'):
+        row_seq = _empty(ws, name, (total_rows,), torch.int32, self.device)
         _lib.call(
             'emph_row_index', _lib.ptr(row_start), _lib.ptr(n_rows), n_seq,
             _lib.ptr(row_seq), total_rows, _lib.stream_ptr())
         return row_seq
 
-    def logmel(self, audio, views, plan, row_seq, normalize=False):
-        out = torch.empty(
-            (plan.total_rows, self.n_mels), dtype=torch.float32,
-            device=self.device)
+    def logmel(self, audio, views, plan, row_seq, normalize=False, ws=None):
+        out = _empty(
+            ws, 'features', (plan.total_rows, self.n_mels), torch.float32,
+            self.device)
         name = {torch.float32: 'emph_logmel_f32', torch.int16: 'emph_logmel_i16'}[
             audio.dtype]
         _lib.call(
@@ -551,8 +591,9 @@ class Engine:
             _lib.ptr(out), _lib.stream_ptr())
         return out
 
-    def conv_stack(self, x, row_seq, stack: ConvStack, precision):
-        y = torch.empty_like(x)
+    def conv_stack(self, x, row_seq, stack: ConvStack, precision, ws=None,
+                   name='conv'):
+        y = _empty(ws, name, tuple(x.shape), torch.float32, self.device)
         acts = stack.acts.astype(np.int32)
         weights = stack.tensor_core_weights() \
             if precision == _lib.PREC_BF16_TC else stack.weights
@@ -564,11 +605,12 @@ class Engine:
             _lib.stream_ptr())
         return y
 
-    def pool(self, x, row_start, n_rows, word_seq, word_lo, word_hi, method):
+    def pool(self, x, row_start, n_rows, word_seq, word_lo, word_hi, method,
+             ws=None):
         total_word_rows = word_seq.shape[0]
-        y = torch.empty(
-            (total_word_rows, x.shape[1]), dtype=torch.float32,
-            device=self.device)
+        y = _empty(
+            ws, 'pooled', (total_word_rows, x.shape[1]), torch.float32,
+            self.device)
         _lib.call(
             'emph_pool_words', _lib.ptr(x), x.shape[1], _lib.ptr(row_start),
             _lib.ptr(n_rows), _lib.ptr(word_seq), _lib.ptr(word_lo),
@@ -577,11 +619,11 @@ class Engine:
         return y
 
     def head(self, x, row_seq, weights: ModelWeights, mode, want_logits=True,
-             want_scores=True):
+             want_scores=True, ws=None):
         rows = x.shape[0]
-        logits = torch.empty(rows, dtype=torch.float32, device=self.device) \
+        logits = _empty(ws, 'logits', (rows,), torch.float32, self.device) \
             if want_logits else None
-        scores = torch.empty(rows, dtype=torch.float32, device=self.device) \
+        scores = _empty(ws, 'scores', (rows,), torch.float32, self.device) \
             if want_scores else None
         _lib.call(
             'emph_output_head', _lib.ptr(x), _lib.ptr(row_seq), rows,
@@ -604,7 +646,8 @@ class Engine:
         normalize=False,
         views=None,
         keep=False,
-        timers=None
+        timers=None,
+        ws=None
     ):
         """audio: packed device tensor (fp32 or int16).  Returns dict with
         `scores` and `logits` per packed word row (device tensors)."""
@@ -627,12 +670,13 @@ class Engine:
             return output
 
         row_seq = timed('row_index_frames', lambda: self.row_index(
-            views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows))
+            views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows,
+            ws))
         word_row_seq = timed('row_index_words', lambda: self.row_index(
             views['word_row_start'], views['n_words'], plan.n_seq,
-            plan.total_word_rows))
+            plan.total_word_rows, ws, 'word_row_seq'))
         features = timed('logmel', lambda: self.logmel(
-            audio, views, plan, row_seq, normalize))
+            audio, views, plan, row_seq, normalize, ws))
         transformer_variant = hasattr(weights, 'input_layer')
         if transformer_variant:
             from . import transformer
@@ -643,10 +687,10 @@ class Engine:
                 plan.n_rows, row_seq, self.device))
         else:
             frames = timed('conv_frames', lambda: self.conv_stack(
-                features, row_seq, weights.frame, precision))
+                features, row_seq, weights.frame, precision, ws, 'frames'))
         pooled = timed('pool', lambda: self.pool(
             frames, views['row_start'], views['n_rows'], views['word_seq'],
-            views['word_lo'], views['word_hi'], method))
+            views['word_lo'], views['word_hi'], method, ws))
         if location == 'intermediate' and transformer_variant:
             from . import transformer
             words = timed('conv_words', lambda: transformer.run_stack(
@@ -654,11 +698,11 @@ class Engine:
                 plan.n_words, plan.n_words, word_row_seq, self.device))
         elif location == 'intermediate':
             words = timed('conv_words', lambda: self.conv_stack(
-                pooled, word_row_seq, weights.word, _lib.PREC_FP32))
+                pooled, word_row_seq, weights.word, _lib.PREC_FP32, ws, 'words'))
         else:
             words = pooled
         logits, scores = timed('head', lambda: self.head(
-            words, word_row_seq, weights, head_mode))
+            words, word_row_seq, weights, head_mode, ws=ws))
         result = {'scores': scores, 'logits': logits}
         if keep:
             result.update(

@@ -193,15 +193,20 @@ def run_on_device(
         end = int(packed.offsets[last] + (packed.lengths[last] + 3) // 4 * 4)
         end = min(end, packed.buffer.numel())
         stream = streams[number % len(streams)]
+        # one grow-only workspace per stream: launches on a stream run in
+        # order, so its buffers can be reused without further synchronisation
+        ws = eng.workspace(number % len(streams))
         with torch.cuda.stream(stream):
-            device_audio = packed.buffer[base:end].to(
-                device, non_blocking=True)
+            device_audio = ws.get('audio', (end - base,), packed.buffer.dtype)
+            device_audio.copy_(packed.buffer[base:end], non_blocking=True)
             result = eng.forward_packed(
                 device_audio, plan, weights, method=method,
                 location=model.location, precision=precision,
                 head_mode=head_mode, normalize=emphases.NORMALIZE,
-                views=eng.upload_plan(plan, slot=number))
+                views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws)
             scores = result['scores']
+            if not to_cpu:
+                scores = scores.clone()       # the workspace is reused
             if to_cpu:
                 host = eng.pinned(
                     ('scores', number), scores.numel(), scores.dtype)
