@@ -44,6 +44,7 @@ SIGNATURES = {
     'emph_pool_words_backward': [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     'emph_output_head_backward': [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     'emph_masked_loss': [_P, _P, _P, _I, _I, _P, _P, _P],
+    'emph_upsample_words': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
 }
 
 _lib = None

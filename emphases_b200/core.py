@@ -24,7 +24,8 @@ __all__ = [
     'from_file', 'from_file_to_file', 'from_files_to_files',
     'from_text_and_audio', 'from_alignment_and_audio',
     'from_alignments_and_audio', 'infer', 'infer_with_model', 'postprocess', 'preprocess',
-    'downsample', 'segment', 'inference_context', 'resample', 'load_model']
+    'downsample', 'upsample', 'segment', 'inference_context', 'resample',
+    'load_model']
 
 
 ###############################################################################
@@ -334,6 +335,30 @@ def downsample(xs, word_bounds, word_lengths):
             (word_starts[:, None] + np.arange(wmax_out)[None]).astype(np.int64)
         ).to(device)
         return pooled[index].transpose(1, 2).contiguous().to(xs.dtype)
+
+
+def upsample(xs, word_bounds, word_lengths, frame_lengths):
+    """Interpolate from word to frame resolution (emphases/core.py:472-544):
+    xs (B, C, Wmax) -> (B, C, max(frame_lengths)), UPSAMPLE_METHOD 'linear' or
+    'nearest'"""
+    method = emphases.UPSAMPLE_METHOD
+    if method not in ('linear', 'nearest'):
+        raise ValueError(f'Interpolation method {method} is not defined')
+    device = emphases.resolve_device(None, xs)
+    batch, channels, wmax = xs.shape
+    tmax = int(frame_lengths.max())
+    with torch.cuda.device(device):
+        values = xs.detach().to(device, torch.float32).contiguous()
+        bounds = word_bounds.detach().to(device, torch.int64).contiguous()
+        words = word_lengths.detach().to(device, torch.int64).contiguous()
+        frames = frame_lengths.detach().to(device, torch.int64).contiguous()
+        out = torch.empty(
+            (batch, channels, tmax), dtype=torch.float32, device=device)
+        _lib.call(
+            'emph_upsample_words', _lib.ptr(values), _lib.ptr(bounds),
+            _lib.ptr(words), _lib.ptr(frames), batch, channels, wmax, tmax,
+            int(method == 'linear'), _lib.ptr(out), _lib.stream_ptr())
+    return out.to(xs.dtype)
 
 
 def segment(xs, word_bounds, word_lengths):

@@ -310,3 +310,71 @@ int emph_masked_loss(
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Word -> frame interpolation (emphases.upsample, emphases/core.py:472-544),
+// used by the frame-resolution training loss of the 'inference' location.
+// Operates on the reference's (B, C, W) / (B, C, T) layouts.  Faithful to two
+// quirks: the 'linear' branch interpolates CHANNEL 0 for every channel
+// (line_idx is all zeros, core.py:516-521) and a single-word item broadcasts
+// x[0] (core.py:497-498).
+namespace emph {
+
+__global__ void upsample_words_kernel(
+    const float* __restrict__ xs, const int64_t* __restrict__ bounds,
+    const int64_t* __restrict__ word_lengths, const int64_t* __restrict__ frame_lengths,
+    int batch, int channels, int wmax, int tmax, int linear, float* __restrict__ out) {
+    const long long n = (long long)batch * channels * tmax;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % tmax);
+        const int c = (int)((i / tmax) % channels);
+        const int b = (int)(i / ((long long)tmax * channels));
+        float value = 0.f;
+        const int words = (int)word_lengths[b];
+        if (t < (int)frame_lengths[b] && words > 0) {
+            const float* x = xs + (size_t)b * channels * wmax;
+            const int64_t* lo = bounds + (size_t)b * 2 * wmax;
+            const int64_t* hi = lo + wmax;
+            if (words == 1) {
+                value = x[0];
+            } else {
+                const float ft = 0.5f + (float)t;
+                int count = 0;
+                for (int j = 0; j < words; ++j) {
+                    const float wt = (float)lo[j] + (float)(hi[j] - lo[j]) / 2.f;
+                    count += ft >= wt;
+                }
+                if (linear) {
+                    const int idx = min(max(count - 1, 0), words - 2);
+                    const float w0 = (float)lo[idx] + (float)(hi[idx] - lo[idx]) / 2.f;
+                    const float w1 = (float)lo[idx + 1] + (float)(hi[idx + 1] - lo[idx + 1]) / 2.f;
+                    const float slope = __fdiv_rn(x[idx + 1] - x[idx], w1 - w0);
+                    const float intercept = __fsub_rn(x[idx], __fmul_rn(slope, w0));
+                    value = __fadd_rn(__fmul_rn(slope, ft), intercept);
+                } else {
+                    const int idx = min(max(count - 1, 0), words - 1);
+                    value = x[(size_t)c * wmax + idx];
+                }
+            }
+        }
+        out[i] = value;
+    }
+}
+
+}  // namespace emph
+
+extern "C" int emph_upsample_words(
+    const float* xs, const int64_t* bounds, const int64_t* word_lengths,
+    const int64_t* frame_lengths, int32_t batch, int32_t channels, int32_t wmax,
+    int32_t tmax, int32_t linear, float* out, void* stream) {
+    EMPH_REQUIRE(batch >= 0 && channels > 0 && wmax > 0 && tmax >= 0, "emph_upsample_words: bad shape");
+    const long long n = (long long)batch * channels * tmax;
+    if (n == 0) return EMPH_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > emph::sm_count() * 8) blocks = emph::sm_count() * 8;
+    emph::upsample_words_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        xs, bounds, word_lengths, frame_lengths, batch, channels, wmax, tmax, linear, out);
+    EMPH_CHECK_LAUNCH("emph_upsample_words");
+    return EMPH_OK;
+}

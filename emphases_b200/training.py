@@ -57,10 +57,10 @@ class _ConvModelFunction(torch.autograd.Function):
         method = emphases.DOWNSAMPLE_METHOD
         if method not in _lib.POOL:
             raise ValueError(f'Interpolation method {method} is not defined')
-        if model.architecture != 'convolution' or model.location != 'intermediate':
+        if model.architecture != 'convolution' or model.location == 'input':
             raise NotImplementedError(
                 'the training step is built for the convolution architecture '
-                "at DOWNSAMPLE_LOCATION='intermediate'")
+                "at the 'intermediate', 'loss' and 'inference' locations")
         if model.activation not in ('ReLU', 'Identity'):
             raise NotImplementedError('training backward supports ReLU only')
         batch, channels, frames = features.shape
@@ -84,6 +84,21 @@ class _ConvModelFunction(torch.autograd.Function):
                 frame_acts.append(eng.conv_stack(
                     frame_acts[-1], row_seq, _stack(weight, bias, act, device),
                     _lib.PREC_FP32))
+            weights = model.packed_weights()
+            if model.location == 'inference':
+                # frame-resolution logits (model/core.py:119-122)
+                logits, _ = eng.head(
+                    frame_acts[-1], row_seq, weights, _lib.HEAD_LOGITS,
+                    want_scores=False)
+                index = torch.from_numpy(
+                    (starts[:, None] + np.arange(frames)[None]).astype(np.int64)
+                ).to(device)
+                ctx.model = model
+                ctx.saved = dict(
+                    frame_acts=frame_acts, row_seq=row_seq, index=index,
+                    total=total, head_weight=weights.head_weight,
+                    head_kernel=weights.head_kernel, frame_level=True)
+                return logits[index][:, None, :]
             views, word_starts, total_words, bounds, lengths = \
                 model_module.word_rows(word_bounds, word_lengths, device)
             pooled = eng.pool(
@@ -96,7 +111,6 @@ class _ConvModelFunction(torch.autograd.Function):
                 word_acts.append(eng.conv_stack(
                     word_acts[-1], word_row_seq, _stack(weight, bias, act, device),
                     _lib.PREC_FP32))
-            weights = model.packed_weights()
             logits, _ = eng.head(
                 word_acts[-1], word_row_seq, weights, _lib.HEAD_LOGITS,
                 want_scores=False)
@@ -109,7 +123,7 @@ class _ConvModelFunction(torch.autograd.Function):
             word_row_seq=word_row_seq, row_start=row_start, n_rows=n_rows,
             views=views, index=index, total=total, total_words=total_words,
             method=method, head_weight=weights.head_weight,
-            head_kernel=weights.head_kernel)
+            head_kernel=weights.head_kernel, frame_level=False)
         return logits[index][:, None, :]
 
     @staticmethod
@@ -118,20 +132,23 @@ class _ConvModelFunction(torch.autograd.Function):
         device = grad_logits.device
         eng = emphases.get_engine(device)
         channels = s['frame_acts'][0].shape[1]
+        frame_level = s['frame_level']
         with torch.cuda.device(device):
-            dz = torch.zeros(s['total_words'], dtype=torch.float32, device=device)
+            rows = s['total'] if frame_level else s['total_words']
+            head_seq = s['row_seq'] if frame_level else s['word_row_seq']
+            dz = torch.zeros(rows, dtype=torch.float32, device=device)
             dz[s['index'].reshape(-1)] = grad_logits.reshape(-1).to(torch.float32)
             frame_layers, word_layers = _layer_list(model)
             grads = {}
 
             # output projection
-            x = s['word_acts'][-1]
+            x = s['frame_acts'][-1] if frame_level else s['word_acts'][-1]
             dx = torch.empty_like(x)
             dw = torch.empty_like(s['head_weight'])
             db = torch.empty(1, dtype=torch.float32, device=device)
             _lib.call(
                 'emph_output_head_backward', _lib.ptr(x), _lib.ptr(dz),
-                _lib.ptr(s['word_row_seq']), s['total_words'], channels,
+                _lib.ptr(head_seq), rows, channels,
                 s['head_kernel'], _lib.ptr(s['head_weight']), _lib.ptr(dx),
                 _lib.ptr(dw), _lib.ptr(db), _lib.stream_ptr())
             grads[model.output_layer.weight] = dw.t()[None].contiguous()
@@ -163,6 +180,12 @@ class _ConvModelFunction(torch.autograd.Function):
                         _lib.PREC_FP32)
                 return dy
 
+            if frame_level:
+                conv_backward(frame_layers, s['frame_acts'], s['row_seq'], dx)
+                ordered = [
+                    grads[p].to(p.dtype) if p in grads else None
+                    for p in model.parameters()]
+                return (None, None, None, None, *ordered)
             d_pooled = conv_backward(
                 word_layers, s['word_acts'], s['word_row_seq'], dx)
             d_frames = torch.empty_like(s['frame_acts'][-1])
@@ -221,13 +244,18 @@ def loss(
     from . import model as model_module
     if loss_fn is None:
         loss_fn = emphases.LOSS
-    if training and emphases.DOWNSAMPLE_LOCATION == 'inference':
-        raise NotImplementedError(
-            'frame-resolution loss (upsample, emphases/core.py:472-544) is a '
-            'next-row item')
     if loss_fn not in ('bce', 'mse'):
         raise ValueError(f'Loss {loss_fn} is not recognized')
-    mask = model_module.mask_from_lengths(word_lengths.to(scores.device))
+    if training and emphases.DOWNSAMPLE_LOCATION == 'inference':
+        # scores are frame resolution: upsample the word targets
+        # (train/core.py:324-338)
+        targets = emphases.upsample(
+            targets.to(scores.device), word_bounds, word_lengths, frame_lengths)
+        if emphases.UPSAMPLE_METHOD == 'linear':
+            targets = torch.clamp(targets, min=0., max=1.)
+        mask = model_module.mask_from_lengths(frame_lengths.to(scores.device))
+    else:
+        mask = model_module.mask_from_lengths(word_lengths.to(scores.device))
     return _MaskedLoss.apply(scores, targets, mask, 0 if loss_fn == 'bce' else 1)
 
 

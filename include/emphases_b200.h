@@ -288,6 +288,17 @@ int emph_output_head_backward(
 int emph_masked_loss(
     const float* logits, const float* targets, const uint8_t* valid,
     int32_t total_rows, int32_t mode, float* loss, float* dlogits, void* stream);
+/*
+ * Word -> frame interpolation (emphases/core.py:472-544 `upsample`) on the
+ * reference's layouts: xs (B, C, Wmax) fp32, bounds (B, 2, Wmax) int64,
+ * lengths int64 -> out (B, C, Tmax), zero past frame_lengths[b].  linear != 0:
+ * UPSAMPLE_METHOD 'linear' (interpolates channel 0 for every channel, as the
+ * reference does), else 'nearest'.
+ */
+int emph_upsample_words(
+    const float* xs, const int64_t* bounds, const int64_t* word_lengths,
+    const int64_t* frame_lengths, int32_t batch, int32_t channels, int32_t wmax,
+    int32_t tmax, int32_t linear, float* out, void* stream);
 
 /*
  * Polyphase windowed-sinc resampling (emphases/core.py:613-619 `resample`, which

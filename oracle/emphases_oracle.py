@@ -284,6 +284,46 @@ def segment(xs, word_bounds_, word_lengths):
     return result, result_bounds, result_lengths
 
 
+def upsample(xs, word_bounds_, word_lengths, frame_lengths, method='linear'):
+    """emphases.upsample, core.py:472-544 (word -> frame resolution)"""
+    result = torch.zeros(
+        (xs.shape[0], xs.shape[1], int(frame_lengths.max())), dtype=xs.dtype)
+    for i in range(xs.shape[0]):
+        word_length, frame_length = int(word_lengths[i]), int(frame_lengths[i])
+        x = xs[i][..., :word_length]
+        word_bound = word_bounds_[i][..., :word_length]
+        word_times = (
+            word_bound[0] + (word_bound[1] - word_bound[0]) / 2.)[None]
+        frame_times = .5 + torch.arange(frame_length)[None]
+        if x.shape[1] == 1:                                      # :497-498
+            result[i, :, :frame_length] = x[0]
+        elif method == 'linear':                                 # :501-523
+            slope = (
+                (x[:, 1:] - x[:, :-1]) /
+                (word_times[:, 1:] - word_times[:, :-1]))
+            intercept = x[:, :-1] - slope.mul(word_times[:, :-1])
+            indices = torch.sum(
+                torch.ge(frame_times[:, :, None], word_times[:, None, :]),
+                -1) - 1
+            indices = torch.clamp(indices, 0, slope.shape[-1] - 1)
+            # line_idx is all zeros in the reference (linspace(0, 1, 1)): the
+            # slope/intercept of channel 0 are used for every channel
+            line_idx = torch.zeros_like(indices)
+            result[i, :, :frame_length] = (
+                slope[line_idx, indices].mul(frame_times) +
+                intercept[line_idx, indices])
+        elif method == 'nearest':                                # :526-536
+            indices = torch.sum(
+                torch.ge(frame_times[:, :, None], word_times[:, None, :]),
+                -1) - 1
+            indices = torch.clamp(indices, 0, word_times.shape[-1] - 1)
+            result[i, :, :frame_length] = torch.index_select(x, 1, indices[0])
+        else:
+            raise ValueError(
+                f'Interpolation method {method} is not defined')
+    return result
+
+
 def mask_from_lengths(lengths):
     """model/core.py:146-149"""
     x = torch.arange(int(lengths.max()), dtype=lengths.dtype)
@@ -492,9 +532,20 @@ def postprocess(logits, loss='bce'):
     return logits
 
 
-def loss(scores, targets, word_lengths, loss_fn='bce'):
-    """emphases.loss word-resolution branch, train/core.py:340-353"""
-    mask = mask_from_lengths(word_lengths)
+def loss(
+    scores, targets, word_lengths, loss_fn='bce', frame_lengths=None,
+    word_bounds_=None, upsample_method=None):
+    """emphases.loss, train/core.py:315-353.  With `upsample_method` set it is
+    the training branch of the 'inference' location: targets are upsampled to
+    frame resolution (and clamped for 'linear') and the mask covers frames."""
+    if upsample_method is not None:
+        targets = upsample(
+            targets, word_bounds_, word_lengths, frame_lengths, upsample_method)
+        if upsample_method == 'linear':
+            targets = torch.clamp(targets, min=0., max=1.)
+        mask = mask_from_lengths(frame_lengths)
+    else:
+        mask = mask_from_lengths(word_lengths)
     if loss_fn == 'bce':
         return torch.nn.functional.binary_cross_entropy_with_logits(
             scores[mask], targets[mask])

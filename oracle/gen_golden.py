@@ -287,6 +287,41 @@ def gen_loss():
     print('loss', out['bce'], out['mse'])
 
 
+def gen_upsample():
+    """emphases.upsample and the frame-resolution loss (inference location)"""
+    out = {}
+    generator = torch.Generator().manual_seed(13)
+    xs = torch.rand(3, 1, 9, generator=generator)
+    bounds = torch.tensor([
+        [[0, 7, 8, 20, 33, 40, 41, 60, 77], [7, 8, 20, 33, 40, 41, 60, 77, 90]],
+        [[2, 25, 30, 31, 0, 0, 0, 0, 0], [25, 30, 31, 48, 0, 0, 0, 0, 0]],
+        [[0, 0, 0, 0, 0, 0, 0, 0, 0], [55, 0, 0, 0, 0, 0, 0, 0, 0]]],
+        dtype=torch.long)
+    word_lengths = torch.tensor([9, 4, 1])
+    frame_lengths = torch.tensor([90, 50, 55])
+    wide = torch.rand(3, 4, 9, generator=generator)
+    scores = torch.randn(3, 1, 90, generator=generator)
+    for name, value in (
+        ('xs', xs), ('wide', wide), ('bounds', bounds), ('scores', scores),
+        ('word_lengths', word_lengths), ('frame_lengths', frame_lengths)
+    ):
+        out[name] = value.numpy()
+    for method in ('linear', 'nearest'):
+        overrides = {
+            'UPSAMPLE_METHOD': method, 'DOWNSAMPLE_LOCATION': 'inference'}
+        with ref_stubs.reference(overrides) as emphases:
+            out[f'{method}.xs'] = emphases.upsample(
+                xs, bounds, word_lengths, frame_lengths).numpy()
+            out[f'{method}.wide'] = emphases.upsample(
+                wide, bounds, word_lengths, frame_lengths).numpy()
+            for loss_fn in ('bce', 'mse'):
+                out[f'{method}.loss.{loss_fn}'] = emphases.loss(
+                    scores, xs, frame_lengths, bounds, word_lengths,
+                    training=True, loss_fn=loss_fn).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, 'upsample.npz'), **out)
+    print('upsample', {k: v.shape for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)
@@ -295,6 +330,7 @@ def main():
     gen_pool()
     gen_transformer()
     gen_loss()
+    gen_upsample()
 
 
 if __name__ == '__main__':

@@ -193,3 +193,23 @@ def test_loss(golden, loss_fn):
         torch.from_numpy(data['scores']), torch.from_numpy(data['targets']),
         torch.from_numpy(data['word_lengths']), loss_fn)
     np.testing.assert_allclose(value.numpy(), data[loss_fn], rtol=1e-6)
+
+
+@pytest.mark.parametrize('method', ['linear', 'nearest'])
+def test_upsample_and_frame_loss(golden, method):
+    data = golden('upsample')
+    bounds = torch.from_numpy(data['bounds'])
+    word_lengths = torch.from_numpy(data['word_lengths'])
+    frame_lengths = torch.from_numpy(data['frame_lengths'])
+    for name in ('xs', 'wide'):
+        result = oracle.upsample(
+            torch.from_numpy(data[name]), bounds, word_lengths, frame_lengths,
+            method)
+        np.testing.assert_allclose(
+            result.numpy(), data[f'{method}.{name}'], rtol=1e-6, atol=1e-6)
+    for loss_fn in ('bce', 'mse'):
+        value = oracle.loss(
+            torch.from_numpy(data['scores']), torch.from_numpy(data['xs']),
+            word_lengths, loss_fn, frame_lengths, bounds, method)
+        np.testing.assert_allclose(
+            value.numpy(), data[f'{method}.loss.{loss_fn}'], rtol=1e-6)

@@ -85,3 +85,62 @@ def test_train_step_reduces_loss(emphases, golden):
     losses = [emphases.training.train_step(model, optimizer, batch).item()
               for _ in range(8)]
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize('method', ['linear', 'nearest'])
+def test_upsample_and_frame_loss_golden(emphases, golden, method):
+    """emphases.upsample and the frame-resolution loss vs the reference"""
+    data = golden('upsample')
+    emphases.configure(UPSAMPLE_METHOD=method, DOWNSAMPLE_LOCATION='inference')
+    bounds = torch.from_numpy(data['bounds'])
+    word_lengths = torch.from_numpy(data['word_lengths'])
+    frame_lengths = torch.from_numpy(data['frame_lengths'])
+    for name in ('xs', 'wide'):
+        result = emphases.upsample(
+            torch.from_numpy(data[name]).cuda(), bounds, word_lengths, frame_lengths)
+        np.testing.assert_allclose(
+            result.cpu().numpy(), data[f'{method}.{name}'], rtol=1e-6, atol=1e-6)
+    for loss_fn in ('bce', 'mse'):
+        value = emphases.loss(
+            torch.from_numpy(data['scores']).cuda(), torch.from_numpy(data['xs']).cuda(),
+            frame_lengths, bounds, word_lengths, training=True, loss_fn=loss_fn)
+        np.testing.assert_allclose(
+            value.item(), float(data[f'{method}.loss.{loss_fn}']), rtol=2e-6)
+
+
+@pytest.mark.parametrize('location', ['loss', 'inference'])
+def test_gradients_other_locations(emphases, golden, location):
+    """Training step at the 'loss' (pool -> head) and 'inference' (frame-level
+    head + upsampled targets) locations vs torch autograd through the oracle"""
+    emphases.configure(DOWNSAMPLE_LOCATION=location)
+    data = golden('sweep')
+    state = state_from_golden(data)
+    model = emphases.Model()
+    own = model.state_dict()
+    model.load_state_dict({k: v for k, v in state.items() if k in own})
+    model = model.cuda().train()
+    features, frame_lengths, bounds, word_lengths, targets = padded_batch(2)
+    scores = model(features.cuda(), frame_lengths, bounds, word_lengths)
+    value = emphases.loss(
+        scores, targets.cuda(), frame_lengths, bounds, word_lengths, training=True)
+    value.backward()
+    reference = {
+        k: v.clone().requires_grad_(True) for k, v in state.items() if k in own}
+    config = {'DOWNSAMPLE_LOCATION': location}
+    expected_scores = oracle.model_forward(
+        reference, features, frame_lengths, bounds, word_lengths, config,
+        training=True)
+    if location == 'inference':
+        expected = oracle.loss(
+            expected_scores, targets, word_lengths, 'bce', frame_lengths, bounds,
+            'linear')
+    else:
+        expected = oracle.loss(expected_scores, targets, word_lengths, 'bce')
+    expected.backward()
+    assert scores.shape == expected_scores.shape
+    assert abs(value.item() - expected.item()) < 1e-5
+    for name, parameter in model.named_parameters():
+        want = reference[name].grad
+        got = parameter.grad.cpu()
+        scale = want.abs().max().item() + 1e-12
+        assert (got - want).abs().max().item() < 2e-4 * scale + 1e-7, name
