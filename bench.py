@@ -114,6 +114,12 @@ def random_state(seed=0):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML
+    polled every ~5 ms from a thread (nvidia-smi -lms as a fallback)"""
+
+    REASONS = {
+        'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
+        'hw_thermal_slowdown': 0x40}
     QUERY = (
         'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
         'clocks_event_reasons.hw_thermal_slowdown,'
@@ -121,50 +127,87 @@ class ClockSampler:
         'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.samples = []
-        self.process = None
         self.index = index
+        self.sm, self.sm_max, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.process = None
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            physical = self.index
+            if visible:
+                entries = [v.strip() for v in visible.split(',') if v.strip()]
+                if self.index < len(entries) and entries[self.index].isdigit():
+                    physical = int(entries[self.index])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
+            maximum = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(
+                            handle, pynvml.NVML_CLOCK_SM)))
+                        self.sm_max.append(float(maximum))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                        for name, bit in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except pynvml.NVMLError:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = 'nvml'
+            return
+        except Exception:
+            self.source = None
         try:
             self.process = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.QUERY}', f'--id={self.index}',
                  '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.lines = []
+            self.thread = threading.Thread(
+                target=lambda: self.lines.extend(self.process.stdout), daemon=True)
             self.thread.start()
+            self.source = 'nvidia-smi'
         except OSError:
             self.process = None
 
-    def _read(self):
-        for line in self.process.stdout:
-            self.samples.append(line.strip())
-
     def stop(self):
-        if self.process is None:
+        self.stop_flag.set()
+        if self.process is not None:
+            self.process.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if self.source == 'nvidia-smi':
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                     'sw_power_cap']
+            for line in self.lines:
+                fields = [f.strip() for f in line.split(',')]
+                if len(fields) < 7:
+                    continue
+                try:
+                    self.sm.append(float(fields[0]))
+                    self.sm_max.append(float(fields[1]))
+                except ValueError:
+                    continue
+                for name, value in zip(names, fields[3:7]):
+                    if value.lower().startswith('active'):
+                        self.reasons.add(name)
+        if not self.sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        self.process.terminate()
-        self.thread.join(timeout=2)
-        sm, sm_max, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                 'sw_power_cap']
-        for line in self.samples:
-            fields = [f.strip() for f in line.split(',')]
-            if len(fields) < 7:
-                continue
-            try:
-                sm.append(float(fields[0]))
-                sm_max.append(float(fields[1]))
-            except ValueError:
-                continue
-            for name, value in zip(names, fields[3:7]):
-                if value.lower().startswith('active'):
-                    reasons.add(name)
         return {
-            'sm_mhz': statistics.median(sm) if sm else None,
-            'sm_max_mhz': max(sm_max) if sm_max else None,
-            'samples': len(sm),
-            'reasons': sorted(reasons)}
+            'sm_mhz': statistics.median(self.sm),
+            'sm_max_mhz': max(self.sm_max),
+            'samples': len(self.sm),
+            'source': self.source,
+            'reasons': sorted(self.reasons)}
 
 
 ###############################################################################

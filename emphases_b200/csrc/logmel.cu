@@ -10,18 +10,19 @@
 //   basis @ spectrogram, log(clamp(., 1e-5)), optional (x+10)/10
 //                               mels.py:94-109, 57-58
 //
-// A persistent CTA of 16 warps works on tiles of 32 consecutive packed rows:
+// Persistent CTAs of 8 warps, two per SM (so one CTA's mel / store phases overlap
+// the other's FFT phase), each working on tiles of 16 consecutive packed rows:
 //   phase 1  one warp per frame: 1024-point real FFT as a 512-point complex
 //            FFT of the even/odd packed signal -- 3 radix-8 Stockham passes
 //            (2 butterflies per lane per pass, twiddles held in registers,
 //            two exchanges through bank-padded shared memory), then the
 //            real-FFT unpacking done in registers with warp shuffles and the
-//            magnitudes written to a [32 frames][513 bins] tile;
-//   phase 2  mel projection with lane = frame: the sparse basis entry is a
-//            warp-wide broadcast and the 32 magnitudes of one bin sit in 32
-//            different banks (row stride 513), so every nnz costs one
-//            conflict-free wavefront for 32 frames;
-//   phase 3  log / clamp and a fully coalesced store of the 32 x n_mels tile.
+//            magnitudes written to a [16 frames][513 bins] tile;
+//   phase 2  mel projection with lane = frame (a half-warp per mel row): the
+//            sparse basis entry is a broadcast and the 16 magnitudes of one
+//            bin sit in different banks (row stride 513), so every nnz costs
+//            one conflict-free wavefront per pair of mel rows;
+//   phase 3  log / clamp and a fully coalesced store of the 16 x n_mels tile.
 // All fp32.  Bound: FP32 issue + shared-memory wavefronts (about 25 kFLOP per
 // frame against 960 B of HBM traffic), see DESIGN.md.
 #include "common.cuh"
@@ -33,8 +34,9 @@ constexpr int kHop = 160;
 constexpr int kPad = (kFft - kHop) / 2;   // 432, both the zero and reflect pad
 constexpr int kBins = kFft / 2 + 1;       // 513
 constexpr int kHalf = kFft / 2;           // 512-point complex FFT
-constexpr int kWarps = 16;
-constexpr int kTile = 32;                 // frames per CTA tile
+constexpr int kWarps = 8;                  // two CTAs per SM: their phases interleave
+constexpr int kTile = 16;                 // frames per CTA tile
+constexpr int kVirtualWarps = 16;         // mel phase: half-warps, lanes = 16 frames
 constexpr int kMaxNnz = 1536;             // mel CSR entries held in smem
 constexpr int kMaxMels = 128;
 
@@ -123,7 +125,7 @@ __device__ __forceinline__ float chunk_sample(
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32, 1)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 logmel_kernel(
     const T* __restrict__ audio,
     const int64_t* __restrict__ audio_off, const int32_t* __restrict__ audio_len,
@@ -318,16 +320,18 @@ logmel_kernel(
         }
         __syncthreads();
 
-        // ================= phase 2: sparse mel projection, lane = frame =================
+        // ============ phase 2: sparse mel projection, half-warp lane = frame ============
         {
-            const int row = row0 + lane;
+            const int f = lane & (kTile - 1);          // frame of this lane
+            const int vw = warp * 2 + (lane >> 4);     // virtual warp = half-warp
+            const int row = row0 + f;
             const bool live = row < total_rows && __ldg(row_seq + row) >= 0;
-            const float* mag = sm.mag[lane];
-            // rows are dealt to warps in a snake so long (high-frequency) and
-            // short (low-frequency) filters balance across warps
+            const float* mag = sm.mag[f];
+            // rows are dealt to half-warps in a snake so long (high-frequency)
+            // and short (low-frequency) filters balance
             const char* const magb = reinterpret_cast<const char*>(mag);
-            for (int j = 0; j * kWarps < n_mels; ++j) {
-                const int m = j * kWarps + ((j & 1) ? kWarps - 1 - warp : warp);
+            for (int j = 0; j * kVirtualWarps < n_mels; ++j) {
+                const int m = j * kVirtualWarps + ((j & 1) ? kVirtualWarps - 1 - vw : vw);
                 if (m >= n_mels) continue;
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
                 int e = sm.mel_ptr[m];
@@ -347,7 +351,7 @@ logmel_kernel(
                 const float acc = (acc0 + acc1) + (acc2 + acc3);
                 float v = logf(fmaxf(acc, 1e-5f));
                 if (normalize) v = (v + 10.f) / 10.f;
-                sm.outs[lane][m] = live ? v : 0.f;
+                sm.outs[f][m] = live ? v : 0.f;
             }
         }
         __syncthreads();
@@ -383,7 +387,7 @@ int launch_logmel(
         "logmel smem attribute");
     if (s != EMPH_OK) return s;
     const int n_tiles = (total_rows + kTile - 1) / kTile;
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    const int grid = n_tiles < 2 * sm_count() ? n_tiles : 2 * sm_count();
     logmel_kernel<T><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
         audio, audio_off, audio_len, chunk_start, chunk_len, row_start,
         row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out);
