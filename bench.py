@@ -50,7 +50,8 @@ def parse_args():
     parser.add_argument('--steps', type=int, default=20)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    parser.add_argument('--precision', default=None, choices=['fp32', 'bf16'])
+    parser.add_argument(
+        '--precision', default=None, choices=['fp32', 'bf16', 'bf16x3'])
     parser.add_argument('--utterances', type=int, default=3000)
     parser.add_argument('--cpu-seconds', type=float, default=15.)
     parser.add_argument('--file-utterances', type=int, default=500)
@@ -518,7 +519,7 @@ def main():
     logmel_gbs = frames * LOGMEL_BYTES_PER_FRAME / (kernel_ms['logmel'] * 1e-3) / 1e9
     pool_gbs = (frames * POOL_BYTES_PER_FRAME + n_words * 328) / (
         kernel_ms['pool'] * 1e-3) / 1e9
-    conv_bound = 'tensor' if precision == 'bf16' else 'tensor (fp32 FFMA mode)'
+    conv_bound = 'tensor (fp32 FFMA mode)' if precision == 'fp32' else 'tensor'
     candidates = {
         'logmel': {
             'kernel': 'logmel_kernel (framing + 1024-pt rFFT + mel + log)',
@@ -580,7 +581,10 @@ def main():
         'higher_is_better': True,
         'scaling': 'weak',
         'vs_baseline': None,
-        'dtype': 'f32' if precision == 'fp32' else 'bf16 (tcgen05, f32 accumulate)',
+        'dtype': {
+            'fp32': 'f32',
+            'bf16': 'bf16 (tcgen05, f32 accumulate)',
+            'bf16x3': 'bf16x3 (tcgen05, hi/lo split operands, f32 accumulate)'}[precision],
         'data': 'synthetic',
         'config': workload_config(args),
         'clocks': clock_summary,

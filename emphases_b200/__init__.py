@@ -79,6 +79,8 @@ def precision_code():
         return _lib.PREC_FP32
     if PRECISION == 'bf16':
         return _lib.PREC_BF16_TC
+    if PRECISION == 'bf16x3':
+        return _lib.PREC_BF16X3_TC
     raise ValueError(f'Precision {PRECISION} is not defined')
 
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get(
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_LEAKY_RELU, ACT_SILU = 0, 1, 2, 3, 4
 POOL = {'average': 0, 'max': 1, 'sum': 2, 'center': 3}
 HEAD_LOGITS, HEAD_SIGMOID, HEAD_CLAMP = 0, 1, 2
-PREC_FP32, PREC_BF16_TC = 0, 1
+PREC_FP32, PREC_BF16_TC, PREC_BF16X3_TC = 0, 1, 2
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int32
@@ -29,7 +29,7 @@ SIGNATURES = {
     'emph_logmel_i16': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
     'emph_conv_stack': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'emph_pack_conv_weights': [_P, _I, _I, _I, _P, _P],
-    'emph_pack_conv_weights_tc': [_P, _P, _I, _I, _I, _P, _P],
+    'emph_pack_conv_weights_tc': [_P, _P, _I, _I, _I, _I, _P, _P],
     'emph_pool_words': [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     'emph_output_head': [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _P],
     'emph_pack_rows': [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
@@ -83,7 +83,7 @@ def load():
     lib.emph_corpus_write_textgrids.restype = ctypes.c_int
     lib.emph_corpus_close.argtypes = [_P]
     lib.emph_corpus_close.restype = None
-    lib.emph_conv_weights_tc_bytes.argtypes = [_I, _I, _I]
+    lib.emph_conv_weights_tc_bytes.argtypes = [_I, _I, _I, _I]
     lib.emph_conv_weights_tc_bytes.restype = ctypes.c_int
     _lib = lib
     return lib

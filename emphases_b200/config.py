@@ -45,7 +45,8 @@ MAX_TRAINING_FRAMES = 75000
 
 # emphases_b200 extensions (not in the reference)
 # 'fp32': CUDA-core FFMA conv stack, scores within 1e-5 of the reference's fp32
-# forward.  'bf16': tcgen05 tensor-core conv stack, within 2e-3.
+# forward.  'bf16': tcgen05 tensor-core conv stack, within 2e-3.  'bf16x3':
+# tcgen05 with hi/lo-split operands (3 MMAs per product), fp32-grade (1e-5).
 PRECISION = 'fp32'
 # Upper bound on packed frame rows per launch (~1 KB of HBM per row).  A corpus
 # larger than this runs as several launches on two alternating streams so the

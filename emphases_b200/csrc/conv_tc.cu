@@ -41,7 +41,6 @@ constexpr int KS = 3;                 // taps
 constexpr int KG = C / 8;             // k-groups of 8 channels
 constexpr int M = 128;                // rows per tile = UMMA M
 constexpr int RB = M + 2;             // buffer rows (one pad row each side)
-constexpr int kSlots = 4;             // tiles in flight per CTA
 constexpr int kStages = 3;            // weight ring
 constexpr int kMaxLayers = 16;
 constexpr int ACT_BYTES = KG * RB * 16;           // 20,800 per slot
@@ -49,16 +48,30 @@ constexpr int W_TAP_BYTES = KG * C * 16;          // 12,800
 constexpr int W_BIAS_BYTES = 2 * C * 16;          // bias chunk: 2 k-groups, 2,560
 constexpr int W_CONV_BYTES = KS * W_TAP_BYTES;    // 38,400
 constexpr int W_LAYER_BYTES = W_CONV_BYTES + W_BIAS_BYTES;   // 40,960
-constexpr int kEpilogueThreads = 128 * kSlots;
-constexpr int kThreads = kEpilogueThreads + 64;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 128;       // TMEM columns between slot accumulators
 
+// SPLIT = false: plain bf16 operands (2e-3 mode), 4 tile slots.
+// SPLIT = true : "bf16x3" -- activations and weights are each split into a
+//   bf16 hi and lo part and every product is formed as hi*hi + lo*hi + hi*lo
+//   (three MMAs into the same fp32 accumulator, the lo*lo term ~2^-16 is
+//   dropped): fp32-grade results from the bf16 tensor pipe.  Activations then
+//   need two operand buffers per slot (2 slots fit) and a layer's weights arrive
+//   as two ring entries (W_hi + bias chunk, W_lo).
+template <bool SPLIT>
+struct Config {
+    static constexpr int kSlots = SPLIT ? 2 : 4;
+    static constexpr int kParts = SPLIT ? 2 : 1;          // hi (, lo)
+    static constexpr int kThreads = 128 * kSlots + 64;
+    static constexpr int kEntriesPerLayer = SPLIT ? 2 : 1;
+};
+
+template <bool SPLIT>
 struct __align__(128) Smem {
-    uint8_t act[kSlots][ACT_BYTES + 64];      // +64 keeps 128-B alignment of each slot
+    static constexpr int kSlots = Config<SPLIT>::kSlots;
+    uint8_t act[kSlots][Config<SPLIT>::kParts][ACT_BYTES + 64];   // +64 keeps 128-B alignment
     uint8_t w[kStages][W_LAYER_BYTES];
     uint8_t ones[2 * RB * 16 + 64];           // A operand of the bias MMA
-    float bias[kMaxLayers][C];
     uint64_t w_full[kStages];
     uint64_t w_empty[kStages];
     uint64_t act_ready[kSlots];
@@ -189,8 +202,32 @@ __device__ __forceinline__ bool elect_one() {
 constexpr uint32_t kInstrDesc =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 
+// value -> bf16 hi word and (SPLIT) bf16 lo word of the residual
+template <bool SPLIT>
+__device__ __forceinline__ void split_pack(float lo_v, float hi_v, uint32_t& hi_word, uint32_t& lo_word) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo_v, hi_v);
+    hi_word = *reinterpret_cast<const uint32_t*>(&h);
+    if constexpr (SPLIT) {
+        const float2 back = __bfloat1622float2(h);
+        lo_word = pack_bf16(lo_v - back.x, hi_v - back.y);
+    }
+}
+
+// Store 8 consecutive channels of one row into the slot's A-operand buffer(s)
+template <bool SPLIT>
+__device__ __forceinline__ void store_kgroup(uint8_t* act_hi, int kg, int buffer_row, const float (&v)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pack<SPLIT>(v[2 * j], v[2 * j + 1], h[j], l[j]);
+    *reinterpret_cast<uint4*>(act_hi + (kg * RB + buffer_row) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    if constexpr (SPLIT)
+        *reinterpret_cast<uint4*>(act_hi + (ACT_BYTES + 64) + (kg * RB + buffer_row) * 16) =
+            make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // Rare path: activations other than ReLU / identity.  Out of line so the hot
 // loop stays small in the instruction cache.
+template <bool SPLIT>
 __device__ __noinline__ void epilogue_generic(
     uint32_t taddr, uint8_t* act, int row, int a, bool valid, bool last, bool store,
     float* yrow) {
@@ -204,13 +241,10 @@ __device__ __noinline__ void epilogue_generic(
         for (int j = 0; j < 16; ++j)
             v[j] = valid ? apply_activation(__uint_as_float(raw[j]), a) : 0.f;
         if (!last) {
-            const int kg = c0 >> 3;
-            *reinterpret_cast<uint4*>(act + (kg * RB + row + 1) * 16) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            *reinterpret_cast<uint4*>(act + ((kg + 1) * RB + row + 1) * 16) =
-                make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            const float (&first)[8] = *reinterpret_cast<const float(*)[8]>(&v[0]);
+            const float (&second)[8] = *reinterpret_cast<const float(*)[8]>(&v[8]);
+            store_kgroup<SPLIT>(act, c0 >> 3, row + 1, first);
+            store_kgroup<SPLIT>(act, (c0 >> 3) + 1, row + 1, second);
         } else if (store) {
             float4* dst = reinterpret_cast<float4*>(yrow + c0);
             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -221,13 +255,18 @@ __device__ __noinline__ void epilogue_generic(
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool SPLIT>
+__global__ void __launch_bounds__(Config<SPLIT>::kThreads, 1)
 conv_stack_tc_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
-    const uint8_t* __restrict__ weights,   // per layer: [tap][kg][n][8] bf16 + bias chunk
+    const uint8_t* __restrict__ weights,   // ring entries: [tap][kg][n][8] bf16 + bias chunk
     Acts acts, int n_layers, int tile_rows, int n_tiles, float* __restrict__ y) {
+    constexpr int kSlots = Config<SPLIT>::kSlots;
+    constexpr int kParts = Config<SPLIT>::kParts;
+    constexpr int kThreads = Config<SPLIT>::kThreads;
+    constexpr int kEntries = Config<SPLIT>::kEntriesPerLayer;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    Smem<SPLIT>& sm = *reinterpret_cast<Smem<SPLIT>*>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int halo = n_layers * ((KS - 1) / 2);
@@ -235,9 +274,11 @@ conv_stack_tc_kernel(
 
     // ---- one-time setup ----
     // pad rows (buffer rows 0 and RB-1) of every k-group stay zero forever
-    for (int i = tid; i < kSlots * KG * 2 * 4; i += kThreads) {
-        int s = i / (KG * 8), rem = i % (KG * 8), kg = rem / 8, edge = (rem / 4) & 1, word = rem & 3;
-        reinterpret_cast<uint32_t*>(sm.act[s] + (kg * RB + (edge ? RB - 1 : 0)) * 16)[word] = 0u;
+    for (int i = tid; i < kSlots * kParts * KG * 2 * 4; i += kThreads) {
+        const int buffer = i / (KG * 8), rem = i % (KG * 8);
+        const int kg = rem / 8, edge = (rem / 4) & 1, word = rem & 3;
+        reinterpret_cast<uint32_t*>(
+            sm.act[buffer / kParts][buffer % kParts] + (kg * RB + (edge ? RB - 1 : 0)) * 16)[word] = 0u;
     }
     // bias chunk A operand: k-group 0 = {1, 1, 0, ...} for every row, k-group 1 = 0,
     // so D = 1 * bias_hi + 1 * bias_lo (bf16 split of the fp32 bias) before the taps
@@ -269,7 +310,7 @@ conv_stack_tc_kernel(
         const int quad = warp & 3;                  // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;           // tile-local row == TMEM lane
         const int gtid = tid & 127;                 // thread within the group
-        uint8_t* act = sm.act[slot];
+        uint8_t* act = sm.act[slot][0];             // hi part; lo part follows it
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * kAccStride;
         uint32_t done_parity = 0;
 
@@ -281,7 +322,7 @@ conv_stack_tc_kernel(
             const bool in_range = g >= 0 && g < total_rows;
             const bool valid = in_range && __ldg(row_seq + g) >= 0;
 
-            // fp32 rows -> bf16 A operand: coalesced float4 reads, 10 in flight
+            // fp32 rows -> bf16 A operand(s): coalesced float4 reads, 10 in flight
             // per thread (M * C / 4 = 2560 float4 = 20 per thread)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -298,9 +339,13 @@ conv_stack_tc_kernel(
                 for (int it = 0; it < 10; ++it) {
                     const int i = gtid + 128 * (half * 10 + it);
                     const int r = i / (C / 4), c4 = i % (C / 4);
-                    *reinterpret_cast<uint2*>(
-                        act + ((c4 >> 1) * RB + r + 1) * 16 + (c4 & 1) * 8) =
-                        make_uint2(pack_bf16(v[it].x, v[it].y), pack_bf16(v[it].z, v[it].w));
+                    uint32_t h0, h1, l0, l1;
+                    split_pack<SPLIT>(v[it].x, v[it].y, h0, l0);
+                    split_pack<SPLIT>(v[it].z, v[it].w, h1, l1);
+                    uint8_t* dst = act + ((c4 >> 1) * RB + r + 1) * 16 + (c4 & 1) * 8;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                    if constexpr (SPLIT)
+                        *reinterpret_cast<uint2*>(dst + ACT_BYTES + 64) = make_uint2(l0, l1);
                 }
             }
             fence_proxy_async();        // generic-proxy writes -> visible to the tensor core
@@ -341,19 +386,33 @@ conv_stack_tc_kernel(
                         tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
                     tmem_ld_wait();
                     if (!last) {
-                        uint8_t* dst = act + (row + 1) * 16;
+                        if constexpr (!SPLIT) {
+                            uint8_t* dst = act + (row + 1) * 16;
 #pragma unroll
-                        for (int kg = 0; kg < KG; ++kg) {
-                            uint32_t p[4];
+                            for (int kg = 0; kg < KG; ++kg) {
+                                uint32_t p[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float lo = __uint_as_float(raw[8 * kg + 2 * j]);
-                                const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]);
-                                p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
+                                for (int j = 0; j < 4; ++j) {
+                                    const float lo = __uint_as_float(raw[8 * kg + 2 * j]);
+                                    const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]);
+                                    p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
+                                }
+                                if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
+                                *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
+                                    make_uint4(p[0], p[1], p[2], p[3]);
                             }
-                            if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
-                            *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
-                                make_uint4(p[0], p[1], p[2], p[3]);
+                        } else {
+#pragma unroll
+                            for (int kg = 0; kg < KG; ++kg) {
+                                float v[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    v[j] = __uint_as_float(raw[8 * kg + j]);
+                                    if (relu) v[j] = fmaxf(v[j], 0.f);
+                                    if (zero) v[j] = 0.f;
+                                }
+                                store_kgroup<true>(act, kg, row + 1, v);
+                            }
                         }
                     } else if (in_range && row >= halo && row < M - halo) {
                         float4* dst = reinterpret_cast<float4*>(y + (size_t)g * C);
@@ -370,7 +429,7 @@ conv_stack_tc_kernel(
                         }
                     }
                 } else {
-                    epilogue_generic(
+                    epilogue_generic<SPLIT>(
                         taddr, act, row, a, valid, last,
                         last && in_range && row >= halo && row < M - halo,
                         y + (size_t)(in_range ? g : 0) * C);
@@ -395,42 +454,58 @@ conv_stack_tc_kernel(
         const uint64_t d_ones = make_desc(smem_u32(sm.ones), RB * 16, 128);
         uint64_t d_act[kSlots];
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) d_act[s] = make_desc(smem_u32(sm.act[s]), RB * 16, 128);
+        for (int s = 0; s < kSlots; ++s) d_act[s] = make_desc(smem_u32(sm.act[s][0]), RB * 16, 128);
+        constexpr uint64_t kLoPart = (ACT_BYTES + 64) >> 4;      // hi -> lo operand buffer
         for (int round = 0; round < rounds; ++round) {
             const int tile0 = (round * gridDim.x + blockIdx.x) * kSlots;
             if (tile0 >= n_tiles) break;
             const int active = min(kSlots, n_tiles - tile0);
             for (int layer = 0; layer < n_layers; ++layer) {
-                mbar_wait(&sm.w_full[stage], full_parity);
-                const uint64_t d_w = make_desc(smem_u32(sm.w[stage]), C * 16, 128);
 #pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    if (s < active) {
-                        mbar_wait(&sm.act_ready[s], (ready_parity >> s) & 1);
-                        ready_parity ^= 1u << s;
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t d = tmem_base + s * kAccStride;
-                            umma_bf16(d, d_ones, d_w + (W_CONV_BYTES >> 4), kInstrDesc, 0);   // D = bias
+                for (int entry = 0; entry < kEntries; ++entry) {
+                    // entry 0: W (or W_hi) + bias chunk; entry 1 (SPLIT): W_lo
+                    mbar_wait(&sm.w_full[stage], full_parity);
+                    const uint64_t d_w = make_desc(smem_u32(sm.w[stage]), C * 16, 128);
 #pragma unroll
-                            for (int tap = 0; tap < KS; ++tap) {
-#pragma unroll
-                                for (int kk = 0; kk < C / 16; ++kk) {
-                                    umma_bf16(
-                                        d,
-                                        d_act[s] + (uint64_t)(((2 * kk) * RB * 16 + tap * 16) >> 4),
-                                        d_w + (uint64_t)((tap * W_TAP_BYTES + (2 * kk) * C * 16) >> 4),
-                                        kInstrDesc, 1);
-                                }
+                    for (int s = 0; s < kSlots; ++s) {
+                        if (s < active) {
+                            if (entry == 0) {
+                                mbar_wait(&sm.act_ready[s], (ready_parity >> s) & 1);
+                                ready_parity ^= 1u << s;
+                                tc_fence_after();
                             }
-                            umma_commit(&sm.mma_done[s]);
+                            if (elect_one()) {
+                                const uint32_t d = tmem_base + s * kAccStride;
+                                if (entry == 0)
+                                    umma_bf16(d, d_ones, d_w + (W_CONV_BYTES >> 4), kInstrDesc, 0);
+                                // entry 0: hi (and lo) activations x W(_hi); entry 1: hi x W_lo
+                                const int parts = entry == 0 ? kParts : 1;
+#pragma unroll
+                                for (int part = 0; part < kParts; ++part) {
+                                    if (part < parts) {
+#pragma unroll
+                                        for (int tap = 0; tap < KS; ++tap) {
+#pragma unroll
+                                            for (int kk = 0; kk < C / 16; ++kk) {
+                                                umma_bf16(
+                                                    d,
+                                                    d_act[s] + part * kLoPart +
+                                                        (uint64_t)(((2 * kk) * RB * 16 + tap * 16) >> 4),
+                                                    d_w + (uint64_t)((tap * W_TAP_BYTES + (2 * kk) * C * 16) >> 4),
+                                                    kInstrDesc, 1);
+                                            }
+                                        }
+                                    }
+                                }
+                                if (entry == kEntries - 1) umma_commit(&sm.mma_done[s]);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
+                    if (elect_one()) umma_commit(&sm.w_empty[stage]);   // ring entry consumed
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; full_parity ^= 1; }
                 }
-                if (elect_one()) umma_commit(&sm.w_empty[stage]);   // layer's weights consumed
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; full_parity ^= 1; }
             }
         }
     } else {
@@ -441,10 +516,10 @@ conv_stack_tc_kernel(
             for (int round = 0; round < rounds; ++round) {
                 const int tile0 = (round * gridDim.x + blockIdx.x) * kSlots;
                 if (tile0 >= n_tiles) break;
-                for (int layer = 0; layer < n_layers; ++layer) {
+                for (int entry = 0; entry < n_layers * kEntries; ++entry) {
                     mbar_wait(&sm.w_empty[stage], empty_parity);
                     mbar_arrive_expect_tx(&sm.w_full[stage], W_LAYER_BYTES);
-                    bulk_load(sm.w[stage], weights + (size_t)layer * W_LAYER_BYTES,
+                    bulk_load(sm.w[stage], weights + (size_t)entry * W_LAYER_BYTES,
                               W_LAYER_BYTES, &sm.w_full[stage]);
                     if (++stage == kStages) { stage = 0; empty_parity ^= 1; }
                 }
@@ -461,17 +536,22 @@ conv_stack_tc_kernel(
     }
 }
 
-// fp32 weights [L][tap][in][out] + bias [L][out] -> per layer
-//   bf16 [tap][kg][out][8 in]  followed by the bias chunk bf16 [2][out][8]:
-//   k-group 0 holds (bias_hi, bias_lo, 0, ...), k-group 1 is zero
+// fp32 weights [L][tap][in][out] + bias [L][out] -> ring entries of
+// W_LAYER_BYTES: bf16 [tap][kg][out][8 in] followed by the bias chunk bf16
+// [2][out][8] (k-group 0 holds (bias_hi, bias_lo, 0, ...), k-group 1 is zero).
+// split = 1: two entries per layer -- (W_hi, bias chunk) and (W_lo, zeros) with
+// W_hi = bf16(W), W_lo = bf16(W - W_hi).
 __global__ void pack_weights_tc_kernel(
-    const float* __restrict__ w, const float* __restrict__ bias, int n_layers,
+    const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int split,
     __nv_bfloat16* __restrict__ out) {
-    const int per_layer = W_LAYER_BYTES / 2;
+    const int per_entry = W_LAYER_BYTES / 2;
     const int conv = W_CONV_BYTES / 2;
-    const int total = n_layers * per_layer;
+    const int entries = split ? 2 : 1;
+    const int total = n_layers * entries * per_entry;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int layer = i / per_layer, local = i % per_layer;
+        const int entry = i / per_entry, local = i % per_entry;
+        const int layer = entry / entries, part = entry % entries;
+        float v = 0.f;
         if (local < conv) {
             const int e = local & 7;
             int rest = local >> 3;
@@ -479,18 +559,19 @@ __global__ void pack_weights_tc_kernel(
             const int kg = rest % KG;
             const int tap = rest / KG;
             const int ci = kg * 8 + e;
-            out[i] = __float2bfloat16_rn(w[((size_t)(layer * KS + tap) * C + ci) * C + n]);
-        } else {
+            const float value = w[((size_t)(layer * KS + tap) * C + ci) * C + n];
+            const float hi = __bfloat162float(__float2bfloat16_rn(value));
+            v = part == 0 ? value : value - hi;      // part 0 rounds to hi below
+        } else if (part == 0) {
             const int rem = local - conv;
             const int e = rem & 7, n = (rem >> 3) % C, kg = (rem >> 3) / C;
-            float v = 0.f;
             if (kg == 0 && e < 2) {
                 const float b = bias[layer * C + n];
                 const float hi = __bfloat162float(__float2bfloat16_rn(b));
                 v = e == 0 ? hi : b - hi;
             }
-            out[i] = __float2bfloat16_rn(v);
         }
+        out[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -518,11 +599,39 @@ static bool use_wide() {
     return cached == 1;
 }
 
+template <bool SPLIT>
+static int launch_tc(
+    const float* x, const int32_t* row_seq, int32_t total_rows, const float* weights,
+    const int32_t* acts_host, int32_t n_layers, float* y, cudaStream_t stream) {
+    EMPH_REQUIRE(n_layers <= tc::kMaxLayers, "emph_conv_stack(tc): too many layers");
+    const int halo = n_layers * ((tc::KS - 1) / 2);
+    const int tile_rows = tc::M - 2 * halo;
+    EMPH_REQUIRE(tile_rows >= 32, "emph_conv_stack(tc): %d layers leave no tile", n_layers);
+    tc::Acts acts;
+    for (int i = 0; i < tc::kMaxLayers; ++i) acts.act[i] = i < n_layers ? acts_host[i] : 0;
+    constexpr int kSlots = tc::Config<SPLIT>::kSlots;
+    const size_t smem = sizeof(tc::Smem<SPLIT>) + 128;
+    int s = check_cuda(
+        cudaFuncSetAttribute(tc::conv_stack_tc_kernel<SPLIT>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        "conv_tc smem attribute");
+    if (s != EMPH_OK) return s;
+    const int n_tiles = (total_rows + tile_rows - 1) / tile_rows;
+    const int want = (n_tiles + kSlots - 1) / kSlots;
+    const int grid = want < sm_count() ? want : sm_count();
+    tc::conv_stack_tc_kernel<SPLIT><<<grid, tc::Config<SPLIT>::kThreads, smem, stream>>>(
+        x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), acts,
+        n_layers, tile_rows, n_tiles, y);
+    EMPH_CHECK_LAUNCH(SPLIT ? "emph_conv_stack(bf16x3 tc)" : "emph_conv_stack(bf16 tc)");
+    return EMPH_OK;
+}
+
 int conv_stack_bf16_tc(
     const float* x, const int32_t* row_seq, int32_t total_rows,
     const float* weights, const float* bias, const int32_t* acts_host,
     int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
     cudaStream_t stream) {
+    (void)bias;
     if (channels != tc::C || kernel_size != tc::KS) {
         set_error("emph_conv_stack(bf16 tc): channels=%d kernel_size=%d not compiled in",
                   channels, kernel_size);
@@ -530,49 +639,49 @@ int conv_stack_bf16_tc(
     }
     if (use_wide())
         return conv_stack_bf16_tc240(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
-    EMPH_REQUIRE(n_layers <= tc::kMaxLayers, "emph_conv_stack(bf16 tc): too many layers");
-    const int halo = n_layers * ((tc::KS - 1) / 2);
-    const int tile_rows = tc::M - 2 * halo;
-    EMPH_REQUIRE(tile_rows >= 32, "emph_conv_stack(bf16 tc): %d layers leave no tile", n_layers);
-    tc::Acts acts;
-    for (int i = 0; i < tc::kMaxLayers; ++i) acts.act[i] = i < n_layers ? acts_host[i] : 0;
-    const size_t smem = sizeof(tc::Smem) + 128;
-    int s = check_cuda(
-        cudaFuncSetAttribute(tc::conv_stack_tc_kernel,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-        "conv_tc smem attribute");
-    if (s != EMPH_OK) return s;
-    const int n_tiles = (total_rows + tile_rows - 1) / tile_rows;
-    const int want = (n_tiles + tc::kSlots - 1) / tc::kSlots;
-    const int grid = want < sm_count() ? want : sm_count();
-    tc::conv_stack_tc_kernel<<<grid, tc::kThreads, smem, stream>>>(
-        x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), acts,
-        n_layers, tile_rows, n_tiles, y);
-    EMPH_CHECK_LAUNCH("emph_conv_stack(bf16 tc)");
-    return EMPH_OK;
+    return launch_tc<false>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+}
+
+int conv_stack_bf16x3_tc(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host,
+    int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
+    cudaStream_t stream) {
+    if (channels != tc::C || kernel_size != tc::KS) {
+        set_error("emph_conv_stack(bf16x3 tc): channels=%d kernel_size=%d not compiled in",
+                  channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    return launch_tc<true>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
 }  // namespace emph
 
-extern "C" int emph_conv_weights_tc_bytes(int32_t n_layers, int32_t channels, int32_t kernel_size) {
+extern "C" int emph_conv_weights_tc_bytes(
+    int32_t n_layers, int32_t channels, int32_t kernel_size, int32_t precision) {
     if (channels != emph::tc::C || kernel_size != emph::tc::KS || n_layers <= 0) return 0;
+    if (precision == EMPH_PREC_BF16X3_TC) return 2 * n_layers * emph::tc::W_LAYER_BYTES;
+    if (precision != EMPH_PREC_BF16_TC) return 0;
     if (emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
     return n_layers * emph::tc::W_LAYER_BYTES;
 }
 
 extern "C" int emph_pack_conv_weights_tc(
     const float* weights, const float* bias, int32_t n_layers, int32_t channels,
-    int32_t kernel_size, void* packed, void* stream) {
+    int32_t kernel_size, int32_t precision, void* packed, void* stream) {
     if (channels != emph::tc::C || kernel_size != emph::tc::KS) {
         emph::set_error("emph_pack_conv_weights_tc: channels=%d kernel_size=%d not compiled in",
                         channels, kernel_size);
         return EMPH_ENOSYS;
     }
     EMPH_REQUIRE(n_layers > 0, "emph_pack_conv_weights_tc: no layers");
-    if (emph::use_wide())
+    EMPH_REQUIRE(precision == EMPH_PREC_BF16_TC || precision == EMPH_PREC_BF16X3_TC,
+                 "emph_pack_conv_weights_tc: precision %d has no tensor-core layout", precision);
+    const int split = precision == EMPH_PREC_BF16X3_TC;
+    if (!split && emph::use_wide())
         return emph::pack_conv_weights_tc240(weights, bias, n_layers, packed, (cudaStream_t)stream);
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
-        weights, bias, n_layers, reinterpret_cast<__nv_bfloat16*>(packed));
+        weights, bias, n_layers, split, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");
     return EMPH_OK;
 }

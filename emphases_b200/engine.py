@@ -360,25 +360,29 @@ class ConvStack:
     acts: np.ndarray             # int32 host
     kernel_size: int
     channels: int
-    weights_tc: Optional[torch.Tensor] = None    # bf16 UMMA-layout blob
+    weights_tc: Optional[dict] = None            # precision -> UMMA-layout blob
 
-    def tensor_core_weights(self):
-        """bf16 operand-layout copy for the tcgen05 path, packed on demand"""
+    def tensor_core_weights(self, precision):
+        """bf16 (or bf16 hi + lo) operand-layout copy for the tcgen05 path,
+        packed on demand"""
         if self.weights_tc is None:
+            self.weights_tc = {}
+        if precision not in self.weights_tc:
             size = _lib.load().emph_conv_weights_tc_bytes(
-                self.n_layers, self.channels, self.kernel_size)
+                self.n_layers, self.channels, self.kernel_size, precision)
             if size <= 0:
                 raise _lib.EmphasesB200Error(
-                    f'bf16 tensor-core conv stack is not compiled for '
-                    f'channels={self.channels} kernel_size={self.kernel_size}')
+                    f'the tensor-core conv stack is not compiled for '
+                    f'channels={self.channels} kernel_size={self.kernel_size}; '
+                    "use PRECISION='fp32'")
             blob = torch.empty(
                 size, dtype=torch.uint8, device=self.weights.device)
             _lib.call(
                 'emph_pack_conv_weights_tc', _lib.ptr(self.weights),
                 _lib.ptr(self.bias), self.n_layers, self.channels,
-                self.kernel_size, _lib.ptr(blob), _lib.stream_ptr())
-            self.weights_tc = blob
-        return self.weights_tc
+                self.kernel_size, precision, _lib.ptr(blob), _lib.stream_ptr())
+            self.weights_tc[precision] = blob
+        return self.weights_tc[precision]
 
     @property
     def n_layers(self):
@@ -472,6 +476,16 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
 ###############################################################################
 # Engine
 ###############################################################################
+
+
+def word_precision(precision, stack):
+    """The word decoder always runs at fp32 grade (bf16 there costs 1.5e-3 of
+    the 2e-3 budget): on the tensor cores as bf16x3 when
+    a tensor-core mode is selected and the shape is compiled in, else FFMA"""
+    if precision != _lib.PREC_FP32 and stack.channels == KERNEL_CHANNELS \
+            and stack.kernel_size == 3:
+        return _lib.PREC_BF16X3_TC
+    return _lib.PREC_FP32
 
 
 class Workspace:
@@ -595,8 +609,8 @@ class Engine:
                    name='conv'):
         y = _empty(ws, name, tuple(x.shape), torch.float32, self.device)
         acts = stack.acts.astype(np.int32)
-        weights = stack.tensor_core_weights() \
-            if precision == _lib.PREC_BF16_TC else stack.weights
+        weights = stack.weights if precision == _lib.PREC_FP32 \
+            else stack.tensor_core_weights(precision)
         _lib.call(
             'emph_conv_stack', _lib.ptr(x), _lib.ptr(row_seq), x.shape[0],
             _lib.ptr(weights), _lib.ptr(stack.bias),
@@ -698,7 +712,8 @@ class Engine:
                 plan.n_words, plan.n_words, word_row_seq, self.device))
         elif location == 'intermediate':
             words = timed('conv_words', lambda: self.conv_stack(
-                pooled, word_row_seq, weights.word, _lib.PREC_FP32, ws, 'words'))
+                pooled, word_row_seq, weights.word,
+                word_precision(precision, weights.word), ws, 'words'))
         else:
             words = pooled
         logits, scores = timed('head', lambda: self.head(

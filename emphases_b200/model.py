@@ -211,7 +211,8 @@ def run_forward(model, features, frame_lengths, word_bounds, word_lengths):
         views['word_row_start'], views['n_words'], batch, total_words)
     if model.location == 'intermediate':
         pooled = eng.conv_stack(
-            pooled, word_row_seq, weights.word, _lib.PREC_FP32)
+            pooled, word_row_seq, weights.word,
+            engine.word_precision(precision, weights.word))
     logits, _ = eng.head(
         pooled, word_row_seq, weights, _lib.HEAD_LOGITS, want_scores=False)
     index = torch.from_numpy(

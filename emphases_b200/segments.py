@@ -145,7 +145,9 @@ def run_forward_input(
         frame_rows, d_seg_start, d_seg_rows, d_word_seq, d_word_lo, d_word_hi,
         method)
     word_row_seq = eng.row_index(d_word_start, d_n_words, batch, total_words)
-    words = eng.conv_stack(pooled, word_row_seq, weights.word, _lib.PREC_FP32)
+    words = eng.conv_stack(
+        pooled, word_row_seq, weights.word,
+        engine.word_precision(precision, weights.word))
     logits, _ = eng.head(
         words, word_row_seq, weights, _lib.HEAD_LOGITS, want_scores=False)
     index = torch.from_numpy(

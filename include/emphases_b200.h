@@ -66,6 +66,8 @@ extern "C" {
 /* precision modes of the conv stack */
 #define EMPH_PREC_FP32 0      /* CUDA-core FFMA, max-abs 1e-5 on scores */
 #define EMPH_PREC_BF16_TC 1   /* tcgen05 bf16 MMA, fp32 accumulate, 2e-3 */
+#define EMPH_PREC_BF16X3_TC 2 /* tcgen05, hi/lo split of both operands (3 MMAs per
+                                product): fp32-grade, max-abs 1e-5 on scores */
 
 int emph_version(void);
 const char* emph_last_error(void);
@@ -133,8 +135,8 @@ int emph_logmel_i16(
  *              rows of x that neighbouring CTAs own in y)
  *   weights    EMPH_PREC_FP32: [n_layers][kernel_size][channels(in)]
  *              [channels(out)] fp32, produced by emph_pack_conv_weights from
- *              Conv1d (out, in, k); EMPH_PREC_BF16_TC: the bf16 blob produced
- *              by emph_pack_conv_weights_tc
+ *              Conv1d (out, in, k); EMPH_PREC_BF16_TC / _BF16X3_TC: the blob
+ *              produced by emph_pack_conv_weights_tc for that precision
  *   bias       [n_layers][channels]
  *   acts       [n_layers] EMPH_ACT_* codes (host pointer)
  *   precision  EMPH_PREC_*
@@ -146,7 +148,8 @@ int emph_conv_stack(
     int32_t precision, float* y, void* stream);
 
 /*
- * Weights for precision == EMPH_PREC_BF16_TC: fp32 weights [n_layers][k][in]
+ * Weights for precision == EMPH_PREC_BF16_TC / EMPH_PREC_BF16X3_TC (the latter
+ * packs a bf16 hi and a bf16 lo blob per layer): fp32 weights [n_layers][k][in]
  * [out] (the layout above) and bias [n_layers][out] -> per layer a bf16 blob in
  * the UMMA shared-memory operand layout [k][in / 8][out][8] followed by a bias
  * K-chunk (bias split into bf16 hi + lo, applied by one extra MMA against a
@@ -155,10 +158,10 @@ int emph_conv_stack(
  * emph_conv_stack; `bias` is then unused.
  */
 int emph_conv_weights_tc_bytes(
-    int32_t n_layers, int32_t channels, int32_t kernel_size);
+    int32_t n_layers, int32_t channels, int32_t kernel_size, int32_t precision);
 int emph_pack_conv_weights_tc(
     const float* weights, const float* bias, int32_t n_layers, int32_t channels,
-    int32_t kernel_size, void* packed, void* stream);
+    int32_t kernel_size, int32_t precision, void* packed, void* stream);
 
 /* (out, in, k) Conv1d weight -> [k][in][out] (device to device). */
 int emph_pack_conv_weights(

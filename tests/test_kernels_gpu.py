@@ -427,3 +427,56 @@ def test_logmel_spectral_tilt_precision(eng):
     our_error = (ours[:frames] - exact[:frames]).abs().max().item()
     assert exact.max() - exact.min() > 6          # a real dynamic range
     assert our_error < 4 * torch_error + 2e-5, (our_error, torch_error)
+
+
+@pytest.mark.parametrize('which', ['frame', 'word'])
+def test_conv_stack_bf16x3_tc(eng, golden, which):
+    """bf16x3 (hi/lo split operands on tcgen05): fp32-grade conv stack"""
+    from emphases_b200 import _lib
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    generator = torch.Generator().manual_seed(5)
+    lengths = [300, 1, 2, 131, 57, 640, 1000, 77]
+    row_start, n_rows, total = make_rows(lengths)
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total)
+    x = torch.randn(total, 80, generator=generator)
+    x[(row_seq < 0).cpu()] = 0
+    if which == 'frame':
+        layers = [(state['input_layer.weight'], state['input_layer.bias'], False)]
+        layers += [
+            (state[f'frame_encoder.{2 * i}.weight'],
+             state[f'frame_encoder.{2 * i}.bias'], True) for i in range(6)]
+        stack = weights.frame
+    else:
+        layers = [
+            (state[f'word_decoder.{2 * i}.weight'],
+             state[f'word_decoder.{2 * i}.bias'], True) for i in range(6)]
+        stack = weights.word
+    y = eng.conv_stack(x.cuda(), row_seq, stack, _lib.PREC_BF16X3_TC).cpu()
+    expected = oracle_conv_rows(state, layers, x, lengths)
+    scale = expected.abs().max().item()
+    error = (y - expected).abs().max().item()
+    assert error < 2e-5 * max(scale, 1.0), (error, scale)
+    assert y[(row_seq < 0).cpu()].abs().max() == 0
+
+
+@pytest.mark.parametrize('batch_size', [None, 300])
+def test_forward_packed_bf16x3_golden(eng, golden, batch_size):
+    """Whole path with the bf16x3 tensor-core conv stacks: scores within 1e-5
+    of the reference's fp32 forward (trained checkpoint, sum pooling)"""
+    from emphases_b200 import _lib, engine
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    times = np.asarray(data['times'])
+    plan = engine.make_plan([(times, 160000)], batch_size)
+    audio = torch.from_numpy(data['audio'])[0].cuda()
+    result = eng.forward_packed(
+        audio, plan, weights, precision=_lib.PREC_BF16X3_TC)
+    tag = 'full' if batch_size is None else f'bs{batch_size}'
+    scores = torch.cat([
+        result['scores'][s:s + n]
+        for s, n in zip(plan.word_row_start, plan.n_words)]).cpu().numpy()
+    error = np.abs(scores - data[f'{tag}.scores'][0]).max()
+    assert error < 1e-5, f'bf16x3 scores max-abs {error}'
