@@ -44,9 +44,13 @@ LOSS = 'bce'
 MAX_TRAINING_FRAMES = 75000
 
 # emphases_b200 extensions (not in the reference)
-# 'fp32': CUDA-core FFMA conv stack, scores within 1e-5 of the reference's fp32
-# forward.  'bf16': tcgen05 tensor-core conv stack, within 2e-3.  'bf16x3':
-# tcgen05 with hi/lo-split operands (3 MMAs per product), fp32-grade (1e-5).
+# 'fp32' (default): CUDA-core FFMA conv stacks, scores within 1e-5 of the
+# reference's fp32 forward.  'bf16': tcgen05 tensor-core frame stack with bf16
+# operands, within 2e-3, fastest (the word decoder then runs as bf16x3).
+# 'bf16x3': tcgen05 with hi/lo-split bf16 operands (3 MMAs per product, 16
+# mantissa bits per operand): within 1e-4 (measured <= 1.3e-5), 3.7x faster
+# than 'fp32'.  Conv shapes the tensor-core kernel is not compiled for (kernel
+# sizes other than 3) always run on the FFMA kernel.
 PRECISION = 'fp32'
 # Upper bound on packed frame rows per launch (~1 KB of HBM per row).  A corpus
 # larger than this runs as several launches on two alternating streams so the

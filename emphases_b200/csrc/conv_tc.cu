@@ -55,7 +55,8 @@ constexpr int kAccStride = 128;       // TMEM columns between slot accumulators
 // SPLIT = true : "bf16x3" -- activations and weights are each split into a
 //   bf16 hi and lo part and every product is formed as hi*hi + lo*hi + hi*lo
 //   (three MMAs into the same fp32 accumulator, the lo*lo term ~2^-16 is
-//   dropped): fp32-grade results from the bf16 tensor pipe.  Activations then
+//   dropped): 16 mantissa bits per operand from the bf16 tensor pipe, i.e.
+//   ~1e-5-class results (between the 2e-3 bf16 mode and the exact FFMA mode).  Activations then
 //   need two operand buffers per slot (2 slots fit) and a layer's weights arrive
 //   as two ring entries (W_hi + bias chunk, W_lo).
 template <bool SPLIT>

@@ -478,12 +478,23 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
 ###############################################################################
 
 
+def tensor_core_shape(stack):
+    return stack.channels == KERNEL_CHANNELS and stack.kernel_size == 3
+
+
+def frame_precision(precision, stack):
+    """Tensor-core modes apply to shapes the tcgen05 kernel is compiled for;
+    any other conv shape runs on the (stricter) fp32 FFMA kernel"""
+    if precision != _lib.PREC_FP32 and not tensor_core_shape(stack):
+        return _lib.PREC_FP32
+    return precision
+
+
 def word_precision(precision, stack):
     """The word decoder always runs at fp32 grade (bf16 there costs 1.5e-3 of
     the 2e-3 budget): on the tensor cores as bf16x3 when
     a tensor-core mode is selected and the shape is compiled in, else FFMA"""
-    if precision != _lib.PREC_FP32 and stack.channels == KERNEL_CHANNELS \
-            and stack.kernel_size == 3:
+    if precision != _lib.PREC_FP32 and tensor_core_shape(stack):
         return _lib.PREC_BF16X3_TC
     return _lib.PREC_FP32
 
@@ -701,7 +712,8 @@ class Engine:
                 plan.n_rows, row_seq, self.device))
         else:
             frames = timed('conv_frames', lambda: self.conv_stack(
-                features, row_seq, weights.frame, precision, ws, 'frames'))
+                features, row_seq, weights.frame,
+                frame_precision(precision, weights.frame), ws, 'frames'))
         pooled = timed('pool', lambda: self.pool(
             frames, views['row_start'], views['n_rows'], views['word_seq'],
             views['word_lo'], views['word_hi'], method, ws))

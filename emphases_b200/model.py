@@ -186,7 +186,9 @@ def run_forward(model, features, frame_lengths, word_bounds, word_lengths):
         'emph_pack_rows', _lib.ptr(features), batch, channels, frames,
         _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
         _lib.ptr(rows), _lib.stream_ptr())
-    frame_rows = eng.conv_stack(rows, row_seq, weights.frame, precision)
+    frame_rows = eng.conv_stack(
+        rows, row_seq, weights.frame,
+        engine.frame_precision(precision, weights.frame))
 
     if model.location == 'inference' and model.training:
         # frame-resolution logits (model/core.py:119-122)

@@ -108,7 +108,9 @@ def run_forward_input(
     n_seg = batch * wmax
     segments, seg_row_seq, d_seg_start, d_seg_rows, _, _ = _gather(
         eng, features, lo, count, max_length)
-    frame_rows = eng.conv_stack(segments, seg_row_seq, weights.frame, precision)
+    frame_rows = eng.conv_stack(
+        segments, seg_row_seq, weights.frame,
+        engine.frame_precision(precision, weights.frame))
 
     # One word row per segment, laid out as B sequences of Wmax word slots
     word_starts, total_words = engine.packed_starts([wmax] * batch)
