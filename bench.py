@@ -527,7 +527,7 @@ def main():
             'achieved': logmel_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': logmel_gbs / hbm_peak,
             # dram read+write per frame from the ncu --set full capture in
-            # profiles/r01e_logmel.md, scaled to this launch
+            # profiles/r01m_final_ncu.md, scaled to this launch
             'traffic': 915.0 * frames,
             'note': ('fp32 FFT: FP32-issue/latency bound, not HBM bound '
                      '(960 algorithmic B/frame vs ~30 kFLOP/frame), DESIGN.md 4.1')},
@@ -536,7 +536,7 @@ def main():
             'bound': conv_bound,
             'achieved': conv_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s',
             'frac': conv_tflops / tensor_peak,
-            'traffic': None},
+            'traffic': 584.0 * frames if precision == 'bf16' else None},
         'pool': {
             'kernel': 'pool_words_kernel',
             'bound': 'hbm',
