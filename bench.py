@@ -53,6 +53,10 @@ def parse_args():
     parser.add_argument(
         '--precision', default=None, choices=['fp32', 'bf16', 'bf16x3'])
     parser.add_argument('--utterances', type=int, default=3000)
+    parser.add_argument(
+        '--architecture', default='convolution',
+        choices=['convolution', 'transformer'],
+        help='transformer = BASELINE config 3 (informational, fp32 kernels)')
     parser.add_argument('--cpu-seconds', type=float, default=15.)
     parser.add_argument('--file-utterances', type=int, default=500)
     return parser.parse_args()
@@ -101,10 +105,11 @@ def make_audio(lengths, seed, device=None, pin=False):
     return buffer, offsets
 
 
-def random_state(seed=0):
+def random_state(seed=0, architecture='convolution'):
     """Random-init weights of the default architecture"""
     import emphases_b200 as emphases
     emphases.reset_configuration()
+    emphases.configure(ARCHITECTURE=architecture)
     torch.manual_seed(seed)
     return {k: v.detach().clone() for k, v in emphases.Model().state_dict().items()}
 
@@ -217,7 +222,8 @@ class ClockSampler:
 
 
 def cpu_reference_pass(
-    state, lengths, times, seed, budget_seconds, max_items, packed=None
+    state, lengths, times, seed, budget_seconds, max_items, packed=None,
+    architecture='convolution'
 ):
     """Time oracle.from_alignment_and_audio (reference numerics: bf16 autocast,
     per-utterance serial loop, emphases/core.py:169-179) over the first
@@ -233,15 +239,21 @@ def cpu_reference_pass(
         else:
             audios.append((0.1 * torch.randn(
                 1, int(count), generator=generator)).clamp(-1, 1))
+    config = {'ARCHITECTURE': architecture}
+    if architecture == 'transformer':
+        state = dict(state)
+        for prefix in ('frame_encoder', 'word_decoder'):
+            state.setdefault(
+                f'{prefix}.position.encoding', oracle.positional_encoding(80))
     oracle.from_alignment_and_audio(                       # warm up
-        [tuple(t) for t in times[0].tolist()], audios[0], state, basis=basis,
-        autocast=True)
+        [tuple(t) for t in times[0].tolist()], audios[0], state, config,
+        basis=basis, autocast=True)
     seconds = words = 0.
     items = 0
     start = time.perf_counter()
     for audio, word_times in zip(audios, times):
         oracle.from_alignment_and_audio(
-            [tuple(t) for t in word_times.tolist()], audio, state,
+            [tuple(t) for t in word_times.tolist()], audio, state, config,
             basis=basis, autocast=True)
         seconds += audio.shape[-1] / SAMPLE_RATE
         words += len(word_times)
@@ -264,13 +276,17 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     lengths, times = corpus_layout(args.utterances, seed=1234)
-    state = random_state()
+    state = random_state(architecture=args.architecture)
     per_step = min(300, args.utterances)
     for _ in range(args.warmup):
-        cpu_reference_pass(state, lengths, times, 99, 1e9, per_step)
+        cpu_reference_pass(
+            state, lengths, times, 99, 1e9, per_step,
+            architecture=args.architecture)
     seconds = words = elapsed = 0.
     for _ in range(args.steps):
-        s, w, _, e = cpu_reference_pass(state, lengths, times, 99, 1e9, per_step)
+        s, w, _, e = cpu_reference_pass(
+            state, lengths, times, 99, 1e9, per_step,
+            architecture=args.architecture)
         seconds += s
         words += w
         elapsed += e
@@ -347,7 +363,10 @@ def time_files_path(emphases, count, state, gpu):
 def workload_config(args):
     return {
         'workload': (
-            f'config2: default framewise conv model (80 mel, 6 layers, sum '
+            ('config2: default framewise conv model'
+             if args.architecture == 'convolution' else
+             'config3: Transformer-layer variant') +
+            f' (80 mel, 6 layers, sum '
             f'pooling @ intermediate, random init) over {args.utterances} '
             'synthetic utterances U(2,20) s @16 kHz, 2.5 words/s, ragged, '
             'one packed batch per GPU'),
@@ -377,7 +396,7 @@ def main():
         dist.init_process_group('nccl', device_id=device)
 
     precision = args.precision or default_precision()
-    state = random_state()              # resets the configuration to defaults
+    state = random_state(architecture=args.architecture)   # resets the configuration
     emphases.configure(PRECISION=precision)
 
     # ---- corpus: each rank owns its own shard of the same size (weak) ----
@@ -556,7 +575,8 @@ def main():
     cpu = None
     if world == 1 and args.cpu_seconds > 0:
         seconds, words, items, elapsed = cpu_reference_pass(
-            state, lengths, times, 99, args.cpu_seconds, len(lengths), packed)
+            state, lengths, times, 99, args.cpu_seconds, len(lengths), packed,
+            architecture=args.architecture)
         cpu = {
             'value': seconds / elapsed,
             'unit': 'audio-s/s',
