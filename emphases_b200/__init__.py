@@ -89,6 +89,7 @@ from .core import *  # noqa: E402,F401,F403
 from .model import Model  # noqa: E402,F401
 from . import convert  # noqa: E402,F401
 from . import data  # noqa: E402,F401
+from . import evaluate  # noqa: E402,F401
 from . import load  # noqa: E402,F401
 from . import model  # noqa: E402,F401
 from . import training  # noqa: E402,F401

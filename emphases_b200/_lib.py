@@ -45,6 +45,8 @@ SIGNATURES = {
     'emph_output_head_backward': [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     'emph_masked_loss': [_P, _P, _P, _I, _I, _P, _P, _P],
     'emph_upsample_words': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    'emph_word_metric_sums': [
+        _P, _P, _P, _P, _I, _I, _I, ctypes.c_double, ctypes.c_double, _P, _P],
 }
 
 _lib = None

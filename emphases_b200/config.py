@@ -5,10 +5,18 @@ Like the reference, code reads them at call time as `emphases_b200.NAME`, so
 `emphases_b200.configure(...)` (the stand-in for yapecs' `--config file.py`
 override, emphases/__init__.py:10-11) takes effect immediately.
 """
+from pathlib import Path
+
 import torch
 
 # Metadata (defaults.py:14)
 CONFIG = 'emphases'
+
+# Directories (defaults.py:22-41), only read by evaluate.datasets
+ASSETS_DIR = Path(__file__).parent / 'assets'
+CACHE_DIR = Path(__file__).parent.parent / 'data' / 'cache'
+EVAL_DIR = Path(__file__).parent.parent / 'eval'
+PARTITION_DIR = ASSETS_DIR / 'partitions'
 
 # Audio parameters (defaults.py:53-74)
 HOPSIZE = 160

@@ -1,1 +1,3 @@
 from . import preprocess
+from .collate import collate
+from .sampler import LengthDataset, Sampler, buckets, sampler

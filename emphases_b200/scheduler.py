@@ -154,13 +154,19 @@ def _prepare(alignments, audios, sample_rate):
 
 
 def run_on_device(
-    model, alignments, audios, sample_rate, batch_size, device, to_cpu=True
+    model, alignments, audios, sample_rate, batch_size, device, to_cpu=True,
+    output='scores'
 ):
     """Run a list of utterances on one device; returns a list of (1, W_i)
-    score tensors (CPU when to_cpu, else on `device`)."""
+    score tensors (CPU when to_cpu, else on `device`).  output='logits'
+    returns the network output before postprocessing (the evaluation caller,
+    emphases/evaluate/core.py:73-94)."""
+    if output not in ('scores', 'logits'):
+        raise ValueError(f'output {output} is not defined')
     if model.location == 'input':
         return _run_via_model(
-            model, alignments, audios, sample_rate, batch_size, device, to_cpu)
+            model, alignments, audios, sample_rate, batch_size, device, to_cpu,
+            output)
     times, packed = _prepare(alignments, audios, sample_rate)
     eng = emphases.get_engine(device)
     weights = model.packed_weights()
@@ -204,7 +210,7 @@ def run_on_device(
                 location=model.location, precision=precision,
                 head_mode=head_mode, normalize=emphases.NORMALIZE,
                 views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws)
-            scores = result['scores']
+            scores = result[output]
             if not to_cpu:
                 scores = scores.clone()       # the workspace is reused
             if to_cpu:
@@ -234,7 +240,8 @@ def run_on_device(
 
 
 def _run_via_model(
-    model, alignments, audios, sample_rate, batch_size, device, to_cpu
+    model, alignments, audios, sample_rate, batch_size, device, to_cpu,
+    output='scores'
 ):
     """Chunk-at-a-time path through Model.forward (transformer variant and
     the 'input' location), structured like the reference loop
@@ -246,7 +253,8 @@ def _run_via_model(
             alignment, audio, sample_rate, batch_size, device.index
         ):
             logits = emphases.infer_with_model(model, features, bounds)[0]
-            scores.append(emphases.postprocess(logits))
+            scores.append(
+                emphases.postprocess(logits) if output == 'scores' else logits)
         result = torch.cat(scores, 1) if scores else torch.zeros(
             (1, 0), device=device)
         outputs.append(result.cpu() if to_cpu else result)

@@ -304,6 +304,22 @@ int emph_upsample_words(
     int32_t tmax, int32_t linear, float* out, void* stream);
 
 /*
+ * Evaluation caller (emphases/evaluate/core.py:27-110 with the metric classes of
+ * emphases/evaluate/metrics.py:13-111): fp64 per-file sums over packed word rows
+ * (file u owns rows word_row_start[u] .. + n_words[u]).  p = sigmoid(logit)
+ * (loss_mode 0, LOSS 'bce') or clamp(logit, 0, 1) (loss_mode 1, LOSS 'mse').
+ *   pass 0: sums[u][0..1] = sum p, sum t            (dataset mean / std pass)
+ *   pass 1: sums[u][0..4] = sum (p-mean_p)^2, sum (t-mean_t)^2,
+ *           sum (p-mean_p)(t-mean_t), sum bce(logit, t), sum (p-t)^2
+ * sums is (n_seq, 5) fp64 on the device.
+ */
+int emph_word_metric_sums(
+    const float* logits, const float* targets,
+    const int32_t* word_row_start, const int32_t* n_words, int32_t n_seq,
+    int32_t loss_mode, int32_t pass, double mean_p, double mean_t,
+    double* sums, void* stream);
+
+/*
  * Polyphase windowed-sinc resampling (emphases/core.py:613-619 `resample`, which
  * is torchaudio.transforms.Resample): y[q * new + p] = sum_k kernel[p][k] *
  * xpad[q * orig + k], xpad = zeros(width) ++ x ++ zeros(width + orig).

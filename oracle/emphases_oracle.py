@@ -29,6 +29,12 @@ because their source is not in the container:
   * `pypar.Alignment` slicing / `word_bounds` (call sites emphases/core.py:
     384-390) -- restated as "re-base slice to its first word's start, then
     int(t * sr / hop)".
+  * `torchutil.metrics.{Average, MeanStd, PearsonCorrelation}` (call sites
+    emphases/evaluate/metrics.py:15-18,59,82,103) -- restated in `evaluate`
+    (running average; Welford mean / SAMPLE std over python floats; Pearson =
+    sum((p - mean_p)(t - mean_t)) / (n std_p std_t)).  The reference's own
+    metric subclasses run unmodified on the same restatement in
+    `oracle/ref_stubs.py` to produce tests/golden/evaluate.npz.
 """
 import math
 
@@ -552,6 +558,109 @@ def loss(
     if loss_fn == 'mse':
         return torch.nn.functional.mse_loss(scores[mask], targets[mask])
     raise ValueError(f'Loss {loss_fn} is not recognized')
+
+
+###############################################################################
+# Evaluation caller (emphases/evaluate/core.py:14-127, evaluate/metrics.py)
+###############################################################################
+
+
+def _welford(values):
+    """torchutil.metrics.MeanStd (third party, absent: restated, PARITY
+    UNPINNED): running mean and SAMPLE standard deviation over python floats,
+    as `Statistics.update(values[mask].flatten().tolist())` feeds it
+    (evaluate/metrics.py:103-111)"""
+    count, mean, m2 = 0, 0., 0.
+    for value in values:
+        count += 1
+        delta = value - mean
+        mean += delta / count
+        m2 += delta * (value - mean)
+    return mean, math.sqrt(m2 / (count - 1))
+
+
+def _bce_values(logits, targets, loss_fn):
+    """evaluate/metrics.py:59-79"""
+    if loss_fn == 'bce':
+        return torch.nn.functional.binary_cross_entropy_with_logits(
+            logits, targets, reduction='none')
+    x = torch.clamp(logits, 0., 1.)
+    return -(
+        targets * torch.log(x + 1e-6) +
+        (1 - targets) * torch.log(1 - x + 1e-6))
+
+
+def evaluate(logits, targets, loss_fn='bce'):
+    """The arithmetic of emphases.evaluate.datasets for one dataset.
+
+    logits, targets: lists with one (W_i,) fp32 tensor per file (the
+    un-postprocessed network output of evaluate/core.py:73-94 and the ground
+    truth).  Pass 1 (core.py:27-46): mean / std of the postprocessed scores and
+    of the targets over the whole dataset.  Pass 2 (core.py:56-110): per file
+    and per dataset, Pearson correlation against those global statistics
+    (torchutil PearsonCorrelation: sum((p - mean_p)(t - mean_t)) / (n std_p
+    std_t)), mean BCE of the logits, mean squared error of the scores.
+    Returns (overall dict, [per-file dict])."""
+    scores = [postprocess(x, loss_fn) for x in logits]
+    mean_p, std_p = _welford(torch.cat(scores).tolist())
+    mean_t, std_t = _welford(torch.cat(targets).tolist())
+
+    def metrics(xs, ps, ts):
+        cross = sum(((p - mean_p) * (t - mean_t)).sum() for p, t in zip(ps, ts))
+        count = sum(p.numel() for p in ps)
+        bce = sum(_bce_values(x, t, loss_fn).sum() for x, t in zip(xs, ts))
+        mse = sum(((p - t) ** 2).sum() for p, t in zip(ps, ts))
+        return {
+            'pearson_correlation':
+                (1. / count * (cross / (std_p * std_t))).item(),
+            'bce': (bce / count).item(),
+            'mse': (mse / count).item()}
+
+    granular = [
+        metrics([x], [p], [t]) for x, p, t in zip(logits, scores, targets)]
+    return metrics(logits, scores, targets), granular
+
+
+###############################################################################
+# Training batch sampler (emphases/data/sampler.py, dataset.py:97-117)
+###############################################################################
+
+
+def length_buckets(lengths, count=2):
+    """Dataset.buckets, dataset.py:97-117"""
+    size = len(lengths) // count
+    indices = np.argsort(lengths)
+    ordered = np.sort(lengths)
+    parts = [
+        np.stack((indices[i:i + size], ordered[i:i + size])).T
+        for i in range(0, len(lengths), size)]
+    if len(parts) == count + 1:
+        residual = parts.pop()
+        parts[-1] = np.concatenate((parts[-1], residual), axis=0)
+    return parts
+
+
+def epoch_batches(lengths, epoch, max_frames=75000, seed=0, count=2):
+    """Sampler.batch, sampler.py:47-83"""
+    generator = torch.Generator()
+    generator.manual_seed(seed + epoch)
+    batches = []
+    for bucket in length_buckets(lengths, count):
+        bucket = bucket[torch.randperm(len(bucket), generator=generator).tolist()]
+        batch, longest = [], 0
+        for index, length in bucket:
+            longest = max(longest, length)
+            if batch and (len(batch) + 1) * longest > max_frames:
+                batches.append(batch)
+                longest = length
+                batch = [index]
+            else:
+                batch.append(index)
+        if batch:
+            batches.append(batch)
+    return [
+        batches[i]
+        for i in torch.randperm(len(batches), generator=generator).tolist()]
 
 
 ###############################################################################

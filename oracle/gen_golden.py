@@ -322,6 +322,109 @@ def gen_upsample():
     print('upsample', {k: v.shape for k, v in out.items()})
 
 
+def gen_sampler():
+    """Sampler.batch / Dataset.buckets / collate of the unmodified reference"""
+    out = {}
+    rng = np.random.default_rng(17)
+    with ref_stubs.reference() as emphases:
+        for name, size, max_frames in (
+            ('a', 101, 20000), ('b', 64, 75000), ('c', 7, 3000)
+        ):
+            lengths = rng.integers(200, 2001, size=size)
+
+            class Fake:
+                def __len__(self):
+                    return len(lengths)
+            fake = Fake()
+            fake.lengths = lengths.tolist()
+            fake.buckets = lambda fake=fake: emphases.data.Dataset.buckets(fake)
+            # (`emphases.data.sampler` is shadowed by the function of that name)
+            sampler = sys.modules['emphases.data.sampler'].Sampler(
+                fake, max_frames)
+            out[f'{name}/lengths'] = lengths
+            out[f'{name}/max_frames'] = np.int64(max_frames)
+            for epoch in (0, 3):
+                sampler.set_epoch(epoch)
+                batches = sampler.batch()
+                out[f'{name}/epoch{epoch}/flat'] = np.array(
+                    [i for batch in batches for i in batch], dtype=np.int64)
+                out[f'{name}/epoch{epoch}/sizes'] = np.array(
+                    [len(batch) for batch in batches], dtype=np.int64)
+
+        # collate (emphases/data/collate.py:11-77)
+        generator = torch.Generator().manual_seed(19)
+        items = []
+        for index, (frames, words) in enumerate(((50, 6), (80, 3), (64, 9))):
+            features = torch.randn(80, frames, generator=generator)
+            scores = torch.rand(1, words, generator=generator)
+            cuts = torch.sort(torch.randperm(
+                frames - 1, generator=generator)[:words - 1] + 1).values
+            edges = torch.cat([
+                torch.zeros(1, dtype=torch.long), cuts,
+                torch.full((1,), frames)])
+            bounds = torch.stack([edges[:-1], edges[1:]])
+            audio = torch.randn(1, frames * 160 + 37 * index, generator=generator)
+            items.append((features, scores, bounds, None, audio, f'stem{index}'))
+            out[f'collate/item{index}/features'] = features.numpy()
+            out[f'collate/item{index}/scores'] = scores.numpy()
+            out[f'collate/item{index}/bounds'] = bounds.numpy()
+            out[f'collate/item{index}/audio'] = audio.numpy()
+        batch = emphases.data.collate(items)
+        for key, value in zip(
+            ('features', 'frame_lengths', 'word_bounds', 'word_lengths',
+             'scores', None, 'audio', None), batch
+        ):
+            if key is not None:
+                out[f'collate/{key}'] = value.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, 'sampler.npz'), **out)
+    print('sampler.npz', len(out))
+
+
+def gen_evaluate():
+    """The loop body of emphases.evaluate.datasets (evaluate/core.py:27-110)
+    with the reference's own Statistics / Metrics classes, on synthetic logits
+    and targets for six 'files' (torchutil restated, see ref_stubs)"""
+    out = {}
+    generator = torch.Generator().manual_seed(23)
+    sizes = (12, 5, 31, 2, 18, 9)
+    logits = [2 * torch.randn(1, 1, n, generator=generator) for n in sizes]
+    targets = [torch.rand(1, 1, n, generator=generator) for n in sizes]
+    for index, (x, t) in enumerate(zip(logits, targets)):
+        # correlate predictions and targets a little
+        logits[index] = x + 3 * (t - .5)
+        out[f'logits{index}'] = logits[index].numpy()
+        out[f'targets{index}'] = t.numpy()
+    for loss_fn in ('bce', 'mse'):
+        with ref_stubs.reference({'LOSS': loss_fn}) as emphases:
+            metrics = emphases.evaluate.metrics
+            target_stats = metrics.Statistics()
+            predicted_stats = metrics.Statistics()
+            for x, t in zip(logits, targets):
+                lengths = torch.tensor([x.shape[-1]])
+                scores = emphases.postprocess(x[0])           # (1, W)
+                target_stats.update(t, lengths)
+                predicted_stats.update(scores[None], lengths)
+            file_metrics = emphases.evaluate.Metrics(predicted_stats, target_stats)
+            dataset_metrics = emphases.evaluate.Metrics(predicted_stats, target_stats)
+            granular = []
+            for x, t in zip(logits, targets):
+                lengths = torch.tensor([x.shape[-1]])
+                file_metrics.reset()
+                file_metrics.update(x, t, lengths)
+                dataset_metrics.update(x, t, lengths)
+                granular.append(file_metrics())
+            overall = dataset_metrics()
+            keys = ('pearson_correlation', 'bce', 'mse')
+            out[f'{loss_fn}/overall'] = np.array(
+                [overall[k] for k in keys], dtype=np.float64)
+            out[f'{loss_fn}/granular'] = np.array(
+                [[g[k] for k in keys] for g in granular], dtype=np.float64)
+            out[f'{loss_fn}/stats'] = np.array(
+                [*predicted_stats(), *target_stats()], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, 'evaluate.npz'), **out)
+    print('evaluate.npz', len(out))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)
@@ -331,6 +434,8 @@ def main():
     gen_transformer()
     gen_loss()
     gen_upsample()
+    gen_sampler()
+    gen_evaluate()
 
 
 if __name__ == '__main__':

@@ -18,6 +18,7 @@ run on CPU exactly as written.
 import contextlib
 import copy
 import importlib
+import math
 import os
 import sys
 import types
@@ -174,8 +175,10 @@ def _checkpoint_load(file, model, optimizer=None, map_location='cpu'):
 
 
 class _Metric:
+    """torchutil.metrics.Metric: the interface the reference subclasses"""
+
     def __init__(self, *args, **kwargs):
-        pass
+        self.reset()
 
     def update(self, *args, **kwargs):
         pass
@@ -185,6 +188,69 @@ class _Metric:
 
     def __call__(self):
         return {}
+
+
+# torchutil (third party, un-pinned, absent here) -- restated from its
+# published metrics module: PARITY UNPINNED for these three classes; the
+# reference's own subclasses (emphases/evaluate/metrics.py) run unmodified on
+# top of them.
+class _Average(_Metric):
+    """Running average: update(values, count) adds values.sum() and count"""
+
+    def __call__(self):
+        return (self.total / self.count).item()
+
+    def update(self, values, count):
+        self.total += values.sum()
+        self.count += count
+
+    def reset(self):
+        self.total = 0.
+        self.count = 0
+
+
+class _MeanStd(_Metric):
+    """Welford running mean / sample standard deviation over python floats"""
+
+    def __call__(self):
+        return self.mean, math.sqrt(self.m2 / (self.count - 1))
+
+    def update(self, values):
+        for value in values:
+            self.count += 1
+            delta = value - self.mean
+            self.mean += delta / self.count
+            self.m2 += delta * (value - self.mean)
+
+    def reset(self):
+        self.m2 = 0.
+        self.mean = 0.
+        self.count = 0
+
+
+class _PearsonCorrelation(_Metric):
+    """Pearson correlation from precomputed means / standard deviations"""
+
+    def __init__(self, predicted_mean, predicted_std, target_mean, target_std):
+        self.reset()
+        self.mean = predicted_mean
+        self.std = predicted_std
+        self.target_mean = target_mean
+        self.target_std = target_std
+
+    def __call__(self):
+        return (
+            1. / self.count *
+            (self.total / (self.std * self.target_std))).item()
+
+    def update(self, predicted, target):
+        self.total += (
+            (predicted - self.mean) * (target - self.target_mean)).sum()
+        self.count += predicted.numel()
+
+    def reset(self):
+        self.count = 0
+        self.total = 0.
 
 
 def install(overrides=None):
@@ -210,9 +276,9 @@ def install(overrides=None):
         best_path=lambda *a, **k: None)
     metrics = _module(
         'torchutil.metrics',
-        Average=_Metric,
-        MeanStd=_Metric,
-        PearsonCorrelation=_Metric)
+        Average=_Average,
+        MeanStd=_MeanStd,
+        PearsonCorrelation=_PearsonCorrelation)
     tensorboard = _module('torchutil.tensorboard', update=lambda *a, **k: None)
     download = _module('torchutil.download', file=lambda *a, **k: None)
     _module(
