@@ -18,10 +18,14 @@
 //            two exchanges through bank-padded shared memory), then the
 //            real-FFT unpacking done in registers with warp shuffles and the
 //            magnitudes written to a [16 frames][513 bins] tile;
-//   phase 2  mel projection with lane = frame (a half-warp per mel row): the
-//            sparse basis entry is a broadcast and the 16 magnitudes of one
-//            bin sit in different banks (row stride 513), so every nnz costs
-//            one conflict-free wavefront per pair of mel rows;
+//   phase 2  mel projection with lane = frame (a half-warp per mel row).  The
+//            CSR basis is expanded once per CTA into a banded dense table: a
+//            row's non-zeros (a triangle = one contiguous run of bins) are
+//            widened to 4-bin-aligned groups, and the two rows a warp works
+//            on together are padded to the same group count, so the inner
+//            loop is branch-uniform: one 16-byte weight broadcast + one
+//            16-byte magnitude load (row stride 516 floats: conflict-free
+//            per quarter-warp) feed 4 FMAs;
 //   phase 3  log / clamp and a fully coalesced store of the 16 x n_mels tile.
 // All fp32.  Bound: FP32 issue + shared-memory wavefronts (about 25 kFLOP per
 // frame against 960 B of HBM traffic), see DESIGN.md.
@@ -36,26 +40,26 @@ constexpr int kBins = kFft / 2 + 1;       // 513
 constexpr int kHalf = kFft / 2;           // 512-point complex FFT
 constexpr int kWarps = 8;                  // two CTAs per SM: their phases interleave
 constexpr int kTile = 16;                 // frames per CTA tile
-constexpr int kVirtualWarps = 16;         // mel phase: half-warps, lanes = 16 frames
-constexpr int kMaxNnz = 1536;             // mel CSR entries held in smem
 constexpr int kMaxMels = 128;
+constexpr int kMagStride = 516;           // floats; 16-byte aligned rows, 129 = 1 mod 8 quads
+constexpr int kMaxQuads = 768;            // banded mel table: float4 groups held in smem
 
 // Exchange buffer index with one float2 of padding per 8 (bank spreading)
 __device__ __forceinline__ int xpad(int i) { return i + (i >> 3); }
 constexpr int kXchg = kHalf + kHalf / 8;  // 576 float2 per warp
 
 struct __align__(16) LogmelSmem {
-    float mag[kTile][kBins];       // stride 513 = 1 mod 32: lane = frame is conflict-free
+    float mag[kTile][kMagStride];  // bins 513..515 stay zero (band padding reads them)
     float2 xchg[kWarps][kXchg];
-    float hann[kFft];
+    float hann[kFft];              // 0.5 * hann: the real-FFT unpacking's 1/2 is folded in
     float outs[kTile][kMaxMels + 1];
-    float2 mel_entry[kMaxNnz];     // (weight, byte offset of the bin within a mag row)
-    int32_t mel_ptr[kMaxMels + 1];
+    float4 mel_quad[kMaxQuads];    // banded dense weights, 4 bins per entry
+    int32_t mel_first[kMaxMels];   // first quad of the row in mel_quad
+    int32_t mel_bin0[kMaxMels];    // first bin of the row's band (multiple of 4)
+    int32_t mel_quads[kMaxMels / 2];   // quads per row of the pair (both rows padded to it)
+    int32_t mel_fits;              // 0: the basis does not fit the table, use the CSR path
 };
 
-// exp(-2 pi i r / 16), r = 0..7 and exp(-2 pi i q / 32), q = 0..15
-__device__ constexpr float kC16[8][2] = {{1.0f, 0.0f}, {0.9238795325112867f, -0.3826834323650898f}, {0.7071067811865476f, -0.7071067811865475f}, {0.38268343236508984f, -0.9238795325112867f}, {0.0f, -1.0f}, {-0.3826834323650897f, -0.9238795325112867f}, {-0.7071067811865475f, -0.7071067811865476f}, {-0.9238795325112867f, -0.3826834323650899f}};
-__device__ constexpr float kC32[16][2] = {{1.0f, 0.0f}, {0.9807852804032304f, -0.19509032201612825f}, {0.9238795325112867f, -0.3826834323650898f}, {0.8314696123025452f, -0.5555702330196022f}, {0.7071067811865476f, -0.7071067811865475f}, {0.5555702330196023f, -0.8314696123025452f}, {0.38268343236508984f, -0.9238795325112867f}, {0.19509032201612833f, -0.9807852804032304f}, {0.0f, -1.0f}, {-0.1950903220161282f, -0.9807852804032304f}, {-0.3826834323650897f, -0.9238795325112867f}, {-0.555570233019602f, -0.8314696123025455f}, {-0.7071067811865475f, -0.7071067811865476f}, {-0.8314696123025453f, -0.5555702330196022f}, {-0.9238795325112867f, -0.3826834323650899f}, {-0.9807852804032304f, -0.1950903220161286f}};
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -65,12 +69,12 @@ __device__ __forceinline__ void bfly2(float2& a, float2& b) {
     a = make_float2(t.x + b.x, t.y + b.y);
     b = make_float2(t.x - b.x, t.y - b.y);
 }
-// sqrt of a strictly positive normal number (x >= 1e-6 here): rsqrt seed + one
-// Newton step, ~1 ulp, no special-case branches
+// sqrt of a strictly positive normal number (x >= 1e-6 here): one MUFU.SQRT
+// (relative error <= 2^-23, far inside the 2e-5 log-mel tolerance)
 __device__ __forceinline__ float sqrt_pos(float x) {
-    const float y = rsqrtf(x);
-    const float s = x * y;
-    return fmaf(fmaf(-s, s, x), 0.5f * y, s);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 // multiply by -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -141,18 +145,69 @@ logmel_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < kFft; i += blockDim.x) {
-        // torch.hann_window(1024) (periodic): 0.5 - 0.5 cos(2 pi n / N)
-        sm.hann[i] = 0.5f - 0.5f * cospif(2.f * (float)i / (float)kFft);
+        // torch.hann_window(1024) (periodic): 0.5 - 0.5 cos(2 pi n / N), times the
+        // 1/2 of the real-FFT unpacking (exact: a power of two)
+        sm.hann[i] = 0.25f - 0.25f * cospif(2.f * (float)i / (float)kFft);
     }
-    const int nnz = mel_ptr[n_mels];
-    for (int i = tid; i < nnz; i += blockDim.x)
-        sm.mel_entry[i] = make_float2(mel_val[i], __int_as_float(4 * (int)mel_col[i]));
-    for (int i = tid; i <= n_mels; i += blockDim.x) sm.mel_ptr[i] = mel_ptr[i];
+
+    // ---- banded mel table, built once per CTA from the CSR basis ----
+    for (int i = tid; i < kTile * (kMagStride - kBins); i += blockDim.x)
+        sm.mag[i / (kMagStride - kBins)][kBins + i % (kMagStride - kBins)] = 0.f;
+    for (int i = tid; i < kMaxQuads; i += blockDim.x)
+        sm.mel_quad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = tid; m < n_mels; m += blockDim.x) {
+        // band of row m: [first bin rounded down to 4, last bin]; empty row: 0 quads
+        const int e0 = mel_ptr[m], e1 = mel_ptr[m + 1];
+        int lo = kBins, hi = -1;
+        for (int e = e0; e < e1; ++e) {
+            const int c = mel_col[e];
+            lo = min(lo, c);
+            hi = max(hi, c);
+        }
+        const bool valid = hi >= lo && lo >= 0 && hi < kBins;
+        sm.mel_bin0[m] = valid ? (lo & ~3) : 0;
+        sm.mel_first[m] = valid ? (hi - (lo & ~3)) / 4 + 1 : (e1 > e0 ? kMaxQuads + 1 : 0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int n_pairs = (n_mels + 1) >> 1;
+        int total = 0;
+        bool fits = true;
+        for (int p = 0; p < n_pairs; ++p) {
+            const int m0 = 2 * p, m1 = min(2 * p + 1, n_mels - 1);
+            const int quads = max(sm.mel_first[m0], sm.mel_first[m1]);
+            if (4 * quads > kMagStride || total + 2 * quads > kMaxQuads) {
+                fits = false;
+                break;
+            }
+            sm.mel_quads[p] = quads;
+            // a band padded past the end of the mag row is moved down instead
+            sm.mel_bin0[m0] = min(sm.mel_bin0[m0], kMagStride - 4 * quads);
+            sm.mel_first[m0] = total;
+            if (m1 != m0) {
+                sm.mel_bin0[m1] = min(sm.mel_bin0[m1], kMagStride - 4 * quads);
+                sm.mel_first[m1] = total + quads;
+            }
+            total += 2 * quads;
+        }
+        sm.mel_fits = fits ? 1 : 0;
+    }
+    __syncthreads();
+    const bool banded = sm.mel_fits != 0;
+    if (banded) {
+        float* const table = reinterpret_cast<float*>(sm.mel_quad);
+        for (int m = warp; m < n_mels; m += kWarps) {
+            const int base = 4 * sm.mel_first[m] - sm.mel_bin0[m];
+            for (int e = mel_ptr[m] + lane; e < mel_ptr[m + 1]; e += 32)
+                table[base + mel_col[e]] = mel_val[e];
+        }
+    }
 
     // Per-lane twiddles, kept in registers for the whole kernel:
-    //   pass 2: exp(-2 pi i * 8 r (lane % 8) / 512), pass 3: exp(-2 pi i r lane / 512)
-    //   unpack: exp(-2 pi i lane / 1024)
-    float2 tw2[8], tw3[8];
+    //   pass 2: exp(-2 pi i * 8 r (lane % 8) / 512)
+    //   pass 3: exp(-2 pi i r lane / 512) and exp(-2 pi i r (lane + 32) / 512)
+    //   unpack: exp(-2 pi i (lane + 32 q) / 1024)
+    float2 tw2[8], tw3[8], tw3b[8], wq[8];
 #pragma unroll
     for (int r = 1; r < 8; ++r) {
         float sn, cs;
@@ -160,9 +215,12 @@ logmel_kernel(
         tw2[r] = make_float2(cs, sn);
         sincospif(-2.f * (float)(r * lane) / (float)kHalf, &sn, &cs);
         tw3[r] = make_float2(cs, sn);
+        sincospif(-2.f * (float)(r * (lane + 32)) / (float)kHalf, &sn, &cs);
+        tw3b[r] = make_float2(cs, sn);
     }
-    float2 wl;
-    sincospif(-2.f * (float)lane / (float)kFft, &wl.y, &wl.x);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        sincospif(-2.f * (float)(lane + 32 * q) / (float)kFft, &wq[q].y, &wq[q].x);
     __syncthreads();
 
     // xpad(lane + 64 r) = px0 + 72 r, xpad(lane + 32 + 64 r) = px0 + 36 + 72 r,
@@ -275,8 +333,7 @@ logmel_kernel(
 #pragma unroll
             for (int r = 1; r < 8; ++r) {
                 v0[r] = cmul(v0[r], tw3[r]);
-                // exp(-2 pi i r (lane + 32) / 512) = tw3[r] * exp(-2 pi i r / 16)
-                v1[r] = cmul(v1[r], cmul(tw3[r], make_float2(kC16[r][0], kC16[r][1])));
+                v1[r] = cmul(v1[r], tw3b[r]);
             }
             fft8(v0);
             fft8(v1);
@@ -284,7 +341,8 @@ logmel_kernel(
             // ---- real-FFT unpacking in registers ----
             // Z_q = Z[lane + 32 q]: q even -> v0[q / 2], q odd -> v1[q / 2].
             // With e = (Z[k] + conj Z[512-k]) / 2, o = -i (Z[k] - conj Z[512-k]) / 2
-            // and w = exp(-2 pi i k / 1024):  X[k] = e + w o,  X[512-k] = conj(e - w o),
+            // (the 1/2 is already in the window) and w = exp(-2 pi i k / 1024):
+            // X[k] = e + w o,  X[512-k] = conj(e - w o),
             // so one (e, w o) serves both bins of a pair.  (The magnitudes are taken
             // from the complex sums, not as |e|^2 + |o|^2 +- 2 Re(e conj(w o)):
             // bins k and 512-k of speech differ by up to 60 dB and subtracting
@@ -305,51 +363,56 @@ logmel_kernel(
                                         __shfl_sync(0xffffffffu, zs.y, partner));
                 pz.x = lane0 ? zo.x : pz.x;
                 pz.y = lane0 ? zo.y : pz.y;
-                const float2 e = make_float2(0.5f * (a.x + pz.x), 0.5f * (a.y - pz.y));
-                const float2 d = make_float2(0.5f * (a.x - pz.x), 0.5f * (a.y + pz.y));
-                const float2 o = make_float2(d.y, -d.x);                    // -i * d
-                const float2 w = cmul(wl, make_float2(kC32[q][0], kC32[q][1]));
-                const float2 wo = cmul(w, o);
+                const float2 e = make_float2(a.x + pz.x, a.y - pz.y);
+                const float2 o = make_float2(a.y + pz.y, pz.x - a.x);       // -i * (a - conj pz)
+                const float2 wo = cmul(wq[q], o);
                 const float xr = e.x + wo.x, xi = e.y + wo.y;
                 const float yr = e.x - wo.x, yi = e.y - wo.y;
                 mag[lane + 32 * q] = sqrt_pos(fmaf(xr, xr, fmaf(xi, xi, 1e-6f)));
                 mag[kHalf - lane - 32 * q] = sqrt_pos(fmaf(yr, yr, fmaf(yi, yi, 1e-6f)));
             }
             // k = 256 pairs with itself: X[256] = conj(Z[256]); Z[256] = Z_8 of lane 0
-            if (lane0) mag[kHalf / 2] = sqrt_pos(fmaf(v0[4].x, v0[4].x, fmaf(v0[4].y, v0[4].y, 1e-6f)));
+            // (Z is halved by the window: |X|^2 = 4 |Z|^2)
+            if (lane0) mag[kHalf / 2] = sqrt_pos(fmaf(4.f * v0[4].x, v0[4].x, fmaf(4.f * v0[4].y, v0[4].y, 1e-6f)));
         }
         __syncthreads();
 
-        // ============ phase 2: sparse mel projection, half-warp lane = frame ============
+        // ============ phase 2: banded mel projection, half-warp lane = frame ============
         {
             const int f = lane & (kTile - 1);          // frame of this lane
-            const int vw = warp * 2 + (lane >> 4);     // virtual warp = half-warp
+            const int h = lane >> 4;                   // which row of the pair
             const int row = row0 + f;
             const bool live = row < total_rows && __ldg(row_seq + row) >= 0;
-            const float* mag = sm.mag[f];
-            // rows are dealt to half-warps in a snake so long (high-frequency)
-            // and short (low-frequency) filters balance
-            const char* const magb = reinterpret_cast<const char*>(mag);
-            for (int j = 0; j * kVirtualWarps < n_mels; ++j) {
-                const int m = j * kVirtualWarps + ((j & 1) ? kVirtualWarps - 1 - vw : vw);
-                if (m >= n_mels) continue;
-                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-                int e = sm.mel_ptr[m];
-                const int e1 = sm.mel_ptr[m + 1];
-                for (; e + 4 <= e1; e += 4) {
-                    const float2 w0 = sm.mel_entry[e], w1 = sm.mel_entry[e + 1];
-                    const float2 w2 = sm.mel_entry[e + 2], w3 = sm.mel_entry[e + 3];
-                    acc0 = fmaf(w0.x, *reinterpret_cast<const float*>(magb + __float_as_int(w0.y)), acc0);
-                    acc1 = fmaf(w1.x, *reinterpret_cast<const float*>(magb + __float_as_int(w1.y)), acc1);
-                    acc2 = fmaf(w2.x, *reinterpret_cast<const float*>(magb + __float_as_int(w2.y)), acc2);
-                    acc3 = fmaf(w3.x, *reinterpret_cast<const float*>(magb + __float_as_int(w3.y)), acc3);
+            const int n_pairs = (n_mels + 1) >> 1;
+            // pairs are dealt to warps in a snake so wide (high-frequency) and
+            // narrow (low-frequency) filters balance
+            for (int j = 0; j * kWarps < n_pairs; ++j) {
+                const int p = j * kWarps + ((j & 1) ? kWarps - 1 - warp : warp);
+                if (p >= n_pairs) continue;
+                const int m = min(2 * p + h, n_mels - 1);
+                float acc;
+                if (banded) {
+                    const int quads = sm.mel_quads[p];
+                    const float4* wt = sm.mel_quad + sm.mel_first[m];
+                    const float4* xq = reinterpret_cast<const float4*>(sm.mag[f]) +
+                                       (sm.mel_bin0[m] >> 2);
+                    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 2
+                    for (int g = 0; g < quads; ++g) {
+                        const float4 w = wt[g], x = xq[g];
+                        acc0 = fmaf(w.x, x.x, acc0);
+                        acc1 = fmaf(w.y, x.y, acc1);
+                        acc2 = fmaf(w.z, x.z, acc2);
+                        acc3 = fmaf(w.w, x.w, acc3);
+                    }
+                    acc = (acc0 + acc1) + (acc2 + acc3);
+                } else {
+                    // any other basis: CSR entries straight from global memory
+                    acc = 0.f;
+                    for (int e = __ldg(mel_ptr + m); e < __ldg(mel_ptr + m + 1); ++e)
+                        acc = fmaf(__ldg(mel_val + e), sm.mag[f][__ldg(mel_col + e)], acc);
                 }
-                for (; e < e1; ++e) {
-                    const float2 w0 = sm.mel_entry[e];
-                    acc0 = fmaf(w0.x, *reinterpret_cast<const float*>(magb + __float_as_int(w0.y)), acc0);
-                }
-                const float acc = (acc0 + acc1) + (acc2 + acc3);
-                float v = logf(fmaxf(acc, 1e-5f));
+                float v = __logf(fmaxf(acc, 1e-5f));
                 if (normalize) v = (v + 10.f) / 10.f;
                 sm.outs[f][m] = live ? v : 0.f;
             }
@@ -360,8 +423,9 @@ logmel_kernel(
         {
             const int rows = min(kTile, total_rows - row0);
             float* dst = out + (size_t)row0 * n_mels;
-            for (int i = tid; i < rows * n_mels; i += blockDim.x)
-                dst[i] = sm.outs[i / n_mels][i % n_mels];
+            for (int f = warp; f < rows; f += kWarps)
+                for (int c = lane; c < n_mels; c += 32)
+                    dst[f * n_mels + c] = sm.outs[f][c];
         }
         // the next tile's phase 1 only touches mag / xchg; outs is rewritten
         // after the next __syncthreads
