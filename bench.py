@@ -89,7 +89,7 @@ def corpus_layout(utterances, seed):
 
 
 def make_audio(lengths, seed, device=None, pin=False):
-    """0.1 * randn audio packed with 4-sample aligned offsets"""
+    """0.1 * randn audio packed with aligned utterance offsets"""
     from emphases_b200 import scheduler
     offsets, total = scheduler.PackedAudio.layout(lengths)
     if device is not None:

@@ -43,6 +43,8 @@ constexpr int kTile = 16;                 // frames per CTA tile
 constexpr int kMaxMels = 128;
 constexpr int kMagStride = 516;           // floats; 16-byte aligned rows, 129 = 1 mod 8 quads
 constexpr int kMaxQuads = 768;            // banded mel table: float4 groups held in smem
+constexpr int kSpan = (kTile - 1) * kHop + kFft;   // samples one interior tile reads: 3424
+constexpr int kRound = 256;               // tile descriptors are computed 256 tiles ahead
 
 // Exchange buffer index with one float2 of padding per 8 (bank spreading)
 __device__ __forceinline__ int xpad(int i) { return i + (i >> 3); }
@@ -58,7 +60,42 @@ struct __align__(16) LogmelSmem {
     int32_t mel_bin0[kMaxMels];    // first bin of the row's band (multiple of 4)
     int32_t mel_quads[kMaxMels / 2];   // quads per row of the pair (both rows padded to it)
     int32_t mel_fits;              // 0: the basis does not fit the table, use the CSR path
+    // audio of one interior tile (16 frames = 3424 samples), fetched with one
+    // cp.async.bulk while the previous tile is in its mel / store phases
+    __align__(16) unsigned char stage[kSpan * sizeof(float)];
+    long long tile_src[kRound];    // per tile of this CTA: element index of the span, or -1
+    unsigned long long bar;        // mbarrier the bulk copy completes on
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// one elected thread: expect `bytes` on the barrier and start the bulk copy
+__device__ __forceinline__ void bulk_fetch(
+    void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile(
+        "{\n\t.reg .b64 state;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 state, [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -233,31 +270,53 @@ logmel_kernel(
     const float2* const ph = reinterpret_cast<const float2*>(sm.hann) + lane;
     const int n_tiles = (total_rows + kTile - 1) / kTile;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // Tile descriptors, kRound tiles of this CTA at a time: the element index of
+    // the tile's first sample when all 16 rows are interior frames of one chunk
+    // (no separator, no zero / reflect padding, span inside the utterance) and
+    // the span is 16-byte aligned; -1 sends the tile down the per-frame path.
+    auto describe_round = [&](int first_it) {
+        const long long t = (long long)blockIdx.x + (long long)(first_it + tid) * gridDim.x;
+        long long desc = -1;
+        const long long r0 = t * kTile;
+        if (tid < kRound && r0 + kTile <= total_rows) {
+            const int u = __ldg(row_seq + r0);
+            if (u >= 0 && __ldg(row_seq + r0 + kTile - 1) == u) {
+                const int frame = (int)r0 - __ldg(row_start + u);
+                const int q0 = frame * kHop;
+                const int a0 = __ldg(chunk_start + u) + q0 - 2 * kPad;
+                const long long index = __ldg(audio_off + u) + a0;
+                const bool ok =
+                    q0 >= kPad && q0 + kSpan - kPad <= __ldg(chunk_len + u) &&
+                    a0 >= 0 && a0 + kSpan <= __ldg(audio_len + u) &&
+                    (reinterpret_cast<uintptr_t>(audio + index) & 15) == 0;
+                if (ok) desc = index;
+            }
+        }
+        if (tid < kRound) sm.tile_src[tid] = desc;
+    };
+    if (tid == 0) mbar_init(&sm.bar, 1);
+    describe_round(0);
+    __syncthreads();
+    if (tid == 0 && sm.tile_src[0] >= 0)
+        bulk_fetch(sm.stage, audio + sm.tile_src[0], kSpan * sizeof(T), &sm.bar);
+    uint32_t parity = 0;
+    int it = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int row0 = tile * kTile;
+        const bool staged = sm.tile_src[it & (kRound - 1)] >= 0;
+        if (staged) {
+            mbar_wait(&sm.bar, parity);
+            parity ^= 1;
+        }
 
         // ======================= phase 1: FFT + magnitude =======================
 #pragma unroll 1
         for (int f = warp; f < kTile; f += kWarps) {
-            const int row = row0 + f;
-            if (row >= total_rows) break;
-            const int u = __ldg(row_seq + row);
-            if (u < 0) continue;                    // separator row
-            const int frame = row - __ldg(row_start + u);
-            const int T_len = __ldg(audio_len + u);
-            const int s = __ldg(chunk_start + u);
-            const int L = __ldg(chunk_len + u);
-            const T* src = audio + __ldg(audio_off + u);
-            const int q0 = frame * kHop;            // first sample in reflect-padded coords
-
             // ---- load 1024 samples as 512 complex, window, first radix-8 pass ----
             // lane handles butterflies j = lane and j = lane + 32; inputs z[j + 64 r]
             float2 v0[8], v1[8];
-            const int a0 = s + q0 - 2 * kPad;       // audio index of sample q0
-            const bool interior = (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
-                                  (a0 >= 0) && (a0 + kFft <= T_len);
-            if (interior) {
-                const T* p = src + a0;
+            auto load_run = [&](const T* p) {    // 1024 contiguous samples
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     int n0 = lane + 64 * r, n1 = n0 + 32;
@@ -271,16 +330,36 @@ logmel_kernel(
                         v1[r] = make_float2(to_float<int16_t>(x1.x), to_float<int16_t>(x1.y));
                     }
                 }
+            };
+            if (staged) {
+                load_run(reinterpret_cast<const T*>(sm.stage) + f * kHop);
             } else {
+                const int row = row0 + f;
+                if (row >= total_rows) break;
+                const int u = __ldg(row_seq + row);
+                if (u < 0) continue;                    // separator row
+                const int frame = row - __ldg(row_start + u);
+                const int T_len = __ldg(audio_len + u);
+                const int s = __ldg(chunk_start + u);
+                const int L = __ldg(chunk_len + u);
+                const T* src = audio + __ldg(audio_off + u);
+                const int q0 = frame * kHop;            // first sample in reflect-padded coords
+                const int a0 = s + q0 - 2 * kPad;       // audio index of sample q0
+                const bool interior = (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
+                                      (a0 >= 0) && (a0 + kFft <= T_len);
+                if (interior) {
+                    load_run(src + a0);
+                } else {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    int n0 = lane + 64 * r, n1 = n0 + 32;
-                    v0[r] = make_float2(
-                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0),
-                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0 + 1));
-                    v1[r] = make_float2(
-                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1),
-                        chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1 + 1));
+                    for (int r = 0; r < 8; ++r) {
+                        int n0 = lane + 64 * r, n1 = n0 + 32;
+                        v0[r] = make_float2(
+                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0),
+                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0 + 1));
+                        v1[r] = make_float2(
+                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1),
+                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1 + 1));
+                    }
                 }
             }
 #pragma unroll
@@ -377,12 +456,23 @@ logmel_kernel(
         }
         __syncthreads();
 
+        // every warp is done with the staged audio: fetch the next tile's span
+        // (it lands while this tile is in its mel / store phases)
+        if (((it + 1) & (kRound - 1)) == 0) {
+            describe_round(it + 1);
+            __syncthreads();
+        }
+        if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
+            const long long next = sm.tile_src[(it + 1) & (kRound - 1)];
+            if (next >= 0) bulk_fetch(sm.stage, audio + next, kSpan * sizeof(T), &sm.bar);
+        }
+
         // ============ phase 2: banded mel projection, half-warp lane = frame ============
         {
             const int f = lane & (kTile - 1);          // frame of this lane
             const int h = lane >> 4;                   // which row of the pair
             const int row = row0 + f;
-            const bool live = row < total_rows && __ldg(row_seq + row) >= 0;
+            const bool live = staged || (row < total_rows && __ldg(row_seq + row) >= 0);
             const int n_pairs = (n_mels + 1) >> 1;
             // pairs are dealt to warps in a snake so wide (high-frequency) and
             // narrow (low-frequency) filters balance

@@ -96,6 +96,17 @@ def basis_to_csr(basis):
 ###############################################################################
 
 
+# Utterances start at multiples of 8 samples in a packed audio buffer: 16 bytes
+# for int16 PCM, 32 for fp32 -- the alignment the log-mel kernel's bulk
+# (cp.async.bulk) staging and vector loads need
+AUDIO_ALIGN = 8
+
+
+def align_samples(samples):
+    """Round a sample count (int or array) up to AUDIO_ALIGN"""
+    return (samples + AUDIO_ALIGN - 1) // AUDIO_ALIGN * AUDIO_ALIGN
+
+
 def seconds_to_frames(seconds):
     """emphases/convert.py:19-31: float floor division"""
     return (seconds * SAMPLE_RATE) // HOPSIZE
@@ -229,7 +240,7 @@ def make_plan(
             chunk_start.append(start)
             chunk_len.append(length)
             bounds_list.append(bounds)
-        cursor += (int(num_samples) + 3) // 4 * 4        # keep offsets % 4 == 0
+        cursor += align_samples(int(num_samples))
     all_bounds = np.concatenate(bounds_list, axis=0) if bounds_list \
         else np.zeros((0, 2), dtype=np.int64)
     return _assemble_plan(
@@ -282,7 +293,7 @@ def _make_plan_single_chunk(utterances, validate_method):
     length = np.maximum(hi - lo, 0)
     if np.any(length <= PADDING):
         return None                       # dropped chunks: general path
-    aligned = (samples + 3) // 4 * 4
+    aligned = align_samples(samples)
     offsets = np.concatenate([[0], np.cumsum(aligned[:-1])])
     return _assemble_plan(
         np.arange(len(utterances), dtype=np.int64),
@@ -332,7 +343,7 @@ def _assemble_plan(
         word_seq=word_seq,
         word_lo=word_lo,
         word_hi=word_hi,
-        audio_samples=max(int(cursor), 4),
+        audio_samples=max(int(cursor), AUDIO_ALIGN),
         audio_offsets=np.asarray(offsets, dtype=np.int64))
 
 

@@ -59,7 +59,8 @@ class PackedAudio:
     """A corpus of mono 16 kHz utterances in ONE pinned host buffer.
 
     Utterance i occupies samples [offsets[i], offsets[i] + lengths[i]);
-    offsets are multiples of 4 samples (the kernels' vector-load alignment).
+    offsets are multiples of engine.AUDIO_ALIGN samples (the kernels' bulk-copy
+    and vector-load alignment).
     A launch covering utterances [a, b) needs a single host->device copy.
     """
 
@@ -78,11 +79,11 @@ class PackedAudio:
     @staticmethod
     def layout(lengths):
         lengths = np.asarray(lengths, dtype=np.int64)
-        padded = (lengths + 3) // 4 * 4
+        padded = engine.align_samples(lengths)
         offsets = np.concatenate([[0], np.cumsum(padded[:-1])]) \
             if len(lengths) else np.zeros(0, dtype=np.int64)
         total = int(padded.sum())
-        return offsets.astype(np.int64), max(total, 4)
+        return offsets.astype(np.int64), max(total, engine.AUDIO_ALIGN)
 
 
 def pack_audio(audios, dtype=torch.float32, pin=True):
@@ -196,7 +197,7 @@ def run_on_device(
             batch_size,
             validate_method=method)
         base = int(packed.offsets[first])
-        end = int(packed.offsets[last] + (packed.lengths[last] + 3) // 4 * 4)
+        end = int(packed.offsets[last] + engine.align_samples(packed.lengths[last]))
         end = min(end, packed.buffer.numel())
         stream = streams[number % len(streams)]
         # one grow-only workspace per stream: launches on a stream run in

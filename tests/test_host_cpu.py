@@ -100,7 +100,7 @@ def test_plan_layout():
     assert plan.row_start[0] == 1
     for u in range(1, 5):
         assert plan.row_start[u] == plan.row_start[u - 1] + plan.n_rows[u - 1] + 1
-        assert plan.audio_off[u] % 4 == 0
+        assert plan.audio_off[u] % engine.AUDIO_ALIGN == 0
     assert plan.total_rows == plan.row_start[-1] + plan.n_rows[-1] + 1
     assert (plan.word_seq >= 0).sum() == plan.n_words.sum()
     for u in range(5):
@@ -182,7 +182,8 @@ def test_scheduler_lpt_and_buckets():
     launches = scheduler.bucket_launches([100, 200, 50, 1000, 20], 400)
     assert launches == [[0, 1, 2], [3], [4]]
     offsets, total = scheduler.PackedAudio.layout([5, 8, 3])
-    assert offsets.tolist() == [0, 8, 16] and total == 20
+    assert offsets.tolist() == [0, 8, 16] and total == 24
+    assert all(o % engine.AUDIO_ALIGN == 0 for o in offsets)
 
 
 def test_vectorised_plan_matches_scalar_chunker():
@@ -212,7 +213,7 @@ def test_vectorised_plan_matches_scalar_chunker():
         np.testing.assert_array_equal(fast.word_lo[s:s + c], bounds[:, 0])
         np.testing.assert_array_equal(fast.word_hi[s:s + c], bounds[:, 1])
         assert (fast.word_seq[s:s + c] == index).all()
-        cursor += (n + 3) // 4 * 4
+        cursor += engine.align_samples(n)
     # utterances that need the general chunker make the fast path bow out
     long_alignment = (np.array([[0.0, 5.0], [5.0, 30.0], [30.0, 31.0]]), 16000)
     assert engine._make_plan_single_chunk(
