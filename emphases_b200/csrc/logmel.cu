@@ -46,9 +46,17 @@ constexpr int kMaxQuads = 768;            // banded mel table: float4 groups hel
 constexpr int kSpan = (kTile - 1) * kHop + kFft;   // samples one interior tile reads: 3424
 constexpr int kRound = 256;               // tile descriptors are computed 256 tiles ahead
 
-// Exchange buffer index with one float2 of padding per 8 (bank spreading)
-__device__ __forceinline__ int xpad(int i) { return i + (i >> 3); }
-constexpr int kXchg = kHalf + kHalf / 8;  // 576 float2 per warp
+// Exchange buffer of one warp (float2 slots).  The two exchanges use different
+// placements, both chosen so that every 8-byte access of a half-warp touches 16
+// distinct banks AND every address is a per-lane base plus a compile-time
+// constant:
+//   after pass 1, element (butterfly j, output r), logical index 8 j + r, sits at
+//     66 r + j                        (written lane = j, read lane % 8 = r)
+//   after pass 2, logical index 64 a + 8 r + b sits at
+//     b + 8 (a % 4) + 40 (r % 4) + 152 (a / 4) + 304 (r / 4)
+//                                      (written lane = 8 (a % 4) + b, read
+//                                       lane = 8 (r % 4) + b)
+constexpr int kXchg = 608;
 
 struct __align__(16) LogmelSmem {
     float mag[kTile][kMagStride];  // bins 513..515 stay zero (band padding reads them)
@@ -58,7 +66,7 @@ struct __align__(16) LogmelSmem {
     float4 mel_quad[kMaxQuads];    // banded dense weights, 4 bins per entry
     int32_t mel_first[kMaxMels];   // first quad of the row in mel_quad
     int32_t mel_bin0[kMaxMels];    // first bin of the row's band (multiple of 4)
-    int32_t mel_quads[kMaxMels / 2];   // quads per row of the pair (both rows padded to it)
+    int32_t mel_quads[kMaxMels / 2];   // double-quads per row of the pair (both rows padded to it)
     int32_t mel_fits;              // 0: the basis does not fit the table, use the CSR path
     // audio of one interior tile (16 frames = 3424 samples), fetched with one
     // cp.async.bulk while the previous tile is in its mel / store phases
@@ -112,6 +120,13 @@ __device__ __forceinline__ float sqrt_pos(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+// natural log of a positive normal number (x >= 1e-5 here): MUFU.LG2 * ln 2,
+// absolute error ~1e-7 relative to log-mel values of magnitude 1..12
+__device__ __forceinline__ float log_pos(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.69314718055994530942f;
 }
 // multiply by -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -212,12 +227,13 @@ logmel_kernel(
         bool fits = true;
         for (int p = 0; p < n_pairs; ++p) {
             const int m0 = 2 * p, m1 = min(2 * p + 1, n_mels - 1);
-            const int quads = max(sm.mel_first[m0], sm.mel_first[m1]);
+            // (an even count: the inner loop takes two quads per step)
+            const int quads = (max(sm.mel_first[m0], sm.mel_first[m1]) + 1) & ~1;
             if (4 * quads > kMagStride || total + 2 * quads > kMaxQuads) {
                 fits = false;
                 break;
             }
-            sm.mel_quads[p] = quads;
+            sm.mel_quads[p] = quads >> 1;
             // a band padded past the end of the mag row is moved down instead
             sm.mel_bin0[m0] = min(sm.mel_bin0[m0], kMagStride - 4 * quads);
             sm.mel_first[m0] = total;
@@ -260,13 +276,10 @@ logmel_kernel(
         sincospif(-2.f * (float)(lane + 32 * q) / (float)kFft, &wq[q].y, &wq[q].x);
     __syncthreads();
 
-    // xpad(lane + 64 r) = px0 + 72 r, xpad(lane + 32 + 64 r) = px0 + 36 + 72 r,
-    // xpad(8 lane + r) = px1 + r, xpad(8 (lane + 32) + r) = px1 + 288 + r,
-    // xpad(b0 + 8 r) = px2 + 9 r with b0 = (lane / 8) 64 + lane % 8, (+256 -> +288)
     float2* const xw = sm.xchg[warp];
-    float2* const px0 = xw + lane + (lane >> 3);
-    float2* const px1 = xw + 9 * lane;
-    float2* const px2 = xw + (lane >> 3) * 72 + (lane & 7);
+    float2* const pw = xw + lane;                               // both stores
+    float2* const pr2 = xw + (lane & 7) * 66 + (lane >> 3);     // pass-2 loads
+    float2* const pr3 = xw + (lane & 7) + 40 * (lane >> 3);     // pass-3 loads
     const float2* const ph = reinterpret_cast<const float2*>(sm.hann) + lane;
     const int n_tiles = (total_rows + kTile - 1) / kTile;
 
@@ -373,8 +386,8 @@ logmel_kernel(
             fft8(v1);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                px1[r] = v0[r];
-                px1[288 + r] = v1[r];
+                pw[66 * r] = v0[r];
+                pw[32 + 66 * r] = v1[r];
             }
             __syncwarp();
 
@@ -382,8 +395,8 @@ logmel_kernel(
             {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    v0[r] = px0[72 * r];
-                    v1[r] = px0[36 + 72 * r];
+                    v0[r] = pr2[8 * r];
+                    v1[r] = pr2[4 + 8 * r];
                 }
 #pragma unroll
                 for (int r = 1; r < 8; ++r) {
@@ -395,8 +408,8 @@ logmel_kernel(
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    px2[9 * r] = v0[r];
-                    px2[288 + 9 * r] = v1[r];
+                    pw[40 * (r & 3) + 304 * (r >> 2)] = v0[r];
+                    pw[152 + 40 * (r & 3) + 304 * (r >> 2)] = v1[r];
                 }
                 __syncwarp();
             }
@@ -405,8 +418,8 @@ logmel_kernel(
             // registers: v0[r] = Z[lane + 64 r], v1[r] = Z[lane + 32 + 64 r]
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                v0[r] = px0[72 * r];
-                v1[r] = px0[36 + 72 * r];
+                v0[r] = pr3[8 * (r & 3) + 152 * (r >> 2)];
+                v1[r] = pr3[304 + 8 * (r & 3) + 152 * (r >> 2)];
             }
             __syncwarp();                      // xw is free for the next frame
 #pragma unroll
@@ -482,18 +495,23 @@ logmel_kernel(
                 const int m = min(2 * p + h, n_mels - 1);
                 float acc;
                 if (banded) {
-                    const int quads = sm.mel_quads[p];
+                    const int steps = sm.mel_quads[p];
                     const float4* wt = sm.mel_quad + sm.mel_first[m];
                     const float4* xq = reinterpret_cast<const float4*>(sm.mag[f]) +
                                        (sm.mel_bin0[m] >> 2);
                     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 2
-                    for (int g = 0; g < quads; ++g) {
-                        const float4 w = wt[g], x = xq[g];
-                        acc0 = fmaf(w.x, x.x, acc0);
-                        acc1 = fmaf(w.y, x.y, acc1);
-                        acc2 = fmaf(w.z, x.z, acc2);
-                        acc3 = fmaf(w.w, x.w, acc3);
+#pragma unroll 1
+                    for (const float4* const end = wt + 2 * steps; wt != end; wt += 2, xq += 2) {
+                        const float4 w0 = wt[0], x0 = xq[0];
+                        const float4 w1 = wt[1], x1 = xq[1];
+                        acc0 = fmaf(w0.x, x0.x, acc0);
+                        acc1 = fmaf(w0.y, x0.y, acc1);
+                        acc2 = fmaf(w0.z, x0.z, acc2);
+                        acc3 = fmaf(w0.w, x0.w, acc3);
+                        acc0 = fmaf(w1.x, x1.x, acc0);
+                        acc1 = fmaf(w1.y, x1.y, acc1);
+                        acc2 = fmaf(w1.z, x1.z, acc2);
+                        acc3 = fmaf(w1.w, x1.w, acc3);
                     }
                     acc = (acc0 + acc1) + (acc2 + acc3);
                 } else {
@@ -502,7 +520,7 @@ logmel_kernel(
                     for (int e = __ldg(mel_ptr + m); e < __ldg(mel_ptr + m + 1); ++e)
                         acc = fmaf(__ldg(mel_val + e), sm.mag[f][__ldg(mel_col + e)], acc);
                 }
-                float v = __logf(fmaxf(acc, 1e-5f));
+                float v = log_pos(fmaxf(acc, 1e-5f));
                 if (normalize) v = (v + 10.f) / 10.f;
                 sm.outs[f][m] = live ? v : 0.f;
             }
