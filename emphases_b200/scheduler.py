@@ -121,16 +121,17 @@ def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
     """Split utterances (kept in order) into launches of <= max_rows packed
     rows; an utterance longer than max_rows gets a launch of its own."""
     gap = engine.separator_rows()
-    launches, current, rows = [], [], gap
-    for index, count in enumerate(frames):
-        need = int(count) + gap
-        if current and rows + need > max_rows:
-            launches.append(current)
-            current, rows = [], gap
-        current.append(index)
-        rows += need
-    if current:
-        launches.append(current)
+    need = np.asarray(frames, dtype=np.int64) + gap
+    # rows used before utterance i if everything were one launch
+    before = np.concatenate([[0], np.cumsum(need)])
+    launches, first, count = [], 0, len(need)
+    while first < count:
+        # largest last with gap + sum(need[first:last]) <= max_rows
+        last = int(np.searchsorted(
+            before, before[first] + max_rows - gap, side='right')) - 1
+        last = min(max(last, first + 1), count)
+        launches.append(list(range(first, last)))
+        first = last
     return launches
 
 
@@ -139,19 +140,18 @@ def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
 ###############################################################################
 
 
-def _prepare(alignments, audios, sample_rate):
-    """Word-time arrays + a PackedAudio for a list of utterances"""
-    times = [as_times(alignment) for alignment in alignments]
+def _prepare(audios, sample_rate):
+    """A PackedAudio for a list of utterances"""
     if isinstance(audios, PackedAudio):
         if sample_rate != emphases.SAMPLE_RATE:
             raise ValueError('PackedAudio must already be at 16 kHz')
-        return times, audios
+        return audios
     if sample_rate != emphases.SAMPLE_RATE:
         audios = [emphases.resample(audio, sample_rate) for audio in audios]
     cuda = [audio for audio in audios if audio.device.type == 'cuda']
     if cuda:
         audios = [audio.cpu() for audio in audios]
-    return times, pack_audio(audios, pin=len(audios) > 1)
+    return pack_audio(audios, pin=len(audios) > 1)
 
 
 def run_on_device(
@@ -168,7 +168,7 @@ def run_on_device(
         return _run_via_model(
             model, alignments, audios, sample_rate, batch_size, device, to_cpu,
             output)
-    times, packed = _prepare(alignments, audios, sample_rate)
+    packed = _prepare(audios, sample_rate)
     eng = emphases.get_engine(device)
     weights = model.packed_weights()
     method = emphases.DOWNSAMPLE_METHOD
@@ -192,10 +192,6 @@ def run_on_device(
     pending = []
     for number, members in enumerate(launches):
         first, last = members[0], members[-1]
-        plan = engine.make_plan(
-            [(times[i], int(packed.lengths[i])) for i in members],
-            batch_size,
-            validate_method=method)
         base = int(packed.offsets[first])
         end = int(packed.offsets[last] + engine.align_samples(packed.lengths[last]))
         end = min(end, packed.buffer.numel())
@@ -204,8 +200,16 @@ def run_on_device(
         # order, so its buffers can be reused without further synchronisation
         ws = eng.workspace(number % len(streams))
         with torch.cuda.stream(stream):
+            # the audio copy goes out first: the host work below (alignment
+            # conversion, planning) then overlaps it, and the copy engine never
+            # waits for the host
             device_audio = ws.get('audio', (end - base,), packed.buffer.dtype)
             device_audio.copy_(packed.buffer[base:end], non_blocking=True)
+        plan = engine.make_plan(
+            [(as_times(alignments[i]), int(packed.lengths[i])) for i in members],
+            batch_size,
+            validate_method=method)
+        with torch.cuda.stream(stream):
             result = eng.forward_packed(
                 device_audio, plan, weights, method=method,
                 location=model.location, precision=precision,
@@ -225,7 +229,7 @@ def run_on_device(
     if to_cpu:
         torch.cuda.current_stream(device).synchronize()
 
-    outputs = [None] * len(times)
+    outputs = [None] * len(alignments)
     for members, plan, scores in pending:
         # word rows without separators are all words of all utterances in order
         keep = torch.from_numpy(np.nonzero(plan.word_seq >= 0)[0])
