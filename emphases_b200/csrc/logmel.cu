@@ -258,8 +258,8 @@ logmel_kernel(
 
     // Per-lane twiddles, kept in registers for the whole kernel:
     //   pass 2: exp(-2 pi i * 8 r (lane % 8) / 512)
-    //   pass 3: exp(-2 pi i r lane / 512) and exp(-2 pi i r (lane + 32) / 512)
-    //   unpack: exp(-2 pi i (lane + 32 q) / 1024)
+    //   pass 3: exp(-2 pi i r j / 512) for j = lane and j = 64 - lane (lane 0: 32)
+    //   unpack: exp(-2 pi i k / 1024), k the bin of slot q
     float2 tw2[8], tw3[8], tw3b[8], wq[8];
 #pragma unroll
     for (int r = 1; r < 8; ++r) {
@@ -268,19 +268,26 @@ logmel_kernel(
         tw2[r] = make_float2(cs, sn);
         sincospif(-2.f * (float)(r * lane) / (float)kHalf, &sn, &cs);
         tw3[r] = make_float2(cs, sn);
-        sincospif(-2.f * (float)(r * (lane + 32)) / (float)kHalf, &sn, &cs);
+        sincospif(-2.f * (float)(r * (lane ? 64 - lane : 32)) / (float)kHalf, &sn, &cs);
         tw3b[r] = make_float2(cs, sn);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        sincospif(-2.f * (float)(lane + 32 * q) / (float)kFft, &wq[q].y, &wq[q].x);
+    for (int q = 0; q < 8; ++q) {
+        // bin of unpacking slot q: lane + 64 q; lane 0 takes 64 q (q < 4) and 32 + 64 (q - 4)
+        const int k = (lane == 0 && q >= 4) ? 64 * q - 224 : lane + 64 * q;
+        sincospif(-2.f * (float)k / (float)kFft, &wq[q].y, &wq[q].x);
+    }
     __syncthreads();
 
     float2* const xw = sm.xchg[warp];
     float2* const pw = xw + lane;                               // both stores
     float2* const pr2 = xw + (lane & 7) * 66 + (lane >> 3);     // pass-2 loads
-    float2* const pr3 = xw + (lane & 7) + 40 * (lane >> 3);     // pass-3 loads
-    const float2* const ph = reinterpret_cast<const float2*>(sm.hann) + lane;
+    float2* const pr3 = xw + (lane & 7) + 40 * (lane >> 3);     // pass-3 loads, butterfly j = lane
+    // pass 3's second butterfly is j = 64 - lane (lane 0: 32), so that Z[k] and
+    // Z[512 - k] of the real-FFT unpacking meet in one lane
+    const int j1 = lane ? 64 - lane : 32;
+    float2* const pr3b = xw + (j1 & 7) + 40 * ((j1 >> 3) & 3) + 304;
+    const float4* const ph = reinterpret_cast<const float4*>(sm.hann) + lane;
     const int n_tiles = (total_rows + kTile - 1) / kTile;
 
     // Tile descriptors, kRound tiles of this CTA at a time: the element index of
@@ -327,20 +334,21 @@ logmel_kernel(
 #pragma unroll 1
         for (int f = warp; f < kTile; f += kWarps) {
             // ---- load 1024 samples as 512 complex, window, first radix-8 pass ----
-            // lane handles butterflies j = lane and j = lane + 32; inputs z[j + 64 r]
+            // pass 1: lane handles butterflies j = 2 lane (v0) and 2 lane + 1 (v1);
+            // inputs z[j + 64 r], so one 16-byte load brings both butterflies' inputs
             float2 v0[8], v1[8];
             auto load_run = [&](const T* p) {    // 1024 contiguous samples
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    int n0 = lane + 64 * r, n1 = n0 + 32;
+                    const int n = 4 * lane + 128 * r;
                     if constexpr (sizeof(T) == 4) {
-                        v0[r] = *reinterpret_cast<const float2*>(p + 2 * n0);
-                        v1[r] = *reinterpret_cast<const float2*>(p + 2 * n1);
+                        const float4 x = *reinterpret_cast<const float4*>(p + n);
+                        v0[r] = make_float2(x.x, x.y);
+                        v1[r] = make_float2(x.z, x.w);
                     } else {
-                        short2 x0 = *reinterpret_cast<const short2*>(p + 2 * n0);
-                        short2 x1 = *reinterpret_cast<const short2*>(p + 2 * n1);
-                        v0[r] = make_float2(to_float<int16_t>(x0.x), to_float<int16_t>(x0.y));
-                        v1[r] = make_float2(to_float<int16_t>(x1.x), to_float<int16_t>(x1.y));
+                        const short4 x = *reinterpret_cast<const short4*>(p + n);
+                        v0[r] = make_float2(to_float<int16_t>(x.x), to_float<int16_t>(x.y));
+                        v1[r] = make_float2(to_float<int16_t>(x.z), to_float<int16_t>(x.w));
                     }
                 }
             };
@@ -365,30 +373,29 @@ logmel_kernel(
                 } else {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        int n0 = lane + 64 * r, n1 = n0 + 32;
+                        const int n = q0 + 4 * lane + 128 * r;
                         v0[r] = make_float2(
-                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0),
-                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n0 + 1));
+                            chunk_sample<T>(src, T_len, s, L, n),
+                            chunk_sample<T>(src, T_len, s, L, n + 1));
                         v1[r] = make_float2(
-                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1),
-                            chunk_sample<T>(src, T_len, s, L, q0 + 2 * n1 + 1));
+                            chunk_sample<T>(src, T_len, s, L, n + 2),
+                            chunk_sample<T>(src, T_len, s, L, n + 3));
                     }
                 }
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const float2 h0 = ph[64 * r], h1 = ph[64 * r + 32];
-                v0[r].x *= h0.x; v0[r].y *= h0.y;
-                v1[r].x *= h1.x; v1[r].y *= h1.y;
+                const float4 h = ph[32 * r];
+                v0[r].x *= h.x; v0[r].y *= h.y;
+                v1[r].x *= h.z; v1[r].y *= h.w;
             }
             // pass 1: Ns = 1, no twiddles, out[8 j + r]
             fft8(v0);
             fft8(v1);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                pw[66 * r] = v0[r];
-                pw[32 + 66 * r] = v1[r];
-            }
+            for (int r = 0; r < 8; ++r)     // slots 66 r + 2 lane, + 1: one 16-byte store
+                *reinterpret_cast<float4*>(pw + lane + 66 * r) =
+                    make_float4(v0[r].x, v0[r].y, v1[r].x, v1[r].y);
             __syncwarp();
 
             // pass 2: Ns = 8; twiddle exp(-2 pi i r (j % 8) / 64)
@@ -415,11 +422,11 @@ logmel_kernel(
             }
 
             // pass 3: Ns = 64; twiddle exp(-2 pi i r j / 512), results stay in
-            // registers: v0[r] = Z[lane + 64 r], v1[r] = Z[lane + 32 + 64 r]
+            // registers: v0[r] = Z[lane + 64 r], v1[r] = Z[j1 + 64 r]
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 v0[r] = pr3[8 * (r & 3) + 152 * (r >> 2)];
-                v1[r] = pr3[304 + 8 * (r & 3) + 152 * (r >> 2)];
+                v1[r] = pr3b[8 * (r & 3) + 152 * (r >> 2)];
             }
             __syncwarp();                      // xw is free for the next frame
 #pragma unroll
@@ -431,7 +438,6 @@ logmel_kernel(
             fft8(v1);
 
             // ---- real-FFT unpacking in registers ----
-            // Z_q = Z[lane + 32 q]: q even -> v0[q / 2], q odd -> v1[q / 2].
             // With e = (Z[k] + conj Z[512-k]) / 2, o = -i (Z[k] - conj Z[512-k]) / 2
             // (the 1/2 is already in the window) and w = exp(-2 pi i k / 1024):
             // X[k] = e + w o,  X[512-k] = conj(e - w o),
@@ -439,29 +445,38 @@ logmel_kernel(
             // from the complex sums, not as |e|^2 + |o|^2 +- 2 Re(e conj(w o)):
             // bins k and 512-k of speech differ by up to 60 dB and subtracting
             // powers would wipe out the weak one.)
-            // A lane handles the 8 pairs k = lane + 32 q, q = 0..7;
-            // Z[512 - k] lives in lane (32 - lane) % 32 as Z_{15-q}
-            // (lane 0: its own Z_{(16-q) % 16}).
+            // Slot q of a lane != 0 pairs k = lane + 64 q (v0[q]) with
+            // 512 - k = (64 - lane) + 64 (7 - q) (v1[7 - q]): no shuffles.  Lane 0
+            // holds the self-paired residues 0 and 32: slots 0..3 pair v0[q] with
+            // v0[(8 - q) % 8] (k = 64 q), slots 4..7 pair v1[q - 4] with v1[11 - q]
+            // (k = 32 + 64 (q - 4)); v0[4] = Z[256] is its own partner (below).
             float* const mag = sm.mag[f];
-            const int partner = (32 - lane) & 31;
             const bool lane0 = lane == 0;
+            float* const mag_lo = mag + lane;                       // slots 0..3: mag_lo[64 q]
+            float* const mag_hi = mag + (lane0 ? -224 : lane);      // slots 4..7: mag_hi[64 q]
+            float* const mir_lo = mag - lane;                       // mir_lo[512 - 64 q]
+            float* const mir_hi = mag - (lane0 ? -224 : lane);      // mir_hi[512 - 64 q]
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float2 a = (q & 1) ? v1[q >> 1] : v0[q >> 1];
-                const float2 zs = ((15 - q) & 1) ? v1[(15 - q) >> 1] : v0[(15 - q) >> 1];
-                const float2 zo = (((16 - q) & 15) & 1) ? v1[((16 - q) & 15) >> 1]
-                                                       : v0[((16 - q) & 15) >> 1];
-                float2 pz = make_float2(__shfl_sync(0xffffffffu, zs.x, partner),
-                                        __shfl_sync(0xffffffffu, zs.y, partner));
-                pz.x = lane0 ? zo.x : pz.x;
-                pz.y = lane0 ? zo.y : pz.y;
+                float2 a = v0[q], pz = v1[7 - q];
+                if (q < 4) {
+                    const float2 alt = v0[(8 - q) & 7];
+                    pz.x = lane0 ? alt.x : pz.x;
+                    pz.y = lane0 ? alt.y : pz.y;
+                } else {
+                    const float2 alt_a = v1[q - 4], alt = v1[11 - q];
+                    a.x = lane0 ? alt_a.x : a.x;
+                    a.y = lane0 ? alt_a.y : a.y;
+                    pz.x = lane0 ? alt.x : pz.x;
+                    pz.y = lane0 ? alt.y : pz.y;
+                }
                 const float2 e = make_float2(a.x + pz.x, a.y - pz.y);
                 const float2 o = make_float2(a.y + pz.y, pz.x - a.x);       // -i * (a - conj pz)
                 const float2 wo = cmul(wq[q], o);
                 const float xr = e.x + wo.x, xi = e.y + wo.y;
                 const float yr = e.x - wo.x, yi = e.y - wo.y;
-                mag[lane + 32 * q] = sqrt_pos(fmaf(xr, xr, fmaf(xi, xi, 1e-6f)));
-                mag[kHalf - lane - 32 * q] = sqrt_pos(fmaf(yr, yr, fmaf(yi, yi, 1e-6f)));
+                (q < 4 ? mag_lo : mag_hi)[64 * q] = sqrt_pos(fmaf(xr, xr, fmaf(xi, xi, 1e-6f)));
+                (q < 4 ? mir_lo : mir_hi)[kHalf - 64 * q] = sqrt_pos(fmaf(yr, yr, fmaf(yi, yi, 1e-6f)));
             }
             // k = 256 pairs with itself: X[256] = conj(Z[256]); Z[256] = Z_8 of lane 0
             // (Z is halved by the window: |X|^2 = 4 |Z|^2)

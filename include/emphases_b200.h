@@ -93,10 +93,11 @@ int emph_row_index(
  *
  *   audio          packed fp32 samples (channel 0 of each utterance)
  *   audio_off[u]   first sample of the utterance chunk u is cut from
- *                  (must be even; when it is a multiple of 4 (fp32) / 8
+ *                  (must be a multiple of 4: frames are read with 4-sample
+ *                  vector loads; when it is a multiple of 4 (fp32) / 8
  *                  (int16) samples, i.e. 16 bytes, tiles of 16 interior
  *                  frames are staged into shared memory with one
- *                  cp.async.bulk instead of per-frame vector loads)
+ *                  cp.async.bulk instead of per-frame loads)
  *   audio_len[u]   T, that utterance's length in samples
  *   chunk_start[u] first sample of the chunk in ZERO-PADDED coordinates
  *                  (432 zeros before the utterance), = 160 * first frame
