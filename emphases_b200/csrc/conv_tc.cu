@@ -72,7 +72,7 @@ struct __align__(128) Smem {
     static constexpr int kSlots = Config<SPLIT>::kSlots;
     uint8_t act[kSlots][Config<SPLIT>::kParts][ACT_BYTES + 64];   // +64 keeps 128-B alignment
     uint8_t w[kStages][W_LAYER_BYTES];
-    uint8_t ones[2 * RB * 16 + 64];           // A operand of the bias MMA
+    float bias[kMaxLayers][C];                // fp32 bias, added by the epilogue
     uint64_t w_full[kStages];
     uint64_t w_empty[kStages];
     uint64_t act_ready[kSlots];
@@ -231,7 +231,7 @@ __device__ __forceinline__ void store_kgroup(uint8_t* act_hi, int kg, int buffer
 template <bool SPLIT>
 __device__ __noinline__ void epilogue_generic(
     uint32_t taddr, uint8_t* act, int row, int a, bool valid, bool last, bool store,
-    float* yrow) {
+    float* yrow, const float* bias) {
 #pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 16) {
         uint32_t raw[16];
@@ -240,7 +240,7 @@ __device__ __noinline__ void epilogue_generic(
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            v[j] = valid ? apply_activation(__uint_as_float(raw[j]), a) : 0.f;
+            v[j] = valid ? apply_activation(__uint_as_float(raw[j]) + bias[c0 + j], a) : 0.f;
         if (!last) {
             const float (&first)[8] = *reinterpret_cast<const float(*)[8]>(&v[0]);
             const float (&second)[8] = *reinterpret_cast<const float(*)[8]>(&v[8]);
@@ -281,11 +281,13 @@ conv_stack_tc_kernel(
         reinterpret_cast<uint32_t*>(
             sm.act[buffer / kParts][buffer % kParts] + (kg * RB + (edge ? RB - 1 : 0)) * 16)[word] = 0u;
     }
-    // bias chunk A operand: k-group 0 = {1, 1, 0, ...} for every row, k-group 1 = 0,
-    // so D = 1 * bias_hi + 1 * bias_lo (bf16 split of the fp32 bias) before the taps
-    for (int i = tid; i < 2 * RB * 4; i += kThreads) {
-        const int kg = i / (RB * 4), word = i & 3;
-        reinterpret_cast<uint32_t*>(sm.ones)[i] = (kg == 0 && word == 0) ? 0x3F803F80u : 0u;
+    // fp32 bias of every layer, rebuilt from the (hi, lo) bf16 pair the packed
+    // blob carries after each layer's taps; the epilogue adds it
+    for (int i = tid; i < n_layers * C; i += kThreads) {
+        const int layer = i / C, n = i % C;
+        const __nv_bfloat16* chunk = reinterpret_cast<const __nv_bfloat16*>(
+            weights + (size_t)layer * kEntries * W_LAYER_BYTES + W_CONV_BYTES);
+        sm.bias[layer][n] = __bfloat162float(chunk[n * 8]) + __bfloat162float(chunk[n * 8 + 1]);
     }
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -315,39 +317,60 @@ conv_stack_tc_kernel(
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * kAccStride;
         uint32_t done_parity = 0;
 
+        // One tile = M * C / 4 = 2560 float4 = 20 per thread, coalesced.  The
+        // first tile is fetched up front; every later one is requested while the
+        // tensor core still works on the previous tile's last layer, so its
+        // latency never reaches the MMA warp.  The rows wait in registers already
+        // converted to bf16 (40 registers; 80 with the lo words in SPLIT mode).
+        uint2 pk_hi[20];
+        uint2 pk_lo[SPLIT ? 20 : 1];
+        auto fetch_tile = [&](int tile) {
+            const int row0 = tile * tile_rows - halo;
+            // two batches of 10 loads in flight (the registers for 20 are not there)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 v[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    const int i = gtid + 128 * (10 * half + k);
+                    const int gr = row0 + i / (C / 4);
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gr >= 0 && gr < total_rows)
+                        v[k] = ld_stream4(x + (size_t)gr * C + 4 * (i % (C / 4)));
+                }
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    uint32_t h0, h1, l0 = 0u, l1 = 0u;
+                    split_pack<SPLIT>(v[k].x, v[k].y, h0, l0);
+                    split_pack<SPLIT>(v[k].z, v[k].w, h1, l1);
+                    pk_hi[10 * half + k] = make_uint2(h0, h1);
+                    if constexpr (SPLIT) pk_lo[10 * half + k] = make_uint2(l0, l1);
+                }
+            }
+        };
+        {
+            const int first = blockIdx.x * kSlots + slot;
+            if (first < n_tiles) fetch_tile(first);
+        }
+
         for (int round = 0; round < rounds; ++round) {
             const int tile = (round * gridDim.x + blockIdx.x) * kSlots + slot;
             if (tile >= n_tiles) break;
+            const int next_tile = tile + gridDim.x * kSlots;
             const int row0 = tile * tile_rows - halo;   // global row of local row 0
             const int g = row0 + row;
             const bool in_range = g >= 0 && g < total_rows;
             const bool valid = in_range && __ldg(row_seq + g) >= 0;
 
-            // fp32 rows -> bf16 A operand(s): coalesced float4 reads, 10 in flight
-            // per thread (M * C / 4 = 2560 float4 = 20 per thread)
+            // bf16 rows -> the slot's A operand buffer(s)
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float4 v[10];
-#pragma unroll
-                for (int it = 0; it < 10; ++it) {
-                    const int i = gtid + 128 * (half * 10 + it);
-                    const int gr = row0 + i / (C / 4);
-                    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gr >= 0 && gr < total_rows)
-                        v[it] = ld_stream4(x + (size_t)gr * C + 4 * (i % (C / 4)));
-                }
-#pragma unroll
-                for (int it = 0; it < 10; ++it) {
-                    const int i = gtid + 128 * (half * 10 + it);
-                    const int r = i / (C / 4), c4 = i % (C / 4);
-                    uint32_t h0, h1, l0, l1;
-                    split_pack<SPLIT>(v[it].x, v[it].y, h0, l0);
-                    split_pack<SPLIT>(v[it].z, v[it].w, h1, l1);
-                    uint8_t* dst = act + ((c4 >> 1) * RB + r + 1) * 16 + (c4 & 1) * 8;
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-                    if constexpr (SPLIT)
-                        *reinterpret_cast<uint2*>(dst + ACT_BYTES + 64) = make_uint2(l0, l1);
-                }
+            for (int it = 0; it < 20; ++it) {
+                const int i = gtid + 128 * it;
+                const int r = i / (C / 4), c4 = i % (C / 4);
+                uint8_t* dst = act + ((c4 >> 1) * RB + r + 1) * 16 + (c4 & 1) * 8;
+                *reinterpret_cast<uint2*>(dst) = pk_hi[it];
+                if constexpr (SPLIT)
+                    *reinterpret_cast<uint2*>(dst + ACT_BYTES + 64) = pk_lo[it];
             }
             fence_proxy_async();        // generic-proxy writes -> visible to the tensor core
             tc_fence_before();          // orders the previous round's TMEM reads too
@@ -355,91 +378,133 @@ conv_stack_tc_kernel(
             if (lane == 0) mbar_arrive(&sm.act_ready[slot]);
 
             // pull the next round's tile of this slot into L2 while this one computes
-            {
-                const int next = tile + gridDim.x * kSlots;
-                if (next < n_tiles) {
-                    const long lo = (long)max(next * tile_rows - halo, 0) * C * 4;
-                    const long hi = (long)min(next * tile_rows - halo + M, total_rows) * C * 4;
-                    const char* base = reinterpret_cast<const char*>(x);
-                    for (long off = lo + 128 * gtid; off < hi; off += 128 * 128)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-                }
+            if (next_tile < n_tiles) {
+                const long lo = (long)max(next_tile * tile_rows - halo, 0) * C * 4;
+                const long hi = (long)min(next_tile * tile_rows - halo + M, total_rows) * C * 4;
+                const char* base = reinterpret_cast<const char*>(x);
+                for (long off = lo + 128 * gtid; off < hi; off += 128 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
             }
 
             // a warp whose 32 rows are all real frames (97 % of warps) skips
             // the separator masking
             const bool zero = !__all_sync(0xffffffffu, valid) && !valid;
 
-            for (int layer = 0; layer < n_layers; ++layer) {
+            // ---- layers 0 .. n-2: accumulator -> next layer's A operand ----
+            for (int layer = 0; layer + 1 < n_layers; ++layer) {
                 const int a = acts.act[layer];
-                const bool last = layer + 1 == n_layers;
                 const bool simple = a == EMPH_ACT_RELU || a == EMPH_ACT_NONE;
                 const bool relu = a == EMPH_ACT_RELU;
                 mbar_wait(&sm.mma_done[slot], done_parity);
                 done_parity ^= 1;
                 tc_fence_after();
                 if (simple) {
-                    // whole accumulator row (bias already added by the bias MMA):
-                    // 5 x 16 columns, one wait
+                    // whole accumulator row, then the fp32 bias: 5 x 16 columns, one wait
                     uint32_t raw[C];
 #pragma unroll
                     for (int c0 = 0; c0 < C; c0 += 16)
                         tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
                     tmem_ld_wait();
-                    if (!last) {
-                        if constexpr (!SPLIT) {
-                            uint8_t* dst = act + (row + 1) * 16;
-#pragma unroll
-                            for (int kg = 0; kg < KG; ++kg) {
-                                uint32_t p[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float lo = __uint_as_float(raw[8 * kg + 2 * j]);
-                                    const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]);
-                                    p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
-                                }
-                                if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
-                                *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
-                                    make_uint4(p[0], p[1], p[2], p[3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int kg = 0; kg < KG; ++kg) {
-                                float v[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    v[j] = __uint_as_float(raw[8 * kg + j]);
-                                    if (relu) v[j] = fmaxf(v[j], 0.f);
-                                    if (zero) v[j] = 0.f;
-                                }
-                                store_kgroup<true>(act, kg, row + 1, v);
-                            }
-                        }
-                    } else if (in_range && row >= halo && row < M - halo) {
-                        float4* dst = reinterpret_cast<float4*>(y + (size_t)g * C);
+                    {
+                        const float4* b4 = reinterpret_cast<const float4*>(sm.bias[layer]);
 #pragma unroll
                         for (int c4 = 0; c4 < C / 4; ++c4) {
-                            float v[4];
+                            const float4 b = b4[c4];
+                            raw[4 * c4 + 0] = __float_as_uint(__uint_as_float(raw[4 * c4 + 0]) + b.x);
+                            raw[4 * c4 + 1] = __float_as_uint(__uint_as_float(raw[4 * c4 + 1]) + b.y);
+                            raw[4 * c4 + 2] = __float_as_uint(__uint_as_float(raw[4 * c4 + 2]) + b.z);
+                            raw[4 * c4 + 3] = __float_as_uint(__uint_as_float(raw[4 * c4 + 3]) + b.w);
+                        }
+                    }
+                    if constexpr (!SPLIT) {
+                        uint8_t* dst = act + (row + 1) * 16;
+#pragma unroll
+                        for (int kg = 0; kg < KG; ++kg) {
+                            uint32_t p[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                v[j] = __uint_as_float(raw[4 * c4 + j]);
-                                if (relu) v[j] = fmaxf(v[j], 0.f);
-                                if (zero) v[j] = 0.f;
+                                const float lo = __uint_as_float(raw[8 * kg + 2 * j]);
+                                const float hi = __uint_as_float(raw[8 * kg + 2 * j + 1]);
+                                p[j] = relu ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi);
                             }
-                            dst[c4] = make_float4(v[0], v[1], v[2], v[3]);
+                            if (zero) p[0] = p[1] = p[2] = p[3] = 0u;
+                            *reinterpret_cast<uint4*>(dst + kg * RB * 16) =
+                                make_uint4(p[0], p[1], p[2], p[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kg = 0; kg < KG; ++kg) {
+                            float w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                w[j] = __uint_as_float(raw[8 * kg + j]);
+                                if (relu) w[j] = fmaxf(w[j], 0.f);
+                                if (zero) w[j] = 0.f;
+                            }
+                            store_kgroup<true>(act, kg, row + 1, w);
                         }
                     }
                 } else {
                     epilogue_generic<SPLIT>(
-                        taddr, act, row, a, valid, last,
-                        last && in_range && row >= halo && row < M - halo,
-                        y + (size_t)(in_range ? g : 0) * C);
+                        taddr, act, row, a, valid, false, false, y, sm.bias[layer]);
                 }
-                if (!last) {
-                    fence_proxy_async();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.act_ready[slot]);
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.act_ready[slot]);
+            }
+
+            // ---- last layer: fp32 rows to HBM ----
+            {
+                const int layer = n_layers - 1;
+                const int a = acts.act[layer];
+                const bool simple = a == EMPH_ACT_RELU || a == EMPH_ACT_NONE;
+                const bool relu = a == EMPH_ACT_RELU;
+                // the next tile's rows travel while this tile's last MMAs run, so
+                // their latency never reaches the MMA warp
+                // (not across the out-of-line generic epilogue: its call would
+                // spill all of them)
+                // (unconditional -- rows past the end load nothing -- so the
+                // registers are provably dead during the earlier layers)
+                if (simple) fetch_tile(next_tile);
+                mbar_wait(&sm.mma_done[slot], done_parity);
+                done_parity ^= 1;
+                tc_fence_after();
+                if (simple) {
+                    // 16 columns at a time (the next tile's 20 float4 are live in
+                    // registers here)
+                    const bool store = in_range && row >= halo && row < M - halo;
+                    float4* dst = reinterpret_cast<float4*>(y + (size_t)(in_range ? g : 0) * C);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C; c0 += 16) {
+                        uint32_t raw[16];
+                        tmem_ld16(taddr + c0, raw);
+                        tmem_ld_wait();
+                        if (store) {
+                            const float4* b4 = reinterpret_cast<const float4*>(sm.bias[layer] + c0);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4) {
+                                const float4 b = b4[c4];
+                                float w[4] = {
+                                    __uint_as_float(raw[4 * c4 + 0]) + b.x,
+                                    __uint_as_float(raw[4 * c4 + 1]) + b.y,
+                                    __uint_as_float(raw[4 * c4 + 2]) + b.z,
+                                    __uint_as_float(raw[4 * c4 + 3]) + b.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (relu) w[j] = fmaxf(w[j], 0.f);
+                                    if (zero) w[j] = 0.f;
+                                }
+                                dst[(c0 >> 2) + c4] = make_float4(w[0], w[1], w[2], w[3]);
+                            }
+                        }
+                    }
+                } else {
+                    epilogue_generic<SPLIT>(
+                        taddr, act, row, a, valid, true,
+                        in_range && row >= halo && row < M - halo,
+                        y + (size_t)(in_range ? g : 0) * C, sm.bias[layer]);
+                    fetch_tile(next_tile);
                 }
             }
         }
@@ -452,7 +517,6 @@ conv_stack_tc_kernel(
         uint32_t ready_parity = 0;                   // bit s = parity of slot s
         int stage = 0;
         uint32_t full_parity = 0;
-        const uint64_t d_ones = make_desc(smem_u32(sm.ones), RB * 16, 128);
         uint64_t d_act[kSlots];
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) d_act[s] = make_desc(smem_u32(sm.act[s][0]), RB * 16, 128);
@@ -477,8 +541,6 @@ conv_stack_tc_kernel(
                             }
                             if (elect_one()) {
                                 const uint32_t d = tmem_base + s * kAccStride;
-                                if (entry == 0)
-                                    umma_bf16(d, d_ones, d_w + (W_CONV_BYTES >> 4), kInstrDesc, 0);
                                 // entry 0: hi (and lo) activations x W(_hi); entry 1: hi x W_lo
                                 const int parts = entry == 0 ? kParts : 1;
 #pragma unroll
@@ -493,7 +555,8 @@ conv_stack_tc_kernel(
                                                     d_act[s] + part * kLoPart +
                                                         (uint64_t)(((2 * kk) * RB * 16 + tap * 16) >> 4),
                                                     d_w + (uint64_t)((tap * W_TAP_BYTES + (2 * kk) * C * 16) >> 4),
-                                                    kInstrDesc, 1);
+                                                    kInstrDesc,
+                                                    (entry | part | tap | kk) != 0);
                                             }
                                         }
                                     }
