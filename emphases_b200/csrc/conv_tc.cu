@@ -36,6 +36,14 @@ namespace emph {
 
 namespace tc {
 
+#ifdef EXP_TRACE
+// timeline of CTA 0 (tuning builds only): [event][index] clock64 values
+__device__ long long g_trace[8][512];
+#define TRACE(ev, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[ev][idx] = clock64(); } while (0)
+#else
+#define TRACE(ev, idx) do {} while (0)
+#endif
+
 constexpr int C = 80;                 // channels (in = out)
 constexpr int KS = 3;                 // taps
 constexpr int KG = C / 8;             // k-groups of 8 channels
@@ -395,7 +403,9 @@ conv_stack_tc_kernel(
                 const int a = acts.act[layer];
                 const bool simple = a == EMPH_ACT_RELU || a == EMPH_ACT_NONE;
                 const bool relu = a == EMPH_ACT_RELU;
+                if (tid == 0) TRACE(0, round * n_layers + layer);
                 mbar_wait(&sm.mma_done[slot], done_parity);
+                if (tid == 0) TRACE(1, round * n_layers + layer);
                 done_parity ^= 1;
                 tc_fence_after();
                 if (simple) {
@@ -448,10 +458,12 @@ conv_stack_tc_kernel(
                     epilogue_generic<SPLIT>(
                         taddr, act, row, a, valid, false, false, y, sm.bias[layer]);
                 }
+                if (tid == 0) TRACE(2, round * n_layers + layer);
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.act_ready[slot]);
+                if (tid == 0) TRACE(3, round * n_layers + layer);
             }
 
             // ---- last layer: fp32 rows to HBM ----
@@ -535,7 +547,9 @@ conv_stack_tc_kernel(
                     for (int s = 0; s < kSlots; ++s) {
                         if (s < active) {
                             if (entry == 0) {
+                                if (s == 0 && lane == 0) TRACE(4, round * n_layers + layer);
                                 mbar_wait(&sm.act_ready[s], (ready_parity >> s) & 1);
+                                if (s == 0 && lane == 0) TRACE(5, round * n_layers + layer);
                                 ready_parity ^= 1u << s;
                                 tc_fence_after();
                             }
@@ -564,6 +578,8 @@ conv_stack_tc_kernel(
                                 if (entry == kEntries - 1) umma_commit(&sm.mma_done[s]);
                             }
                             __syncwarp();
+                            if (s == 0 && lane == 0) TRACE(6, round * n_layers + layer);
+                            if (s == kSlots - 1 && lane == 0) TRACE(7, round * n_layers + layer);
                         }
                     }
                     if (elect_one()) umma_commit(&sm.w_empty[stage]);   // ring entry consumed
@@ -720,6 +736,12 @@ int conv_stack_bf16x3_tc(
 }
 
 }  // namespace emph
+
+#ifdef EXP_TRACE
+extern "C" int emph_conv_trace_read(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, emph::tc::g_trace, sizeof(long long) * 8 * 512);
+}
+#endif
 
 extern "C" int emph_conv_weights_tc_bytes(
     int32_t n_layers, int32_t channels, int32_t kernel_size, int32_t precision) {
