@@ -114,6 +114,90 @@ def test_logmel_ragged_edges(eng):
         assert (rows - expected).abs().max().item() < 2e-5
 
 
+def _logmel_corpus(seed=11):
+    """A few utterances long enough for bulk-staged interior tiles, plus short ones"""
+    from emphases_b200 import engine
+    generator = torch.Generator().manual_seed(seed)
+    utterances, audios = [], []
+    for samples, words in [(52000, 7), (9000, 2), (160000, 20), (31111, 4), (16 * 160 + 1000, 2)]:
+        audio = (0.1 * torch.randn(1, samples, generator=generator)).clamp(-1, 1)
+        duration = samples / 16000.
+        cuts = torch.sort(torch.rand(words - 1, generator=generator) * duration).values
+        edges = np.concatenate([[0.], cuts.numpy(), [duration]])
+        utterances.append((np.stack([edges[:-1], edges[1:]], axis=1), samples))
+        audios.append(audio)
+    plan = engine.make_plan(utterances)
+    packed = torch.zeros(plan.audio_samples)
+    for offset, audio in zip(plan.audio_offsets, audios):
+        packed[offset:offset + audio.shape[-1]] = audio[0]
+    return utterances, audios, plan, packed
+
+
+def _check_logmel(out, plan, utterances, audios, basis=None, tolerance=2e-5):
+    for u in range(plan.n_seq):
+        index = int(plan.utterance[u])
+        expected = list(oracle.preprocess(
+            times_list(utterances[index][0]), audios[index], None, basis))[0][0][0].T
+        rows = out[plan.row_start[u]:plan.row_start[u] + plan.n_rows[u]]
+        assert rows.shape == expected.shape
+        assert (rows - expected).abs().max().item() < tolerance
+        assert out[plan.row_start[u] - 1].abs().max() == 0      # separator row
+
+
+@pytest.mark.parametrize('dtype', ['f32', 'i16'])
+def test_logmel_staged_tiles_match_per_frame_path(eng, dtype):
+    """Interior tiles are fetched by cp.async.bulk when the span is 16-byte
+    aligned; a buffer shifted by 4 samples (8 bytes of int16) sends every tile
+    down the per-frame vector-load path.  Both must agree bit for bit and
+    match the oracle."""
+    utterances, audios, plan, packed = _logmel_corpus()
+    if dtype == 'i16':
+        pcm = (packed * 32768.).round().clamp(-32768, 32767).to(torch.int16)
+        audios = [
+            (a * 32768.).round().clamp(-32768, 32767).to(torch.int16).float() / 32768.
+            for a in audios]
+        packed = pcm
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(
+        views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    staged = eng.logmel(packed.cuda(), views, plan, row_seq).cpu().clone()
+    _check_logmel(staged, plan, utterances, audios)
+    # 32-byte aligned allocation + 4 samples: still 16-byte aligned for fp32,
+    # only 8-byte aligned for int16
+    shifted = torch.zeros(packed.numel() + 8, dtype=packed.dtype, device='cuda:0')
+    shifted[4:4 + packed.numel()] = packed.cuda()
+    other = eng.logmel(shifted[4:], views, plan, row_seq).cpu()
+    assert torch.equal(staged, other)
+
+
+@pytest.mark.parametrize('kind', ['narrow33', 'scattered'])
+def test_logmel_other_bases(kind):
+    """The banded mel table is built from whatever CSR basis is passed: an odd
+    number of triangular filters, and a basis too scattered for the table
+    (the kernel then reads the CSR entries from global memory)."""
+    from emphases_b200 import engine
+    generator = np.random.default_rng(5)
+    if kind == 'narrow33':
+        basis = engine.mel_basis(n_mels=33)
+    else:
+        basis = np.zeros((80, 513), dtype=np.float32)
+        for m in range(80):
+            cols = generator.choice(513, size=24, replace=False)
+            basis[m, cols] = generator.uniform(0.001, 0.02, size=24).astype(np.float32)
+    local = engine.Engine('cuda:0', n_mels=basis.shape[0])
+    ptr, col, val = engine.basis_to_csr(basis)
+    local.mel_ptr = torch.from_numpy(ptr).cuda()
+    local.mel_col = torch.from_numpy(col).cuda()
+    local.mel_val = torch.from_numpy(val).cuda()
+    utterances, audios, plan, packed = _logmel_corpus(seed=12)
+    views = local.upload_plan(plan)
+    row_seq = local.row_index(
+        views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    out = local.logmel(packed.cuda(), views, plan, row_seq).cpu()
+    assert out.shape[1] == basis.shape[0]
+    _check_logmel(out, plan, utterances, audios, basis=basis)
+
+
 def oracle_conv_rows(state, prefix_layers, x_rows, lengths):
     """Apply convs per sequence with the oracle, return packed rows"""
     from emphases_b200 import engine
