@@ -546,16 +546,21 @@ def main():
             'achieved': logmel_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': logmel_gbs / hbm_peak,
             # dram read+write per frame from the ncu --set full capture in
-            # profiles/r01m_final_ncu.md, scaled to this launch
-            'traffic': 915.0 * frames,
-            'note': ('fp32 FFT: FP32-issue/latency bound, not HBM bound '
-                     '(960 algorithmic B/frame vs ~30 kFLOP/frame), DESIGN.md 4.1')},
+            # profiles/r01w_ncu.md, scaled to this launch
+            'traffic': 921.0 * frames,
+            # what actually binds it (same capture): warp-instruction issue and
+            # the shared-memory pipe, both ~64 % busy; the FP32 pipe 38 %
+            'pipes_ncu': {'issue_active': 0.636, 'smem_wavefronts': 0.644,
+                          'fma_pipe': 0.383},
+            'note': ('fp32 FFT: instruction-issue / shared-memory-pipe bound, not '
+                     'HBM bound (960 algorithmic B/frame vs ~30 kFLOP/frame), '
+                     'DESIGN.md 4.1')},
         'conv_frames': {
             'kernel': 'conv_stack (7 fused frame layers)',
             'bound': conv_bound,
             'achieved': conv_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s',
             'frac': conv_tflops / tensor_peak,
-            'traffic': 584.0 * frames if precision == 'bf16' else None},
+            'traffic': 624.0 * frames if precision == 'bf16' else None},
         'pool': {
             'kernel': 'pool_words_kernel',
             'bound': 'hbm',
