@@ -10,7 +10,6 @@ Differences from the reference, all documented in DESIGN.md:
 """
 import contextlib
 import os
-from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
@@ -104,11 +103,11 @@ def from_files_to_files(
             parsed.write_textgrids(
                 [f'{prefix}.TextGrid' for prefix in output_prefixes], usable)
 
-    def save(index):
-        torch.save(scores[index], f'{output_prefixes[index]}.pt')
-
-    with ThreadPoolExecutor(workers) as pool:
-        list(pool.map(save, [int(i) for i in indices]))
+    # {prefix}.pt: same archives torch.save would write, from the native pool
+    done = [int(i) for i in indices]
+    corpus.write_scores(
+        [f'{output_prefixes[i]}.pt' for i in done], [scores[i] for i in done],
+        workers)
 
     # Everything else (other encodings / sample rates) goes file by file
     first_gpu = gpu[0] if isinstance(gpu, (list, tuple)) and gpu else gpu

@@ -105,3 +105,27 @@ class Corpus:
         array = (ctypes.c_char_p * len(encoded))(*encoded)
         if self.lib.emph_corpus_write_textgrids(self.handle, array, self.threads):
             raise OSError('could not write some TextGrid files')
+
+
+def write_scores(paths, scores, threads=None):
+    """torch.save(scores[i], paths[i]) for a list of (1, W) float32 CPU tensors
+    (emphases/core.py:112,177) on the native thread pool: the files are the zip
+    archives torch.load reads, written without the Python pickler."""
+    import numpy as np
+    import torch
+    lib = _lib.load()
+    counts = np.array([int(score.shape[-1]) for score in scores], dtype=np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts[:-1])]).astype(np.int64) \
+        if len(counts) else np.zeros(0, dtype=np.int64)
+    flat = torch.cat([
+        score.detach().reshape(-1).to(device='cpu', dtype=torch.float32)
+        for score in scores]) if len(scores) else torch.zeros(0)
+    flat = np.ascontiguousarray(flat.numpy())
+    encoded = [os.fsencode(str(path)) for path in paths]
+    array = (ctypes.c_char_p * len(encoded))(*encoded)
+    threads = threads or min(32, os.cpu_count() or 1)
+    if lib.emph_write_score_files(
+        array, flat.ctypes.data, offsets.ctypes.data, counts.ctypes.data,
+        len(encoded), threads
+    ):
+        raise OSError('could not write some score files')

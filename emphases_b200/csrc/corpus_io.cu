@@ -226,6 +226,122 @@ bool write_textgrid(const std::string& path, const std::vector<Word>& words) {
     return wrote == out.size();
 }
 
+// ---------------------------------------------------------------------------
+// torch.save(scores, f'{prefix}.pt') (emphases/core.py:112,177) without the
+// Python pickler: a (1, W) float32 tensor as the zip archive torch.load reads
+// (records <stem>/data.pkl, byteorder, data/0 (64-byte aligned), version; all
+// stored, CRC-32 in the headers).
+uint32_t crc32_of(const unsigned char* data, size_t size) {
+    static uint32_t table[256];
+    static std::atomic<bool> ready(false);
+    if (!ready.load(std::memory_order_acquire)) {
+        uint32_t local[256];
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            local[i] = c;
+        }
+        std::memcpy(table, local, sizeof(table));     // idempotent if two threads race
+        ready.store(true, std::memory_order_release);
+    }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < size; ++i) c = table[(c ^ data[i]) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+
+void put16(std::string& out, uint32_t v) {
+    out.push_back((char)(v & 0xFF));
+    out.push_back((char)((v >> 8) & 0xFF));
+}
+void put32(std::string& out, uint32_t v) {
+    put16(out, v & 0xFFFF);
+    put16(out, v >> 16);
+}
+// pickle protocol-2 integer (BININT1 / BININT2 / BININT)
+void put_pickle_int(std::string& out, uint32_t v) {
+    if (v < 256) {
+        out.push_back('K');
+        out.push_back((char)v);
+    } else if (v < 65536) {
+        out.push_back('M');
+        put16(out, v);
+    } else {
+        out.push_back('J');
+        put32(out, v);
+    }
+}
+
+bool write_score_file(const char* path, const float* values, uint32_t count) {
+    // archive name = file stem, as torch.save chooses it
+    std::string stem(path);
+    size_t slash = stem.find_last_of('/');
+    if (slash != std::string::npos) stem = stem.substr(slash + 1);
+    size_t dot = stem.find_last_of('.');
+    if (dot != std::string::npos && dot > 0) stem = stem.substr(0, dot);
+    if (stem.empty()) stem = "archive";
+
+    // pickle protocol 2 of torch._utils._rebuild_tensor_v2(FloatStorage '0' on cpu
+    // with W elements, offset 0, size (1, W), stride (W, 1), requires_grad False,
+    // OrderedDict()) -- byte for byte what torch.save emits; the three integers
+    // are spliced in between the constant pieces
+    static const unsigned char kHead[93] = {128, 2, 99, 116, 111, 114, 99, 104, 46, 95, 117, 116, 105, 108, 115, 10, 95, 114, 101, 98, 117, 105, 108, 100, 95, 116, 101, 110, 115, 111, 114, 95, 118, 50, 10, 113, 0, 40, 40, 88, 7, 0, 0, 0, 115, 116, 111, 114, 97, 103, 101, 113, 1, 99, 116, 111, 114, 99, 104, 10, 70, 108, 111, 97, 116, 83, 116, 111, 114, 97, 103, 101, 10, 113, 2, 88, 1, 0, 0, 0, 48, 113, 3, 88, 3, 0, 0, 0, 99, 112, 117, 113, 4};
+    static const unsigned char kAfterNumel[8] = {116, 113, 5, 81, 75, 0, 75, 1};
+    static const unsigned char kAfterShape[3] = {134, 113, 6};
+    static const unsigned char kTail[44] = {75, 1, 134, 113, 7, 137, 99, 99, 111, 108, 108, 101, 99, 116, 105, 111, 110, 115, 10, 79, 114, 100, 101, 114, 101, 100, 68, 105, 99, 116, 10, 113, 8, 41, 82, 113, 9, 116, 113, 10, 82, 113, 11, 46};
+    std::string pickle;
+    pickle.append(reinterpret_cast<const char*>(kHead), sizeof(kHead));
+    put_pickle_int(pickle, count);                  // storage numel
+    pickle.append(reinterpret_cast<const char*>(kAfterNumel), sizeof(kAfterNumel));
+    put_pickle_int(pickle, count);                  // size (1, W)
+    pickle.append(reinterpret_cast<const char*>(kAfterShape), sizeof(kAfterShape));
+    put_pickle_int(pickle, count);                  // stride (W, 1)
+    pickle.append(reinterpret_cast<const char*>(kTail), sizeof(kTail));
+
+    struct Record { std::string name; const unsigned char* data; size_t size; bool align; };
+    const char* order = "little";
+    const char* version = "3\n";
+    const Record records[4] = {
+        {stem + "/data.pkl", reinterpret_cast<const unsigned char*>(pickle.data()), pickle.size(), false},
+        {stem + "/byteorder", reinterpret_cast<const unsigned char*>(order), 6, false},
+        {stem + "/data/0", reinterpret_cast<const unsigned char*>(values), (size_t)count * 4, true},
+        {stem + "/version", reinterpret_cast<const unsigned char*>(version), 2, false}};
+    std::string out, central;
+    out.reserve(512 + (size_t)count * 4 + 4 * stem.size());
+    for (const Record& r : records) {
+        std::string extra;
+        if (r.align) {
+            const size_t start = out.size() + 30 + r.name.size() + 4;
+            const size_t pad = (64 - start % 64) % 64;
+            extra = "FB";
+            put16(extra, (uint32_t)pad);
+            extra.append(pad, 'Z');
+        }
+        const uint32_t crc = crc32_of(r.data, r.size);
+        const uint32_t offset = (uint32_t)out.size();
+        put32(out, 0x04034b50u); put16(out, 20); put16(out, 0); put16(out, 0);
+        put16(out, 0); put16(out, 0x21); put32(out, crc);
+        put32(out, (uint32_t)r.size); put32(out, (uint32_t)r.size);
+        put16(out, (uint32_t)r.name.size()); put16(out, (uint32_t)extra.size());
+        out += r.name; out += extra;
+        out.append(reinterpret_cast<const char*>(r.data), r.size);
+        put32(central, 0x02014b50u); put16(central, 20); put16(central, 20); put16(central, 0);
+        put16(central, 0); put16(central, 0); put16(central, 0x21); put32(central, crc);
+        put32(central, (uint32_t)r.size); put32(central, (uint32_t)r.size);
+        put16(central, (uint32_t)r.name.size()); put16(central, 0); put16(central, 0);
+        put16(central, 0); put16(central, 0); put32(central, 0); put32(central, offset);
+        central += r.name;
+    }
+    const uint32_t directory = (uint32_t)out.size();
+    out += central;
+    put32(out, 0x06054b50u); put16(out, 0); put16(out, 0); put16(out, 4); put16(out, 4);
+    put32(out, (uint32_t)central.size()); put32(out, directory); put16(out, 0);
+
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return false;
+    const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    return (std::fclose(f) == 0) && ok;
+}
+
 template <typename Fn>
 void parallel_for(int n, int n_threads, Fn fn) {
     if (n_threads < 1) n_threads = 1;
@@ -324,6 +440,19 @@ int emph_corpus_write_textgrids(
         const FileEntry& e = corpus->files[i];
         if (e.status != 0 || output_paths[i] == nullptr || output_paths[i][0] == 0) return;
         if (!write_textgrid(output_paths[i], e.words)) ++failures;
+    });
+    return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
+}
+
+int emph_write_score_files(
+    const char* const* paths, const float* scores, const int64_t* offsets,
+    const int32_t* counts, int32_t n_files, int32_t n_threads) {
+    if (n_files < 0 || (n_files > 0 && (!paths || !scores || !offsets || !counts))) return EMPH_EINVAL;
+    std::atomic<int> failures(0);
+    parallel_for(n_files, n_threads, [&](int i) {
+        if (paths[i] == nullptr || paths[i][0] == 0) return;
+        if (counts[i] < 0 || !write_score_file(paths[i], scores + offsets[i], (uint32_t)counts[i]))
+            ++failures;
     });
     return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
 }

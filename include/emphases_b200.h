@@ -362,6 +362,17 @@ int emph_corpus_write_textgrids(
     const emph_corpus* corpus, const char* const* output_paths, int32_t n_threads);
 void emph_corpus_close(emph_corpus* corpus);
 
+/*
+ * torch.save(scores, f'{prefix}.pt') for a whole file list (emphases/core.py:
+ * 112,177) on the native thread pool: file i receives scores[offsets[i] ..
+ * + counts[i]) as a (1, counts[i]) float32 tensor in the zip-archive layout
+ * torch.load reads (data.pkl, byteorder, data/0, version; stored, CRC-32).
+ * HOST pointers; a NULL / empty path skips the file.
+ */
+int emph_write_score_files(
+    const char* const* paths, const float* scores, const int64_t* offsets,
+    const int32_t* counts, int32_t n_files, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from emphases_b200 import _lib, engine
 from golden_util import ROOT, times_list
@@ -283,3 +284,26 @@ def test_resample_filter_bank_matches_torchaudio(rates):
     kernels, our_width, o, n = resampling.filter_bank(orig, new)
     assert our_width == width and (o, n) == (orig // gcd, new // gcd)
     np.testing.assert_array_equal(kernels, expected[:, 0].numpy())
+
+
+def test_native_score_files_load_like_torch_save(tmp_path):
+    """emph_write_score_files (the .pt egress of from_files_to_files,
+    emphases/core.py:112,177) writes archives torch.load reads back as the
+    (1, W) float32 tensors torch.save would have stored"""
+    from emphases_b200 import corpus
+    generator = torch.Generator().manual_seed(0)
+    scores = [torch.rand(1, w, generator=generator) for w in (1, 5, 255, 256, 300, 70000, 0)]
+    paths = [tmp_path / f'utt{i}.pt' for i in range(len(scores))]
+    corpus.write_scores(paths, scores, threads=3)
+    for path, score in zip(paths, scores):
+        for weights_only in (True, False):
+            loaded = torch.load(path, weights_only=weights_only)
+            assert loaded.dtype == torch.float32 and loaded.shape == score.shape
+            assert torch.equal(loaded, score)
+            assert loaded.is_contiguous()
+        reference = tmp_path / 'reference.pt'
+        torch.save(score, reference)
+        assert torch.equal(torch.load(reference), torch.load(path))
+    # unwritable path -> loud failure
+    with pytest.raises(OSError):
+        corpus.write_scores([tmp_path / 'missing' / 'x.pt'], [scores[0]])
