@@ -10,6 +10,7 @@ Differences from the reference, all documented in DESIGN.md:
 """
 import contextlib
 import os
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -78,10 +79,10 @@ def from_files_to_files(
     """emphases/core.py:115-179.  All files are decoded by a thread pool,
     packed into length-balanced launches (one shard per GPU when `gpu` is a
     list of indices) and written back as {prefix}.TextGrid / {prefix}.pt."""
-    text_files = [Path(file) for file in text_files]
     if output_prefixes is None:
-        output_prefixes = [file.stem for file in text_files]
-    if any(str(file).endswith('.txt') for file in text_files):
+        output_prefixes = [Path(file).stem for file in text_files]
+    text_files = [os.fspath(file) for file in text_files]
+    if any(file.endswith('.txt') for file in text_files):
         raise NotImplementedError(
             'Transcript (.txt) inputs need forced alignment with pyfoal/HTK '
             '(emphases/core.py:138-166), which is outside this build; pass '
@@ -96,12 +97,28 @@ def from_files_to_files(
         indices, times, packed = parsed.load(usable)
         scores = [None] * len(text_files)
         if len(indices):
-            results = from_alignments_and_audio(
-                times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size, gpu)
+            # the alignments do not depend on the scores: they are written
+            # while the GPU works
+            failure = []
+
+            def write_alignments():
+                try:
+                    parsed.write_textgrids(
+                        [f'{prefix}.TextGrid' for prefix in output_prefixes], usable)
+                except Exception as error:      # re-raised on the caller's thread
+                    failure.append(error)
+
+            writer = threading.Thread(target=write_alignments)
+            writer.start()
+            try:
+                results = from_alignments_and_audio(
+                    times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size, gpu)
+            finally:
+                writer.join()
+            if failure:
+                raise failure[0]
             for index, result in zip(indices, results):
                 scores[index] = result
-            parsed.write_textgrids(
-                [f'{prefix}.TextGrid' for prefix in output_prefixes], usable)
 
     # {prefix}.pt: same archives torch.save would write, from the native pool
     done = [int(i) for i in indices]

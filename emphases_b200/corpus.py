@@ -5,6 +5,7 @@ array; files the native reader does not understand fall back to the Python
 loaders."""
 import ctypes
 import os
+import threading
 
 import numpy as np
 import torch
@@ -13,9 +14,24 @@ from . import _lib, scheduler
 
 
 def _paths(paths):
-    encoded = [os.fsencode(str(path)) for path in paths]
+    encoded = [os.fsencode(path) for path in paths]
     array = (ctypes.c_char_p * len(encoded))(*encoded)
     return array, encoded          # keep `encoded` alive with the array
+
+
+_staging_buffers = {}
+
+
+def _staging(samples, pinned):
+    """Grow-only int16 staging buffer of the process (pinned allocation costs
+    ~15 ms per GB; the corpus path reuses one)"""
+    key = bool(pinned)
+    buffer = _staging_buffers.get(key)
+    if buffer is None or buffer.numel() < samples:
+        buffer = torch.empty(
+            max(int(samples * 1.25), 8), dtype=torch.int16, pin_memory=key)
+        _staging_buffers[key] = buffer
+    return buffer[:samples]
 
 
 class Corpus:
@@ -50,6 +66,10 @@ class Corpus:
         self.close()
 
     def close(self):
+        worker = getattr(self, '_fill_worker', None)
+        if worker is not None:
+            worker.join()                 # the native reader still uses the handle
+            self._fill_worker = None
         if self.handle:
             self.lib.emph_corpus_close(self.handle)
             self.handle = None
@@ -61,9 +81,14 @@ class Corpus:
         """Files the fast path can take: parsed, at the model's sample rate"""
         return (self.status == 0) & (self.sample_rate == sample_rate) & (self.n_words > 0)
 
-    def load(self, mask, pin=True):
+    def load(self, mask, pin=True, group_samples=1 << 25):
         """(indices, word-time arrays, PackedAudio[int16]) of the files
-        selected by `mask` (compact: entry j belongs to file indices[j])"""
+        selected by `mask` (compact: entry j belongs to file indices[j]).
+
+        Decoding runs on a background thread, group by group (about
+        `group_samples` samples each, in file order): the returned
+        PackedAudio's `ready(j)` blocks until entries 0..j are resident, so
+        the first launches upload while later files are still being read."""
         mask = np.asarray(mask, dtype=bool) & (self.status == 0)
         indices = np.nonzero(mask)[0]
         lengths = self.n_samples[indices]
@@ -71,36 +96,61 @@ class Corpus:
         words = self.n_words[indices].astype(np.int64)
         word_offsets = np.concatenate([[0], np.cumsum(words[:-1])]) \
             if len(indices) else np.zeros(0, dtype=np.int64)
-        buffer = torch.zeros(
-            total, dtype=torch.int16,
-            pin_memory=pin and torch.cuda.is_available())
+        buffer = _staging(total, pin and torch.cuda.is_available())
         times = np.zeros((int(words.sum()), 2), dtype=np.float64)
-        # the native fill visits every parsed file: files outside the mask
-        # (e.g. another sample rate) get a scratch destination
-        others = (self.status == 0) & ~mask
-        scratch_audio = np.zeros(
-            max(int(self.n_samples[others].max(initial=0)), 1), dtype=np.int16)
-        scratch_times = np.zeros(
-            (max(int(self.n_words[others].max(initial=0)), 1), 2))
-        base_audio, base_times = buffer.data_ptr(), times.ctypes.data
-        sample_offsets = np.full(
-            self.count, (scratch_audio.ctypes.data - base_audio) // 2, dtype=np.int64)
-        time_offsets = np.full(
-            self.count, (scratch_times.ctypes.data - base_times) // 16, dtype=np.int64)
+        sample_offsets = np.zeros(self.count, dtype=np.int64)
+        time_offsets = np.zeros(self.count, dtype=np.int64)
         sample_offsets[indices] = offsets
         time_offsets[indices] = word_offsets
-        status = self.lib.emph_corpus_fill(
-            self.handle, ctypes.c_void_p(base_audio),
-            sample_offsets.ctypes.data, ctypes.c_void_p(base_times),
-            time_offsets.ctypes.data, self.threads)
-        if status != 0:
-            raise _lib.EmphasesB200Error('emph_corpus_fill failed (short read)')
         per_file = [times[o:o + w] for o, w in zip(word_offsets, words)]
-        return indices, per_file, scheduler.PackedAudio(buffer, offsets, lengths)
+        packed = scheduler.PackedAudio(buffer, offsets, lengths)
+        if not len(indices):
+            return indices, per_file, packed
+
+        # groups of consecutive entries, ~group_samples each
+        ends = np.cumsum(lengths)
+        cuts = np.searchsorted(
+            ends, np.arange(group_samples, int(ends[-1]) + group_samples, group_samples))
+        bounds = sorted(set([0] + [min(int(c) + 1, len(indices)) for c in cuts] + [len(indices)]))
+        groups = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        file_ids = indices.astype(np.int32)
+        state = {'filled': 0, 'error': None}
+        condition = threading.Condition()
+        keep = (buffer, times, sample_offsets, time_offsets, file_ids)
+
+        def fill():
+            for first, last in groups:
+                part = np.ascontiguousarray(file_ids[first:last])
+                status = self.lib.emph_corpus_fill_files(
+                    self.handle, part.ctypes.data, len(part),
+                    ctypes.c_void_p(keep[0].data_ptr()), sample_offsets.ctypes.data,
+                    ctypes.c_void_p(times.ctypes.data), time_offsets.ctypes.data,
+                    self.threads)
+                with condition:
+                    if status != 0:
+                        state['error'] = _lib.EmphasesB200Error(
+                            'emph_corpus_fill_files failed (short read)')
+                    state['filled'] = last
+                    condition.notify_all()
+                if status != 0:
+                    return
+
+        def ready(entry):
+            with condition:
+                condition.wait_for(
+                    lambda: state['filled'] > entry or state['error'] is not None)
+                if state['error'] is not None:
+                    raise state['error']
+
+        worker = threading.Thread(target=fill, daemon=True)
+        worker.start()
+        self._fill_worker = worker
+        packed.ready = ready
+        return indices, per_file, packed
 
     def write_textgrids(self, output_paths, mask):
         encoded = [
-            os.fsencode(str(path)) if m else b''
+            os.fsencode(path) if m else b''
             for path, m in zip(output_paths, mask)]
         array = (ctypes.c_char_p * len(encoded))(*encoded)
         if self.lib.emph_corpus_write_textgrids(self.handle, array, self.threads):
@@ -121,7 +171,7 @@ def write_scores(paths, scores, threads=None):
         score.detach().reshape(-1).to(device='cpu', dtype=torch.float32)
         for score in scores]) if len(scores) else torch.zeros(0)
     flat = np.ascontiguousarray(flat.numpy())
-    encoded = [os.fsencode(str(path)) for path in paths]
+    encoded = [os.fsencode(path) for path in paths]
     array = (ctypes.c_char_p * len(encoded))(*encoded)
     threads = threads or min(32, os.cpu_count() or 1)
     if lib.emph_write_score_files(

@@ -396,12 +396,16 @@ const char* emph_corpus_error(const emph_corpus* corpus, int32_t index) {
     return corpus->files[index].error.c_str();
 }
 
-int emph_corpus_fill(
-    emph_corpus* corpus, int16_t* audio_dst, const int64_t* sample_offsets,
+int emph_corpus_fill_files(
+    emph_corpus* corpus, const int32_t* file_indices, int32_t n_indices,
+    int16_t* audio_dst, const int64_t* sample_offsets,
     double* times_dst, const int64_t* word_offsets, int32_t n_threads) {
-    if (!corpus) return EMPH_EINVAL;
+    if (!corpus || n_indices < 0 || (n_indices > 0 && !file_indices)) return EMPH_EINVAL;
+    const int n_files = (int)corpus->files.size();
     std::atomic<int> failures(0);
-    parallel_for((int)corpus->files.size(), n_threads, [&](int i) {
+    parallel_for(n_indices, n_threads, [&](int k) {
+        const int i = file_indices[k];
+        if (i < 0 || i >= n_files) { ++failures; return; }
         FileEntry& e = corpus->files[i];
         if (e.status != 0) return;
         double* times = times_dst + 2 * word_offsets[i];
@@ -422,7 +426,7 @@ int emph_corpus_fill(
             while (done < e.n_samples && ok) {
                 long long want = e.n_samples - done < 4096 ? e.n_samples - done : 4096;
                 ok = std::fread(frame_buffer.data(), 2 * e.channels, (size_t)want, f) == (size_t)want;
-                for (long long k = 0; k < want; ++k) dst[done + k] = frame_buffer[(size_t)k * e.channels];
+                for (long long k2 = 0; k2 < want; ++k2) dst[done + k2] = frame_buffer[(size_t)k2 * e.channels];
                 done += want;
             }
         }
@@ -430,6 +434,17 @@ int emph_corpus_fill(
         if (!ok) { fail(e, 1, "short read: " + e.audio_path); ++failures; }
     });
     return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
+}
+
+int emph_corpus_fill(
+    emph_corpus* corpus, int16_t* audio_dst, const int64_t* sample_offsets,
+    double* times_dst, const int64_t* word_offsets, int32_t n_threads) {
+    if (!corpus) return EMPH_EINVAL;
+    std::vector<int32_t> all(corpus->files.size());
+    for (size_t i = 0; i < all.size(); ++i) all[i] = (int32_t)i;
+    return emph_corpus_fill_files(
+        corpus, all.data(), (int32_t)all.size(), audio_dst, sample_offsets, times_dst,
+        word_offsets, n_threads);
 }
 
 int emph_corpus_write_textgrids(

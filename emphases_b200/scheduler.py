@@ -68,11 +68,16 @@ class PackedAudio:
         self.buffer = buffer
         self.offsets = np.asarray(offsets, dtype=np.int64)
         self.lengths = np.asarray(lengths, dtype=np.int64)
+        # optional callable(j): blocks until utterances 0..j are resident in
+        # `buffer` (a corpus still being decoded in the background)
+        self.ready = None
 
     def __len__(self):
         return len(self.lengths)
 
     def __getitem__(self, index):
+        if self.ready is not None:
+            self.ready(int(index))
         start = int(self.offsets[index])
         return self.buffer[start:start + int(self.lengths[index])][None]
 
@@ -199,6 +204,8 @@ def run_on_device(
         # one grow-only workspace per stream: launches on a stream run in
         # order, so its buffers can be reused without further synchronisation
         ws = eng.workspace(number % len(streams))
+        if packed.ready is not None:
+            packed.ready(last)
         with torch.cuda.stream(stream):
             # the audio copy goes out first: the host work below (alignment
             # conversion, planning) then overlaps it, and the copy engine never

@@ -358,6 +358,12 @@ const char* emph_corpus_error(const emph_corpus* corpus, int32_t index);
 int emph_corpus_fill(
     emph_corpus* corpus, int16_t* audio_dst, const int64_t* sample_offsets,
     double* times_dst, const int64_t* word_offsets, int32_t n_threads);
+/* The same for the listed files only (offset arrays still indexed by file), so
+ * a corpus can be decoded group by group while earlier groups upload. */
+int emph_corpus_fill_files(
+    emph_corpus* corpus, const int32_t* file_indices, int32_t n_indices,
+    int16_t* audio_dst, const int64_t* sample_offsets,
+    double* times_dst, const int64_t* word_offsets, int32_t n_threads);
 int emph_corpus_write_textgrids(
     const emph_corpus* corpus, const char* const* output_paths, int32_t n_threads);
 void emph_corpus_close(emph_corpus* corpus);

@@ -255,13 +255,17 @@ def test_native_corpus_reader_matches_python(tmp_path):
         assert usable.tolist() == [True, True, True, True, False, False, True]
         assert parsed.sample_rate[4] == 22050 and parsed.status[5] != 0
         assert 'PCM' in parsed.error(5)
-        indices, times, packed = parsed.load(usable, pin=False)
+        # decoded in the background, here in several groups: indexing (or
+        # ready(j)) waits for the entry's group
+        indices, times, packed = parsed.load(usable, pin=False, group_samples=20000)
         assert indices.tolist() == [0, 1, 2, 3, 6]
         for j, index in enumerate(indices):
+            samples = packed[j][0]
             expected = alignment.Alignment(text_files[index])
             np.testing.assert_array_equal(times[j], expected.times())
             pcm, rate = load.wav(audio_files[index], normalize=False)
-            assert torch.equal(packed[j][0], pcm[0])
+            assert torch.equal(samples, pcm[0])
+        packed.ready(len(indices) - 1)
         outputs = [tmp_path / f'out{index}.TextGrid' for index in range(7)]
         parsed.write_textgrids(outputs, usable)
         for index in indices:
