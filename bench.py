@@ -58,7 +58,7 @@ def parse_args():
         choices=['convolution', 'transformer'],
         help='transformer = BASELINE config 3 (informational, fp32 kernels)')
     parser.add_argument('--cpu-seconds', type=float, default=15.)
-    parser.add_argument('--file-utterances', type=int, default=500)
+    parser.add_argument('--file-utterances', type=int, default=3000)
     return parser.parse_args()
 
 
