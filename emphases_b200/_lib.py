@@ -34,6 +34,7 @@ SIGNATURES = {
     'emph_output_head': [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _P],
     'emph_pack_rows': [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     'emph_unpack_rows': [_P, _P, _P, _I, _I, _I, _P, _P],
+    'emph_widen_rows': [_P, _I, _I, _I, _P, _P],
     'emph_segment_rows': [_P, _I, _P, _P, _P, _I, _P, _I, _P, _P],
     'emph_add_positional': [_P, _P, _P, _I, _I, _P, _I, _P, _P],
     'emph_attention_rows': [_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _I, _F, _P, _P],

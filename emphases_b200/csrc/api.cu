@@ -122,6 +122,21 @@ __global__ void segment_rows_kernel(
     }
 }
 
+// [rows][c_in] -> [rows][c_out], new channels zero (models wider than the 80
+// log-mel features: CHANNELS=128 of the reference's hyper-parameter sweep)
+__global__ void widen_rows_kernel(
+    const float* __restrict__ x, int rows, int quads_in, int quads_out, float* __restrict__ y) {
+    const long total = (long)rows * quads_out;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+         i += (long)gridDim.x * blockDim.x) {
+        const long r = i / quads_out;
+        const int q = (int)(i % quads_out);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < quads_in) v = reinterpret_cast<const float4*>(x)[r * quads_in + q];
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
 }  // namespace emph
 
 extern "C" {
@@ -185,6 +200,23 @@ int emph_pack_rows(
     emph::zero_separator_rows_kernel<<<total_rows, 32, 0, (cudaStream_t)stream>>>(
         row_seq, total_rows, channels, rows);
     EMPH_CHECK_LAUNCH("emph_pack_rows(separators)");
+    return EMPH_OK;
+}
+
+int emph_widen_rows(
+    const float* x, int32_t rows, int32_t channels_in, int32_t channels_out, float* y,
+    void* stream) {
+    EMPH_REQUIRE(rows >= 0 && channels_in > 0 && channels_out >= channels_in &&
+                 channels_in % 4 == 0 && channels_out % 4 == 0,
+                 "emph_widen_rows: bad shape (%d rows, %d -> %d channels)", rows,
+                 channels_in, channels_out);
+    if (rows == 0) return EMPH_OK;
+    const long quads = (long)rows * (channels_out / 4);
+    const long want = (quads + 255) / 256;
+    const long cap = (long)emph::sm_count() * 16;
+    emph::widen_rows_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        x, rows, channels_in / 4, channels_out / 4, y);
+    EMPH_CHECK_LAUNCH("emph_widen_rows");
     return EMPH_OK;
 }
 

@@ -19,7 +19,8 @@ HOPSIZE = 160
 NUM_FFT = 1024
 WINDOW_SIZE = 1024
 PADDING = int((WINDOW_SIZE - HOPSIZE) / 2)   # 432, emphases/core.py:357
-KERNEL_CHANNELS = 80      # channel width the conv / tensor-core kernels are compiled for
+KERNEL_CHANNELS = 80      # channel width of the tensor-core kernels and of the default model
+WIDE_CHANNELS = 128       # fp32 tap-streamed conv kernel: CHANNELS=128 of the reference's sweep
 
 ACTIVATIONS = {
     'ReLU': _lib.ACT_RELU,
@@ -431,7 +432,11 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
     """
     step = 3 if dropout is not None else 2
     act = ACTIVATIONS[activation]
-    width = KERNEL_CHANNELS            # channel count the kernels are built for
+    # channel count the kernels are built for: 80, or 128 for wider models
+    largest = max(
+        max(value.shape[0], value.shape[1]) for key, value in state.items()
+        if key.endswith('.weight') and value.dim() == 3)
+    width = KERNEL_CHANNELS if largest <= KERNEL_CHANNELS else WIDE_CHANNELS
 
     def pad(tensor, shape):
         """Zero-pad a weight/bias to the kernels' channel count.  Padded
@@ -627,8 +632,19 @@ class Engine:
             _lib.ptr(out), _lib.stream_ptr())
         return out
 
+    def widen(self, x, channels, ws=None, name='widened'):
+        """Zero-extend packed rows to `channels` columns"""
+        y = _empty(ws, name, (x.shape[0], channels), torch.float32, self.device)
+        _lib.call(
+            'emph_widen_rows', _lib.ptr(x), x.shape[0], x.shape[1], channels,
+            _lib.ptr(y), _lib.stream_ptr())
+        return y
+
     def conv_stack(self, x, row_seq, stack: ConvStack, precision, ws=None,
                    name='conv'):
+        if x.shape[1] < stack.channels:
+            # the 80 log-mel features entering a wider model
+            x = self.widen(x, stack.channels, ws, name + '_in')
         y = _empty(ws, name, tuple(x.shape), torch.float32, self.device)
         acts = stack.acts.astype(np.int32)
         weights = stack.weights if precision == _lib.PREC_FP32 \

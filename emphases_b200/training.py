@@ -63,6 +63,10 @@ class _ConvModelFunction(torch.autograd.Function):
                 "at the 'intermediate', 'loss' and 'inference' locations")
         if model.activation not in ('ReLU', 'Identity'):
             raise NotImplementedError('training backward supports ReLU only')
+        if emphases.CHANNELS > engine.KERNEL_CHANNELS:
+            raise NotImplementedError(
+                f'the backward kernels are built for up to {engine.KERNEL_CHANNELS} '
+                f'channels (CHANNELS={emphases.CHANNELS})')
         batch, channels, frames = features.shape
         wmax = word_bounds.shape[2]
         with torch.cuda.device(device):

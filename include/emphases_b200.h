@@ -220,6 +220,16 @@ int emph_unpack_rows(
     int32_t batch, int32_t channels, int32_t frames, float* bct, void* stream);
 
 /*
+ * Zero-extend packed rows [rows][channels_in] to [rows][channels_out] (both
+ * multiples of 4): the 80 log-mel features entering a model whose CHANNELS is
+ * larger (128 in the reference's config/hparam-search), emphases/model/
+ * core.py:17-20 input_layer being Conv1d(NUM_FEATURES -> CHANNELS).
+ */
+int emph_widen_rows(
+    const float* x, int32_t rows, int32_t channels_in, int32_t channels_out, float* y,
+    void* stream);
+
+/*
  * Word segmentation for the 'input' downsample location (emphases/core.py:
  * 552-586 `segment`): segment q copies count[q] rows of x starting at absolute
  * row src_row[q] into its own sequence of seg_len rows (zero-filled tail),

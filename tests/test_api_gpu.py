@@ -307,6 +307,8 @@ def test_transformer_packed_corpus(emphases, golden, tmp_path):
 HPARAMS = [
     # the reference's config/hparam-search space
     dict(CHANNELS=64),
+    dict(CHANNELS=128),
+    dict(CHANNELS=128, ENCODER_KERNEL_SIZE=5, DECODER_KERNEL_SIZE=1),
     dict(LAYERS=5),
     dict(LAYERS=7),
     dict(ENCODER_KERNEL_SIZE=5, DECODER_KERNEL_SIZE=7),
@@ -351,7 +353,7 @@ def test_hyperparameter_shapes(emphases, overrides):
 
 
 def test_wide_model_is_rejected_loudly(emphases):
-    emphases.configure(CHANNELS=128)
+    emphases.configure(CHANNELS=256)
     model = emphases.Model().cuda().eval()
     with pytest.raises(NotImplementedError):
         model.packed_weights()
