@@ -97,9 +97,16 @@ def segment(xs, word_bounds, word_lengths):
 
 
 def run_forward_input(
-    model, eng, weights, features, word_bounds, word_lengths, method, precision
+    model, eng, weights, features, word_bounds, word_lengths, method, precision,
+    encode=None, decode=None
 ):
-    """Model.forward for DOWNSAMPLE_LOCATION == 'input'"""
+    """Model.forward for DOWNSAMPLE_LOCATION == 'input'.
+
+    `encode(segments, seg_row_seq, seg_start, max_length, counts)` and
+    `decode(pooled, word_row_seq, word_start, wmax, lengths)` replace the
+    convolutional frame encoder / word decoder (the Transformer variant
+    attends within each word segment: keys are the segment's own `counts`
+    frames, queries all `max_length` rows)."""
     device = features.device
     batch, channels, frames = features.shape
     wmax = word_bounds.shape[2]
@@ -108,9 +115,13 @@ def run_forward_input(
     n_seg = batch * wmax
     segments, seg_row_seq, d_seg_start, d_seg_rows, _, _ = _gather(
         eng, features, lo, count, max_length)
-    frame_rows = eng.conv_stack(
-        segments, seg_row_seq, weights.frame,
-        engine.frame_precision(precision, weights.frame))
+    if encode is not None:
+        frame_rows = encode(
+            segments, seg_row_seq, d_seg_start, max_length, count.reshape(-1))
+    else:
+        frame_rows = eng.conv_stack(
+            segments, seg_row_seq, weights.frame,
+            engine.frame_precision(precision, weights.frame))
 
     # One word row per segment, laid out as B sequences of Wmax word slots
     word_starts, total_words = engine.packed_starts([wmax] * batch)
@@ -147,9 +158,12 @@ def run_forward_input(
         frame_rows, d_seg_start, d_seg_rows, d_word_seq, d_word_lo, d_word_hi,
         method)
     word_row_seq = eng.row_index(d_word_start, d_n_words, batch, total_words)
-    words = eng.conv_stack(
-        pooled, word_row_seq, weights.word,
-        engine.word_precision(precision, weights.word))
+    if decode is not None:
+        words = decode(pooled, word_row_seq, d_word_start, wmax, lengths)
+    else:
+        words = eng.conv_stack(
+            pooled, word_row_seq, weights.word,
+            engine.word_precision(precision, weights.word))
     logits, _ = eng.head(
         words, word_row_seq, weights, _lib.HEAD_LOGITS, want_scores=False)
     index = torch.from_numpy(

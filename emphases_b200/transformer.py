@@ -226,11 +226,28 @@ def run_forward(
 ):
     """Model.forward for the transformer variant (padded (B, C, T) batch)"""
     from . import model as model_module
-    if model.location == 'input':
-        raise NotImplementedError(
-            "the transformer variant at DOWNSAMPLE_LOCATION='input' is not built")
     method = emphases.DOWNSAMPLE_METHOD
     device = features.device
+    if model.location == 'input':
+        # every word segment is its own attention sequence
+        # (emphases/model/core.py:41-87 with frame_encoder = Transformer)
+        from . import segments
+
+        def encode(rows, seg_row_seq, seg_start, max_length, counts):
+            embedded = eng.conv_stack(
+                rows, seg_row_seq, weights.input_layer, _lib.PREC_FP32)
+            return run_stack(
+                eng, weights.frame, embedded, seg_start,
+                np.full(len(counts), max_length), counts, seg_row_seq, device)
+
+        def decode(pooled, word_row_seq, word_start, wmax, lengths):
+            return run_stack(
+                eng, weights.word, pooled, word_start,
+                np.full(len(lengths), wmax), lengths, word_row_seq, device)
+
+        return segments.run_forward_input(
+            model, eng, weights, features, word_bounds, word_lengths, method,
+            _lib.PREC_FP32, encode, decode)
     batch, channels, frames = features.shape
     frame_keys = frame_lengths.detach().to('cpu', torch.int64).numpy()
     starts, total = engine.packed_starts([frames] * batch)

@@ -270,6 +270,48 @@ def gen_transformer():
     print('transformer', len(out))
 
 
+def gen_transformer_input():
+    """Transformer variant at DOWNSAMPLE_LOCATION='input' (word segments are
+    the sequences the encoder attends over, emphases/model/core.py:41-87),
+    B=1 and a padded B=2 batch"""
+    out = {}
+    t1, a1 = oracle.synthetic_utterance(41, duration=1.6, words=6)
+    t2, a2 = oracle.synthetic_utterance(42, duration=1.1, words=4)
+    overrides = {'ARCHITECTURE': 'transformer', 'DOWNSAMPLE_LOCATION': 'input'}
+    with ref_stubs.reference(overrides) as emphases:
+        assert emphases.DOWNSAMPLE_LOCATION == 'input'
+        state = scaled_random_state(emphases, 1.0, seed=5)
+        model = emphases.Model()
+        model.load_state_dict(state)
+        model.eval()
+        for key, value in to_numpy(state).items():
+            if key.endswith('position.encoding'):
+                continue
+            out[f'state.{key}'] = value
+        items = []
+        for times, audio in ((t1, a1), (t2, a2)):
+            alignment = ref_stubs.Alignment.from_times(times)
+            items.append(next(iter(emphases.preprocess(
+                alignment, audio, 16000, None, None))))
+        with torch.no_grad():
+            features, bounds = items[0]
+            out['b1.features'] = features.numpy()
+            out['b1.bounds'] = bounds.numpy()
+            out['b1.logits'] = model(
+                features,
+                torch.tensor([features.shape[-1]]),
+                bounds,
+                torch.tensor([bounds.shape[-1]])).numpy()
+            batch = padded_batch(items)
+            for name, value in zip(
+                ('features', 'frame_lengths', 'bounds', 'word_lengths'), batch
+            ):
+                out[f'b2.{name}'] = value.numpy()
+            out['b2.logits'] = model(*batch).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, 'transformer_input.npz'), **out)
+    print('transformer_input', len(out))
+
+
 def gen_loss():
     out = {}
     generator = torch.Generator().manual_seed(9)
@@ -428,10 +470,15 @@ def gen_evaluate():
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)
+    if len(sys.argv) > 1:            # e.g. `python oracle/gen_golden.py transformer_input`
+        for name in sys.argv[1:]:
+            globals()[f'gen_{name}']()
+        return
     gen_c1()
     gen_sweep()
     gen_pool()
     gen_transformer()
+    gen_transformer_input()
     gen_loss()
     gen_upsample()
     gen_sampler()

@@ -260,6 +260,35 @@ def test_transformer_variant(emphases, golden):
                 rtol=0, atol=3e-5)
 
 
+def test_transformer_variant_input_location(emphases, golden):
+    """Transformer variant at DOWNSAMPLE_LOCATION='input' vs the reference
+    (B=1 and a padded B=2 batch): attention runs inside each word segment"""
+    data = golden('transformer_input')
+    emphases.configure(ARCHITECTURE='transformer', DOWNSAMPLE_LOCATION='input')
+    model = emphases.Model()
+    state = state_from_golden(data)
+    missing = model.load_state_dict(state, strict=False)
+    assert all('position.encoding' in key for key in missing.missing_keys)
+    assert not missing.unexpected_keys
+    model = model.cuda().eval()
+    with torch.no_grad():
+        features = torch.from_numpy(data['b1.features']).cuda()
+        bounds = torch.from_numpy(data['b1.bounds'])
+        logits = model(
+            features, torch.tensor([features.shape[-1]]), bounds,
+            torch.tensor([bounds.shape[-1]]))
+        np.testing.assert_allclose(
+            logits.cpu().numpy(), data['b1.logits'], rtol=0, atol=3e-5)
+        batch = [torch.from_numpy(data[f'b2.{name}']) for name in (
+            'features', 'frame_lengths', 'bounds', 'word_lengths')]
+        batch[0] = batch[0].cuda()
+        logits = model(*batch).cpu().numpy()
+        for i, words in enumerate(batch[3].tolist()):
+            np.testing.assert_allclose(
+                logits[i, :, :words], data['b2.logits'][i, :, :words],
+                rtol=0, atol=3e-5)
+
+
 def test_transformer_end_to_end(emphases, golden, tmp_path):
     """from_alignment_and_audio with the transformer variant vs the oracle"""
     data = golden('transformer')

@@ -186,6 +186,32 @@ def test_transformer(golden):
                 data['b2.logits'][i, :, :words], rtol=0, atol=2e-5)
 
 
+def test_transformer_input_location(golden):
+    """Transformer variant with the word segments as attention sequences
+    (DOWNSAMPLE_LOCATION='input', emphases/model/core.py:41-87)"""
+    data = golden('transformer_input')
+    state = state_from_golden(data)
+    encoding = oracle.positional_encoding(80)
+    state['frame_encoder.position.encoding'] = encoding
+    state['word_decoder.position.encoding'] = encoding
+    config = {'ARCHITECTURE': 'transformer', 'DOWNSAMPLE_LOCATION': 'input'}
+    with torch.no_grad():
+        features = torch.from_numpy(data['b1.features'])
+        bounds = torch.from_numpy(data['b1.bounds'])
+        logits = oracle.model_forward(
+            state, features, torch.tensor([features.shape[-1]]), bounds,
+            torch.tensor([bounds.shape[-1]]), config)
+        np.testing.assert_allclose(
+            logits.numpy(), data['b1.logits'], rtol=0, atol=2e-5)
+        batch = [torch.from_numpy(data[f'b2.{name}']) for name in (
+            'features', 'frame_lengths', 'bounds', 'word_lengths')]
+        logits = oracle.model_forward(state, *batch, config)
+        for i, words in enumerate(batch[3].tolist()):
+            np.testing.assert_allclose(
+                logits.numpy()[i, :, :words],
+                data['b2.logits'][i, :, :words], rtol=0, atol=2e-5)
+
+
 @pytest.mark.parametrize('loss_fn', ['bce', 'mse'])
 def test_loss(golden, loss_fn):
     data = golden('loss')
