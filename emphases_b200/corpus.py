@@ -19,18 +19,20 @@ def _paths(paths):
     return array, encoded          # keep `encoded` alive with the array
 
 
-_staging_buffers = {}
+_staging_buffers = threading.local()
 
 
 def _staging(samples, pinned):
-    """Grow-only int16 staging buffer of the process (pinned allocation costs
-    ~15 ms per GB; the corpus path reuses one)"""
+    """Grow-only int16 staging buffer of the calling thread (pinned allocation
+    costs ~15 ms per GB; repeated corpus calls reuse one).  A PackedAudio
+    returned by Corpus.load is valid until the same thread loads again."""
+    cache = _staging_buffers.__dict__.setdefault('buffers', {})
     key = bool(pinned)
-    buffer = _staging_buffers.get(key)
+    buffer = cache.get(key)
     if buffer is None or buffer.numel() < samples:
         buffer = torch.empty(
             max(int(samples * 1.25), 8), dtype=torch.int16, pin_memory=key)
-        _staging_buffers[key] = buffer
+        cache[key] = buffer
     return buffer[:samples]
 
 
