@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 import emphases_b200 as emphases
-from . import _lib, engine
+from . import _lib, engine, resampling
 from .alignment import Alignment, as_times
 
 __all__ = [
@@ -91,34 +91,48 @@ def from_files_to_files(
     from . import corpus
     workers = min(32, (os.cpu_count() or 1))
     with corpus.Corpus(text_files, audio_files, workers) as parsed:
-        # Fast path: 16-bit PCM wav at the model rate + a parsable TextGrid go
-        # through the native reader into pinned int16 / float64 buffers
-        usable = parsed.usable(emphases.SAMPLE_RATE)
-        indices, times, packed = parsed.load(usable)
+        # Fast path: 16-bit PCM wav + a parsable TextGrid go through the native
+        # reader into pinned int16 / float64 buffers; files at the model rate
+        # first, then one packed GPU resampling pass per other sample rate
+        # (the reference resamples file by file, core.py:613-619)
+        parsable = parsed.usable(None)
+        rates = sorted(
+            {int(rate) for rate in parsed.sample_rate[parsable]},
+            key=lambda rate: rate != emphases.SAMPLE_RATE)
         scores = [None] * len(text_files)
-        if len(indices):
-            # the alignments do not depend on the scores: they are written
-            # while the GPU works
-            failure = []
+        failure = []
 
-            def write_alignments():
-                try:
-                    parsed.write_textgrids(
-                        [f'{prefix}.TextGrid' for prefix in output_prefixes], usable)
-                except Exception as error:      # re-raised on the caller's thread
-                    failure.append(error)
-
-            writer = threading.Thread(target=write_alignments)
-            writer.start()
+        def write_alignments():
             try:
+                parsed.write_textgrids(
+                    [f'{prefix}.TextGrid' for prefix in output_prefixes], parsable)
+            except Exception as error:      # re-raised on the caller's thread
+                failure.append(error)
+
+        # the alignments do not depend on the scores: they are written while
+        # the GPU works
+        writer = threading.Thread(target=write_alignments)
+        if parsable.any():
+            writer.start()
+        try:
+            for rate in rates:
+                indices, times, packed = parsed.load(
+                    parsable & (parsed.sample_rate == rate))
+                if rate != emphases.SAMPLE_RATE:
+                    device = emphases.resolve_device(
+                        gpu[0] if isinstance(gpu, (list, tuple)) and gpu else gpu)
+                    packed = resampling.resample_packed(
+                        packed, rate, emphases.SAMPLE_RATE, device)
                 results = from_alignments_and_audio(
                     times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size, gpu)
-            finally:
+                for index, result in zip(indices, results):
+                    scores[index] = result
+        finally:
+            if parsable.any():
                 writer.join()
-            if failure:
-                raise failure[0]
-            for index, result in zip(indices, results):
-                scores[index] = result
+        if failure:
+            raise failure[0]
+        indices = np.nonzero(parsable)[0]
 
     # {prefix}.pt: same archives torch.save would write, from the native pool
     done = [int(i) for i in indices]

@@ -80,8 +80,12 @@ class Corpus:
         return self.lib.emph_corpus_error(self.handle, index).decode('utf-8', 'replace')
 
     def usable(self, sample_rate=16000):
-        """Files the fast path can take: parsed, at the model's sample rate"""
-        return (self.status == 0) & (self.sample_rate == sample_rate) & (self.n_words > 0)
+        """Files the fast path can take: parsed (16-bit PCM + TextGrid), at
+        `sample_rate` (None: any rate)"""
+        mask = (self.status == 0) & (self.n_words > 0)
+        if sample_rate is not None:
+            mask &= self.sample_rate == sample_rate
+        return mask
 
     def load(self, mask, pin=True, group_samples=1 << 25):
         """(indices, word-time arrays, PackedAudio[int16]) of the files

@@ -62,3 +62,37 @@ def resample(audio, sample_rate, target_rate, device):
                 _lib.ptr(bank), orig, new, width, _lib.ptr(out[channel]), target,
                 _lib.stream_ptr())
     return out
+
+
+def resample_packed(packed, sample_rate, target_rate, device):
+    """A PackedAudio of int16 PCM at `sample_rate` (host) -> a PackedAudio of
+    fp32 audio at `target_rate` resident on `device`: one upload and ONE
+    kernel launch for the whole corpus (the reference resamples file by file,
+    emphases/core.py:613-619)."""
+    import numpy as np
+    from . import scheduler
+    if packed.buffer.dtype != torch.int16:
+        raise ValueError('resample_packed expects int16 PCM')
+    if packed.ready is not None and len(packed):
+        packed.ready(len(packed) - 1)
+    kernels, width, orig, new = filter_bank(int(sample_rate), int(target_rate))
+    key = (int(sample_rate), int(target_rate), device)
+    if key not in _device_banks:
+        _device_banks[key] = torch.from_numpy(kernels).to(device)
+    bank = _device_banks[key]
+    lengths = -(-(new * packed.lengths) // orig)            # ceil(new * T / orig)
+    offsets, total = scheduler.PackedAudio.layout(lengths)
+    with torch.cuda.device(device):
+        source = packed.buffer.to(device, non_blocking=True)
+        meta = torch.from_numpy(np.concatenate([
+            packed.offsets, packed.lengths, offsets, lengths]).astype(np.int64)
+        ).to(device)
+        count = len(lengths)
+        out = torch.empty(total, dtype=torch.float32, device=device)
+        _lib.call(
+            'emph_resample_packed_i16', _lib.ptr(source), _lib.ptr(meta[:count]),
+            _lib.ptr(meta[count:2 * count]), _lib.ptr(meta[2 * count:3 * count]),
+            _lib.ptr(meta[3 * count:]), count, _lib.ptr(bank), orig, new, width,
+            _lib.ptr(out), total, _lib.stream_ptr())
+        torch.cuda.current_stream(device).synchronize()     # `source` / staging may be reused
+    return scheduler.PackedAudio(out, offsets, lengths)

@@ -345,6 +345,21 @@ int emph_resample_f32(
     int32_t new_freq, int32_t width, float* y, int64_t target_length, void* stream);
 
 /*
+ * The same resampler over a packed int16 PCM corpus (samples are x / 32768,
+ * what torchaudio.load returns, emphases/load.py:11-17) in one launch:
+ * utterance u reads x[in_off[u] .. + in_len[u]) and writes
+ * y[out_off[u] .. + out_len[u]), out_len = ceil(new * in_len / orig); out_off
+ * ascending; y positions outside every utterance (alignment gaps) are zeroed.
+ * This is the non-16 kHz branch of from_files_to_files (core.py:169-179 calls
+ * emphases.resample per file).
+ */
+int emph_resample_packed_i16(
+    const int16_t* x, const int64_t* in_off, const int64_t* in_len,
+    const int64_t* out_off, const int64_t* out_len, int32_t n_utterances,
+    const float* kernel, int32_t orig_freq, int32_t new_freq, int32_t width,
+    float* y, int64_t total_out, void* stream);
+
+/*
  * Host-side corpus ingest / egress for from_files_to_files (HOST pointers, no
  * CUDA): reads n_files (TextGrid, 16-bit PCM wav) pairs on a thread pool,
  * replacing per file emphases.load.audio (emphases/load.py:11-17),

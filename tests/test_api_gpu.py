@@ -231,6 +231,56 @@ def test_errors(emphases, golden, c1_checkpoint):
         emphases.Model()
 
 
+def test_files_at_other_sample_rates_take_the_packed_path(
+    emphases, golden, c1_checkpoint, tmp_path
+):
+    """from_files_to_files on a corpus mixing 16 kHz, 24 kHz and 22.05 kHz
+    wavs: every rate goes through the native reader and ONE packed GPU
+    resampling launch; results equal the per-file API (which resamples like
+    torchaudio, test_resample_matches_torchaudio) and the oracle"""
+    import torchaudio
+    data = golden('c1')
+    state = state_from_golden(data)
+    text_files, audio_files, expected, rates = [], [], [], []
+    for seed, rate in enumerate([24000, 16000, 22050, 24000, 16000, 24000]):
+        times, audio = oracle.synthetic_utterance(760 + seed, duration=1.5 + seed / 3)
+        generator = torch.Generator().manual_seed(seed)
+        native = 0.1 * torch.randn(
+            1, int(audio.shape[-1] * rate / 16000), generator=generator)
+        wav = tmp_path / f'utt{seed}.wav'
+        emphases.load.save_wav(wav, native, rate)
+        loaded, loaded_rate = emphases.load.wav(wav)
+        assert loaded_rate == rate
+        resampled = loaded if rate == 16000 else \
+            torchaudio.transforms.Resample(rate, 16000)(loaded)
+        grid = tmp_path / f'utt{seed}.TextGrid'
+        emphases.Alignment.from_times(times).save(grid)
+        text_files.append(grid)
+        audio_files.append(wav)
+        expected.append(oracle.from_alignment_and_audio(times, resampled, state))
+        rates.append(rate)
+    prefixes = [tmp_path / 'out' / f'utt{seed}' for seed in range(len(rates))]
+    (tmp_path / 'out').mkdir()
+    # no per-file fallback may be needed
+    calls = []
+    original = emphases.core.from_file_to_file
+    emphases.core.from_file_to_file = lambda *a, **k: calls.append(a)
+    try:
+        emphases.from_files_to_files(
+            text_files, audio_files, prefixes, checkpoint=c1_checkpoint, gpu=0)
+    finally:
+        emphases.core.from_file_to_file = original
+    assert not calls
+    for index, (prefix, want) in enumerate(zip(prefixes, expected)):
+        got = torch.load(f'{prefix}.pt')
+        assert got.shape == want.shape
+        assert (got - want).abs().max() < 2e-5, rates[index]
+        single = emphases.from_file(
+            text_files[index], audio_files[index], checkpoint=c1_checkpoint, gpu=0)
+        assert (got - single.cpu()).abs().max() < 2e-6
+        assert os.path.exists(f'{prefix}.TextGrid')
+
+
 def test_transformer_variant(emphases, golden):
     """ARCHITECTURE='transformer' Model.forward vs the reference (B=1 and a
     padded B=2 batch whose key-padding mask matters)"""
