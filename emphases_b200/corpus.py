@@ -19,21 +19,8 @@ def _paths(paths):
     return array, encoded          # keep `encoded` alive with the array
 
 
-_staging_buffers = threading.local()
-
-
 def _staging(samples, pinned):
-    """Grow-only int16 staging buffer of the calling thread (pinned allocation
-    costs ~15 ms per GB; repeated corpus calls reuse one).  A PackedAudio
-    returned by Corpus.load is valid until the same thread loads again."""
-    cache = _staging_buffers.__dict__.setdefault('buffers', {})
-    key = bool(pinned)
-    buffer = cache.get(key)
-    if buffer is None or buffer.numel() < samples:
-        buffer = torch.empty(
-            max(int(samples * 1.25), 8), dtype=torch.int16, pin_memory=key)
-        cache[key] = buffer
-    return buffer[:samples]
+    return scheduler.staging(samples, torch.int16, pinned)
 
 
 class Corpus:

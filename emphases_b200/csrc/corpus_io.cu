@@ -11,6 +11,9 @@
 // Files this reader does not understand (other encodings, UTF-16 TextGrids)
 // get a non-zero status and are left to the Python path.
 #include <atomic>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <charconv>
 #include <cstdio>
 #include <cstdlib>
@@ -457,6 +460,76 @@ int emph_corpus_write_textgrids(
         if (!write_textgrid(output_paths[i], e.words)) ++failures;
     });
     return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
+}
+
+int emph_pack_audio_f32(
+    const float* const* sources, const int64_t* lengths, const int64_t* offsets,
+    int32_t n_utterances, float* dst_f32, int16_t* dst_i16, int32_t* narrowed,
+    int32_t n_threads) {
+    if (n_utterances < 0 || (n_utterances > 0 && (!sources || !lengths || !offsets || !dst_f32)))
+        return EMPH_EINVAL;
+    if (narrowed) *narrowed = 0;
+    // Lossless narrowing: decoded 16-bit PCM (what load.audio returns) is
+    // k / 32768 with integer k in [-32768, 32767]; then the int16 copy holds the
+    // same values in half the bytes.  A probe of each utterance's head decides
+    // before the full pass; the full pass re-checks every sample.
+    auto exact = [](float v, int16_t& out) {
+        const float scaled = v * 32768.f;
+        if (!(scaled >= -32768.f && scaled <= 32767.f)) return false;   // also NaN
+        const int k = (int)scaled;
+        out = (int16_t)k;
+        return (float)k == scaled;
+    };
+    bool try_narrow = dst_i16 != nullptr && narrowed != nullptr;
+    if (try_narrow) {
+        for (int i = 0; i < n_utterances && try_narrow; ++i) {
+            const int64_t probe = lengths[i] < 64 ? lengths[i] : 64;
+            int16_t unused;
+            for (int64_t k = 0; k < probe; ++k)
+                if (!exact(sources[i][k], unused)) { try_narrow = false; break; }
+        }
+    }
+    if (try_narrow) {
+        std::atomic<int> inexact(0);
+        parallel_for(n_utterances, n_threads, [&](int i) {
+            const float* src = sources[i];
+            int16_t* dst = dst_i16 + offsets[i];
+            const int64_t n = lengths[i];
+            for (int64_t base = 0; base < n && !inexact.load(std::memory_order_relaxed); base += 4096) {
+                const int64_t end = base + 4096 < n ? base + 4096 : n;
+                int bad = 0;
+                int64_t k = base;
+#if defined(__SSE2__)
+                // 8 samples per step: scale, truncate, compare back, saturating
+                // pack (a value outside int16 fails the range compare)
+                const __m128 scale = _mm_set1_ps(32768.f);
+                const __m128 low = _mm_set1_ps(-32768.f), high = _mm_set1_ps(32767.f);
+                __m128 wrong = _mm_setzero_ps();
+                for (; k + 8 <= end; k += 8) {
+                    const __m128 a = _mm_mul_ps(_mm_loadu_ps(src + k), scale);
+                    const __m128 b = _mm_mul_ps(_mm_loadu_ps(src + k + 4), scale);
+                    const __m128i ia = _mm_cvttps_epi32(a), ib = _mm_cvttps_epi32(b);
+                    wrong = _mm_or_ps(wrong, _mm_cmpneq_ps(_mm_cvtepi32_ps(ia), a));
+                    wrong = _mm_or_ps(wrong, _mm_cmpneq_ps(_mm_cvtepi32_ps(ib), b));
+                    wrong = _mm_or_ps(wrong, _mm_or_ps(_mm_cmplt_ps(a, low), _mm_cmpgt_ps(a, high)));
+                    wrong = _mm_or_ps(wrong, _mm_or_ps(_mm_cmplt_ps(b, low), _mm_cmpgt_ps(b, high)));
+                    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packs_epi32(ia, ib));
+                }
+                bad |= _mm_movemask_ps(wrong);
+#endif
+                for (; k < end; ++k) bad |= !exact(src[k], dst[k]);
+                if (bad) inexact.store(1, std::memory_order_relaxed);
+            }
+        });
+        if (!inexact.load()) {
+            *narrowed = 1;
+            return EMPH_OK;
+        }
+    }
+    parallel_for(n_utterances, n_threads, [&](int i) {
+        std::memcpy(dst_f32 + offsets[i], sources[i], (size_t)lengths[i] * sizeof(float));
+    });
+    return EMPH_OK;
 }
 
 int emph_write_score_files(

@@ -5,6 +5,8 @@ Utterances are independent (emphases/core.py:169-179 loops over files), so a
 corpus shards by utterance with no collective: each GPU runs its shard
 through the packed kernels and the host gathers the per-word scores.
 """
+import ctypes
+import os
 import threading
 from typing import List, Sequence
 
@@ -81,6 +83,15 @@ class PackedAudio:
         start = int(self.offsets[index])
         return self.buffer[start:start + int(self.lengths[index])][None]
 
+    def launch_source(self, number, first, last):
+        """Host (or device) samples of utterances first..last, one contiguous
+        slice -- the source of launch `number`'s single copy"""
+        if self.ready is not None:
+            self.ready(int(last))
+        base = int(self.offsets[first])
+        end = int(self.offsets[last] + engine.align_samples(self.lengths[last]))
+        return self.buffer[base:min(end, self.buffer.numel())]
+
     @staticmethod
     def layout(lengths):
         lengths = np.asarray(lengths, dtype=np.int64)
@@ -89,6 +100,96 @@ class PackedAudio:
             if len(lengths) else np.zeros(0, dtype=np.int64)
         total = int(padded.sum())
         return offsets.astype(np.int64), max(total, engine.AUDIO_ALIGN)
+
+
+_staging_buffers = threading.local()
+
+
+def staging(samples, dtype, pinned=True):
+    """Grow-only host staging buffer of the calling thread (pinning costs
+    ~15 ms per GB; repeated corpus calls reuse one buffer per dtype).  Valid
+    until the same thread asks for the same dtype again."""
+    cache = _staging_buffers.__dict__.setdefault('buffers', {})
+    key = (dtype, bool(pinned))
+    buffer = cache.get(key)
+    if buffer is None or buffer.numel() < samples:
+        buffer = torch.empty(
+            max(int(samples * 1.25), 8), dtype=dtype,
+            pin_memory=bool(pinned) and torch.cuda.is_available())
+        cache[key] = buffer
+    return buffer[:samples]
+
+
+class StreamedPack(PackedAudio):
+    """A list of per-utterance fp32 CPU tensors (what a caller of the
+    reference holds, emphases/core.py:223-230) on its way into pinned
+    staging: a background thread packs launch after launch on the native
+    pool (emph_pack_audio_f32) while earlier launches upload and run.  A
+    launch whose samples are all 16-bit PCM values (audio from load.audio) is
+    staged as int16 -- same values, half the PCIe bytes."""
+
+    def __init__(self, audios):
+        rows = []
+        for audio in audios:
+            row = audio[0] if audio.dim() == 2 else audio
+            if row.dtype != torch.float32 or not row.is_contiguous():
+                row = row.to(torch.float32).contiguous()
+            rows.append(row)
+        self.rows = rows                                   # keeps the sources alive
+        lengths = [int(row.shape[0]) for row in rows]
+        offsets, total = PackedAudio.layout(lengths)
+        super().__init__(staging(total, torch.float32), offsets, lengths)
+        self.narrow_buffer = staging(total, torch.int16)
+        self.pointers = np.array([row.data_ptr() for row in rows], dtype=np.uint64)
+        self.narrowed = {}
+        self.condition = threading.Condition()
+        self.error = None
+        self.worker = None
+
+    def start(self, launches, threads=None):
+        lib = _lib.load()
+        threads = threads or min(16, os.cpu_count() or 1)
+
+        def pack():
+            try:
+                for number, members in enumerate(launches):
+                    first, count = members[0], len(members)
+                    flag = ctypes.c_int32(0)
+                    pointers = np.ascontiguousarray(self.pointers[first:first + count])
+                    status = lib.emph_pack_audio_f32(
+                        pointers.ctypes.data, self.lengths[first:].ctypes.data,
+                        self.offsets[first:].ctypes.data, count,
+                        ctypes.c_void_p(self.buffer.data_ptr()),
+                        ctypes.c_void_p(self.narrow_buffer.data_ptr()),
+                        ctypes.byref(flag), threads)
+                    if status != 0:
+                        raise _lib.EmphasesB200Error('emph_pack_audio_f32 failed')
+                    with self.condition:
+                        self.narrowed[number] = bool(flag.value)
+                        self.condition.notify_all()
+            except Exception as error:          # surfaced by launch_source
+                with self.condition:
+                    self.error = error
+                    self.condition.notify_all()
+
+        self.worker = threading.Thread(target=pack, daemon=True)
+        self.worker.start()
+
+    def launch_source(self, number, first, last):
+        with self.condition:
+            self.condition.wait_for(
+                lambda: number in self.narrowed or self.error is not None)
+            if self.error is not None:
+                raise self.error
+        base = int(self.offsets[first])
+        end = int(self.offsets[last] + engine.align_samples(self.lengths[last]))
+        source = self.narrow_buffer if self.narrowed[number] else self.buffer
+        return source[base:min(end, source.numel())]
+
+    def finish(self):
+        if self.worker is not None:
+            self.worker.join()
+            self.worker = None
 
 
 def pack_audio(audios, dtype=torch.float32, pin=True):
@@ -156,7 +257,9 @@ def _prepare(audios, sample_rate):
     cuda = [audio for audio in audios if audio.device.type == 'cuda']
     if cuda:
         audios = [audio.cpu() for audio in audios]
-    return pack_audio(audios, pin=len(audios) > 1)
+    if len(audios) > 1:
+        return StreamedPack(audios)
+    return pack_audio(audios, pin=False)
 
 
 def run_on_device(
@@ -189,6 +292,8 @@ def run_on_device(
 
     frames = (packed.lengths + 2 * engine.PADDING) // engine.HOPSIZE
     launches = bucket_launches(frames, emphases.MAX_ROWS_PER_LAUNCH)
+    if isinstance(packed, StreamedPack):
+        packed.start(launches)
     streams = [torch.cuda.current_stream(device)]
     if len(launches) > 1:
         streams = [torch.cuda.Stream(device) for _ in range(2)]
@@ -197,21 +302,18 @@ def run_on_device(
     pending = []
     for number, members in enumerate(launches):
         first, last = members[0], members[-1]
-        base = int(packed.offsets[first])
-        end = int(packed.offsets[last] + engine.align_samples(packed.lengths[last]))
-        end = min(end, packed.buffer.numel())
         stream = streams[number % len(streams)]
         # one grow-only workspace per stream: launches on a stream run in
         # order, so its buffers can be reused without further synchronisation
         ws = eng.workspace(number % len(streams))
-        if packed.ready is not None:
-            packed.ready(last)
+        source = packed.launch_source(number, first, last)
         with torch.cuda.stream(stream):
             # the audio copy goes out first: the host work below (alignment
             # conversion, planning) then overlaps it, and the copy engine never
             # waits for the host
-            device_audio = ws.get('audio', (end - base,), packed.buffer.dtype)
-            device_audio.copy_(packed.buffer[base:end], non_blocking=True)
+            device_audio = ws.get(
+                f'audio_{source.dtype}', (source.numel(),), source.dtype)
+            device_audio.copy_(source, non_blocking=True)
         plan = engine.make_plan(
             [(as_times(alignments[i]), int(packed.lengths[i])) for i in members],
             batch_size,
@@ -233,7 +335,11 @@ def run_on_device(
         pending.append((members, plan, scores))
     for stream in streams:
         torch.cuda.current_stream(device).wait_stream(stream)
-    if to_cpu:
+    if isinstance(packed, StreamedPack):
+        packed.finish()
+        # the staging buffers are reused by this thread's next call
+        torch.cuda.current_stream(device).synchronize()
+    elif to_cpu:
         torch.cuda.current_stream(device).synchronize()
 
     outputs = [None] * len(alignments)

@@ -394,6 +394,22 @@ int emph_corpus_write_textgrids(
 void emph_corpus_close(emph_corpus* corpus);
 
 /*
+ * Pack a list of utterances (channel 0, fp32 HOST pointers) into one staging
+ * buffer on the native thread pool: utterance i goes to dst[offsets[i] ..
+ * + lengths[i]).  When dst_i16 and narrowed are given and EVERY sample is
+ * k / 32768 with integer k in [-32768, 32767] -- audio decoded from 16-bit PCM,
+ * which is what emphases.load.audio returns (emphases/load.py:11-17) -- the
+ * samples are written to dst_i16 instead (same values, half the upload) and
+ * *narrowed is set to 1; otherwise dst_f32 is filled and *narrowed is 0.
+ * The caller's per-utterance tensors of from_alignment_and_audio
+ * (emphases/core.py:223-230), batched.
+ */
+int emph_pack_audio_f32(
+    const float* const* sources, const int64_t* lengths, const int64_t* offsets,
+    int32_t n_utterances, float* dst_f32, int16_t* dst_i16, int32_t* narrowed,
+    int32_t n_threads);
+
+/*
  * torch.save(scores, f'{prefix}.pt') for a whole file list (emphases/core.py:
  * 112,177) on the native thread pool: file i receives scores[offsets[i] ..
  * + counts[i]) as a (1, counts[i]) float32 tensor in the zip-archive layout

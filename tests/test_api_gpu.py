@@ -281,6 +281,51 @@ def test_files_at_other_sample_rates_take_the_packed_path(
         assert os.path.exists(f'{prefix}.TextGrid')
 
 
+def test_list_api_streams_and_narrows_losslessly(emphases, golden, c1_checkpoint):
+    """from_alignments_and_audio on a list of CPU tensors: packed launch by
+    launch in the background; 16-bit-PCM-valued audio travels as int16 and
+    gives bit-identical scores to the fp32 upload"""
+    from emphases_b200 import scheduler
+    data = golden('c1')
+    state = state_from_golden(data)
+    alignments, audios, expected = [], [], []
+    for seed in range(6):
+        times, audio = oracle.synthetic_utterance(820 + seed, duration=1.5 + seed / 2)
+        audio = (audio * 32768.).round().clamp(-32768, 32767) / 32768.   # PCM values
+        alignments.append(emphases.Alignment.from_times(times))
+        audios.append(audio)
+        expected.append(oracle.from_alignment_and_audio(times, audio, state))
+    emphases.configure(MAX_ROWS_PER_LAUNCH=600)          # several launches
+    seen = []
+    original = scheduler.StreamedPack.launch_source
+
+    def spy(self, number, first, last):
+        source = original(self, number, first, last)
+        seen.append(source.dtype)
+        return source
+
+    scheduler.StreamedPack.launch_source = spy
+    try:
+        narrow = emphases.from_alignments_and_audio(
+            alignments, audios, 16000, checkpoint=c1_checkpoint, gpu=0)
+        assert len(seen) > 1 and all(dtype == torch.int16 for dtype in seen)
+        seen.clear()
+        noisy = [audio.clone() for audio in audios]
+        noisy[3][0, 5000] += 1e-5                        # one launch cannot narrow
+        mixed = emphases.from_alignments_and_audio(
+            alignments, noisy, 16000, checkpoint=c1_checkpoint, gpu=0)
+        assert torch.float32 in seen and torch.int16 in seen
+    finally:
+        scheduler.StreamedPack.launch_source = original
+    packed = scheduler.pack_audio(audios)
+    plain = emphases.from_alignments_and_audio(
+        alignments, packed, 16000, checkpoint=c1_checkpoint, gpu=0)
+    for got, same, other, want in zip(narrow, plain, mixed, expected):
+        assert torch.equal(got, same)
+        assert (got - want).abs().max() < 1e-5
+        assert (other - want).abs().max() < 1e-4
+
+
 def test_transformer_variant(emphases, golden):
     """ARCHITECTURE='transformer' Model.forward vs the reference (B=1 and a
     padded B=2 batch whose key-padding mask matters)"""

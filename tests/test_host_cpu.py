@@ -311,3 +311,44 @@ def test_native_score_files_load_like_torch_save(tmp_path):
     # unwritable path -> loud failure
     with pytest.raises(OSError):
         corpus.write_scores([tmp_path / 'missing' / 'x.pt'], [scores[0]])
+
+
+def test_native_audio_packer_and_lossless_narrowing():
+    """emph_pack_audio_f32: utterances land at their offsets; audio made of
+    16-bit PCM values is narrowed to int16 (bit-identical after / 32768), any
+    other sample keeps the fp32 copy"""
+    lib = _lib.load()
+    generator = torch.Generator().manual_seed(1)
+    lengths = np.array([1000, 37, 5001, 64], dtype=np.int64)
+    offsets = np.array([0, 1000, 1040, 6048], dtype=np.int64)
+    pcm = [torch.randint(-32768, 32768, (int(n),), generator=generator).to(torch.int16)
+           for n in lengths]
+    pcm[0][:4] = torch.tensor([-32768, 32767, 0, -1], dtype=torch.int16)
+    for case in ('pcm', 'float', 'late'):
+        rows = [p.float() / 32768. for p in pcm]
+        if case == 'float':
+            rows[1] = rows[1] + 1e-6                    # caught by the head probe
+        if case == 'late':
+            rows[2][4000] = 0.3                          # caught by the full pass only
+        pointers = np.array([r.data_ptr() for r in rows], dtype=np.uint64)
+        dst = torch.full((6200,), 7., dtype=torch.float32)
+        narrow = torch.full((6200,), 7, dtype=torch.int16)
+        flag = ctypes.c_int32(-1)
+        assert lib.emph_pack_audio_f32(
+            pointers.ctypes.data, lengths.ctypes.data, offsets.ctypes.data, 4,
+            ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(narrow.data_ptr()),
+            ctypes.byref(flag), 3) == 0
+        if case == 'pcm':
+            assert flag.value == 1
+            for o, n, p in zip(offsets, lengths, pcm):
+                assert torch.equal(narrow[o:o + n], p)
+                assert torch.equal(narrow[o:o + n].float() / 32768., p.float() / 32768.)
+        else:
+            assert flag.value == 0
+            for o, n, r in zip(offsets, lengths, rows):
+                assert torch.equal(dst[o:o + n], r)
+    # without an int16 destination the copy is always fp32
+    flag = ctypes.c_int32(-1)
+    assert lib.emph_pack_audio_f32(
+        pointers.ctypes.data, lengths.ctypes.data, offsets.ctypes.data, 4,
+        ctypes.c_void_p(dst.data_ptr()), None, None, 2) == 0
