@@ -326,6 +326,40 @@ def test_list_api_streams_and_narrows_losslessly(emphases, golden, c1_checkpoint
         assert (other - want).abs().max() < 1e-4
 
 
+def test_batched_api_edge_cases(emphases, golden, c1_checkpoint):
+    """Empty list, an utterance too short to yield a chunk (dropped like
+    emphases/core.py:413-415), stereo (channel 0 is used, mels.py:48),
+    float64 and CUDA inputs, a zero-length word under `sum`, chunked and
+    resampled inputs -- all through the list API in one call each"""
+    data = golden('c1')
+    state = state_from_golden(data)
+    make = emphases.Alignment.from_times
+    generator = torch.Generator().manual_seed(4)
+    run = lambda alignments, audios, rate=16000, **kw: emphases.from_alignments_and_audio(
+        alignments, audios, rate, checkpoint=c1_checkpoint, gpu=0, **kw)
+    assert run([], []) == []
+    times = [(0., .4), (.4, .4), (.4, 1.1), (1.1, 2.)]          # one empty word
+    audio = 0.1 * torch.randn(1, 32000, generator=generator)
+    want = oracle.from_alignment_and_audio(times, audio, state)
+    short = 0.1 * torch.randn(1, 400, generator=generator)
+    got = run([make([(0., .02)]), make(times)], [short, audio])
+    assert got[0].shape == (1, 0)
+    assert (got[1] - want).abs().max() < 1e-5
+    stereo = torch.cat([audio, -audio])
+    for variant in (stereo, audio.double(), audio.cuda()):
+        both = run([make(times)] * 2, [variant] * 2)
+        assert all((b - want).abs().max() < 1e-5 for b in both)
+    chunked = run([make(times)] * 2, [audio] * 2, batch_size=60)
+    want_chunked = oracle.from_alignment_and_audio(times, audio, state, batch_size=60)
+    assert all((c - want_chunked).abs().max() < 1e-5 for c in chunked)
+    native = 0.1 * torch.randn(1, 48000, generator=generator)
+    import torchaudio
+    want_24k = oracle.from_alignment_and_audio(
+        times, torchaudio.transforms.Resample(24000, 16000)(native), state)
+    assert all((r - want_24k).abs().max() < 2e-5
+               for r in run([make(times)] * 2, [native] * 2, 24000))
+
+
 def test_transformer_variant(emphases, golden):
     """ARCHITECTURE='transformer' Model.forward vs the reference (B=1 and a
     padded B=2 batch whose key-padding mask matters)"""
