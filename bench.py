@@ -51,7 +51,7 @@ def parse_args():
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     parser.add_argument(
-        '--precision', default=None, choices=['fp32', 'bf16', 'bf16x3'])
+        '--precision', default=None, choices=['fp32', 'bf16', 'bf16x3', 'bf16x6'])
     parser.add_argument('--utterances', type=int, default=3000)
     parser.add_argument(
         '--architecture', default='convolution',
@@ -633,7 +633,8 @@ def main():
         'dtype': {
             'fp32': 'f32',
             'bf16': 'bf16 (tcgen05, f32 accumulate)',
-            'bf16x3': 'bf16x3 (tcgen05, hi/lo split operands, f32 accumulate)'}[precision],
+            'bf16x3': 'bf16x3 (tcgen05, hi/lo split operands, f32 accumulate)',
+            'bf16x6': 'bf16x6 (tcgen05, hi/mid/lo split operands, f32 accumulate: fp32-grade)'}[precision],
         'data': 'synthetic',
         'config': workload_config(args),
         'clocks': clock_summary,

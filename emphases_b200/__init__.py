@@ -81,6 +81,8 @@ def precision_code():
         return _lib.PREC_BF16_TC
     if PRECISION == 'bf16x3':
         return _lib.PREC_BF16X3_TC
+    if PRECISION == 'bf16x6':
+        return _lib.PREC_BF16X6_TC
     raise ValueError(f'Precision {PRECISION} is not defined')
 
 

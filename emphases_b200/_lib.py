@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get(
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_LEAKY_RELU, ACT_SILU = 0, 1, 2, 3, 4
 POOL = {'average': 0, 'max': 1, 'sum': 2, 'center': 3}
 HEAD_LOGITS, HEAD_SIGMOID, HEAD_CLAMP = 0, 1, 2
-PREC_FP32, PREC_BF16_TC, PREC_BF16X3_TC = 0, 1, 2
+PREC_FP32, PREC_BF16_TC, PREC_BF16X3_TC, PREC_BF16X6_TC = 0, 1, 2, 3
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int32

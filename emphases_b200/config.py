@@ -56,8 +56,10 @@ MAX_TRAINING_FRAMES = 75000
 # reference's fp32 forward.  'bf16': tcgen05 tensor-core frame stack with bf16
 # operands, within 2e-3, fastest (the word decoder then runs as bf16x3).
 # 'bf16x3': tcgen05 with hi/lo-split bf16 operands (3 MMAs per product, 16
-# mantissa bits per operand): within 1e-4 (measured <= 1.3e-5), 3.7x faster
-# than 'fp32'.  Conv shapes the tensor-core kernel is not compiled for (kernel
+# mantissa bits per operand): within 2e-5 (measured 5.7e-6), 3.7x faster
+# than 'fp32'.  'bf16x6': hi/mid/lo split (6 MMAs per product, all 24 mantissa
+# bits of both operands): fp32-grade on the tensor cores, within 1e-5 like
+# 'fp32' (measured 8.6e-7), 3.4x faster than it.  Conv shapes the tensor-core kernel is not compiled for (kernel
 # sizes other than 3) always run on the FFMA kernel.
 PRECISION = 'fp32'
 # Upper bound on packed frame rows per launch (~1 KB of HBM per row).  A corpus

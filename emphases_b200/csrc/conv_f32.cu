@@ -407,6 +407,11 @@ int conv_stack_bf16x3_tc(
     const float* weights, const int32_t* acts_host,
     int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
     cudaStream_t stream);
+int conv_stack_bf16x6_tc(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host,
+    int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
+    cudaStream_t stream);
 
 }  // namespace emph
 
@@ -428,6 +433,9 @@ extern "C" int emph_conv_stack(
                                         n_layers, channels, kernel_size, y, (cudaStream_t)stream);
     if (precision == EMPH_PREC_BF16X3_TC)
         return emph::conv_stack_bf16x3_tc(x, row_seq, total_rows, weights, acts_host,
+                                          n_layers, channels, kernel_size, y, (cudaStream_t)stream);
+    if (precision == EMPH_PREC_BF16X6_TC)
+        return emph::conv_stack_bf16x6_tc(x, row_seq, total_rows, weights, acts_host,
                                           n_layers, channels, kernel_size, y, (cudaStream_t)stream);
     emph::set_error("emph_conv_stack: unknown precision %d", precision);
     return EMPH_EINVAL;

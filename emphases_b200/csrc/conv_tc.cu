@@ -57,29 +57,41 @@ constexpr int W_BIAS_BYTES = 2 * C * 16;          // bias chunk: 2 k-groups, 2,5
 constexpr int W_CONV_BYTES = KS * W_TAP_BYTES;    // 38,400
 constexpr int W_LAYER_BYTES = W_CONV_BYTES + W_BIAS_BYTES;   // 40,960
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 128;       // TMEM columns between slot accumulators
 
-// SPLIT = false: plain bf16 operands (2e-3 mode), 4 tile slots.
-// SPLIT = true : "bf16x3" -- activations and weights are each split into a
-//   bf16 hi and lo part and every product is formed as hi*hi + lo*hi + hi*lo
-//   (three MMAs into the same fp32 accumulator, the lo*lo term ~2^-16 is
-//   dropped): 16 mantissa bits per operand from the bf16 tensor pipe, i.e.
-//   ~1e-5-class results (between the 2e-3 bf16 mode and the exact FFMA mode).  Activations then
-//   need two operand buffers per slot (2 slots fit) and a layer's weights arrive
-//   as two ring entries (W_hi + bias chunk, W_lo).
-template <bool SPLIT>
+// PARTS = 1: plain bf16 operands (2e-3 mode), 4 tile slots.
+// PARTS = 2: "bf16x3" -- activations and weights are each split into a bf16 hi
+//   and lo part and every product is formed as hi*hi + lo*hi + hi*lo (three
+//   MMAs into the same fp32 accumulator, the lo*lo term ~2^-16 is dropped):
+//   16 mantissa bits per operand from the bf16 tensor pipe, ~1e-5-class
+//   results.  Two operand buffers per slot (2 slots fit); a layer's weights
+//   arrive as two ring entries (W_hi + bias chunk, W_lo).
+// PARTS = 3: "bf16x6" -- hi + mid + lo (24 mantissa bits, i.e. all of fp32) and
+//   the six products whose weight is above 2^-24: hh, mh, lh, hm, mm, hl.
+//   fp32-grade results (the tensor-core form of the exact mode); three operand
+//   buffers per slot, three ring entries per layer, a two-stage ring.
+// In general ring entry e (weight part e) multiplies activation parts 0 ..
+// PARTS-1-e.
+template <int PARTS>
 struct Config {
-    static constexpr int kSlots = SPLIT ? 2 : 4;
-    static constexpr int kParts = SPLIT ? 2 : 1;          // hi (, lo)
+    static constexpr int kSlots = PARTS == 1 ? 4 : 2;
+    static constexpr int kParts = PARTS;
     static constexpr int kThreads = 128 * kSlots + 64;
-    static constexpr int kEntriesPerLayer = SPLIT ? 2 : 1;
+    static constexpr int kEntriesPerLayer = PARTS;
+    static constexpr int kRing = PARTS == 3 ? 2 : kStages;     // weight ring stages
+    // The tensor core accumulates with truncation, so every MMA costs ~2^-24 of
+    // the ACCUMULATOR's magnitude: products of the same order (hi*hi | mid*hi,
+    // hi*mid | ...) therefore go to their own accumulator ("class" = weight
+    // part + activation part) and the epilogue adds the classes in fp32.
+    static constexpr int kClasses = PARTS;
+    static constexpr int kClassStride = PARTS == 3 ? 80 : 128;   // TMEM columns
+    static constexpr int kSlotStride = PARTS == 1 ? 128 : 256;
 };
 
-template <bool SPLIT>
+template <int PARTS>
 struct __align__(128) Smem {
-    static constexpr int kSlots = Config<SPLIT>::kSlots;
-    uint8_t act[kSlots][Config<SPLIT>::kParts][ACT_BYTES + 64];   // +64 keeps 128-B alignment
-    uint8_t w[kStages][W_LAYER_BYTES];
+    static constexpr int kSlots = Config<PARTS>::kSlots;
+    uint8_t act[kSlots][Config<PARTS>::kParts][ACT_BYTES + 64];   // +64 keeps 128-B alignment
+    uint8_t w[Config<PARTS>::kRing][W_LAYER_BYTES];
     float bias[kMaxLayers][C];                // fp32 bias, added by the epilogue
     uint64_t w_full[kStages];
     uint64_t w_empty[kStages];
@@ -176,8 +188,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait();
+// 16 columns of each of CLASSES accumulators (STRIDE columns apart), added in
+// fp32 from the smallest-magnitude class up
+template <int CLASSES, int STRIDE>
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t (&r)[16]);
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int CLASSES, int STRIDE>
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, uint32_t (&r)[16]) {
+    if constexpr (CLASSES == 1) {
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+    } else {
+        uint32_t part[CLASSES][16];
+#pragma unroll
+        for (int c = 0; c < CLASSES; ++c) tmem_ld16(taddr + c * STRIDE, part[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(part[CLASSES - 1][j]);
+#pragma unroll
+            for (int c = CLASSES - 2; c >= 0; --c) v += __uint_as_float(part[c][j]);
+            r[j] = __float_as_uint(v);
+        }
+    }
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -211,40 +247,43 @@ __device__ __forceinline__ bool elect_one() {
 constexpr uint32_t kInstrDesc =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 
-// value -> bf16 hi word and (SPLIT) bf16 lo word of the residual
-template <bool SPLIT>
-__device__ __forceinline__ void split_pack(float lo_v, float hi_v, uint32_t& hi_word, uint32_t& lo_word) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(lo_v, hi_v);
-    hi_word = *reinterpret_cast<const uint32_t*>(&h);
-    if constexpr (SPLIT) {
-        const float2 back = __bfloat1622float2(h);
-        lo_word = pack_bf16(lo_v - back.x, hi_v - back.y);
+// two values -> PARTS bf16x2 words: hi, then the bf16 of what is left, ...
+template <int PARTS>
+__device__ __forceinline__ void split_pack(float lo_v, float hi_v, uint32_t (&words)[PARTS]) {
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(lo_v, hi_v);
+        words[p] = *reinterpret_cast<const uint32_t*>(&h);
+        if (p + 1 < PARTS) {
+            const float2 back = __bfloat1622float2(h);
+            lo_v -= back.x;
+            hi_v -= back.y;
+        }
     }
 }
 
 // Store 8 consecutive channels of one row into the slot's A-operand buffer(s)
-template <bool SPLIT>
+template <int PARTS>
 __device__ __forceinline__ void store_kgroup(uint8_t* act_hi, int kg, int buffer_row, const float (&v)[8]) {
-    uint32_t h[4], l[4];
+    uint32_t words[4][PARTS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split_pack<SPLIT>(v[2 * j], v[2 * j + 1], h[j], l[j]);
-    *reinterpret_cast<uint4*>(act_hi + (kg * RB + buffer_row) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-    if constexpr (SPLIT)
-        *reinterpret_cast<uint4*>(act_hi + (ACT_BYTES + 64) + (kg * RB + buffer_row) * 16) =
-            make_uint4(l[0], l[1], l[2], l[3]);
+    for (int j = 0; j < 4; ++j) split_pack<PARTS>(v[2 * j], v[2 * j + 1], words[j]);
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p)
+        *reinterpret_cast<uint4*>(act_hi + p * (ACT_BYTES + 64) + (kg * RB + buffer_row) * 16) =
+            make_uint4(words[0][p], words[1][p], words[2][p], words[3][p]);
 }
 
 // Rare path: activations other than ReLU / identity.  Out of line so the hot
 // loop stays small in the instruction cache.
-template <bool SPLIT>
+template <int PARTS>
 __device__ __noinline__ void epilogue_generic(
     uint32_t taddr, uint8_t* act, int row, int a, bool valid, bool last, bool store,
     float* yrow, const float* bias) {
 #pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 16) {
         uint32_t raw[16];
-        tmem_ld16(taddr + c0, raw);
-        tmem_ld_wait();
+        tmem_ld16_sum<Config<PARTS>::kClasses, Config<PARTS>::kClassStride>(taddr + c0, raw);
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -252,8 +291,8 @@ __device__ __noinline__ void epilogue_generic(
         if (!last) {
             const float (&first)[8] = *reinterpret_cast<const float(*)[8]>(&v[0]);
             const float (&second)[8] = *reinterpret_cast<const float(*)[8]>(&v[8]);
-            store_kgroup<SPLIT>(act, c0 >> 3, row + 1, first);
-            store_kgroup<SPLIT>(act, (c0 >> 3) + 1, row + 1, second);
+            store_kgroup<PARTS>(act, c0 >> 3, row + 1, first);
+            store_kgroup<PARTS>(act, (c0 >> 3) + 1, row + 1, second);
         } else if (store) {
             float4* dst = reinterpret_cast<float4*>(yrow + c0);
             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -264,18 +303,19 @@ __device__ __noinline__ void epilogue_generic(
     }
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(Config<SPLIT>::kThreads, 1)
+template <int PARTS>
+__global__ void __launch_bounds__(Config<PARTS>::kThreads, 1)
 conv_stack_tc_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
     const uint8_t* __restrict__ weights,   // ring entries: [tap][kg][n][8] bf16 + bias chunk
     Acts acts, int n_layers, int tile_rows, int n_tiles, float* __restrict__ y) {
-    constexpr int kSlots = Config<SPLIT>::kSlots;
-    constexpr int kParts = Config<SPLIT>::kParts;
-    constexpr int kThreads = Config<SPLIT>::kThreads;
-    constexpr int kEntries = Config<SPLIT>::kEntriesPerLayer;
+    constexpr int kSlots = Config<PARTS>::kSlots;
+    constexpr int kParts = Config<PARTS>::kParts;
+    constexpr int kThreads = Config<PARTS>::kThreads;
+    constexpr int kEntries = Config<PARTS>::kEntriesPerLayer;
+    constexpr int kRing = Config<PARTS>::kRing;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem<SPLIT>& sm = *reinterpret_cast<Smem<SPLIT>*>(smem_raw);
+    Smem<PARTS>& sm = *reinterpret_cast<Smem<PARTS>*>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int halo = n_layers * ((KS - 1) / 2);
@@ -289,16 +329,17 @@ conv_stack_tc_kernel(
         reinterpret_cast<uint32_t*>(
             sm.act[buffer / kParts][buffer % kParts] + (kg * RB + (edge ? RB - 1 : 0)) * 16)[word] = 0u;
     }
-    // fp32 bias of every layer, rebuilt from the (hi, lo) bf16 pair the packed
-    // blob carries after each layer's taps; the epilogue adds it
+    // fp32 bias of every layer, rebuilt exactly from the three bf16 parts the
+    // packed blob carries after each layer's taps; the epilogue adds it
     for (int i = tid; i < n_layers * C; i += kThreads) {
         const int layer = i / C, n = i % C;
         const __nv_bfloat16* chunk = reinterpret_cast<const __nv_bfloat16*>(
             weights + (size_t)layer * kEntries * W_LAYER_BYTES + W_CONV_BYTES);
-        sm.bias[layer][n] = __bfloat162float(chunk[n * 8]) + __bfloat162float(chunk[n * 8 + 1]);
+        sm.bias[layer][n] = __bfloat162float(chunk[n * 8]) + __bfloat162float(chunk[n * 8 + 1]) +
+                            __bfloat162float(chunk[n * 8 + 2]);
     }
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kRing; ++i) {
             mbar_init(&sm.w_full[i], 1);
             mbar_init(&sm.w_empty[i], 1);
         }
@@ -322,16 +363,19 @@ conv_stack_tc_kernel(
         const int row = quad * 32 + lane;           // tile-local row == TMEM lane
         const int gtid = tid & 127;                 // thread within the group
         uint8_t* act = sm.act[slot][0];             // hi part; lo part follows it
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * kAccStride;
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quad * 32) << 16) + slot * Config<PARTS>::kSlotStride;
         uint32_t done_parity = 0;
 
         // One tile = M * C / 4 = 2560 float4 = 20 per thread, coalesced.  The
         // first tile is fetched up front; every later one is requested while the
         // tensor core still works on the previous tile's last layer, so its
         // latency never reaches the MMA warp.  The rows wait in registers already
-        // converted to bf16 (40 registers; 80 with the lo words in SPLIT mode).
-        uint2 pk_hi[20];
-        uint2 pk_lo[SPLIT ? 20 : 1];
+        // converted to bf16 (40 registers per part; with three parts the 80
+        // registers of the raw fp32 values are kept instead and split on store).
+        constexpr bool kKeepRaw = PARTS == 3;
+        uint2 pk[kKeepRaw ? 1 : PARTS][kKeepRaw ? 1 : 20];
+        float4 raw_rows[kKeepRaw ? 20 : 1];
         auto fetch_tile = [&](int tile) {
             const int row0 = tile * tile_rows - halo;
             // two batches of 10 loads in flight (the registers for 20 are not there)
@@ -348,11 +392,15 @@ conv_stack_tc_kernel(
                 }
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
-                    uint32_t h0, h1, l0 = 0u, l1 = 0u;
-                    split_pack<SPLIT>(v[k].x, v[k].y, h0, l0);
-                    split_pack<SPLIT>(v[k].z, v[k].w, h1, l1);
-                    pk_hi[10 * half + k] = make_uint2(h0, h1);
-                    if constexpr (SPLIT) pk_lo[10 * half + k] = make_uint2(l0, l1);
+                    if constexpr (kKeepRaw) {
+                        raw_rows[10 * half + k] = v[k];
+                    } else {
+                        uint32_t a[PARTS], b[PARTS];
+                        split_pack<PARTS>(v[k].x, v[k].y, a);
+                        split_pack<PARTS>(v[k].z, v[k].w, b);
+#pragma unroll
+                        for (int p = 0; p < PARTS; ++p) pk[p][10 * half + k] = make_uint2(a[p], b[p]);
+                    }
                 }
             }
         };
@@ -376,9 +424,18 @@ conv_stack_tc_kernel(
                 const int i = gtid + 128 * it;
                 const int r = i / (C / 4), c4 = i % (C / 4);
                 uint8_t* dst = act + ((c4 >> 1) * RB + r + 1) * 16 + (c4 & 1) * 8;
-                *reinterpret_cast<uint2*>(dst) = pk_hi[it];
-                if constexpr (SPLIT)
-                    *reinterpret_cast<uint2*>(dst + ACT_BYTES + 64) = pk_lo[it];
+                if constexpr (kKeepRaw) {
+                    uint32_t a[PARTS], b[PARTS];
+                    split_pack<PARTS>(raw_rows[it].x, raw_rows[it].y, a);
+                    split_pack<PARTS>(raw_rows[it].z, raw_rows[it].w, b);
+#pragma unroll
+                    for (int p = 0; p < PARTS; ++p)
+                        *reinterpret_cast<uint2*>(dst + p * (ACT_BYTES + 64)) = make_uint2(a[p], b[p]);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PARTS; ++p)
+                        *reinterpret_cast<uint2*>(dst + p * (ACT_BYTES + 64)) = pk[p][it];
+                }
             }
             fence_proxy_async();        // generic-proxy writes -> visible to the tensor core
             tc_fence_before();          // orders the previous round's TMEM reads too
@@ -411,10 +468,17 @@ conv_stack_tc_kernel(
                 if (simple) {
                     // whole accumulator row, then the fp32 bias: 5 x 16 columns, one wait
                     uint32_t raw[C];
+                    if constexpr (PARTS == 1) {
 #pragma unroll
-                    for (int c0 = 0; c0 < C; c0 += 16)
-                        tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
-                    tmem_ld_wait();
+                        for (int c0 = 0; c0 < C; c0 += 16)
+                            tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int c0 = 0; c0 < C; c0 += 16)
+                            tmem_ld16_sum<Config<PARTS>::kClasses, Config<PARTS>::kClassStride>(
+                                taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&raw[c0]));
+                    }
                     {
                         const float4* b4 = reinterpret_cast<const float4*>(sm.bias[layer]);
 #pragma unroll
@@ -426,7 +490,7 @@ conv_stack_tc_kernel(
                             raw[4 * c4 + 3] = __float_as_uint(__uint_as_float(raw[4 * c4 + 3]) + b.w);
                         }
                     }
-                    if constexpr (!SPLIT) {
+                    if constexpr (PARTS == 1) {
                         uint8_t* dst = act + (row + 1) * 16;
 #pragma unroll
                         for (int kg = 0; kg < KG; ++kg) {
@@ -451,11 +515,11 @@ conv_stack_tc_kernel(
                                 if (relu) w[j] = fmaxf(w[j], 0.f);
                                 if (zero) w[j] = 0.f;
                             }
-                            store_kgroup<true>(act, kg, row + 1, w);
+                            store_kgroup<PARTS>(act, kg, row + 1, w);
                         }
                     }
                 } else {
-                    epilogue_generic<SPLIT>(
+                    epilogue_generic<PARTS>(
                         taddr, act, row, a, valid, false, false, y, sm.bias[layer]);
                 }
                 if (tid == 0) TRACE(2, round * n_layers + layer);
@@ -490,8 +554,8 @@ conv_stack_tc_kernel(
 #pragma unroll 1
                     for (int c0 = 0; c0 < C; c0 += 16) {
                         uint32_t raw[16];
-                        tmem_ld16(taddr + c0, raw);
-                        tmem_ld_wait();
+                        tmem_ld16_sum<Config<PARTS>::kClasses, Config<PARTS>::kClassStride>(
+                            taddr + c0, raw);
                         if (store) {
                             const float4* b4 = reinterpret_cast<const float4*>(sm.bias[layer] + c0);
 #pragma unroll
@@ -512,7 +576,7 @@ conv_stack_tc_kernel(
                         }
                     }
                 } else {
-                    epilogue_generic<SPLIT>(
+                    epilogue_generic<PARTS>(
                         taddr, act, row, a, valid, true,
                         in_range && row >= halo && row < M - halo,
                         y + (size_t)(in_range ? g : 0) * C, sm.bias[layer]);
@@ -540,7 +604,7 @@ conv_stack_tc_kernel(
             for (int layer = 0; layer < n_layers; ++layer) {
 #pragma unroll
                 for (int entry = 0; entry < kEntries; ++entry) {
-                    // entry 0: W (or W_hi) + bias chunk; entry 1 (SPLIT): W_lo
+                    // entry e: weight part e (entry 0 also carries the bias chunk)
                     mbar_wait(&sm.w_full[stage], full_parity);
                     const uint64_t d_w = make_desc(smem_u32(sm.w[stage]), C * 16, 128);
 #pragma unroll
@@ -554,9 +618,9 @@ conv_stack_tc_kernel(
                                 tc_fence_after();
                             }
                             if (elect_one()) {
-                                const uint32_t d = tmem_base + s * kAccStride;
-                                // entry 0: hi (and lo) activations x W(_hi); entry 1: hi x W_lo
-                                const int parts = entry == 0 ? kParts : 1;
+                                const uint32_t d0 = tmem_base + s * Config<PARTS>::kSlotStride;
+                                // weight part e x activation parts 0 .. kParts-1-e
+                                const int parts = kParts - entry;
 #pragma unroll
                                 for (int part = 0; part < kParts; ++part) {
                                     if (part < parts) {
@@ -565,12 +629,13 @@ conv_stack_tc_kernel(
 #pragma unroll
                                             for (int kk = 0; kk < C / 16; ++kk) {
                                                 umma_bf16(
-                                                    d,
+                                                    d0 + (entry + part) * Config<PARTS>::kClassStride,
                                                     d_act[s] + part * kLoPart +
                                                         (uint64_t)(((2 * kk) * RB * 16 + tap * 16) >> 4),
                                                     d_w + (uint64_t)((tap * W_TAP_BYTES + (2 * kk) * C * 16) >> 4),
                                                     kInstrDesc,
-                                                    (entry | part | tap | kk) != 0);
+                                                    // a class is opened by its entry-0 MMA
+                                                    (entry | tap | kk) != 0);
                                             }
                                         }
                                     }
@@ -584,7 +649,7 @@ conv_stack_tc_kernel(
                     }
                     if (elect_one()) umma_commit(&sm.w_empty[stage]);   // ring entry consumed
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; full_parity ^= 1; }
+                    if (++stage == kRing) { stage = 0; full_parity ^= 1; }
                 }
             }
         }
@@ -601,7 +666,7 @@ conv_stack_tc_kernel(
                     mbar_arrive_expect_tx(&sm.w_full[stage], W_LAYER_BYTES);
                     bulk_load(sm.w[stage], weights + (size_t)entry * W_LAYER_BYTES,
                               W_LAYER_BYTES, &sm.w_full[stage]);
-                    if (++stage == kStages) { stage = 0; empty_parity ^= 1; }
+                    if (++stage == kRing) { stage = 0; empty_parity ^= 1; }
                 }
             }
         }
@@ -618,15 +683,17 @@ conv_stack_tc_kernel(
 
 // fp32 weights [L][tap][in][out] + bias [L][out] -> ring entries of
 // W_LAYER_BYTES: bf16 [tap][kg][out][8 in] followed by the bias chunk bf16
-// [2][out][8] (k-group 0 holds (bias_hi, bias_lo, 0, ...), k-group 1 is zero).
-// split = 1: two entries per layer -- (W_hi, bias chunk) and (W_lo, zeros) with
-// W_hi = bf16(W), W_lo = bf16(W - W_hi).
+// [2][out][8] (k-group 0 holds the fp32 bias as three bf16 parts (hi, mid, lo,
+// 0, ...), k-group 1 is zero).
+// parts = 2 / 3: that many entries per layer -- (W_hi, bias chunk), (W_mid, zeros)
+// (, (W_lo, zeros)) with W_hi = bf16(W), W_mid = bf16(W - W_hi), W_lo = bf16 of
+// what is still left.
 __global__ void pack_weights_tc_kernel(
-    const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int split,
+    const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int parts,
     __nv_bfloat16* __restrict__ out) {
     const int per_entry = W_LAYER_BYTES / 2;
     const int conv = W_CONV_BYTES / 2;
-    const int entries = split ? 2 : 1;
+    const int entries = parts;
     const int total = n_layers * entries * per_entry;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int entry = i / per_entry, local = i % per_entry;
@@ -640,15 +707,16 @@ __global__ void pack_weights_tc_kernel(
             const int tap = rest / KG;
             const int ci = kg * 8 + e;
             const float value = w[((size_t)(layer * KS + tap) * C + ci) * C + n];
-            const float hi = __bfloat162float(__float2bfloat16_rn(value));
-            v = part == 0 ? value : value - hi;      // part 0 rounds to hi below
+            v = value;                               // part p: rounded below after
+            for (int q = 0; q < part; ++q)           // removing the earlier parts
+                v -= __bfloat162float(__float2bfloat16_rn(v));
         } else if (part == 0) {
             const int rem = local - conv;
             const int e = rem & 7, n = (rem >> 3) % C, kg = (rem >> 3) / C;
-            if (kg == 0 && e < 2) {
-                const float b = bias[layer * C + n];
-                const float hi = __bfloat162float(__float2bfloat16_rn(b));
-                v = e == 0 ? hi : b - hi;
+            if (kg == 0 && e < 3) {                  // bias as three bf16 parts: exact fp32
+                v = bias[layer * C + n];
+                for (int q = 0; q < e; ++q)
+                    v -= __bfloat162float(__float2bfloat16_rn(v));
             }
         }
         out[i] = __float2bfloat16_rn(v);
@@ -679,7 +747,7 @@ static bool use_wide() {
     return cached == 1;
 }
 
-template <bool SPLIT>
+template <int PARTS>
 static int launch_tc(
     const float* x, const int32_t* row_seq, int32_t total_rows, const float* weights,
     const int32_t* acts_host, int32_t n_layers, float* y, cudaStream_t stream) {
@@ -689,20 +757,21 @@ static int launch_tc(
     EMPH_REQUIRE(tile_rows >= 32, "emph_conv_stack(tc): %d layers leave no tile", n_layers);
     tc::Acts acts;
     for (int i = 0; i < tc::kMaxLayers; ++i) acts.act[i] = i < n_layers ? acts_host[i] : 0;
-    constexpr int kSlots = tc::Config<SPLIT>::kSlots;
-    const size_t smem = sizeof(tc::Smem<SPLIT>) + 128;
+    constexpr int kSlots = tc::Config<PARTS>::kSlots;
+    const size_t smem = sizeof(tc::Smem<PARTS>) + 128;
     int s = check_cuda(
-        cudaFuncSetAttribute(tc::conv_stack_tc_kernel<SPLIT>,
+        cudaFuncSetAttribute(tc::conv_stack_tc_kernel<PARTS>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
         "conv_tc smem attribute");
     if (s != EMPH_OK) return s;
     const int n_tiles = (total_rows + tile_rows - 1) / tile_rows;
     const int want = (n_tiles + kSlots - 1) / kSlots;
     const int grid = want < sm_count() ? want : sm_count();
-    tc::conv_stack_tc_kernel<SPLIT><<<grid, tc::Config<SPLIT>::kThreads, smem, stream>>>(
+    tc::conv_stack_tc_kernel<PARTS><<<grid, tc::Config<PARTS>::kThreads, smem, stream>>>(
         x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), acts,
         n_layers, tile_rows, n_tiles, y);
-    EMPH_CHECK_LAUNCH(SPLIT ? "emph_conv_stack(bf16x3 tc)" : "emph_conv_stack(bf16 tc)");
+    EMPH_CHECK_LAUNCH(PARTS == 1 ? "emph_conv_stack(bf16 tc)"
+                      : PARTS == 2 ? "emph_conv_stack(bf16x3 tc)" : "emph_conv_stack(bf16x6 tc)");
     return EMPH_OK;
 }
 
@@ -719,7 +788,7 @@ int conv_stack_bf16_tc(
     }
     if (use_wide())
         return conv_stack_bf16_tc240(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
-    return launch_tc<false>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    return launch_tc<1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
 int conv_stack_bf16x3_tc(
@@ -732,7 +801,20 @@ int conv_stack_bf16x3_tc(
                   channels, kernel_size);
         return EMPH_ENOSYS;
     }
-    return launch_tc<true>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    return launch_tc<2>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+}
+
+int conv_stack_bf16x6_tc(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host,
+    int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
+    cudaStream_t stream) {
+    if (channels != tc::C || kernel_size != tc::KS) {
+        set_error("emph_conv_stack(bf16x6 tc): channels=%d kernel_size=%d not compiled in",
+                  channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    return launch_tc<3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
 }  // namespace emph
@@ -747,6 +829,7 @@ extern "C" int emph_conv_weights_tc_bytes(
     int32_t n_layers, int32_t channels, int32_t kernel_size, int32_t precision) {
     if (channels != emph::tc::C || kernel_size != emph::tc::KS || n_layers <= 0) return 0;
     if (precision == EMPH_PREC_BF16X3_TC) return 2 * n_layers * emph::tc::W_LAYER_BYTES;
+    if (precision == EMPH_PREC_BF16X6_TC) return 3 * n_layers * emph::tc::W_LAYER_BYTES;
     if (precision != EMPH_PREC_BF16_TC) return 0;
     if (emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
     return n_layers * emph::tc::W_LAYER_BYTES;
@@ -761,13 +844,14 @@ extern "C" int emph_pack_conv_weights_tc(
         return EMPH_ENOSYS;
     }
     EMPH_REQUIRE(n_layers > 0, "emph_pack_conv_weights_tc: no layers");
-    EMPH_REQUIRE(precision == EMPH_PREC_BF16_TC || precision == EMPH_PREC_BF16X3_TC,
+    EMPH_REQUIRE(precision == EMPH_PREC_BF16_TC || precision == EMPH_PREC_BF16X3_TC ||
+                     precision == EMPH_PREC_BF16X6_TC,
                  "emph_pack_conv_weights_tc: precision %d has no tensor-core layout", precision);
-    const int split = precision == EMPH_PREC_BF16X3_TC;
-    if (!split && emph::use_wide())
+    const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
+    if (parts == 1 && emph::use_wide())
         return emph::pack_conv_weights_tc240(weights, bias, n_layers, packed, (cudaStream_t)stream);
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
-        weights, bias, n_layers, split, reinterpret_cast<__nv_bfloat16*>(packed));
+        weights, bias, n_layers, parts, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");
     return EMPH_OK;
 }

@@ -510,6 +510,8 @@ def word_precision(precision, stack):
     """The word decoder always runs at fp32 grade (bf16 there costs 1.5e-3 of
     the 2e-3 budget): on the tensor cores as bf16x3 when
     a tensor-core mode is selected and the shape is compiled in, else FFMA"""
+    if precision == _lib.PREC_BF16X6_TC and tensor_core_shape(stack):
+        return _lib.PREC_BF16X6_TC
     if precision != _lib.PREC_FP32 and tensor_core_shape(stack):
         return _lib.PREC_BF16X3_TC
     return _lib.PREC_FP32

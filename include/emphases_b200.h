@@ -68,6 +68,9 @@ extern "C" {
 #define EMPH_PREC_BF16_TC 1   /* tcgen05 bf16 MMA, fp32 accumulate, 2e-3 */
 #define EMPH_PREC_BF16X3_TC 2 /* tcgen05, hi/lo split of both operands (3 MMAs per
                                 product, 16 mantissa bits per operand): 1e-4 */
+#define EMPH_PREC_BF16X6_TC 3 /* tcgen05, hi/mid/lo split of both operands (6 MMAs per
+                                product, 24 mantissa bits per operand): fp32-grade,
+                                1e-5 on scores like EMPH_PREC_FP32 */
 
 int emph_version(void);
 const char* emph_last_error(void);
@@ -152,12 +155,12 @@ int emph_conv_stack(
     int32_t precision, float* y, void* stream);
 
 /*
- * Weights for precision == EMPH_PREC_BF16_TC / EMPH_PREC_BF16X3_TC (the latter
- * packs a bf16 hi and a bf16 lo blob per layer): fp32 weights [n_layers][k][in]
- * [out] (the layout above) and bias [n_layers][out] -> per layer a bf16 blob in
- * the UMMA shared-memory operand layout [k][in / 8][out][8] followed by a bias
- * K-chunk (bias split into bf16 hi + lo, applied by one extra MMA against a
- * constant ones operand).  emph_conv_weights_tc_bytes gives the blob size (0 if
+ * Weights for precision == EMPH_PREC_BF16_TC / _BF16X3_TC / _BF16X6_TC (the
+ * split modes pack 2 / 3 bf16 blobs per layer: hi, (mid,) lo): fp32 weights
+ * [n_layers][k][in][out] (the layout above) and bias [n_layers][out] -> per
+ * layer a bf16 blob in the UMMA shared-memory operand layout [k][in / 8][out][8]
+ * followed by a bias chunk (the bias as three bf16 parts, rebuilt exactly to
+ * fp32 and added by the kernel's epilogue).  emph_conv_weights_tc_bytes gives the blob size (0 if
  * the configuration is not compiled in).  Pass the blob as `weights` of
  * emph_conv_stack; `bias` is then unused.
  */

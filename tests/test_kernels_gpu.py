@@ -513,9 +513,11 @@ def test_logmel_spectral_tilt_precision(eng):
     assert our_error < 4 * torch_error + 2e-5, (our_error, torch_error)
 
 
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16x6'])
 @pytest.mark.parametrize('which', ['frame', 'word'])
-def test_conv_stack_bf16x3_tc(eng, golden, which):
-    """bf16x3 (hi/lo split operands on tcgen05): fp32-grade conv stack"""
+def test_conv_stack_bf16x3_tc(eng, golden, which, mode):
+    """Split-operand modes on tcgen05: bf16x3 (hi/lo, 16 mantissa bits per
+    operand) and bf16x6 (hi/mid/lo, all 24: as tight as the FFMA kernel)"""
     from emphases_b200 import _lib
     data = golden('c1')
     state = state_from_golden(data)
@@ -537,18 +539,41 @@ def test_conv_stack_bf16x3_tc(eng, golden, which):
             (state[f'word_decoder.{2 * i}.weight'],
              state[f'word_decoder.{2 * i}.bias'], True) for i in range(6)]
         stack = weights.word
-    y = eng.conv_stack(x.cuda(), row_seq, stack, _lib.PREC_BF16X3_TC).cpu()
+    precision = _lib.PREC_BF16X3_TC if mode == 'bf16x3' else _lib.PREC_BF16X6_TC
+    y = eng.conv_stack(x.cuda(), row_seq, stack, precision).cpu()
     expected = oracle_conv_rows(state, layers, x, lengths)
     scale = expected.abs().max().item()
     error = (y - expected).abs().max().item()
-    assert error < 5e-5 * max(scale, 1.0), (error, scale)
+    tolerance = 5e-5 if mode == 'bf16x3' else 2e-6       # 2e-6: the fp32 kernel's own bar
+    assert error < tolerance * max(scale, 1.0), (error, scale)
     assert y[(row_seq < 0).cpu()].abs().max() == 0
 
 
 @pytest.mark.parametrize('batch_size', [None, 300])
+def test_forward_packed_bf16x6_golden(eng, golden, batch_size):
+    """Whole path with the bf16x6 conv stacks: scores within 1e-5 of the
+    reference's fp32 forward, the exact mode's tolerance, on tensor cores"""
+    from emphases_b200 import _lib, engine
+    data = golden('c1')
+    state = state_from_golden(data)
+    weights = default_weights(state)
+    times = np.asarray(data['times'])
+    plan = engine.make_plan([(times, 160000)], batch_size)
+    audio = torch.from_numpy(data['audio'])[0].cuda()
+    result = eng.forward_packed(
+        audio, plan, weights, precision=_lib.PREC_BF16X6_TC)
+    tag = 'full' if batch_size is None else f'bs{batch_size}'
+    scores = torch.cat([
+        result['scores'][s:s + n]
+        for s, n in zip(plan.word_row_start, plan.n_words)]).cpu().numpy()
+    error = np.abs(scores - data[f'{tag}.scores'][0]).max()
+    assert error < 1e-5, f'bf16x6 scores max-abs {error}'
+
+
+@pytest.mark.parametrize('batch_size', [None, 300])
 def test_forward_packed_bf16x3_golden(eng, golden, batch_size):
-    """Whole path with the bf16x3 tensor-core conv stacks: scores within 1e-4
-    (measured ~1e-5) of the reference's fp32 forward (trained checkpoint, sum
+    """Whole path with the bf16x3 tensor-core conv stacks: scores within 2e-5
+    (measured 5.7e-6) of the reference's fp32 forward (trained checkpoint, sum
     pooling)"""
     from emphases_b200 import _lib, engine
     data = golden('c1')
@@ -564,4 +589,4 @@ def test_forward_packed_bf16x3_golden(eng, golden, batch_size):
         result['scores'][s:s + n]
         for s, n in zip(plan.word_row_start, plan.n_words)]).cpu().numpy()
     error = np.abs(scores - data[f'{tag}.scores'][0]).max()
-    assert error < 1e-4, f'bf16x3 scores max-abs {error}'
+    assert error < 2e-5, f'bf16x3 scores max-abs {error}'
