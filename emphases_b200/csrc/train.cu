@@ -16,8 +16,10 @@
 
 namespace emph {
 
-// dpre = dy * act'(y) (y is the POST-activation output; ReLU/identity only
-// need y), separator rows zeroed
+// dpre = dy * act'(.), separator rows zeroed.  `y` is the layer's OUTPUT for
+// ReLU / LeakyReLU / identity (the sign of the output decides) and the
+// PRE-activation for GELU / SiLU (their derivative is not a function of the
+// output; the training forward keeps it, emph_activation_forward)
 __global__ void activation_backward_kernel(
     const float* __restrict__ dy, const float* __restrict__ y,
     const int32_t* __restrict__ row_seq, int total_rows, int channels, int act,
@@ -27,8 +29,34 @@ __global__ void activation_backward_kernel(
          i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / channels);
         float g = dy[i];
-        if (act == EMPH_ACT_RELU) g = y[i] > 0.f ? g : 0.f;
+        const float v = y[i];
+        if (act == EMPH_ACT_RELU) {
+            g = v > 0.f ? g : 0.f;
+        } else if (act == EMPH_ACT_LEAKY_RELU) {
+            g = v > 0.f ? g : 0.01f * g;
+        } else if (act == EMPH_ACT_GELU) {
+            // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+            const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+            const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
+            g *= cdf + v * pdf;
+        } else if (act == EMPH_ACT_SILU) {
+            const float sig = 1.f / (1.f + expf(-v));
+            g *= sig * (1.f + v * (1.f - sig));
+        }
         dpre[i] = row_seq[r] >= 0 ? g : 0.f;
+    }
+}
+
+// y = act(pre), separator rows zeroed (training forward of GELU / SiLU layers,
+// whose pre-activation is kept for the backward pass)
+__global__ void activation_forward_kernel(
+    const float* __restrict__ pre, const int32_t* __restrict__ row_seq, int total_rows,
+    int channels, int act, float* __restrict__ y) {
+    const size_t n = (size_t)total_rows * channels;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / channels);
+        y[i] = row_seq[r] >= 0 ? apply_activation(pre[i], act) : 0.f;
     }
 }
 
@@ -238,12 +266,24 @@ extern "C" {
 int emph_activation_backward(
     const float* dy, const float* y, const int32_t* row_seq, int32_t total_rows,
     int32_t channels, int32_t act, float* dpre, void* stream) {
-    EMPH_REQUIRE(act == EMPH_ACT_RELU || act == EMPH_ACT_NONE,
-                 "emph_activation_backward: only ReLU / identity are built");
+    EMPH_REQUIRE(act >= EMPH_ACT_NONE && act <= EMPH_ACT_SILU,
+                 "emph_activation_backward: unknown activation %d", act);
     if (total_rows == 0) return EMPH_OK;
     emph::activation_backward_kernel<<<emph::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(
         dy, y, row_seq, total_rows, channels, act, dpre);
     EMPH_CHECK_LAUNCH("emph_activation_backward");
+    return EMPH_OK;
+}
+
+int emph_activation_forward(
+    const float* pre, const int32_t* row_seq, int32_t total_rows, int32_t channels,
+    int32_t act, float* y, void* stream) {
+    EMPH_REQUIRE(act >= EMPH_ACT_NONE && act <= EMPH_ACT_SILU,
+                 "emph_activation_forward: unknown activation %d", act);
+    if (total_rows == 0) return EMPH_OK;
+    emph::activation_forward_kernel<<<emph::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(
+        pre, row_seq, total_rows, channels, act, y);
+    EMPH_CHECK_LAUNCH("emph_activation_forward");
     return EMPH_OK;
 }
 

@@ -61,8 +61,6 @@ class _ConvModelFunction(torch.autograd.Function):
             raise NotImplementedError(
                 'the training step is built for the convolution architecture '
                 "at the 'intermediate', 'loss' and 'inference' locations")
-        if model.activation not in ('ReLU', 'Identity'):
-            raise NotImplementedError('training backward supports ReLU only')
         if emphases.CHANNELS > engine.KERNEL_CHANNELS:
             raise NotImplementedError(
                 f'the backward kernels are built for up to {engine.KERNEL_CHANNELS} '
@@ -83,11 +81,29 @@ class _ConvModelFunction(torch.autograd.Function):
                 _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
                 _lib.ptr(rows), _lib.stream_ptr())
             frame_layers, word_layers = _layer_list(model)
-            frame_acts = [rows]
+
+            def layer_forward(x, seq, weight, bias, act):
+                """(output, what emph_activation_backward needs): GELU / SiLU
+                keep the pre-activation, the others their output"""
+                if act in (_lib.ACT_GELU, _lib.ACT_SILU):
+                    pre = eng.conv_stack(
+                        x, seq, _stack(weight, bias, _lib.ACT_NONE, device),
+                        _lib.PREC_FP32)
+                    y = torch.empty_like(pre)
+                    _lib.call(
+                        'emph_activation_forward', _lib.ptr(pre), _lib.ptr(seq),
+                        pre.shape[0], pre.shape[1], act, _lib.ptr(y),
+                        _lib.stream_ptr())
+                    return y, pre
+                y = eng.conv_stack(
+                    x, seq, _stack(weight, bias, act, device), _lib.PREC_FP32)
+                return y, y
+
+            frame_acts, frame_keys = [rows], []
             for weight, bias, act in frame_layers:
-                frame_acts.append(eng.conv_stack(
-                    frame_acts[-1], row_seq, _stack(weight, bias, act, device),
-                    _lib.PREC_FP32))
+                y, key = layer_forward(frame_acts[-1], row_seq, weight, bias, act)
+                frame_acts.append(y)
+                frame_keys.append(key)
             weights = model.packed_weights()
             if model.location == 'inference':
                 # frame-resolution logits (model/core.py:119-122)
@@ -99,7 +115,8 @@ class _ConvModelFunction(torch.autograd.Function):
                 ).to(device)
                 ctx.model = model
                 ctx.saved = dict(
-                    frame_acts=frame_acts, row_seq=row_seq, index=index,
+                    frame_acts=frame_acts, frame_keys=frame_keys,
+                    row_seq=row_seq, index=index,
                     total=total, head_weight=weights.head_weight,
                     head_kernel=weights.head_kernel, frame_level=True)
                 return logits[index][:, None, :]
@@ -110,11 +127,11 @@ class _ConvModelFunction(torch.autograd.Function):
                 views['word_lo'], views['word_hi'], method)
             word_row_seq = eng.row_index(
                 views['word_row_start'], views['n_words'], batch, total_words)
-            word_acts = [pooled]
+            word_acts, word_keys = [pooled], []
             for weight, bias, act in word_layers:
-                word_acts.append(eng.conv_stack(
-                    word_acts[-1], word_row_seq, _stack(weight, bias, act, device),
-                    _lib.PREC_FP32))
+                y, key = layer_forward(word_acts[-1], word_row_seq, weight, bias, act)
+                word_acts.append(y)
+                word_keys.append(key)
             logits, _ = eng.head(
                 word_acts[-1], word_row_seq, weights, _lib.HEAD_LOGITS,
                 want_scores=False)
@@ -123,7 +140,8 @@ class _ConvModelFunction(torch.autograd.Function):
             ).to(device)
         ctx.model = model
         ctx.saved = dict(
-            frame_acts=frame_acts, word_acts=word_acts, row_seq=row_seq,
+            frame_acts=frame_acts, word_acts=word_acts, frame_keys=frame_keys,
+            word_keys=word_keys, row_seq=row_seq,
             word_row_seq=word_row_seq, row_start=row_start, n_rows=n_rows,
             views=views, index=index, total=total, total_words=total_words,
             method=method, head_weight=weights.head_weight,
@@ -158,10 +176,10 @@ class _ConvModelFunction(torch.autograd.Function):
             grads[model.output_layer.weight] = dw.t()[None].contiguous()
             grads[model.output_layer.bias] = db
 
-            def conv_backward(layers, acts, row_seq, dy):
+            def conv_backward(layers, acts, keys, row_seq, dy):
                 for position in range(len(layers) - 1, -1, -1):
                     weight, bias, act = layers[position]
-                    x_in, y_out = acts[position], acts[position + 1]
+                    x_in, y_out = acts[position], keys[position]
                     dpre = torch.empty_like(dy)
                     _lib.call(
                         'emph_activation_backward', _lib.ptr(dy), _lib.ptr(y_out),
@@ -185,13 +203,14 @@ class _ConvModelFunction(torch.autograd.Function):
                 return dy
 
             if frame_level:
-                conv_backward(frame_layers, s['frame_acts'], s['row_seq'], dx)
+                conv_backward(
+                    frame_layers, s['frame_acts'], s['frame_keys'], s['row_seq'], dx)
                 ordered = [
                     grads[p].to(p.dtype) if p in grads else None
                     for p in model.parameters()]
                 return (None, None, None, None, *ordered)
             d_pooled = conv_backward(
-                word_layers, s['word_acts'], s['word_row_seq'], dx)
+                word_layers, s['word_acts'], s['word_keys'], s['word_row_seq'], dx)
             d_frames = torch.empty_like(s['frame_acts'][-1])
             views = s['views']
             _lib.call(
@@ -201,7 +220,8 @@ class _ConvModelFunction(torch.autograd.Function):
                 _lib.ptr(views['word_lo']), _lib.ptr(views['word_hi']),
                 s['total_words'], _lib.POOL[s['method']], s['total'],
                 _lib.ptr(d_frames), _lib.stream_ptr())
-            conv_backward(frame_layers, s['frame_acts'], s['row_seq'], d_frames)
+            conv_backward(
+                frame_layers, s['frame_acts'], s['frame_keys'], s['row_seq'], d_frames)
         ordered = [
             grads[p].to(p.dtype) if p in grads else None
             for p in model.parameters()]

@@ -281,7 +281,11 @@ int emph_add_layernorm(
  * Training step (BASELINE config 5; the reference's single-device step is
  * emphases/train/core.py:86-142, its loss :315-353), fp32.  Forward keeps each
  * layer's output (one emph_conv_stack launch per layer); per layer backward:
- *   emph_activation_backward  dpre = dy * act'(y), separators zeroed
+ *   emph_activation_backward  dpre = dy * act'(.), separators zeroed; `y` is the
+ *                             layer output for ReLU / LeakyReLU / identity and
+ *                             the pre-activation for GELU / SiLU, which the
+ *                             forward keeps by running the conv with
+ *                             EMPH_ACT_NONE and emph_activation_forward after it
  *   emph_conv_stack           dx = conv(dpre, W flipped and transposed)
  *   emph_conv_weight_grad     dw [k][in][out], db [out] (zeroed, then summed)
  * emph_pool_words_backward / emph_output_head_backward are the adjoints of
@@ -292,6 +296,9 @@ int emph_add_layernorm(
 int emph_activation_backward(
     const float* dy, const float* y, const int32_t* row_seq, int32_t total_rows,
     int32_t channels, int32_t act, float* dpre, void* stream);
+int emph_activation_forward(
+    const float* pre, const int32_t* row_seq, int32_t total_rows, int32_t channels,
+    int32_t act, float* y, void* stream);
 int emph_conv_weight_grad(
     const float* x, const float* dpre, int32_t total_rows, int32_t channels,
     int32_t kernel_size, float* dw, float* db, void* stream);

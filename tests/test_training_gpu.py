@@ -73,6 +73,38 @@ def test_gradients_match_autograd(emphases, golden, method, loss_fn):
         assert error < 2e-4 * scale + 1e-7, (name, error, scale)
 
 
+@pytest.mark.parametrize('activation', ['GELU', 'LeakyReLU', 'SiLU'])
+def test_gradients_other_activations(emphases, golden, activation):
+    """The activations of the reference's hyper-parameter sweep in training:
+    loss and every parameter gradient vs torch autograd through the oracle"""
+    emphases.configure(ACTIVATION_FUNCTION=getattr(torch.nn, activation))
+    data = golden('sweep')
+    state = state_from_golden(data)
+    model = emphases.Model()
+    model.load_state_dict({k: v for k, v in state.items() if k in model.state_dict()})
+    model = model.cuda().train()
+    features, frame_lengths, bounds, word_lengths, targets = padded_batch()
+    scores = model(features.cuda(), frame_lengths, bounds, word_lengths)
+    value = emphases.loss(
+        scores, targets.cuda(), frame_lengths, bounds, word_lengths, training=True)
+    value.backward()
+
+    reference = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    config = {'ACTIVATION': {
+        'GELU': 'gelu', 'LeakyReLU': 'leaky_relu', 'SiLU': 'silu'}[activation]}
+    expected_scores = oracle.model_forward(
+        reference, features, frame_lengths, bounds, word_lengths, config)
+    expected = oracle.loss(expected_scores, targets, word_lengths, 'bce')
+    expected.backward()
+    assert abs(value.item() - expected.item()) < 1e-5 * max(1, abs(expected.item()))
+    for name, parameter in model.named_parameters():
+        want = reference[name].grad
+        got = parameter.grad.cpu()
+        scale = want.abs().max().item() + 1e-12
+        error = (got - want).abs().max().item()
+        assert error < 2e-4 * scale + 1e-7, (name, error, scale)
+
+
 def test_train_step_reduces_loss(emphases, golden):
     data = golden('sweep')
     state = state_from_golden(data)
