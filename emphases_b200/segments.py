@@ -96,6 +96,46 @@ def segment(xs, word_bounds, word_lengths):
         return result, result_bounds, lengths
 
 
+def input_word_rows(batch, wmax, lengths, count, max_length, method, device):
+    """Packed word rows of the 'input' location: one word row per segment, laid
+    out as B sequences of Wmax word slots; row w pools segment word_seq[w] over
+    its padded length (model/core.py:55-63), masked slots are (-2, -2).
+    Returns (device views, host word_starts, total_words)."""
+    word_starts, total_words = engine.packed_starts([wmax] * batch)
+    word_seq = np.full(total_words, -1, dtype=np.int32)
+    word_lo = np.zeros(total_words, dtype=np.int32)
+    word_hi = np.zeros(total_words, dtype=np.int32)
+    for b in range(batch):
+        s = int(word_starts[b])
+        word_seq[s:s + wmax] = b * wmax + np.arange(wmax)
+        if method == 'center':
+            # downsample(frame_embeddings, [0, frames], ones): (0 + frames) // 2
+            word_lo[s:s + wmax] = 0
+            word_hi[s:s + wmax] = count[b]
+        else:
+            # reduction over the whole padded segment (model/core.py:55-63)
+            word_lo[s:s + wmax] = 0
+            word_hi[s:s + wmax] = max_length
+        word_lo[s + int(lengths[b]):s + wmax] = -2         # word mask (:77-82)
+        word_hi[s + int(lengths[b]):s + wmax] = -2
+    if method == 'max' and max_length == 0:
+        raise IndexError('max(): Expected reduction dim 2 to have non-zero size')
+    if method == 'center':
+        valid = np.arange(wmax)[None] < lengths[:, None]
+        if np.any((count // 2)[valid] >= max(max_length, 1)):
+            raise IndexError('center frame index out of range for a word')
+    meta = torch.from_numpy(np.concatenate([
+        word_starts.astype(np.int32), np.full(batch, wmax, dtype=np.int32),
+        word_seq, word_lo, word_hi])).to(device)
+    views = {
+        'word_row_start': meta[:batch],
+        'n_words': meta[batch:2 * batch],
+        'word_seq': meta[2 * batch:2 * batch + total_words],
+        'word_lo': meta[2 * batch + total_words:2 * batch + 2 * total_words],
+        'word_hi': meta[2 * batch + 2 * total_words:]}
+    return views, word_starts, total_words
+
+
 def run_forward_input(
     model, eng, weights, features, word_bounds, word_lengths, method, precision,
     encode=None, decode=None
@@ -123,37 +163,11 @@ def run_forward_input(
             segments, seg_row_seq, weights.frame,
             engine.frame_precision(precision, weights.frame))
 
-    # One word row per segment, laid out as B sequences of Wmax word slots
-    word_starts, total_words = engine.packed_starts([wmax] * batch)
-    word_seq = np.full(total_words, -1, dtype=np.int32)
-    word_lo = np.zeros(total_words, dtype=np.int32)
-    word_hi = np.zeros(total_words, dtype=np.int32)
-    for b in range(batch):
-        s = int(word_starts[b])
-        word_seq[s:s + wmax] = b * wmax + np.arange(wmax)
-        if method == 'center':
-            # downsample(frame_embeddings, [0, frames], ones): (0 + frames) // 2
-            word_lo[s:s + wmax] = 0
-            word_hi[s:s + wmax] = count[b]
-        else:
-            # reduction over the whole padded segment (model/core.py:55-63)
-            word_lo[s:s + wmax] = 0
-            word_hi[s:s + wmax] = max_length
-        word_lo[s + int(lengths[b]):s + wmax] = -2         # word mask (:77-82)
-        word_hi[s + int(lengths[b]):s + wmax] = -2
-    if method == 'max' and max_length == 0:
-        raise IndexError('max(): Expected reduction dim 2 to have non-zero size')
-    if method == 'center':
-        valid = np.arange(wmax)[None] < lengths[:, None]
-        if np.any((count // 2)[valid] >= max(max_length, 1)):
-            raise IndexError('center frame index out of range for a word')
-    meta = torch.from_numpy(np.concatenate([
-        word_starts.astype(np.int32), np.full(batch, wmax, dtype=np.int32),
-        word_seq, word_lo, word_hi])).to(device)
-    d_word_start, d_n_words = meta[:batch], meta[batch:2 * batch]
-    d_word_seq = meta[2 * batch:2 * batch + total_words]
-    d_word_lo = meta[2 * batch + total_words:2 * batch + 2 * total_words]
-    d_word_hi = meta[2 * batch + 2 * total_words:]
+    views, word_starts, total_words = input_word_rows(
+        batch, wmax, lengths, count, max_length, method, device)
+    d_word_start, d_n_words = views['word_row_start'], views['n_words']
+    d_word_seq, d_word_lo, d_word_hi = (
+        views['word_seq'], views['word_lo'], views['word_hi'])
     pooled = eng.pool(
         frame_rows, d_seg_start, d_seg_rows, d_word_seq, d_word_lo, d_word_hi,
         method)

@@ -57,10 +57,9 @@ class _ConvModelFunction(torch.autograd.Function):
         method = emphases.DOWNSAMPLE_METHOD
         if method not in _lib.POOL:
             raise ValueError(f'Interpolation method {method} is not defined')
-        if model.architecture != 'convolution' or model.location == 'input':
+        if model.architecture != 'convolution':
             raise NotImplementedError(
-                'the training step is built for the convolution architecture '
-                "at the 'intermediate', 'loss' and 'inference' locations")
+                'the training step is built for the convolution architecture')
         if emphases.CHANNELS > engine.KERNEL_CHANNELS:
             raise NotImplementedError(
                 f'the backward kernels are built for up to {engine.KERNEL_CHANNELS} '
@@ -68,18 +67,30 @@ class _ConvModelFunction(torch.autograd.Function):
         batch, channels, frames = features.shape
         wmax = word_bounds.shape[2]
         with torch.cuda.device(device):
-            starts, total = engine.packed_starts([frames] * batch)
-            meta = torch.from_numpy(np.concatenate([
-                starts.astype(np.int32), np.full(batch, frames, dtype=np.int32)])
-            ).to(device)
-            row_start, n_rows = meta[:batch], meta[batch:]
-            row_seq = eng.row_index(row_start, n_rows, batch, total)
-            rows = torch.empty((total, channels), dtype=torch.float32, device=device)
-            features32 = features.detach().to(torch.float32).contiguous()
-            _lib.call(
-                'emph_pack_rows', _lib.ptr(features32), batch, channels, frames,
-                _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
-                _lib.ptr(rows), _lib.stream_ptr())
+            input_location = model.location == 'input'
+            if input_location:
+                # every word segment is a packed sequence of max_length rows
+                # (emphases/model/core.py:41-87); the features carry no
+                # gradient, so the gather needs no adjoint
+                from . import segments
+                _, seg_lengths, max_length, lo, count = segments._segment_plan(
+                    word_bounds, word_lengths, frames)
+                rows, row_seq, row_start, n_rows, _, total = segments._gather(
+                    eng, features, lo, count, max_length)
+            else:
+                starts, total = engine.packed_starts([frames] * batch)
+                meta = torch.from_numpy(np.concatenate([
+                    starts.astype(np.int32), np.full(batch, frames, dtype=np.int32)])
+                ).to(device)
+                row_start, n_rows = meta[:batch], meta[batch:]
+                row_seq = eng.row_index(row_start, n_rows, batch, total)
+                rows = torch.empty(
+                    (total, channels), dtype=torch.float32, device=device)
+                features32 = features.detach().to(torch.float32).contiguous()
+                _lib.call(
+                    'emph_pack_rows', _lib.ptr(features32), batch, channels, frames,
+                    _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
+                    _lib.ptr(rows), _lib.stream_ptr())
             frame_layers, word_layers = _layer_list(model)
 
             def layer_forward(x, seq, weight, bias, act):
@@ -120,8 +131,12 @@ class _ConvModelFunction(torch.autograd.Function):
                     total=total, head_weight=weights.head_weight,
                     head_kernel=weights.head_kernel, frame_level=True)
                 return logits[index][:, None, :]
-            views, word_starts, total_words, bounds, lengths = \
-                model_module.word_rows(word_bounds, word_lengths, device)
+            if input_location:
+                views, word_starts, total_words = segments.input_word_rows(
+                    batch, wmax, seg_lengths, count, max_length, method, device)
+            else:
+                views, word_starts, total_words, bounds, lengths = \
+                    model_module.word_rows(word_bounds, word_lengths, device)
             pooled = eng.pool(
                 frame_acts[-1], row_start, n_rows, views['word_seq'],
                 views['word_lo'], views['word_hi'], method)

@@ -105,6 +105,39 @@ def test_gradients_other_activations(emphases, golden, activation):
         assert error < 2e-4 * scale + 1e-7, (name, error, scale)
 
 
+@pytest.mark.parametrize('method', ['sum', 'average', 'max', 'center'])
+def test_gradients_input_location(emphases, golden, method):
+    """Training at DOWNSAMPLE_LOCATION='input' (every word segment is encoded
+    on its own, reduction over the padded segment, model/core.py:41-87): loss
+    and every parameter gradient vs torch autograd through the oracle"""
+    emphases.configure(DOWNSAMPLE_LOCATION='input', DOWNSAMPLE_METHOD=method)
+    data = golden('sweep')
+    state = state_from_golden(data)
+    model = emphases.Model()
+    model.load_state_dict({k: v for k, v in state.items() if k in model.state_dict()})
+    model = model.cuda().train()
+    features, frame_lengths, bounds, word_lengths, targets = padded_batch()
+    scores = model(features.cuda(), frame_lengths, bounds, word_lengths)
+    assert scores.requires_grad
+    value = emphases.loss(
+        scores, targets.cuda(), frame_lengths, bounds, word_lengths, training=True)
+    value.backward()
+
+    reference = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    expected_scores = oracle.model_forward(
+        reference, features, frame_lengths, bounds, word_lengths,
+        {'DOWNSAMPLE_METHOD': method, 'DOWNSAMPLE_LOCATION': 'input'})
+    expected = oracle.loss(expected_scores, targets, word_lengths, 'bce')
+    expected.backward()
+    assert abs(value.item() - expected.item()) < 1e-5 * max(1, abs(expected.item()))
+    for name, parameter in model.named_parameters():
+        want = reference[name].grad
+        got = parameter.grad.cpu()
+        scale = want.abs().max().item() + 1e-12
+        error = (got - want).abs().max().item()
+        assert error < 2e-4 * scale + 1e-7, (name, error, scale)
+
+
 def test_train_step_reduces_loss(emphases, golden):
     data = golden('sweep')
     state = state_from_golden(data)
