@@ -1,6 +1,6 @@
 """Where does the end-to-end step time go?  (run under gpurun)"""
 import os, sys, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import emphases_b200 as emphases

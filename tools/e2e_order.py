@@ -1,6 +1,6 @@
 """Per-step e2e timings, fp32 / int16 / fp32 again, inside a bench-like process"""
 import os, sys, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import emphases_b200 as emphases

@@ -1,6 +1,6 @@
 """Time emphases_b200.from_files_to_files on an on-disk synthetic corpus"""
 import os, sys, time, tempfile, cProfile, pstats
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import emphases_b200 as emphases

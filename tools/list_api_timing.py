@@ -1,6 +1,8 @@
+"""Time from_alignments_and_audio on a LIST of pageable per-utterance CPU tensors
+(the reference's calling convention), generic fp32 and 16-bit-PCM-valued audio"""
 import os, sys, time
-import numpy as np, torch
-sys.path.insert(0, '/root/repo')
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import emphases_b200 as emphases
 from emphases_b200 import scheduler
