@@ -300,39 +300,47 @@ def run_on_device(
         for stream in streams:
             stream.wait_stream(torch.cuda.current_stream(device))
     pending = []
-    for number, members in enumerate(launches):
-        first, last = members[0], members[-1]
-        stream = streams[number % len(streams)]
-        # one grow-only workspace per stream: launches on a stream run in
-        # order, so its buffers can be reused without further synchronisation
-        ws = eng.workspace(number % len(streams))
-        source = packed.launch_source(number, first, last)
-        with torch.cuda.stream(stream):
-            # the audio copy goes out first: the host work below (alignment
-            # conversion, planning) then overlaps it, and the copy engine never
-            # waits for the host
-            device_audio = ws.get(
-                f'audio_{source.dtype}', (source.numel(),), source.dtype)
-            device_audio.copy_(source, non_blocking=True)
-        plan = engine.make_plan(
-            [(as_times(alignments[i]), int(packed.lengths[i])) for i in members],
-            batch_size,
-            validate_method=method)
-        with torch.cuda.stream(stream):
-            result = eng.forward_packed(
-                device_audio, plan, weights, method=method,
-                location=model.location, precision=precision,
-                head_mode=head_mode, normalize=emphases.NORMALIZE,
-                views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws)
-            scores = result[output]
-            if not to_cpu:
-                scores = scores.clone()       # the workspace is reused
-            if to_cpu:
-                host = eng.pinned(
-                    ('scores', number), scores.numel(), scores.dtype)
-                host.copy_(scores, non_blocking=True)
-                scores = host
-        pending.append((members, plan, scores))
+    try:
+        for number, members in enumerate(launches):
+            first, last = members[0], members[-1]
+            stream = streams[number % len(streams)]
+            # one grow-only workspace per stream: launches on a stream run in
+            # order, so its buffers can be reused without further synchronisation
+            ws = eng.workspace(number % len(streams))
+            source = packed.launch_source(number, first, last)
+            with torch.cuda.stream(stream):
+                # the audio copy goes out first: the host work below (alignment
+                # conversion, planning) then overlaps it, and the copy engine never
+                # waits for the host
+                device_audio = ws.get(
+                    f'audio_{source.dtype}', (source.numel(),), source.dtype)
+                device_audio.copy_(source, non_blocking=True)
+            plan = engine.make_plan(
+                [(as_times(alignments[i]), int(packed.lengths[i])) for i in members],
+                batch_size,
+                validate_method=method)
+            with torch.cuda.stream(stream):
+                result = eng.forward_packed(
+                    device_audio, plan, weights, method=method,
+                    location=model.location, precision=precision,
+                    head_mode=head_mode, normalize=emphases.NORMALIZE,
+                    views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws)
+                scores = result[output]
+                if not to_cpu:
+                    scores = scores.clone()       # the workspace is reused
+                if to_cpu:
+                    host = eng.pinned(
+                        ('scores', number), scores.numel(), scores.dtype)
+                    host.copy_(scores, non_blocking=True)
+                    scores = host
+            pending.append((members, plan, scores))
+    except BaseException:
+        # an error (e.g. a word without frames) must not leave the background
+        # packer writing into staging buffers the next call reuses
+        if isinstance(packed, StreamedPack):
+            packed.finish()
+        torch.cuda.synchronize(device)
+        raise
     for stream in streams:
         torch.cuda.current_stream(device).wait_stream(stream)
     if isinstance(packed, StreamedPack):
