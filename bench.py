@@ -589,7 +589,8 @@ def main():
             'kernel': 'pool_words_kernel',
             'bound': 'hbm',
             'achieved': pool_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-            'frac': pool_gbs / hbm_peak, 'traffic': None}}
+            # ncu: 209.3 MB read + 5.6 MB written per 655,899 frames (r01w_ncu.md)
+            'frac': pool_gbs / hbm_peak, 'traffic': 328.0 * frames}}
     for name, entry in candidates.items():
         entry['ms'] = kernel_ms[name]
         entry['share_of_step'] = kernel_ms[name] / ms_per_step
