@@ -590,3 +590,22 @@ def test_forward_packed_bf16x3_golden(eng, golden, batch_size):
         for s, n in zip(plan.word_row_start, plan.n_words)]).cpu().numpy()
     error = np.abs(scores - data[f'{tag}.scores'][0]).max()
     assert error < 2e-5, f'bf16x3 scores max-abs {error}'
+
+
+def test_wide_n_conv_kernel_variant():
+    """EMPHASES_B200_TC=wide selects the experimental N=240 formulation
+    (csrc/conv_tc240.cu: the three taps as output columns, tap shift applied to
+    the accumulators).  The choice is read once per process, so the bf16 conv
+    parity tests are re-run in a child process with the variable set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EMPHASES_B200_TC='wide')
+    result = subprocess.run(
+        [sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_kernels_gpu.py'),
+         '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
+         '-k', 'test_conv_stack_bf16_tc or test_forward_packed_bf16_golden'],
+        cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    assert ' passed' in result.stdout
