@@ -708,6 +708,15 @@ class Engine:
         if location not in ('intermediate', 'loss', 'inference'):
             raise ValueError(
                 f'Downsample location {location} not handled by the packed path')
+        with _lib.same_stream():
+            return self._forward_packed(
+                audio, plan, weights, method, location, precision, head_mode,
+                normalize, views, keep, timers, ws)
+
+    def _forward_packed(
+        self, audio, plan, weights, method, location, precision, head_mode,
+        normalize, views, keep, timers, ws
+    ):
         if views is None:
             views = self.upload_plan(plan)
 

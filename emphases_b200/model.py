@@ -88,7 +88,12 @@ class Model(torch.nn.Module):
 
     def packed_weights(self):
         """Kernel-layout weights, re-packed only when parameters change"""
-        parameters = list(self.parameters())
+        # (walking the module tree costs more than a small launch: the
+        # Parameter objects are stable, only their storage / version change)
+        parameters = getattr(self, '_parameter_list', None)
+        if parameters is None:
+            parameters = list(self.parameters())
+            object.__setattr__(self, '_parameter_list', parameters)
         device = parameters[0].device
         key = (device, tuple((p.data_ptr(), p._version) for p in parameters))
         if self._packed_key != key:
