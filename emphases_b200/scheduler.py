@@ -92,6 +92,21 @@ class PackedAudio:
         end = int(self.offsets[last] + engine.align_samples(self.lengths[last]))
         return self.buffer[base:min(end, self.buffer.numel())]
 
+    def view(self, first, stop):
+        """Utterances [first, stop) as a PackedAudio over the same buffer"""
+        if stop <= first:
+            return PackedAudio(self.buffer[:0], [], [])
+        base = int(self.offsets[first])
+        end = min(
+            int(self.offsets[stop - 1] + engine.align_samples(self.lengths[stop - 1])),
+            self.buffer.numel())
+        part = PackedAudio(
+            self.buffer[base:end], self.offsets[first:stop] - base,
+            self.lengths[first:stop])
+        if self.ready is not None:
+            part.ready = lambda j, parent=self.ready: parent(first + int(j))
+        return part
+
     @staticmethod
     def layout(lengths):
         lengths = np.asarray(lengths, dtype=np.int64)
@@ -221,6 +236,22 @@ def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
         shards[worker].append(index)
         heapq.heappush(heap, (load + costs[index], worker))
     return [sorted(shard) for shard in shards]
+
+
+def contiguous_assign(costs, workers: int) -> List[List[int]]:
+    """Cut the item list into `workers` contiguous ranges of (nearly) equal
+    total cost; returns, per worker, the item indices (possibly empty)"""
+    costs = np.asarray(costs, dtype=np.float64)
+    if len(costs) == 0:
+        return [[] for _ in range(workers)]
+    total = np.concatenate([[0.], np.cumsum(costs)])
+    targets = total[-1] * np.arange(1, workers) / workers
+    upper = np.clip(np.searchsorted(total, targets, side='left'), 1, len(costs))
+    nearest = np.where(
+        np.abs(total[upper - 1] - targets) <= np.abs(total[upper] - targets), upper - 1, upper)
+    cuts = [0] + [int(c) for c in nearest] + [len(costs)]
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, len(costs)))
+    return [list(range(int(a), int(b))) for a, b in zip(cuts[:-1], cuts[1:])]
 
 
 def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
@@ -396,7 +427,15 @@ def run_sharded(alignments, audios, sample_rate, checkpoint, batch_size, gpus):
     rate = emphases.SAMPLE_RATE / float(sample_rate)
     frames = lengths * rate / engine.HOPSIZE
     costs = frames ** 2 if emphases.ARCHITECTURE == 'transformer' else frames
-    shards = lpt_assign(costs.tolist(), len(gpus))
+    packed = isinstance(audios, PackedAudio) and emphases.DOWNSAMPLE_LOCATION != 'input' \
+        and emphases.ARCHITECTURE == 'convolution'
+    if packed:
+        # a packed corpus is cut into CONTIGUOUS ranges of equal cost: every
+        # shard is a zero-copy view of the pinned buffer (an LPT shard would
+        # have to be gathered utterance by utterance)
+        shards = contiguous_assign(costs, len(gpus))
+    else:
+        shards = lpt_assign(costs.tolist(), len(gpus))
     outputs = [None] * len(alignments)
     errors = []
 
@@ -409,7 +448,8 @@ def run_sharded(alignments, audios, sample_rate, checkpoint, batch_size, gpus):
                 results = run_on_device(
                     model,
                     [alignments[i] for i in shard],
-                    [audios[i] for i in shard],
+                    audios.view(shard[0], shard[-1] + 1) if packed
+                    else [audios[i] for i in shard],
                     sample_rate, batch_size, device, True)
             for index, result in zip(shard, results):
                 outputs[index] = result

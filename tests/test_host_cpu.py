@@ -182,6 +182,11 @@ def test_scheduler_lpt_and_buckets():
     assert max(loads) - min(loads) <= 2
     launches = scheduler.bucket_launches([100, 200, 50, 1000, 20], 400)
     assert launches == [[0, 1, 2], [3], [4]]
+    shards = scheduler.contiguous_assign([5, 1, 1, 1, 4, 4, 2, 2], 3)
+    assert [i for shard in shards for i in shard] == list(range(8))
+    assert [sum([5, 1, 1, 1, 4, 4, 2, 2][i] for i in shard) for shard in shards] == [7, 5, 8]
+    few = scheduler.contiguous_assign([1, 1], 4)
+    assert len(few) == 4 and sorted(i for shard in few for i in shard) == [0, 1]
     offsets, total = scheduler.PackedAudio.layout([5, 8, 3])
     assert offsets.tolist() == [0, 8, 16] and total == 24
     assert all(o % engine.AUDIO_ALIGN == 0 for o in offsets)
