@@ -44,6 +44,8 @@ SIGNATURES = {
     'emph_resample_f32': [_P, ctypes.c_int64, _P, _I, _I, _I, _P, ctypes.c_int64, _P],
     'emph_resample_packed_i16': [
         _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, ctypes.c_int64, _P],
+    'emph_resample_packed_f32': [
+        _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, ctypes.c_int64, _P],
     'emph_activation_backward': [_P, _P, _P, _I, _I, _I, _P, _P],
     'emph_activation_forward': [_P, _P, _I, _I, _I, _P, _P],
     'emph_conv_weight_grad': [_P, _P, _I, _I, _I, _P, _P, _P],

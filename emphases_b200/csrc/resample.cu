@@ -32,9 +32,19 @@ resample_kernel(
 // sample n of the packed 16 kHz buffer belongs to the utterance found by a
 // binary search over out_off (ascending); samples are x / 32768 exactly as
 // torchaudio.load returns them.  Gaps between utterances are zeroed.
+template <typename T>
+__device__ __forceinline__ float packed_sample(const T* p);
+template <>
+__device__ __forceinline__ float packed_sample<int16_t>(const int16_t* p) {
+    return (float)__ldg(p) * (1.f / 32768.f);
+}
+template <>
+__device__ __forceinline__ float packed_sample<float>(const float* p) { return __ldg(p); }
+
+template <typename T>
 __global__ void __launch_bounds__(256)
 resample_packed_kernel(
-    const int16_t* __restrict__ x, const int64_t* __restrict__ in_off,
+    const T* __restrict__ x, const int64_t* __restrict__ in_off,
     const int64_t* __restrict__ in_len, const int64_t* __restrict__ out_off,
     const int64_t* __restrict__ out_len, int n_utterances,
     const float* __restrict__ kernel, int orig, int fresh, int width, int taps,
@@ -51,7 +61,7 @@ resample_packed_kernel(
         y[n] = 0.f;
         return;
     }
-    const int16_t* src = x + __ldg(in_off + lo);
+    const T* src = x + __ldg(in_off + lo);
     const long long length = __ldg(in_len + lo);
     const long long q = local / fresh;
     const int p = (int)(local - q * fresh);
@@ -62,10 +72,30 @@ resample_packed_kernel(
     long long k1 = length - first;
     if (k1 > taps) k1 = taps;
     for (int k = k0; k < (int)k1; ++k)
-        acc = fmaf(__ldg(w + k), (float)__ldg(src + first + k) * (1.f / 32768.f), acc);
+        acc = fmaf(__ldg(w + k), packed_sample<T>(src + first + k), acc);
     y[n] = acc;
 }
 
+}  // namespace emph
+
+namespace emph {
+template <typename T>
+int launch_resample_packed(
+    const T* x, const int64_t* in_off, const int64_t* in_len,
+    const int64_t* out_off, const int64_t* out_len, int32_t n_utterances,
+    const float* kernel, int32_t orig_freq, int32_t new_freq, int32_t width,
+    float* y, int64_t total_out, void* stream) {
+    EMPH_REQUIRE(orig_freq > 0 && new_freq > 0 && width >= 0, "emph_resample_packed: bad filter");
+    EMPH_REQUIRE(n_utterances >= 0 && total_out >= 0, "emph_resample_packed: negative size");
+    if (total_out == 0 || n_utterances == 0) return EMPH_OK;
+    const int taps = 2 * width + orig_freq;
+    const long long blocks = (total_out + 255) / 256;
+    resample_packed_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        x, in_off, in_len, out_off, out_len, n_utterances, kernel, orig_freq, new_freq,
+        width, taps, y, total_out);
+    EMPH_CHECK_LAUNCH("emph_resample_packed");
+    return EMPH_OK;
+}
 }  // namespace emph
 
 extern "C" int emph_resample_packed_i16(
@@ -73,16 +103,19 @@ extern "C" int emph_resample_packed_i16(
     const int64_t* out_off, const int64_t* out_len, int32_t n_utterances,
     const float* kernel, int32_t orig_freq, int32_t new_freq, int32_t width,
     float* y, int64_t total_out, void* stream) {
-    EMPH_REQUIRE(orig_freq > 0 && new_freq > 0 && width >= 0, "emph_resample_packed_i16: bad filter");
-    EMPH_REQUIRE(n_utterances >= 0 && total_out >= 0, "emph_resample_packed_i16: negative size");
-    if (total_out == 0 || n_utterances == 0) return EMPH_OK;
-    const int taps = 2 * width + orig_freq;
-    const long long blocks = (total_out + 255) / 256;
-    emph::resample_packed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        x, in_off, in_len, out_off, out_len, n_utterances, kernel, orig_freq, new_freq,
-        width, taps, y, total_out);
-    EMPH_CHECK_LAUNCH("emph_resample_packed_i16");
-    return EMPH_OK;
+    return emph::launch_resample_packed<int16_t>(
+        x, in_off, in_len, out_off, out_len, n_utterances, kernel, orig_freq, new_freq, width,
+        y, total_out, stream);
+}
+
+extern "C" int emph_resample_packed_f32(
+    const float* x, const int64_t* in_off, const int64_t* in_len,
+    const int64_t* out_off, const int64_t* out_len, int32_t n_utterances,
+    const float* kernel, int32_t orig_freq, int32_t new_freq, int32_t width,
+    float* y, int64_t total_out, void* stream) {
+    return emph::launch_resample_packed<float>(
+        x, in_off, in_len, out_off, out_len, n_utterances, kernel, orig_freq, new_freq, width,
+        y, total_out, stream);
 }
 
 extern "C" int emph_resample_f32(

@@ -65,14 +65,23 @@ def resample(audio, sample_rate, target_rate, device):
 
 
 def resample_packed(packed, sample_rate, target_rate, device):
-    """A PackedAudio of int16 PCM at `sample_rate` (host) -> a PackedAudio of
-    fp32 audio at `target_rate` resident on `device`: one upload and ONE
-    kernel launch for the whole corpus (the reference resamples file by file,
-    emphases/core.py:613-619)."""
+    """A PackedAudio of int16 PCM or fp32 samples at `sample_rate` (host; or
+    a StreamedPack over a caller's list of tensors) -> a PackedAudio of fp32
+    audio at `target_rate` resident on `device`: one upload and ONE kernel
+    launch for the whole corpus (the reference resamples utterance by
+    utterance, emphases/core.py:613-619)."""
     import numpy as np
     from . import scheduler
-    if packed.buffer.dtype != torch.int16:
-        raise ValueError('resample_packed expects int16 PCM')
+    if packed.buffer.dtype not in (torch.int16, torch.float32):
+        raise ValueError('resample_packed expects int16 PCM or fp32 samples')
+    if isinstance(packed, scheduler.StreamedPack):
+        # a caller's list of tensors: packed (and narrowed when lossless) in
+        # one go on the native pool
+        everything = list(range(len(packed)))
+        packed.start([everything])
+        host = packed.launch_source(0, 0, len(packed) - 1)
+        packed.finish()
+        packed = scheduler.PackedAudio(host, packed.offsets, packed.lengths)
     if packed.ready is not None and len(packed):
         packed.ready(len(packed) - 1)
     kernels, width, orig, new = filter_bank(int(sample_rate), int(target_rate))
@@ -89,8 +98,10 @@ def resample_packed(packed, sample_rate, target_rate, device):
         ).to(device)
         count = len(lengths)
         out = torch.empty(total, dtype=torch.float32, device=device)
+        name = 'emph_resample_packed_i16' if source.dtype == torch.int16 \
+            else 'emph_resample_packed_f32'
         _lib.call(
-            'emph_resample_packed_i16', _lib.ptr(source), _lib.ptr(meta[:count]),
+            name, _lib.ptr(source), _lib.ptr(meta[:count]),
             _lib.ptr(meta[count:2 * count]), _lib.ptr(meta[2 * count:3 * count]),
             _lib.ptr(meta[3 * count:]), count, _lib.ptr(bank), orig, new, width,
             _lib.ptr(out), total, _lib.stream_ptr())

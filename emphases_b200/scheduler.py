@@ -277,17 +277,23 @@ def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
 ###############################################################################
 
 
-def _prepare(audios, sample_rate):
+def _prepare(audios, sample_rate, device=None):
     """A PackedAudio for a list of utterances"""
     if isinstance(audios, PackedAudio):
         if sample_rate != emphases.SAMPLE_RATE:
             raise ValueError('PackedAudio must already be at 16 kHz')
         return audios
-    if sample_rate != emphases.SAMPLE_RATE:
-        audios = [emphases.resample(audio, sample_rate) for audio in audios]
     cuda = [audio for audio in audios if audio.device.type == 'cuda']
+    if sample_rate != emphases.SAMPLE_RATE and (cuda or len(audios) < 2):
+        audios = [emphases.resample(audio, sample_rate) for audio in audios]
+        sample_rate = emphases.SAMPLE_RATE
     if cuda:
         audios = [audio.cpu() for audio in audios]
+    if sample_rate != emphases.SAMPLE_RATE:
+        # one packed resampling launch for the whole list
+        from . import resampling
+        return resampling.resample_packed(
+            StreamedPack(audios), sample_rate, emphases.SAMPLE_RATE, device)
     if len(audios) > 1:
         return StreamedPack(audios)
     return pack_audio(audios, pin=False)
@@ -307,7 +313,7 @@ def run_on_device(
         return _run_via_model(
             model, alignments, audios, sample_rate, batch_size, device, to_cpu,
             output)
-    packed = _prepare(audios, sample_rate)
+    packed = _prepare(audios, sample_rate, device)
     eng = emphases.get_engine(device)
     weights = model.packed_weights()
     method = emphases.DOWNSAMPLE_METHOD

@@ -368,6 +368,12 @@ int emph_resample_packed_i16(
     const int64_t* out_off, const int64_t* out_len, int32_t n_utterances,
     const float* kernel, int32_t orig_freq, int32_t new_freq, int32_t width,
     float* y, int64_t total_out, void* stream);
+/* The same for packed fp32 samples (a caller's list of tensors at another rate). */
+int emph_resample_packed_f32(
+    const float* x, const int64_t* in_off, const int64_t* in_len,
+    const int64_t* out_off, const int64_t* out_len, int32_t n_utterances,
+    const float* kernel, int32_t orig_freq, int32_t new_freq, int32_t width,
+    float* y, int64_t total_out, void* stream);
 
 /*
  * Host-side corpus ingest / egress for from_files_to_files (HOST pointers, no
