@@ -16,17 +16,34 @@
 
 namespace emph {
 
-constexpr int kAttnQ = 64;     // queries per CTA (one thread each)
+constexpr int kAttnThreads = 128;
+
+// 2^x, x <= 0 here (ex2.approx: relative error 2^-22; exp2(-inf) = 0)
+__device__ __forceinline__ float exp2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 128 queries per CTA (the host cuts query blocks of that size): a lane PAIR owns two queries
 constexpr int kAttnK = 64;     // keys per shared-memory tile
 
+// Block-diagonal attention with online softmax, fp32.  Two lanes share two
+// queries: lane h of the pair holds dims [h D/2, (h+1) D/2) of both queries'
+// q and o vectors, so every 16-byte K / V shared-memory load (a broadcast: the
+// 16 pairs of a warp read two addresses) feeds 8 FMAs instead of 4 and the
+// partial dot products meet through one shuffle per query and key.  (One
+// query per thread, the first version, was bound by the shared-memory pipe at
+// 75 % with the FP32 pipe at 45 %, profiles/r01z_attention.md.)
 template <int D>
-__global__ void __launch_bounds__(kAttnQ)
+__global__ void __launch_bounds__(kAttnThreads)
 attention_rows_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
     int channels, const int32_t* __restrict__ row_start, const int32_t* __restrict__ n_queries,
     const int32_t* __restrict__ n_keys,
     const int32_t* __restrict__ block_seq, const int32_t* __restrict__ block_q0,
     float scale, float* __restrict__ out) {
+    constexpr int H = D / 2;                   // dims per lane
+    static_assert(H % 4 == 0, "head dim must be a multiple of 8");
     __shared__ __align__(16) float ks[kAttnK][D];
     __shared__ __align__(16) float vs[kAttnK][D];
     const int u = block_seq[blockIdx.x];
@@ -34,63 +51,94 @@ attention_rows_kernel(
     const int head = blockIdx.y;
     const int base = row_start[u];
     const int nk = n_keys[u];
-    const int qi = q0 + threadIdx.x;
-    const bool active = qi < n_queries[u];
-    const size_t column = (size_t)head * D;
+    const int nq = n_queries[u];
+    const int half = threadIdx.x & 1;
+    const int qa = q0 + 2 * (threadIdx.x >> 1), qb = qa + 1;
+    const bool active_a = qa < nq, active_b = qb < nq;
+    const size_t column = (size_t)head * D + half * H;
 
-    float qr[D], o[D];
+    // scores are kept in the log2 domain (log2 e folded into the query scale):
+    // every exponential is then one MUFU.EX2
+    scale *= 1.4426950408889634f;
+    float qra[H], qrb[H], oa[H], ob[H];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        qr[d] = active ? q[(size_t)(base + qi) * channels + column + d] * scale : 0.f;
-        o[d] = 0.f;
+    for (int d = 0; d < H; ++d) {
+        qra[d] = active_a ? q[(size_t)(base + qa) * channels + column + d] * scale : 0.f;
+        qrb[d] = active_b ? q[(size_t)(base + qb) * channels + column + d] * scale : 0.f;
+        oa[d] = 0.f;
+        ob[d] = 0.f;
     }
-    float m = -CUDART_INF_F, l = 0.f;
+    float ma = -CUDART_INF_F, la = 0.f, mb = -CUDART_INF_F, lb = 0.f;
 
     for (int kt = 0; kt < nk; kt += kAttnK) {
         const int count = min(kAttnK, nk - kt);
         __syncthreads();
-        for (int i = threadIdx.x; i < count * (D / 4); i += kAttnQ) {
+        for (int i = threadIdx.x; i < count * (D / 4); i += kAttnThreads) {
             const int j = i / (D / 4), d4 = i % (D / 4);
-            const size_t src = (size_t)(base + kt + j) * channels + column + 4 * d4;
+            const size_t src = (size_t)(base + kt + j) * channels + (size_t)head * D + 4 * d4;
             *reinterpret_cast<float4*>(&ks[j][4 * d4]) = *reinterpret_cast<const float4*>(k + src);
             *reinterpret_cast<float4*>(&vs[j][4 * d4]) = *reinterpret_cast<const float4*>(v + src);
         }
         __syncthreads();
-        if (!active) continue;
+        // (inactive pairs run along: the shuffles below need every lane)
         for (int j = 0; j < count; ++j) {
-            float s = 0.f;
+            float sa = 0.f, sb = 0.f;
 #pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 kk = *reinterpret_cast<const float4*>(&ks[j][4 * d4]);
-                s = fmaf(qr[4 * d4], kk.x, s);
-                s = fmaf(qr[4 * d4 + 1], kk.y, s);
-                s = fmaf(qr[4 * d4 + 2], kk.z, s);
-                s = fmaf(qr[4 * d4 + 3], kk.w, s);
+            for (int d4 = 0; d4 < H / 4; ++d4) {
+                const float4 kk = *reinterpret_cast<const float4*>(&ks[j][half * H + 4 * d4]);
+                sa = fmaf(qra[4 * d4], kk.x, sa);
+                sa = fmaf(qra[4 * d4 + 1], kk.y, sa);
+                sa = fmaf(qra[4 * d4 + 2], kk.z, sa);
+                sa = fmaf(qra[4 * d4 + 3], kk.w, sa);
+                sb = fmaf(qrb[4 * d4], kk.x, sb);
+                sb = fmaf(qrb[4 * d4 + 1], kk.y, sb);
+                sb = fmaf(qrb[4 * d4 + 2], kk.z, sb);
+                sb = fmaf(qrb[4 * d4 + 3], kk.w, sb);
             }
-            if (s > m) {                       // new running maximum: rescale
-                const float correction = expf(m - s);
-                l *= correction;
+            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+            sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+            if (sa > ma) {                     // new running maximum: rescale
+                const float correction = exp2_fast(ma - sa);
+                la *= correction;
 #pragma unroll
-                for (int d = 0; d < D; ++d) o[d] *= correction;
-                m = s;
+                for (int d = 0; d < H; ++d) oa[d] *= correction;
+                ma = sa;
             }
-            const float p = expf(s - m);
-            l += p;
+            if (sb > mb) {
+                const float correction = exp2_fast(mb - sb);
+                lb *= correction;
 #pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 vv = *reinterpret_cast<const float4*>(&vs[j][4 * d4]);
-                o[4 * d4] = fmaf(p, vv.x, o[4 * d4]);
-                o[4 * d4 + 1] = fmaf(p, vv.y, o[4 * d4 + 1]);
-                o[4 * d4 + 2] = fmaf(p, vv.z, o[4 * d4 + 2]);
-                o[4 * d4 + 3] = fmaf(p, vv.w, o[4 * d4 + 3]);
+                for (int d = 0; d < H; ++d) ob[d] *= correction;
+                mb = sb;
+            }
+            const float pa = exp2_fast(sa - ma), pb = exp2_fast(sb - mb);
+            la += pa;
+            lb += pb;
+#pragma unroll
+            for (int d4 = 0; d4 < H / 4; ++d4) {
+                const float4 vv = *reinterpret_cast<const float4*>(&vs[j][half * H + 4 * d4]);
+                oa[4 * d4] = fmaf(pa, vv.x, oa[4 * d4]);
+                oa[4 * d4 + 1] = fmaf(pa, vv.y, oa[4 * d4 + 1]);
+                oa[4 * d4 + 2] = fmaf(pa, vv.z, oa[4 * d4 + 2]);
+                oa[4 * d4 + 3] = fmaf(pa, vv.w, oa[4 * d4 + 3]);
+                ob[4 * d4] = fmaf(pb, vv.x, ob[4 * d4]);
+                ob[4 * d4 + 1] = fmaf(pb, vv.y, ob[4 * d4 + 1]);
+                ob[4 * d4 + 2] = fmaf(pb, vv.z, ob[4 * d4 + 2]);
+                ob[4 * d4 + 3] = fmaf(pb, vv.w, ob[4 * d4 + 3]);
             }
         }
     }
-    if (active) {
-        const float inv = 1.f / l;
-        float* dst = out + (size_t)(base + qi) * channels + column;
+    if (active_a) {
+        const float inv = 1.f / la;
+        float* dst = out + (size_t)(base + qa) * channels + column;
 #pragma unroll
-        for (int d = 0; d < D; ++d) dst[d] = o[d] * inv;
+        for (int d = 0; d < H; ++d) dst[d] = oa[d] * inv;
+    }
+    if (active_b) {
+        const float inv = 1.f / lb;
+        float* dst = out + (size_t)(base + qb) * channels + column;
+#pragma unroll
+        for (int d = 0; d < H; ++d) dst[d] = ob[d] * inv;
     }
 }
 
@@ -194,13 +242,13 @@ int emph_attention_rows(
     if (n_blocks == 0) return EMPH_OK;
     dim3 grid(n_blocks, heads);
     if (head_dim == 40) {
-        emph::attention_rows_kernel<40><<<grid, emph::kAttnQ, 0, st>>>(
+        emph::attention_rows_kernel<40><<<grid, emph::kAttnThreads, 0, st>>>(
             q, k, v, channels, row_start, n_queries, n_keys, block_seq, block_q0, scale, out);
     } else if (head_dim == 32) {
-        emph::attention_rows_kernel<32><<<grid, emph::kAttnQ, 0, st>>>(
+        emph::attention_rows_kernel<32><<<grid, emph::kAttnThreads, 0, st>>>(
             q, k, v, channels, row_start, n_queries, n_keys, block_seq, block_q0, scale, out);
     } else if (head_dim == 64) {
-        emph::attention_rows_kernel<64><<<grid, emph::kAttnQ, 0, st>>>(
+        emph::attention_rows_kernel<64><<<grid, emph::kAttnThreads, 0, st>>>(
             q, k, v, channels, row_start, n_queries, n_keys, block_seq, block_q0, scale, out);
     } else {
         emph::set_error("emph_attention_rows: head_dim %d not compiled in", head_dim);

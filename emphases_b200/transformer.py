@@ -158,8 +158,9 @@ def pack_weights(model, device):
 ###############################################################################
 
 
-def query_blocks(n_keys, block=64):
-    """(block_seq, block_q0): 64-query blocks that never cross a sequence"""
+def query_blocks(n_keys, block=128):
+    """(block_seq, block_q0): 128-query blocks (kAttnQ of csrc/attention.cu)
+    that never cross a sequence"""
     n_keys = np.asarray(n_keys, dtype=np.int64)
     counts = (n_keys + block - 1) // block
     sequence = np.repeat(np.arange(len(n_keys)), counts)

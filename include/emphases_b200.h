@@ -258,7 +258,7 @@ int emph_segment_rows(
  *   All n_queries[u] rows are computed as queries, padded ones included, as
  *   nn.TransformerEncoder does (their values reach valid words through the
  *   k=3 output conv).  The caller supplies the query blocks (block_seq[b],
- *   block_q0[b]): 64 queries each, never crossing a sequence.
+ *   block_q0[b]): 128 queries each, never crossing a sequence.
  * emph_add_layernorm: y = LayerNorm(x + residual; gamma, beta, eps).
  */
 int emph_add_positional(
