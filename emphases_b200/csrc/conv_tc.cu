@@ -45,7 +45,6 @@ __device__ long long g_trace[8][512];
 #endif
 
 constexpr int C = 80;                 // channels (in = out)
-constexpr int KS = 3;                 // taps
 constexpr int KG = C / 8;             // k-groups of 8 channels
 constexpr int M = 128;                // rows per tile = UMMA M
 constexpr int RB = M + 2;             // buffer rows (one pad row each side)
@@ -54,8 +53,10 @@ constexpr int kMaxLayers = 16;
 constexpr int ACT_BYTES = KG * RB * 16;           // 20,800 per slot
 constexpr int W_TAP_BYTES = KG * C * 16;          // 12,800
 constexpr int W_BIAS_BYTES = 2 * C * 16;          // bias chunk: 2 k-groups, 2,560
-constexpr int W_CONV_BYTES = KS * W_TAP_BYTES;    // 38,400
-constexpr int W_LAYER_BYTES = W_CONV_BYTES + W_BIAS_BYTES;   // 40,960
+// per kernel size (3: the conv stacks; 1: the per-row linear maps of the
+// Transformer variant): bytes of one ring entry
+__host__ __device__ constexpr int conv_bytes(int ks) { return ks * W_TAP_BYTES; }                  // 38,400 at k = 3
+__host__ __device__ constexpr int layer_bytes(int ks) { return conv_bytes(ks) + W_BIAS_BYTES; }    // 40,960 at k = 3
 constexpr int kTmemCols = 512;
 
 // PARTS = 1: plain bf16 operands (2e-3 mode), 4 tile slots.
@@ -87,11 +88,11 @@ struct Config {
     static constexpr int kSlotStride = PARTS == 1 ? 128 : 256;
 };
 
-template <int PARTS>
+template <int PARTS, int KSIZE>
 struct __align__(128) Smem {
     static constexpr int kSlots = Config<PARTS>::kSlots;
     uint8_t act[kSlots][Config<PARTS>::kParts][ACT_BYTES + 64];   // +64 keeps 128-B alignment
-    uint8_t w[Config<PARTS>::kRing][W_LAYER_BYTES];
+    uint8_t w[Config<PARTS>::kRing][layer_bytes(KSIZE)];
     float bias[kMaxLayers][C];                // fp32 bias, added by the epilogue
     uint64_t w_full[kStages];
     uint64_t w_empty[kStages];
@@ -303,7 +304,7 @@ __device__ __noinline__ void epilogue_generic(
     }
 }
 
-template <int PARTS>
+template <int PARTS, int KSIZE>
 __global__ void __launch_bounds__(Config<PARTS>::kThreads, 1)
 conv_stack_tc_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
@@ -315,10 +316,13 @@ conv_stack_tc_kernel(
     constexpr int kEntries = Config<PARTS>::kEntriesPerLayer;
     constexpr int kRing = Config<PARTS>::kRing;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem<PARTS>& sm = *reinterpret_cast<Smem<PARTS>*>(smem_raw);
+    Smem<PARTS, KSIZE>& sm = *reinterpret_cast<Smem<PARTS, KSIZE>*>(smem_raw);
+    constexpr int W_CONV_BYTES = conv_bytes(KSIZE);
+    constexpr int W_LAYER_BYTES = layer_bytes(KSIZE);
+    constexpr int HALF = (KSIZE - 1) / 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int halo = n_layers * ((KS - 1) / 2);
+    const int halo = n_layers * HALF;
     const int rounds = (n_tiles + gridDim.x * kSlots - 1) / (gridDim.x * kSlots);
 
     // ---- one-time setup ----
@@ -625,13 +629,14 @@ conv_stack_tc_kernel(
                                 for (int part = 0; part < kParts; ++part) {
                                     if (part < parts) {
 #pragma unroll
-                                        for (int tap = 0; tap < KS; ++tap) {
+                                        for (int tap = 0; tap < KSIZE; ++tap) {
 #pragma unroll
                                             for (int kk = 0; kk < C / 16; ++kk) {
                                                 umma_bf16(
                                                     d0 + (entry + part) * Config<PARTS>::kClassStride,
                                                     d_act[s] + part * kLoPart +
-                                                        (uint64_t)(((2 * kk) * RB * 16 + tap * 16) >> 4),
+                                                        // tap t reads buffer row r + t + 1 - HALF
+                                                        (uint64_t)(((2 * kk) * RB * 16 + (tap + 1 - HALF) * 16) >> 4),
                                                     d_w + (uint64_t)((tap * W_TAP_BYTES + (2 * kk) * C * 16) >> 4),
                                                     kInstrDesc,
                                                     // a class is opened by its entry-0 MMA
@@ -690,9 +695,9 @@ conv_stack_tc_kernel(
 // what is still left.
 __global__ void pack_weights_tc_kernel(
     const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int parts,
-    __nv_bfloat16* __restrict__ out) {
-    const int per_entry = W_LAYER_BYTES / 2;
-    const int conv = W_CONV_BYTES / 2;
+    int ks, __nv_bfloat16* __restrict__ out) {
+    const int per_entry = layer_bytes(ks) / 2;
+    const int conv = conv_bytes(ks) / 2;
     const int entries = parts;
     const int total = n_layers * entries * per_entry;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -706,7 +711,7 @@ __global__ void pack_weights_tc_kernel(
             const int kg = rest % KG;
             const int tap = rest / KG;
             const int ci = kg * 8 + e;
-            const float value = w[((size_t)(layer * KS + tap) * C + ci) * C + n];
+            const float value = w[((size_t)(layer * ks + tap) * C + ci) * C + n];
             v = value;                               // part p: rounded below after
             for (int q = 0; q < part; ++q)           // removing the earlier parts
                 v -= __bfloat162float(__float2bfloat16_rn(v));
@@ -747,27 +752,27 @@ static bool use_wide() {
     return cached == 1;
 }
 
-template <int PARTS>
+template <int PARTS, int KSIZE>
 static int launch_tc(
     const float* x, const int32_t* row_seq, int32_t total_rows, const float* weights,
     const int32_t* acts_host, int32_t n_layers, float* y, cudaStream_t stream) {
     EMPH_REQUIRE(n_layers <= tc::kMaxLayers, "emph_conv_stack(tc): too many layers");
-    const int halo = n_layers * ((tc::KS - 1) / 2);
+    const int halo = n_layers * ((KSIZE - 1) / 2);
     const int tile_rows = tc::M - 2 * halo;
     EMPH_REQUIRE(tile_rows >= 32, "emph_conv_stack(tc): %d layers leave no tile", n_layers);
     tc::Acts acts;
     for (int i = 0; i < tc::kMaxLayers; ++i) acts.act[i] = i < n_layers ? acts_host[i] : 0;
     constexpr int kSlots = tc::Config<PARTS>::kSlots;
-    const size_t smem = sizeof(tc::Smem<PARTS>) + 128;
+    const size_t smem = sizeof(tc::Smem<PARTS, KSIZE>) + 128;
     int s = check_cuda(
-        cudaFuncSetAttribute(tc::conv_stack_tc_kernel<PARTS>,
+        cudaFuncSetAttribute(tc::conv_stack_tc_kernel<PARTS, KSIZE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
         "conv_tc smem attribute");
     if (s != EMPH_OK) return s;
     const int n_tiles = (total_rows + tile_rows - 1) / tile_rows;
     const int want = (n_tiles + kSlots - 1) / kSlots;
     const int grid = want < sm_count() ? want : sm_count();
-    tc::conv_stack_tc_kernel<PARTS><<<grid, tc::Config<PARTS>::kThreads, smem, stream>>>(
+    tc::conv_stack_tc_kernel<PARTS, KSIZE><<<grid, tc::Config<PARTS>::kThreads, smem, stream>>>(
         x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), acts,
         n_layers, tile_rows, n_tiles, y);
     EMPH_CHECK_LAUNCH(PARTS == 1 ? "emph_conv_stack(bf16 tc)"
@@ -781,14 +786,16 @@ int conv_stack_bf16_tc(
     int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
     cudaStream_t stream) {
     (void)bias;
-    if (channels != tc::C || kernel_size != tc::KS) {
+    if (channels != tc::C || (kernel_size != 3 && kernel_size != 1)) {
         set_error("emph_conv_stack(bf16 tc): channels=%d kernel_size=%d not compiled in",
                   channels, kernel_size);
         return EMPH_ENOSYS;
     }
+    if (kernel_size == 1)
+        return launch_tc<1, 1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
     if (use_wide())
         return conv_stack_bf16_tc240(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
-    return launch_tc<1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    return launch_tc<1, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
 int conv_stack_bf16x3_tc(
@@ -796,12 +803,14 @@ int conv_stack_bf16x3_tc(
     const float* weights, const int32_t* acts_host,
     int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
     cudaStream_t stream) {
-    if (channels != tc::C || kernel_size != tc::KS) {
+    if (channels != tc::C || (kernel_size != 3 && kernel_size != 1)) {
         set_error("emph_conv_stack(bf16x3 tc): channels=%d kernel_size=%d not compiled in",
                   channels, kernel_size);
         return EMPH_ENOSYS;
     }
-    return launch_tc<2>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    if (kernel_size == 1)
+        return launch_tc<2, 1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    return launch_tc<2, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
 int conv_stack_bf16x6_tc(
@@ -809,12 +818,14 @@ int conv_stack_bf16x6_tc(
     const float* weights, const int32_t* acts_host,
     int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
     cudaStream_t stream) {
-    if (channels != tc::C || kernel_size != tc::KS) {
+    if (channels != tc::C || (kernel_size != 3 && kernel_size != 1)) {
         set_error("emph_conv_stack(bf16x6 tc): channels=%d kernel_size=%d not compiled in",
                   channels, kernel_size);
         return EMPH_ENOSYS;
     }
-    return launch_tc<3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    if (kernel_size == 1)
+        return launch_tc<3, 1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    return launch_tc<3, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
 }  // namespace emph
@@ -827,18 +838,19 @@ extern "C" int emph_conv_trace_read(long long* host) {
 
 extern "C" int emph_conv_weights_tc_bytes(
     int32_t n_layers, int32_t channels, int32_t kernel_size, int32_t precision) {
-    if (channels != emph::tc::C || kernel_size != emph::tc::KS || n_layers <= 0) return 0;
-    if (precision == EMPH_PREC_BF16X3_TC) return 2 * n_layers * emph::tc::W_LAYER_BYTES;
-    if (precision == EMPH_PREC_BF16X6_TC) return 3 * n_layers * emph::tc::W_LAYER_BYTES;
+    if (channels != emph::tc::C || (kernel_size != 3 && kernel_size != 1) || n_layers <= 0) return 0;
+    const int entry = emph::tc::layer_bytes(kernel_size);
+    if (precision == EMPH_PREC_BF16X3_TC) return 2 * n_layers * entry;
+    if (precision == EMPH_PREC_BF16X6_TC) return 3 * n_layers * entry;
     if (precision != EMPH_PREC_BF16_TC) return 0;
-    if (emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
-    return n_layers * emph::tc::W_LAYER_BYTES;
+    if (kernel_size == 3 && emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
+    return n_layers * entry;
 }
 
 extern "C" int emph_pack_conv_weights_tc(
     const float* weights, const float* bias, int32_t n_layers, int32_t channels,
     int32_t kernel_size, int32_t precision, void* packed, void* stream) {
-    if (channels != emph::tc::C || kernel_size != emph::tc::KS) {
+    if (channels != emph::tc::C || (kernel_size != 3 && kernel_size != 1)) {
         emph::set_error("emph_pack_conv_weights_tc: channels=%d kernel_size=%d not compiled in",
                         channels, kernel_size);
         return EMPH_ENOSYS;
@@ -848,10 +860,10 @@ extern "C" int emph_pack_conv_weights_tc(
                      precision == EMPH_PREC_BF16X6_TC,
                  "emph_pack_conv_weights_tc: precision %d has no tensor-core layout", precision);
     const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
-    if (parts == 1 && emph::use_wide())
+    if (parts == 1 && kernel_size == 3 && emph::use_wide())
         return emph::pack_conv_weights_tc240(weights, bias, n_layers, packed, (cudaStream_t)stream);
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
-        weights, bias, n_layers, parts, reinterpret_cast<__nv_bfloat16*>(packed));
+        weights, bias, n_layers, parts, kernel_size, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");
     return EMPH_OK;
 }

@@ -495,7 +495,22 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
 
 
 def tensor_core_shape(stack):
-    return stack.channels == KERNEL_CHANNELS and stack.kernel_size == 3
+    return stack.channels == KERNEL_CHANNELS and stack.kernel_size in (1, 3)
+
+
+def linear_precision(stack):
+    """Per-row linear maps of the Transformer variant (kernel-size-1 stacks):
+    the fp32-grade tensor-core mode whenever a tensor-core PRECISION is
+    selected (attention, LayerNorm and the residual path stay fp32, so the
+    variant keeps its fp32-grade parity), else the FFMA kernel"""
+    if emphases_precision() != _lib.PREC_FP32 and tensor_core_shape(stack):
+        return _lib.PREC_BF16X6_TC
+    return _lib.PREC_FP32
+
+
+def emphases_precision():
+    import emphases_b200
+    return emphases_b200.precision_code()
 
 
 def frame_precision(precision, stack):
@@ -744,7 +759,8 @@ class Engine:
         if transformer_variant:
             from . import transformer
             embedded = self.conv_stack(
-                features, row_seq, weights.input_layer, _lib.PREC_FP32)
+                features, row_seq, weights.input_layer,
+                linear_precision(weights.input_layer))
             frames = timed('conv_frames', lambda: transformer.run_stack(
                 self, weights.frame, embedded, views['row_start'], plan.n_rows,
                 plan.n_rows, row_seq, self.device))

@@ -197,7 +197,8 @@ def run_stack(
         stack.table.shape[0], _lib.ptr(h), _lib.stream_ptr())
     for layer in stack.layers:
         q, k, v = (
-            eng.conv_stack(h, row_seq, part, _lib.PREC_FP32) for part in layer.qkv)
+            eng.conv_stack(h, row_seq, part, engine.linear_precision(part))
+            for part in layer.qkv)
         context = torch.empty_like(h)
         _lib.call(
             'emph_attention_rows', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v),
@@ -205,14 +206,17 @@ def run_stack(
             _lib.ptr(n_keys), _lib.ptr(row_seq), total_rows, _lib.ptr(d_block_seq),
             _lib.ptr(d_block_q0), len(block_seq), scale, _lib.ptr(context),
             _lib.stream_ptr())
-        attended = eng.conv_stack(context, row_seq, layer.out_proj, _lib.PREC_FP32)
+        attended = eng.conv_stack(
+            context, row_seq, layer.out_proj, engine.linear_precision(layer.out_proj))
         normed = torch.empty_like(h)
         _lib.call(
             'emph_add_layernorm', _lib.ptr(h), _lib.ptr(attended),
             _lib.ptr(layer.norm1[0]), _lib.ptr(layer.norm1[1]), 1e-5,
             _lib.ptr(row_seq), total_rows, channels, _lib.ptr(normed),
             _lib.stream_ptr())
-        forward = eng.conv_stack(normed, row_seq, layer.feedforward, _lib.PREC_FP32)
+        forward = eng.conv_stack(
+            normed, row_seq, layer.feedforward,
+            engine.linear_precision(layer.feedforward))
         h = torch.empty_like(normed)
         _lib.call(
             'emph_add_layernorm', _lib.ptr(normed), _lib.ptr(forward),
@@ -236,7 +240,8 @@ def run_forward(
 
         def encode(rows, seg_row_seq, seg_start, max_length, counts):
             embedded = eng.conv_stack(
-                rows, seg_row_seq, weights.input_layer, _lib.PREC_FP32)
+                rows, seg_row_seq, weights.input_layer,
+                engine.linear_precision(weights.input_layer))
             return run_stack(
                 eng, weights.frame, embedded, seg_start,
                 np.full(len(counts), max_length), counts, seg_row_seq, device)
@@ -264,7 +269,9 @@ def run_forward(
         _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(row_seq), total,
         _lib.ptr(rows), _lib.stream_ptr())
     # input_layer is a Conv1d over ALL T columns, padding included
-    embedded = eng.conv_stack(rows, row_seq, weights.input_layer, _lib.PREC_FP32)
+    embedded = eng.conv_stack(
+        rows, row_seq, weights.input_layer,
+        engine.linear_precision(weights.input_layer))
     frame_rows = run_stack(
         eng, weights.frame, embedded, row_start, np.full(batch, frames),
         frame_keys, row_seq, device)

@@ -418,6 +418,27 @@ def test_transformer_variant_input_location(emphases, golden):
                 rtol=0, atol=3e-5)
 
 
+def test_transformer_variant_linear_maps_on_tensor_cores(emphases, golden):
+    """With a tensor-core PRECISION the Transformer variant's per-row linear
+    maps (kernel-size-1 stacks: QKV, output projection, feed-forward) run in
+    the fp32-grade bf16x6 tcgen05 mode; attention stays fp32.  Same parity bar
+    as the all-fp32 path."""
+    data = golden('transformer')
+    emphases.configure(ARCHITECTURE='transformer', PRECISION='bf16')
+    model = emphases.Model()
+    model.load_state_dict(state_from_golden(data), strict=False)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        batch = [torch.from_numpy(data[f'b2.{name}']) for name in (
+            'features', 'frame_lengths', 'bounds', 'word_lengths')]
+        batch[0] = batch[0].cuda()
+        logits = model(*batch).cpu().numpy()
+        for i, words in enumerate(batch[3].tolist()):
+            np.testing.assert_allclose(
+                logits[i, :, :words], data['b2.logits'][i, :, :words],
+                rtol=0, atol=3e-5)
+
+
 def test_transformer_end_to_end(emphases, golden, tmp_path):
     """from_alignment_and_audio with the transformer variant vs the oracle"""
     data = golden('transformer')
