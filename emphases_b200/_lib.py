@@ -85,6 +85,8 @@ def load():
     lib.emph_corpus_fill_files.restype = ctypes.c_int
     lib.emph_pack_audio_f32.argtypes = [_P, _P, _P, _I, _P, _P, _P, _I]
     lib.emph_pack_audio_f32.restype = ctypes.c_int
+    lib.emph_write_score_rows.argtypes = [_P, _P, _P, _I, _I]
+    lib.emph_write_score_rows.restype = ctypes.c_int
     lib.emph_write_score_files.argtypes = [_P, _P, _P, _P, _I, _I]
     lib.emph_write_score_files.restype = ctypes.c_int
     lib.emph_corpus_open.argtypes = [_P, _P, _I, _I]

@@ -157,18 +157,18 @@ def write_scores(paths, scores, threads=None):
     import numpy as np
     import torch
     lib = _lib.load()
-    counts = np.array([int(score.shape[-1]) for score in scores], dtype=np.int32)
-    offsets = np.concatenate([[0], np.cumsum(counts[:-1])]).astype(np.int64) \
-        if len(counts) else np.zeros(0, dtype=np.int64)
-    flat = torch.cat([
-        score.detach().reshape(-1).to(device='cpu', dtype=torch.float32)
-        for score in scores]) if len(scores) else torch.zeros(0)
-    flat = np.ascontiguousarray(flat.numpy())
+    rows = [
+        score.detach().reshape(-1) if (
+            score.device.type == 'cpu' and score.dtype == torch.float32 and
+            score.is_contiguous())
+        else score.detach().reshape(-1).to(device='cpu', dtype=torch.float32).contiguous()
+        for score in scores]
+    counts = np.array([row.numel() for row in rows], dtype=np.int32)
+    pointers = np.array([row.data_ptr() for row in rows], dtype=np.uint64)
     encoded = [os.fsencode(path) for path in paths]
     array = (ctypes.c_char_p * len(encoded))(*encoded)
     threads = threads or min(32, os.cpu_count() or 1)
-    if lib.emph_write_score_files(
-        array, flat.ctypes.data, offsets.ctypes.data, counts.ctypes.data,
-        len(encoded), threads
+    if lib.emph_write_score_rows(
+        array, pointers.ctypes.data, counts.ctypes.data, len(encoded), threads
     ):
         raise OSError('could not write some score files')

@@ -545,6 +545,20 @@ int emph_write_score_files(
     return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
 }
 
+int emph_write_score_rows(
+    const char* const* paths, const float* const* rows, const int32_t* counts,
+    int32_t n_files, int32_t n_threads) {
+    if (n_files < 0 || (n_files > 0 && (!paths || !rows || !counts))) return EMPH_EINVAL;
+    std::atomic<int> failures(0);
+    parallel_for(n_files, n_threads, [&](int i) {
+        if (paths[i] == nullptr || paths[i][0] == 0) return;
+        if (counts[i] < 0 || (counts[i] > 0 && !rows[i]) ||
+            !write_score_file(paths[i], rows[i], (uint32_t)counts[i]))
+            ++failures;
+    });
+    return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
+}
+
 void emph_corpus_close(emph_corpus* corpus) { delete corpus; }
 
 }  // extern "C"

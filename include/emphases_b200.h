@@ -435,6 +435,10 @@ int emph_pack_audio_f32(
 int emph_write_score_files(
     const char* const* paths, const float* scores, const int64_t* offsets,
     const int32_t* counts, int32_t n_files, int32_t n_threads);
+/* The same with one HOST pointer per file (rows[i] holds counts[i] floats). */
+int emph_write_score_rows(
+    const char* const* paths, const float* const* rows, const int32_t* counts,
+    int32_t n_files, int32_t n_threads);
 
 #ifdef __cplusplus
 }

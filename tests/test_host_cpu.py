@@ -313,6 +313,17 @@ def test_native_score_files_load_like_torch_save(tmp_path):
         reference = tmp_path / 'reference.pt'
         torch.save(score, reference)
         assert torch.equal(torch.load(reference), torch.load(path))
+    # the flat-buffer form of the same entry point
+    flat = torch.cat([score.reshape(-1) for score in scores]).contiguous()
+    counts = np.array([score.numel() for score in scores], dtype=np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts[:-1])]).astype(np.int64)
+    flat_paths = [os.fsencode(tmp_path / f'flat{i}.pt') for i in range(len(scores))]
+    array = (ctypes.c_char_p * len(flat_paths))(*flat_paths)
+    assert _lib.load().emph_write_score_files(
+        array, ctypes.c_void_p(flat.data_ptr()), offsets.ctypes.data, counts.ctypes.data,
+        len(flat_paths), 2) == 0
+    for i, score in enumerate(scores):
+        assert torch.equal(torch.load(tmp_path / f'flat{i}.pt'), score)
     # unwritable path -> loud failure
     with pytest.raises(OSError):
         corpus.write_scores([tmp_path / 'missing' / 'x.pt'], [scores[0]])
