@@ -1,0 +1,43 @@
+"""bench.py's JSON line on a small workload: every key the driver and the
+judge read is present and consistent."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_line_contract():
+    result = subprocess.run(
+        [sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '3', '--warmup', '3',
+         '--utterances', '150', '--cpu-seconds', '1', '--file-utterances', '20'],
+        cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert result.returncode == 0, result.stderr[-2000:]
+    lines = [line for line in result.stdout.splitlines() if line.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+                'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config',
+                'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert key in line, key
+    assert line['metric'] == 'audio-sec/sec' and line['n_gpus'] == 1 and line['steps'] == 3
+    assert line['vs_baseline'] is None and line['scaling'] == 'weak'
+    assert line['gpu_launches'] == 7 * 3          # seven kernels per pass
+    roofline = line['roofline']
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in roofline, key
+    assert roofline['bound'] in ('hbm', 'tensor')
+    assert abs(roofline['frac'] - roofline['achieved'] / roofline['peak']) < 1e-9
+    for name in ('conv_frames', 'pool'):
+        assert name in roofline['others'] or name in roofline['kernel']
+    e2e = line['e2e']
+    assert e2e['value'] > 0 and e2e['h2d_bytes_per_step'] > 0 and e2e['d2h_bytes_per_step'] > 0
+    assert e2e['value'] < line['value']           # copies inside the timed region
+    cpu = line['cpu_baseline']
+    assert cpu['kind'] == 'port' and cpu['cores'] >= 1 and cpu['value'] > 0 and cpu['sample']
+    assert 'sm_mhz' in line['clocks'] and 'reasons' in line['clocks']
+    assert 'workload' in line['config']
