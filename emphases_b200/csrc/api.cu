@@ -43,6 +43,19 @@ __global__ void pack_conv_weights_kernel(
     packed[i] = w[(o * ci + c) * ks + k];
 }
 
+// (out, in, k) -> the ADJOINT conv in the same packed layout: [k][out][in] with
+// the taps flipped (dX = conv(dY, W^T flipped), emphases_b200/training.py)
+__global__ void pack_conv_weights_adjoint_kernel(
+    const float* __restrict__ w, int co, int ci, int ks, float* __restrict__ packed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = co * ci * ks;
+    if (i >= total) return;
+    int c = i % ci;                 // output channel of the adjoint = input channel of the conv
+    int o = (i / ci) % co;          // input channel of the adjoint = output channel of the conv
+    int k = i / (co * ci);
+    packed[i] = w[(o * ci + c) * ks + (ks - 1 - k)];
+}
+
 // (B, C, T) -> packed rows; 32x32 smem transpose tiles per sequence
 __global__ void pack_rows_kernel(
     const float* __restrict__ bct, int channels, int frames,
@@ -185,6 +198,17 @@ int emph_pack_conv_weights(
     emph::pack_conv_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         conv_weight, out_channels, in_channels, kernel_size, packed);
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights");
+    return EMPH_OK;
+}
+
+int emph_pack_conv_weights_adjoint(
+    const float* conv_weight, int32_t out_channels, int32_t in_channels,
+    int32_t kernel_size, float* packed, void* stream) {
+    int total = out_channels * in_channels * kernel_size;
+    EMPH_REQUIRE(total > 0, "emph_pack_conv_weights_adjoint: empty weight");
+    emph::pack_conv_weights_adjoint_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        conv_weight, out_channels, in_channels, kernel_size, packed);
+    EMPH_CHECK_LAUNCH("emph_pack_conv_weights_adjoint");
     return EMPH_OK;
 }
 

@@ -36,15 +36,32 @@ def _layer_list(model):
 def _stack(weight, bias, act, device, backward=False):
     """One-layer ConvStack; backward=True packs the adjoint (taps flipped,
     channel matrix transposed) with zero bias and no activation"""
-    packed = engine._pack_conv(weight, device)          # [k][in][out]
     if backward:
-        packed = packed.flip(0).transpose(1, 2).contiguous()
-        bias = torch.zeros_like(bias)
+        source = weight.detach().to(device=device, dtype=torch.float32).contiguous()
+        out_channels, in_channels, kernel = source.shape
+        packed = torch.empty(
+            (kernel, out_channels, in_channels), dtype=torch.float32, device=device)
+        _lib.call(
+            'emph_pack_conv_weights_adjoint', _lib.ptr(source), out_channels,
+            in_channels, kernel, _lib.ptr(packed), _lib.stream_ptr())
+        bias = _zero_bias(weight.shape[0], device)
         act = _lib.ACT_NONE
+    else:
+        packed = engine._pack_conv(weight, device)      # [k][in][out]
+        bias = bias.detach().to(device, torch.float32)
     return engine.ConvStack(
-        packed[None].contiguous(),
-        bias.detach().to(device, torch.float32)[None].contiguous(),
+        packed[None], bias[None],
         np.asarray([act], dtype=np.int32), weight.shape[2], weight.shape[0])
+
+
+_zero_biases = {}
+
+
+def _zero_bias(channels, device):
+    key = (channels, device)
+    if key not in _zero_biases:
+        _zero_biases[key] = torch.zeros(channels, dtype=torch.float32, device=device)
+    return _zero_biases[key]
 
 
 class _ConvModelFunction(torch.autograd.Function):
@@ -66,7 +83,7 @@ class _ConvModelFunction(torch.autograd.Function):
                 f'channels (CHANNELS={emphases.CHANNELS})')
         batch, channels, frames = features.shape
         wmax = word_bounds.shape[2]
-        with torch.cuda.device(device):
+        with torch.cuda.device(device), _lib.same_stream():
             input_location = model.location == 'input'
             if input_location:
                 # every word segment is a packed sequence of max_length rows
@@ -170,7 +187,7 @@ class _ConvModelFunction(torch.autograd.Function):
         eng = emphases.get_engine(device)
         channels = s['frame_acts'][0].shape[1]
         frame_level = s['frame_level']
-        with torch.cuda.device(device):
+        with torch.cuda.device(device), _lib.same_stream():
             rows = s['total'] if frame_level else s['total_words']
             head_seq = s['row_seq'] if frame_level else s['word_row_seq']
             dz = torch.zeros(rows, dtype=torch.float32, device=device)
@@ -259,7 +276,7 @@ class _MaskedLoss(torch.autograd.Function):
         valid = mask.reshape(-1).to(device, torch.uint8).contiguous()
         loss = torch.empty(1, dtype=torch.float32, device=device)
         grad = torch.empty_like(flat)
-        with torch.cuda.device(device):
+        with torch.cuda.device(device), _lib.same_stream():
             _lib.call(
                 'emph_masked_loss', _lib.ptr(flat), _lib.ptr(target),
                 _lib.ptr(valid), flat.numel(), mode, _lib.ptr(loss),

@@ -174,6 +174,12 @@ int emph_pack_conv_weights_tc(
 int emph_pack_conv_weights(
     const float* conv_weight, int32_t out_channels, int32_t in_channels,
     int32_t kernel_size, float* packed, void* stream);
+/* (out, in, k) Conv1d weight -> the adjoint convolution in the same packed
+ * layout, [k][out][in] with the taps flipped: the input gradient of a layer is
+ * emph_conv_stack(dY, adjoint weights, zero bias, no activation). */
+int emph_pack_conv_weights_adjoint(
+    const float* conv_weight, int32_t out_channels, int32_t in_channels,
+    int32_t kernel_size, float* packed, void* stream);
 
 /*
  * Frame -> word segment pooling (emphases/core.py:426-469 `downsample`).
