@@ -330,7 +330,20 @@ def time_files_path(emphases, count, state, gpu):
     import tempfile
     from pathlib import Path
     lengths, times = corpus_layout(count, seed=4321)
-    base = '/dev/shm' if os.path.isdir('/dev/shm') else None
+    # tmpfs when it has room for the corpus (2 bytes per sample + outputs),
+    # else the default temporary directory
+    need = int(lengths.sum()) * 2 * 1.2 + count * 16384
+    base = None
+    for candidate in ('/dev/shm', tempfile.gettempdir()):
+        try:
+            stats = os.statvfs(candidate)
+            if stats.f_bavail * stats.f_frsize > need:
+                base = candidate
+                break
+        except OSError:
+            continue
+    if base is None:
+        return {'unavailable': f'no temporary directory with {need / 1e9:.1f} GB free'}
     root = Path(tempfile.mkdtemp(dir=base))
     try:
         generator = torch.Generator().manual_seed(5)
@@ -524,7 +537,11 @@ def main():
     # ---- the same API through files on disk (from_files_to_files), rank 0 ----
     files_leg = None
     if rank == 0 and args.file_utterances > 0:
-        files_leg = time_files_path(emphases, args.file_utterances, state, local_rank)
+        try:
+            files_leg = time_files_path(
+                emphases, args.file_utterances, state, local_rank)
+        except OSError as error:          # e.g. the disk filled up: the leg is optional
+            files_leg = {'unavailable': f'{type(error).__name__}: {error}'}
 
     # ---- reduce over ranks: max time, summed units ----
     stats = torch.tensor(
