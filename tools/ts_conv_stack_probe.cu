@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(128, 1) probe(
     const float* __restrict__ bias,               // [L][C]
     const __nv_bfloat16* __restrict__ x_packed,   // [kg][RB][8]
     float* __restrict__ out,                      // [N][C] of CTA 0
-    long long* cycles) {                          // [grid][2]: MMA phase, epilogue phase (sum over layers)
+    long long* cycles,                            // [grid][3]: MMA phase, epilogue phase, weight phase (sums over layers)
+    int mode) {                                   // 0: tcgen05.cp from shared memory, 1: tcgen05.st from registers
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sw = smem;
     uint8_t* sx = smem + W_BYTES;
@@ -51,22 +52,43 @@ __global__ void __launch_bounds__(128, 1) probe(
     const uint32_t tmem = tmem_base_s, tmem_w = tmem + 256;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
     uint32_t parity = 0;
-    long long mma_clk = 0, epi_clk = 0;
+    long long mma_clk = 0, epi_clk = 0, wgt_clk = 0;
 
     for (int layer = 0; layer < L; ++layer) {
-        // this layer's weights: global -> shared (a plain copy; the product kernel streams them with TMA)
-        for (int i = tid; i < W_BYTES / 16; i += 128)
-            reinterpret_cast<uint4*>(sw)[i] =
-                reinterpret_cast<const uint4*>(w_packed + (size_t)layer * W_BYTES / 2)[i];
+        long long tw = clock64();
+        if (mode == 0) {
+            // this layer's weights: global -> shared (a plain copy; the product kernel streams them with TMA)
+            for (int i = tid; i < W_BYTES / 16; i += 128)
+                reinterpret_cast<uint4*>(sw)[i] =
+                    reinterpret_cast<const uint4*>(w_packed + (size_t)layer * W_BYTES / 2)[i];
+        } else {
+            // weights straight from global (L2) into TMEM through registers: thread = TMEM lane = weight
+            // row m; chunk c = (tap, kk) is the 32-byte K16 slice [kg 2kk | kg 2kk+1] of that row -> 8 columns
+            const uint8_t* wl = reinterpret_cast<const uint8_t*>(w_packed) + (size_t)layer * W_BYTES;
+            const uint32_t lane_base = tmem_w + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < 15; ++c) {
+                const uint8_t* src = wl + ((size_t)((c / 5) * KG + 2 * (c % 5)) * MROWS + tid) * 16;
+                const uint4 lo = *reinterpret_cast<const uint4*>(src);
+                const uint4 hi = *reinterpret_cast<const uint4*>(src + MROWS * 16);
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                    ::"r"(lane_base + c * 8), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+                      "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         long long t0 = clock64();
+        wgt_clk += t0 - tw;
         if (warp == 0) {
             uint32_t elected;
             asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(elected));
             if (elected) {
+                if (mode == 0)
 #pragma unroll
                 for (int c = 0; c < 15; ++c) {
                     const uint64_t src = make_desc(
@@ -132,8 +154,9 @@ __global__ void __launch_bounds__(128, 1) probe(
         epi_clk += t2 - t1;
     }
     if (tid == 0) {
-        cycles[2 * blockIdx.x] = mma_clk;
-        cycles[2 * blockIdx.x + 1] = epi_clk;
+        cycles[3 * blockIdx.x] = mma_clk;
+        cycles[3 * blockIdx.x + 1] = epi_clk;
+        cycles[3 * blockIdx.x + 2] = wgt_clk;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -178,29 +201,35 @@ int main() {
     const int grid = 148;
     __nv_bfloat16 *dw, *dx; float *dbias, *dout; long long* dcyc;
     cudaMalloc(&dw, wp.size() * 2); cudaMalloc(&dx, xp.size() * 2);
-    cudaMalloc(&dbias, bias.size() * 4); cudaMalloc(&dout, (size_t)N * C * 4); cudaMalloc(&dcyc, grid * 16);
+    cudaMalloc(&dbias, bias.size() * 4); cudaMalloc(&dout, (size_t)N * C * 4); cudaMalloc(&dcyc, grid * 24);
     cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dx, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
     const size_t smem = W_BYTES + X_BYTES + 1024;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    probe<<<grid, 128, smem>>>(dw, dbias, dx, dout, dcyc);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("ERROR %s\n", cudaGetErrorString(e)); return 1; }
-    std::vector<float> out((size_t)N * C);
-    std::vector<long long> cyc(2 * grid);
-    cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cyc.data(), dcyc, grid * 16, cudaMemcpyDeviceToHost);
-    double worst = 0, scale = 0;
-    for (int n = 0; n < N; ++n)
-        for (int c = 0; c < C; ++c) {
-            worst = fmax(worst, fabs(out[(size_t)n * C + c] - cur[(size_t)(n + 1) * C + c]));
-            scale = fmax(scale, fabs(cur[(size_t)(n + 1) * C + c]));
-        }
-    double mma = 0, epi = 0;
-    for (int i = 0; i < grid; ++i) { mma += cyc[2 * i]; epi += cyc[2 * i + 1]; }
-    printf("%d fused layers on a %d-row tile: max |err| %.3e (scale %.2f)\n", L, N, worst, scale);
-    printf("per layer: weights copy + 15 MMA %.0f clk, transposed epilogue (4 warps, 2-byte stores) %.0f clk\n",
-           mma / grid / L, epi / grid / L);
+    for (int mode = 0; mode < 2; ++mode) {
+        cudaMemset(dout, 0, (size_t)N * C * 4);
+        probe<<<grid, 128, smem>>>(dw, dbias, dx, dout, dcyc, mode);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("ERROR %s\n", cudaGetErrorString(e)); return 1; }
+        std::vector<float> out((size_t)N * C);
+        std::vector<long long> cyc(3 * grid);
+        cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(cyc.data(), dcyc, grid * 24, cudaMemcpyDeviceToHost);
+        double worst = 0, scale = 0;
+        for (int n = 0; n < N; ++n)
+            for (int c = 0; c < C; ++c) {
+                worst = fmax(worst, fabs(out[(size_t)n * C + c] - cur[(size_t)(n + 1) * C + c]));
+                scale = fmax(scale, fabs(cur[(size_t)(n + 1) * C + c]));
+            }
+        double mma = 0, epi = 0, wgt = 0;
+        for (int i = 0; i < grid; ++i) { mma += cyc[3 * i]; epi += cyc[3 * i + 1]; wgt += cyc[3 * i + 2]; }
+        printf("%s: %d fused layers on a %d-row tile: max |err| %.3e (scale %.2f)\n",
+               mode == 0 ? "weights via shared memory + tcgen05.cp" : "weights via registers + tcgen05.st   ",
+               L, N, worst, scale);
+        printf("   per layer: weight phase (all threads) %.0f clk, tensor phase (%s15 MMA, commit, wait) %.0f clk, "
+               "transposed epilogue %.0f clk\n",
+               wgt / grid / L, mode == 0 ? "15 cp, " : "", mma / grid / L, epi / grid / L);
+    }
     return 0;
 }
