@@ -23,7 +23,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
-__global__ void __launch_bounds__(128, 1) probe(
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) probe(
     const __nv_bfloat16* __restrict__ w_packed,   // [L][tap][kg][128][8]
     const float* __restrict__ bias,               // [L][C]
     const __nv_bfloat16* __restrict__ x_packed,   // [kg][RB][8]
@@ -36,7 +37,9 @@ __global__ void __launch_bounds__(128, 1) probe(
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < X_BYTES / 16; i += 128)
+    constexpr int THREADS = 32 * WARPS;
+    constexpr int SPLIT = WARPS / 4;               // warps per TMEM lane quadrant
+    for (int i = tid; i < X_BYTES / 16; i += THREADS)
         reinterpret_cast<uint4*>(sx)[i] = reinterpret_cast<const uint4*>(x_packed)[i];
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -58,17 +61,18 @@ __global__ void __launch_bounds__(128, 1) probe(
         long long tw = clock64();
         if (mode == 0) {
             // this layer's weights: global -> shared (a plain copy; the product kernel streams them with TMA)
-            for (int i = tid; i < W_BYTES / 16; i += 128)
+            for (int i = tid; i < W_BYTES / 16; i += THREADS)
                 reinterpret_cast<uint4*>(sw)[i] =
                     reinterpret_cast<const uint4*>(w_packed + (size_t)layer * W_BYTES / 2)[i];
         } else {
             // weights straight from global (L2) into TMEM through registers: thread = TMEM lane = weight
             // row m; chunk c = (tap, kk) is the 32-byte K16 slice [kg 2kk | kg 2kk+1] of that row -> 8 columns
             const uint8_t* wl = reinterpret_cast<const uint8_t*>(w_packed) + (size_t)layer * W_BYTES;
-            const uint32_t lane_base = tmem_w + ((uint32_t)(warp * 32) << 16);
+            const uint32_t lane_base = tmem_w + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
             for (int c = 0; c < 15; ++c) {
-                const uint8_t* src = wl + ((size_t)((c / 5) * KG + 2 * (c % 5)) * MROWS + tid) * 16;
+                if (c % SPLIT != (warp >> 2)) continue;
+                const uint8_t* src = wl + ((size_t)((c / 5) * KG + 2 * (c % 5)) * MROWS + (tid & 127)) * 16;
                 const uint4 lo = *reinterpret_cast<const uint4*>(src);
                 const uint4 hi = *reinterpret_cast<const uint4*>(src + MROWS * 16);
                 asm volatile(
@@ -118,12 +122,12 @@ __global__ void __launch_bounds__(128, 1) probe(
         long long t1 = clock64();
 
         // transposed epilogue: thread = TMEM lane = output channel
-        const int c = tid;
+        const int c = tid & 127;
         const bool live = c < C;
         const float b = live ? bias[layer * C + c] : 0.f;
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint8_t* column = sx + ((c >> 3) * RB + 1) * 16 + (c & 7) * 2;     // row n -> + n * 16
-        for (int n0 = 0; n0 < N; n0 += 32) {
+        for (int n0 = (warp >> 2) * (N / SPLIT); n0 < ((warp >> 2) + 1) * (N / SPLIT); n0 += 32) {
             uint32_t r[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -206,10 +210,13 @@ int main() {
     cudaMemcpy(dx, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
     const size_t smem = W_BYTES + X_BYTES + 1024;
-    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mode = 0; mode < 2; ++mode) {
+    cudaFuncSetAttribute(probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(probe<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int run = 0; run < 3; ++run) {
+        const int mode = run == 0 ? 0 : 1, warps = run == 2 ? 8 : 4;
         cudaMemset(dout, 0, (size_t)N * C * 4);
-        probe<<<grid, 128, smem>>>(dw, dbias, dx, dout, dcyc, mode);
+        if (warps == 4) probe<4><<<grid, 128, smem>>>(dw, dbias, dx, dout, dcyc, mode);
+        else probe<8><<<grid, 256, smem>>>(dw, dbias, dx, dout, dcyc, mode);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("ERROR %s\n", cudaGetErrorString(e)); return 1; }
         std::vector<float> out((size_t)N * C);
@@ -224,9 +231,9 @@ int main() {
             }
         double mma = 0, epi = 0, wgt = 0;
         for (int i = 0; i < grid; ++i) { mma += cyc[3 * i]; epi += cyc[3 * i + 1]; wgt += cyc[3 * i + 2]; }
-        printf("%s: %d fused layers on a %d-row tile: max |err| %.3e (scale %.2f)\n",
+        printf("%s, %d warps: %d fused layers on a %d-row tile: max |err| %.3e (scale %.2f)\n",
                mode == 0 ? "weights via shared memory + tcgen05.cp" : "weights via registers + tcgen05.st   ",
-               L, N, worst, scale);
+               warps, L, N, worst, scale);
         printf("   per layer: weight phase (all threads) %.0f clk, tensor phase (%s15 MMA, commit, wait) %.0f clk, "
                "transposed epilogue %.0f clk\n",
                wgt / grid / L, mode == 0 ? "15 cp, " : "", mma / grid / L, epi / grid / L);
