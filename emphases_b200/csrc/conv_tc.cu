@@ -743,14 +743,24 @@ int pack_conv_weights_tc240(
 // numerically identical, currently epilogue-bound and slower);
 // the default is the N=80 / 16-MMA kernel in this file.  The weight blob layout
 // follows the choice, so it must not change within a process.
-static bool use_wide() {
+static int tc_variant() {
     static int cached = -1;
     if (cached < 0) {
         const char* value = getenv("EMPHASES_B200_TC");
-        cached = (value && !strcmp(value, "wide")) ? 1 : 0;
+        cached = (value && !strcmp(value, "wide")) ? 1
+               : (value && !strcmp(value, "transposed")) ? 2 : 0;
     }
-    return cached == 1;
+    return cached;
 }
+static bool use_wide() { return tc_variant() == 1; }
+// conv_tct.cu: the transposed formulation (weights in TMEM, EMPHASES_B200_TC=transposed)
+static bool use_transposed() { return tc_variant() == 2; }
+int conv_stack_bf16_tct(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const float* bias, const int32_t* acts_host, int32_t n_layers,
+    float* y, cudaStream_t stream);
+int conv_weights_tct_bytes(int n_layers);
+int pack_conv_weights_tct(const float* weights, int n_layers, void* packed, cudaStream_t stream);
 
 template <int PARTS, int KSIZE>
 static int launch_tc(
@@ -785,7 +795,6 @@ int conv_stack_bf16_tc(
     const float* weights, const float* bias, const int32_t* acts_host,
     int32_t n_layers, int32_t channels, int32_t kernel_size, float* y,
     cudaStream_t stream) {
-    (void)bias;
     if (channels != tc::C || (kernel_size != 3 && kernel_size != 1)) {
         set_error("emph_conv_stack(bf16 tc): channels=%d kernel_size=%d not compiled in",
                   channels, kernel_size);
@@ -795,6 +804,9 @@ int conv_stack_bf16_tc(
         return launch_tc<1, 1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
     if (use_wide())
         return conv_stack_bf16_tc240(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
+    if (use_transposed())
+        return conv_stack_bf16_tct(
+            x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
     return launch_tc<1, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
@@ -844,6 +856,7 @@ extern "C" int emph_conv_weights_tc_bytes(
     if (precision == EMPH_PREC_BF16X6_TC) return 3 * n_layers * entry;
     if (precision != EMPH_PREC_BF16_TC) return 0;
     if (kernel_size == 3 && emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
+    if (kernel_size == 3 && emph::use_transposed()) return emph::conv_weights_tct_bytes(n_layers);
     return n_layers * entry;
 }
 
@@ -860,6 +873,8 @@ extern "C" int emph_pack_conv_weights_tc(
                      precision == EMPH_PREC_BF16X6_TC,
                  "emph_pack_conv_weights_tc: precision %d has no tensor-core layout", precision);
     const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
+    if (parts == 1 && kernel_size == 3 && emph::use_transposed())
+        return emph::pack_conv_weights_tct(weights, n_layers, packed, (cudaStream_t)stream);
     if (parts == 1 && kernel_size == 3 && emph::use_wide())
         return emph::pack_conv_weights_tc240(weights, bias, n_layers, packed, (cudaStream_t)stream);
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
