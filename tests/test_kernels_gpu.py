@@ -609,3 +609,22 @@ def test_wide_n_conv_kernel_variant():
         cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
     assert ' passed' in result.stdout
+
+
+def test_transposed_conv_kernel_variant():
+    """EMPHASES_B200_TC=transposed selects the experimental transposed
+    formulation (csrc/conv_tct.cu: weights held in TMEM as the A operand,
+    written there by tcgen05.st; the activation tile is the B operand, so one
+    MMA covers 128 rows at N = 128).  Same child-process scheme as above."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EMPHASES_B200_TC='transposed')
+    result = subprocess.run(
+        [sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_kernels_gpu.py'),
+         '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
+         '-k', 'test_conv_stack_bf16_tc or test_forward_packed_bf16_golden'],
+        cwd=root, env=env, capture_output=True, text=True, timeout=180)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    assert ' passed' in result.stdout
