@@ -145,9 +145,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+#ifdef TCT_STSM
+// 16 TMEM lanes x 32 columns in the mma-fragment layout: thread t gets lane t / 4, columns
+// 8 i + 2 (t % 4) and + 1 in r[4 i], r[4 i + 1], and lane t / 4 + 8, same columns, in r[4 i + 2], r[4 i + 3]
+__device__ __forceinline__ void tmem_ld16x256(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// Four 8 x 8 b16 fragments stored transposed: lane 8 k + j supplies the address of stored row j of matrix k
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+                 ::"r"(addr), "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+}
+#endif
+
 // D fp32, A / B bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr uint32_t kInstrDesc =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+#ifdef TCT_STSM
+__device__ __noinline__ void activate_pairs(uint32_t (&r)[16], float b_lo, float b_hi, int a) {
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j)
+        r[j] = __float_as_uint(apply_activation(__uint_as_float(r[j]) + ((j & 2) ? b_hi : b_lo), a));
+}
+#endif
 
 // Any activation other than ReLU (rolled and out of line on purpose)
 __device__ __noinline__ void activate_rows(uint32_t (&r)[32], float b, int a) {
@@ -249,6 +276,60 @@ conv_stack_tct_kernel(
                 tc_fence_after();
 #pragma unroll 1
                 for (int n0 = half * (NT / 2); n0 < (half + 1) * (NT / 2); n0 += 32) {
+#ifdef TCT_STSM
+                    if (!last) {
+                        // Experimental epilogue (profiles/r01z_ts_conv_probe.md, last section):
+                        // accumulators in the mma-fragment layout, operand rows written by
+                        // transposed 8 x 8 stores - 16-byte rows instead of 2-byte elements
+                        const uint32_t mask = sm.row_mask[slot][n0 >> 5];
+                        const int q = lane & 3, k = lane >> 3, jrow = lane & 7;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int ch0 = quad * 32 + h * 16;           // warp-uniform
+                            if (ch0 >= C) break;
+                            uint32_t f[16];
+                            tmem_ld16x256(tmem_base + ((uint32_t)ch0 << 16) + slot * kAccCols + n0, f);
+                            const float b_lo = sm.bias[layer][ch0 + (lane >> 2)];
+                            const float b_hi = sm.bias[layer][ch0 + 8 + (lane >> 2)];
+                            if (a == EMPH_ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    f[j] = __float_as_uint(fmaxf(
+                                        __uint_as_float(f[j]) + ((j & 2) ? b_hi : b_lo), 0.f));
+                            } else if (a == EMPH_ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    f[j] = __float_as_uint(__uint_as_float(f[j]) + ((j & 2) ? b_hi : b_lo));
+                            } else {
+                                activate_pairs(f, b_lo, b_hi, a);
+                            }
+                            uint32_t m[8];                                 // [block i][lo / hi channel group]
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                m[2 * i] = pack_bf16(__uint_as_float(f[4 * i]), __uint_as_float(f[4 * i + 1]));
+                                m[2 * i + 1] = pack_bf16(__uint_as_float(f[4 * i + 2]), __uint_as_float(f[4 * i + 3]));
+                            }
+                            if (mask != 0xffffffffu) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t two = (mask >> (8 * i + 2 * q)) & 3u;
+                                    const uint32_t keep = ((two & 1u) ? 0x0000ffffu : 0u) | ((two & 2u) ? 0xffff0000u : 0u);
+                                    m[2 * i] &= keep;
+                                    m[2 * i + 1] &= keep;
+                                }
+                            }
+                            // matrix k of a store: channel group (k & 1), row block (k >> 1) of the pair
+                            const int kg = (ch0 >> 3) + (k & 1);
+#pragma unroll
+                            for (int pair = 0; pair < 2; ++pair) {
+                                const int n = n0 + 8 * (2 * pair + (k >> 1)) + jrow;
+                                stmatrix_x4_trans(smem_u32(act + (kg * RB + 1 + n) * 16),
+                                                  m[4 * pair], m[4 * pair + 1], m[4 * pair + 2], m[4 * pair + 3]);
+                            }
+                        }
+                        continue;
+                    }
+#endif
                     uint32_t r[32];
                     tmem_ld32(taddr + n0, r);
                     if (tid == 0 && n0 == 0) TRACE_T(10, round * n_layers + layer);
