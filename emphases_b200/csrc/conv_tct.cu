@@ -301,7 +301,12 @@ conv_stack_tct_kernel(
                                 for (int j = 0; j < 16; ++j)
                                     f[j] = __float_as_uint(__uint_as_float(f[j]) + ((j & 2) ? b_hi : b_lo));
                             } else {
-                                activate_pairs(f, b_lo, b_hi, a);
+                                uint32_t t[16];   // only this branch goes through local memory
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) t[j] = f[j];
+                                activate_pairs(t, b_lo, b_hi, a);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) f[j] = t[j];
                             }
                             uint32_t m[8];                                 // [block i][lo / hi channel group]
 #pragma unroll
