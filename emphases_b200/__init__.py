@@ -74,6 +74,17 @@ def get_engine(device):
     return _engines[device]
 
 
+def require_mel_features_only():
+    """Only the mel feature exists here: pitch / periodicity / loudness are
+    disabled by default in the reference (emphases/config/defaults.py) and
+    need the `penn` network.  Every entry point that builds or consumes
+    features checks this, so that an 81-wide input layer is never fed zeros."""
+    if PITCH_FEATURE or PERIODICITY_FEATURE or LOUDNESS_FEATURE or not MEL_FEATURE:
+        raise NotImplementedError(
+            'pitch / periodicity / loudness features are out of scope: '
+            'emphases_b200 computes the mel feature only')
+
+
 def precision_code():
     if PRECISION == 'fp32':
         return _lib.PREC_FP32

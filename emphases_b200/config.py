@@ -52,16 +52,17 @@ LOSS = 'bce'
 MAX_TRAINING_FRAMES = 75000
 
 # emphases_b200 extensions (not in the reference)
-# 'fp32' (default): CUDA-core FFMA conv stacks, scores within 1e-5 of the
-# reference's fp32 forward.  'bf16': tcgen05 tensor-core frame stack with bf16
-# operands, within 2e-3, fastest (the word decoder then runs as bf16x3).
-# 'bf16x3': tcgen05 with hi/lo-split bf16 operands (3 MMAs per product, 16
-# mantissa bits per operand): within 2e-5 (measured 5.7e-6), 3.7x faster
-# than 'fp32'.  'bf16x6': hi/mid/lo split (6 MMAs per product, all 24 mantissa
-# bits of both operands): fp32-grade on the tensor cores, within 1e-5 like
-# 'fp32' (measured 8.6e-7), 3.4x faster than it.  Conv shapes the tensor-core kernel is not compiled for (kernel
-# sizes other than 3) always run on the FFMA kernel.
-PRECISION = 'fp32'
+# 'bf16x6' (default): tcgen05 tensor-core conv stacks with hi/mid/lo-split bf16
+# operands (6 MMAs per product, all 24 mantissa bits of both operands):
+# fp32-grade, scores within 1e-5 of the reference's fp32 forward (measured
+# 8.6e-7).  'bf16x3': hi/lo split (3 MMAs per product, 16 mantissa bits per
+# operand): within 2e-5 (measured 5.7e-6).  'bf16': plain bf16 operands, the
+# reference's own autocast precision class, within 2e-3, fastest (the word
+# decoder then runs as bf16x3).  'fp32': CUDA-core FFMA conv stacks, within
+# 1e-5, 6x slower than 'bf16x6'.  Conv shapes the tensor-core kernel is not
+# compiled for (channels other than 80, kernel sizes other than 1 and 3)
+# always run on the FFMA kernel, whatever the mode.
+PRECISION = 'bf16x6'
 # Upper bound on packed frame rows per launch (~1 KB of HBM per row).  A corpus
 # larger than this runs as several launches on two alternating streams so the
 # host->device copy of launch i+1 overlaps the kernels of launch i.

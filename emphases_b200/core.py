@@ -223,33 +223,49 @@ def from_alignments_and_audio(
 ###############################################################################
 
 
+def resolve_checkpoint(checkpoint):
+    """checkpoint=None is the published model (emphases/core.py:307-310)"""
+    if checkpoint is not None:
+        return checkpoint
+    try:
+        import huggingface_hub
+        return huggingface_hub.hf_hub_download('maxrmorrison/emphases', 'model.pt')
+    except Exception as error:
+        raise RuntimeError(
+            'checkpoint=None downloads maxrmorrison/emphases from the '
+            'HuggingFace hub (emphases/core.py:307-310), which needs '
+            'network access; pass a checkpoint path') from error
+
+
+_models = {}                       # device -> (key, model): one entry per device
+_models_lock = threading.Lock()
+
+
 def load_model(checkpoint, device):
     """Model cache of emphases.infer (core.py:298-315), keyed on
-    (checkpoint, device) and on the configuration the Model captured"""
+    (checkpoint, device) and on the configuration the Model captured.  One
+    model is kept per device (the multi-GPU workers of from_files_to_files
+    share this loader), replaced when the key changes."""
     device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
     key = (
-        None if checkpoint is None else str(checkpoint), device,
+        None if checkpoint is None else str(checkpoint),
         emphases.ARCHITECTURE, emphases.DOWNSAMPLE_LOCATION, emphases.LAYERS,
         emphases.CHANNELS, emphases.DROPOUT,
         emphases.ACTIVATION_FUNCTION.__name__, emphases.ENCODER_KERNEL_SIZE,
         emphases.DECODER_KERNEL_SIZE)
-    if getattr(load_model, 'key', None) != key:
-        model = emphases.Model()
-        if checkpoint is None:
-            try:
-                import huggingface_hub
-                checkpoint = huggingface_hub.hf_hub_download(
-                    'maxrmorrison/emphases', 'model.pt')
-            except Exception as error:
-                raise RuntimeError(
-                    'checkpoint=None downloads maxrmorrison/emphases from the '
-                    'HuggingFace hub (emphases/core.py:307-310), which needs '
-                    'network access; pass a checkpoint path') from error
-        state = torch.load(checkpoint, map_location='cpu', weights_only=False)
-        model.load_state_dict(state['model'] if 'model' in state else state)
-        load_model.model = model.to(device).eval()
-        load_model.key = key
-    return load_model.model
+    with _models_lock:
+        cached = _models.get(device)
+        if cached is None or cached[0] != key:
+            model = emphases.Model()
+            state = torch.load(
+                resolve_checkpoint(checkpoint), map_location='cpu',
+                weights_only=False)
+            model.load_state_dict(state['model'] if 'model' in state else state)
+            cached = (key, model.to(device).eval())
+            _models[device] = cached
+        return cached[1]
 
 
 def infer(features, word_bounds, checkpoint=None):

@@ -7,11 +7,5 @@ def from_audio(audio, gpu=None):
 
     Only the mel feature exists here (pitch / periodicity / loudness are
     disabled by default in the reference and need the `penn` network)."""
-    if (
-        emphases.PITCH_FEATURE or
-        emphases.PERIODICITY_FEATURE or
-        emphases.LOUDNESS_FEATURE
-    ):
-        raise NotImplementedError(
-            'pitch / periodicity / loudness features are out of scope')
+    emphases.require_mel_features_only()
     return emphases.data.preprocess.mels.from_audio(audio, gpu)[None]

@@ -703,6 +703,20 @@ class Engine:
 
     # -- whole path --------------------------------------------------------
 
+    def prepare_weights(self, weights, precision):
+        """Pack (and cache) the tensor-core operand blobs the packed path will
+        use at `precision`, on the current stream"""
+        if hasattr(weights, 'input_layer'):      # transformer variant: packed by its own code
+            return
+        with _lib.same_stream():
+            chosen = frame_precision(precision, weights.frame)
+            if chosen != _lib.PREC_FP32:
+                weights.frame.tensor_core_weights(chosen)
+            if weights.word is not None:
+                chosen = word_precision(precision, weights.word)
+                if chosen != _lib.PREC_FP32:
+                    weights.word.tensor_core_weights(chosen)
+
     def forward_packed(
         self,
         audio,

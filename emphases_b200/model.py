@@ -117,6 +117,14 @@ class Model(torch.nn.Module):
             raise _lib.EmphasesB200Error(
                 'emphases_b200.Model runs on CUDA tensors only '
                 '(there is no CPU fallback)')
+        if self.input_layer.in_channels != emphases.NUM_MELS:
+            emphases.require_mel_features_only()
+        if self.training and self.dropout is not None:
+            # the reference applies torch.nn.Dropout after every activation in
+            # training mode (emphases/model/layers/convolution.py:29-30)
+            raise NotImplementedError(
+                'dropout is not implemented in the training-mode forward: set '
+                'DROPOUT=None or call model.eval()')
         if torch.is_grad_enabled() and any(
             p.requires_grad for p in self.parameters()
         ) and self.training:

@@ -309,6 +309,7 @@ def run_on_device(
     emphases/evaluate/core.py:73-94)."""
     if output not in ('scores', 'logits'):
         raise ValueError(f'output {output} is not defined')
+    emphases.require_mel_features_only()
     if model.location == 'input':
         return _run_via_model(
             model, alignments, audios, sample_rate, batch_size, device, to_cpu,
@@ -326,6 +327,10 @@ def run_on_device(
     else:
         head_mode = _lib.HEAD_LOGITS
     precision = emphases.precision_code()
+    # the tensor-core operand blobs are packed lazily and cached: do it here, on
+    # the current stream, so that the side streams below (which wait on it)
+    # never read a blob another stream is still packing
+    eng.prepare_weights(weights, precision)
 
     frames = (packed.lengths + 2 * engine.PADDING) // engine.HOPSIZE
     launches = bucket_launches(frames, emphases.MAX_ROWS_PER_LAUNCH)
@@ -449,8 +454,8 @@ def run_sharded(alignments, audios, sample_rate, checkpoint, batch_size, gpus):
         try:
             device = torch.device('cuda', gpu)
             with torch.cuda.device(device):
-                # one model per device (load_model caches a single entry)
-                model = _model_for(checkpoint, device)
+                # the same per-device cache emphases.infer uses
+                model = emphases.load_model(checkpoint, device)
                 results = run_on_device(
                     model,
                     [alignments[i] for i in shard],
@@ -472,19 +477,3 @@ def run_sharded(alignments, audios, sample_rate, checkpoint, batch_size, gpus):
     if errors:
         raise errors[0]
     return outputs
-
-
-_models = {}
-_models_lock = threading.Lock()
-
-
-def _model_for(checkpoint, device):
-    with _models_lock:
-        key = (str(checkpoint), device)
-        if key not in _models:
-            state = torch.load(
-                checkpoint, map_location='cpu', weights_only=False)
-            model = emphases.Model()
-            model.load_state_dict(state['model'] if 'model' in state else state)
-            _models[key] = model.to(device).eval()
-        return _models[key]

@@ -82,6 +82,51 @@ def test_batching_invariance_and_oracle_samples(corpus):
         assert (packed.cpu() - expected).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize('precision,tolerance', [
+    ('bf16', 2e-3), ('bf16x3', 2e-5), ('bf16x6', 1e-5)])
+def test_tensor_core_modes_against_oracle_at_full_size(corpus, precision, tolerance):
+    """The benchmarked launch (3000 utterances, one packed batch) in every
+    tensor-core mode against the CPU ORACLE on 32 sampled utterances, with
+    gain-scaled weights (random-init weights leave every score near 0.5 and
+    would hide a broken layer)"""
+    import emphases_b200 as emphases
+    from emphases_b200 import _lib
+    plan, eng = corpus['plan'], corpus['eng']
+    torch.manual_seed(7)
+    emphases.reset_configuration()
+    model = emphases.Model()
+    for parameter in model.parameters():
+        if parameter.dim() > 1:
+            parameter.data.mul_(1.5)
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    weights = model.cuda().eval().packed_weights()
+    code = {'bf16': _lib.PREC_BF16_TC, 'bf16x3': _lib.PREC_BF16X3_TC,
+            'bf16x6': _lib.PREC_BF16X6_TC}[precision]
+    scores = eng.forward_packed(corpus['audio'], plan, weights, precision=code)['scores']
+    assert torch.isfinite(scores).all()
+    keep = torch.from_numpy(plan.word_seq >= 0).cuda()
+    assert (scores[~keep] == 0).all()
+    spread = scores[keep]
+    assert spread.min() < 0.35 and spread.max() > 0.65     # the gain does its job
+    key = ('oracle', 7)
+    if key not in corpus:
+        sample = list(range(0, plan.n_seq, 97)) + [plan.n_seq - 1]
+        corpus[key] = sample, [
+            oracle.from_alignment_and_audio(
+                [tuple(t) for t in corpus['times'][u].tolist()],
+                corpus['audio'][int(corpus['offsets'][u]):
+                                int(corpus['offsets'][u]) + int(corpus['lengths'][u])
+                                ].cpu()[None], state)[0]
+            for u in sample]
+    sample, expected = corpus[key]
+    assert len(sample) >= 30
+    worst = 0.
+    for u, want in zip(sample, expected):
+        s, n = int(plan.word_row_start[u]), int(plan.n_words[u])
+        worst = max(worst, (scores[s:s + n].cpu() - want).abs().max().item())
+    assert worst < tolerance, (precision, worst)
+
+
 def test_bf16_mode_tracks_fp32_at_full_size(corpus):
     from emphases_b200 import _lib
     plan, eng, weights = corpus['plan'], corpus['eng'], corpus['weights']
