@@ -1,7 +1,7 @@
 """Benchmark of the emphases batched-inference hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--precision fp32|bf16] [--utterances U]
+                    [--precision fp32|bf16|bf16x3|bf16x6] [--utterances U]
 
 Workload (BASELINE.json configs[1]): the default framewise conv model
 (80 mels, 6 layers, sum pooling at the intermediate location, random init)
@@ -10,16 +10,22 @@ over a synthetic corpus of U = 3000 utterances of 2-20 s of 16 kHz audio with
 A "step" is one pass of the whole path over the whole corpus:
     log-mel -> 7 frame convs -> word pooling -> 6 word convs -> head+sigmoid.
 
-`value`  : audio-seconds per wall-second, inputs resident in HBM (kernel-only).
-`e2e`    : same metric through emphases_b200.from_alignments_and_audio with
-           HOST (pinned) audio: planning, H2D, kernels, D2H inside the timing.
-`roofline`: the dominant kernel (the frame conv stack) from CUDA events
-           recorded on the launch stream inside the timed region.
+`value`  : audio-seconds per wall-second, inputs resident in HBM (kernel-only);
+           with N > 1 (torchrun) every rank runs its own corpus of the same
+           size (weak scaling, no data-path collective), max time over ranks.
+`e2e`    : the same metric through the API BASELINE.json names for this
+           config, emphases_b200.from_files_to_files, on ONE on-disk corpus of
+           wav + TextGrid files shared by all N ranks (strong scaling, 8 x the
+           kernel corpus so that 8 GPUs have work): file reads, int16 H2D,
+           kernels, D2H and the .pt / .TextGrid outputs inside the timing.
+           Sub-keys keep the packed-pinned-host-buffer figures of the same
+           kernels (`pinned_packed`, `int16_pcm_upload`, `list_of_tensors`).
+`roofline`: the dominant kernel (log-mel: framing + FFT + mel + log) from CUDA
+           events recorded on the launch stream inside the timed region; DRAM
+           traffic and pipe utilisation come from the committed ncu summary
+           profiles/kernel_metrics.json (keyed by kernel, with its commit).
 `cpu_baseline`: the CPU oracle port of the reference path (its own bf16
            autocast numerics) on a bounded sample, all host threads.
-
-With N > 1 (torchrun) every rank runs its own corpus of the same size (weak
-scaling, no data-path collective); times are the max over ranks.
 """
 import argparse
 import json
@@ -41,7 +47,21 @@ HOPSIZE = 160
 # Algorithmic work
 CONV_FLOP_PER_FRAME = 7 * 2 * 80 * 80 * 3          # 268,800
 LOGMEL_BYTES_PER_FRAME = 640 + 320
+# fp32 operations the log-mel kernel issues per frame (packed FADD2 / FMUL2 = 2,
+# FFMA2 = 4, FFMA = 2 per lane, 32 lanes; FFT + unpack 24.6 k, mel 2.0 k)
+LOGMEL_FLOP_PER_FRAME = 26600
 POOL_BYTES_PER_FRAME = 320
+
+
+def kernel_metrics():
+    """ncu measurements per kernel (dram bytes per frame, pipe utilisation)
+    with the capture they come from: profiles/kernel_metrics.json"""
+    path = os.path.join(ROOT, 'profiles', 'kernel_metrics.json')
+    try:
+        with open(path) as file:
+            return json.load(file)['kernels']
+    except (OSError, KeyError, ValueError):
+        return {}
 
 
 def parse_args():
@@ -59,6 +79,10 @@ def parse_args():
         help='transformer = BASELINE config 3 (informational, fp32 kernels)')
     parser.add_argument('--cpu-seconds', type=float, default=15.)
     parser.add_argument('--file-utterances', type=int, default=3000)
+    parser.add_argument(
+        '--corpus-copies', type=int, default=8,
+        help='the shared on-disk corpus of the e2e leg holds this many hard-linked '
+             'copies of the --file-utterances base files')
     parser.add_argument(
         '--no-list-api', dest='list_api', action='store_false',
         help='skip the list-of-tensors end-to-end leg')
@@ -322,58 +346,116 @@ def run_reference(args, rank, world):
             'd2h_bytes_per_step': 0}}))
 
 
-def time_files_path(emphases, count, state, gpu):
-    """emphases_b200.from_files_to_files on an on-disk corpus of `count`
-    16-bit wav + TextGrid pairs (tmpfs when available): native threaded
-    ingest -> int16 H2D -> kernels -> .pt / .TextGrid outputs"""
-    import shutil
+def corpus_root():
+    """tmpfs when present (the files leg measures the path, not a disk)"""
     import tempfile
+    base = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
+    token = os.environ.get('MASTER_PORT', 'single')
+    return os.path.join(base, f'emphases_b200_bench_{os.getuid()}_{token}')
+
+
+def build_corpus(emphases, root, count, copies, state):
+    """`count` base utterances (16-bit wav + TextGrid) written once and
+    hard-linked `copies` times: one corpus of count * copies files.  Returns
+    (text_files, audio_files, prefixes, checkpoint, audio_seconds, words)."""
+    import shutil
     from pathlib import Path
+    root = Path(root)
+    shutil.rmtree(root, ignore_errors=True)
+    (root / 'out').mkdir(parents=True)
     lengths, times = corpus_layout(count, seed=4321)
-    # tmpfs when it has room for the corpus (2 bytes per sample + outputs),
-    # else the default temporary directory
-    need = int(lengths.sum()) * 2 * 1.2 + count * 16384
-    base = None
-    for candidate in ('/dev/shm', tempfile.gettempdir()):
+    need = int(lengths.sum()) * 2 * 1.1 + count * copies * 16384
+    stats = os.statvfs(root)
+    if stats.f_bavail * stats.f_frsize < need:
+        raise OSError(f'{root}: {need / 1e9:.1f} GB needed')
+    generator = torch.Generator().manual_seed(5)
+    for i, (n, t) in enumerate(zip(lengths, times)):
+        audio = (0.1 * torch.randn(1, int(n), generator=generator)).clamp(-1, 1)
+        emphases.load.save_wav(root / f'u0_{i}.wav', audio)
+        emphases.Alignment.from_times(
+            [tuple(x) for x in t.tolist()]).save(root / f'u0_{i}.TextGrid')
+        for c in range(1, copies):
+            os.link(root / f'u0_{i}.wav', root / f'u{c}_{i}.wav')
+            os.link(root / f'u0_{i}.TextGrid', root / f'u{c}_{i}.TextGrid')
+    torch.save({'model': state}, root / 'checkpoint.pt')
+    return corpus_files(root, count, copies)
+
+
+def corpus_files(root, count, copies):
+    from pathlib import Path
+    root = Path(root)
+    lengths, times = corpus_layout(count, seed=4321)
+    names = [f'u{c}_{i}' for c in range(copies) for i in range(count)]
+    return (
+        [root / f'{name}.TextGrid' for name in names],
+        [root / f'{name}.wav' for name in names],
+        [root / 'out' / name for name in names],
+        root / 'checkpoint.pt',
+        float(lengths.sum()) / SAMPLE_RATE * copies,
+        int(sum(len(t) for t in times)) * copies,
+        int(lengths.sum()) * copies)
+
+
+def time_files_path(emphases, args, state, rank, world, local_rank, device, barrier):
+    """The end-to-end leg: emphases_b200.from_files_to_files (through
+    emphases_b200.distributed: every rank takes its LPT shard of the SAME file
+    list and writes its own outputs) on one on-disk corpus.  Wall clock
+    between barriers, max over ranks by construction."""
+    import shutil
+    from emphases_b200 import distributed
+    root = corpus_root()
+    count, copies = args.file_utterances, max(1, args.corpus_copies)
+    failure = None
+    if rank == 0:
         try:
-            stats = os.statvfs(candidate)
-            if stats.f_bavail * stats.f_frsize > need:
-                base = candidate
-                break
-        except OSError:
-            continue
-    if base is None:
-        return {'unavailable': f'no temporary directory with {need / 1e9:.1f} GB free'}
-    root = Path(tempfile.mkdtemp(dir=base))
+            build_corpus(emphases, root, count, copies, state)
+        except OSError as error:      # e.g. no room: the leg is reported as unavailable
+            failure = f'{type(error).__name__}: {error}'
+    if world > 1:
+        import torch.distributed as dist
+        box = [failure]
+        dist.broadcast_object_list(box, src=0)
+        failure = box[0]
+    if failure is not None:
+        return {'unavailable': failure}
     try:
-        generator = torch.Generator().manual_seed(5)
-        text_files, audio_files, prefixes = [], [], []
-        (root / 'out').mkdir()
-        for i, (n, t) in enumerate(zip(lengths, times)):
-            audio = (0.1 * torch.randn(1, int(n), generator=generator)).clamp(-1, 1)
-            emphases.load.save_wav(root / f'u{i}.wav', audio)
-            emphases.Alignment.from_times(
-                [tuple(x) for x in t.tolist()]).save(root / f'u{i}.TextGrid')
-            text_files.append(root / f'u{i}.TextGrid')
-            audio_files.append(root / f'u{i}.wav')
-            prefixes.append(root / 'out' / f'u{i}')
-        checkpoint = root / 'checkpoint.pt'
-        torch.save({'model': state}, checkpoint)
-        emphases.from_files_to_files(
-            text_files, audio_files, prefixes, checkpoint=checkpoint, gpu=gpu)
+        text, audio, prefixes, checkpoint, seconds, words, samples = corpus_files(
+            root, count, copies)
+
+        def run():
+            distributed.from_files_to_files(
+                text, audio, prefixes, checkpoint=checkpoint, gpu=local_rank)
+            torch.cuda.synchronize(device)
+
+        run()                               # warm-up: model load, workspaces, page cache
+        barrier()
         repeats = 3
         start = time.perf_counter()
         for _ in range(repeats):
-            emphases.from_files_to_files(
-                text_files, audio_files, prefixes, checkpoint=checkpoint, gpu=gpu)
+            run()
+            barrier()
         elapsed = (time.perf_counter() - start) / repeats
-        seconds = float(lengths.sum()) / SAMPLE_RATE
+        written = len(os.listdir(os.path.join(root, 'out'))) if rank == 0 else None
+        barrier()
         return {
             'value': seconds / elapsed, 'unit': 'audio-s/s',
-            'files': count, 'ms_per_file': 1e3 * elapsed / count,
-            'note': 'wav + TextGrid read, inference, .pt + .TextGrid written'}
+            'words_per_s': words / elapsed,
+            'ms_per_step': 1e3 * elapsed,
+            'files': count * copies, 'ms_per_file': 1e3 * elapsed / (count * copies),
+            'audio_hours': seconds / 3600.,
+            'h2d_bytes_per_step': int(samples * 2),
+            'd2h_bytes_per_step': int(words * 4),
+            'h2d_gbs_aggregate': samples * 2 / elapsed / 1e9,
+            'outputs_written': written,
+            'scaling': 'strong',
+            'api': 'emphases_b200.distributed.from_files_to_files (one rank per GPU, '
+                   'LPT shard of one file list per rank)',
+            'note': 'wav + TextGrid read, int16 H2D, inference, D2H, .pt + .TextGrid '
+                    'written; wall clock between barriers'}
     finally:
-        shutil.rmtree(root, ignore_errors=True)
+        barrier()
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)
 
 
 def workload_config(args):
@@ -534,14 +616,11 @@ def main():
     h2d_bytes = host_audio.numel() * 4 + plan.int32_blob().nbytes + plan.n_seq * 8
     d2h_bytes = plan.total_word_rows * 4
 
-    # ---- the same API through files on disk (from_files_to_files), rank 0 ----
+    # ---- the API BASELINE.json names: from_files_to_files on one shared corpus ----
     files_leg = None
-    if rank == 0 and args.file_utterances > 0:
-        try:
-            files_leg = time_files_path(
-                emphases, args.file_utterances, state, local_rank)
-        except OSError as error:          # e.g. the disk filled up: the leg is optional
-            files_leg = {'unavailable': f'{type(error).__name__}: {error}'}
+    if args.file_utterances > 0:
+        files_leg = time_files_path(
+            emphases, args, state, rank, world, local_rank, device, barrier)
 
     # ---- reduce over ranks: max time, summed units ----
     stats = torch.tensor(
@@ -580,34 +659,49 @@ def main():
     pool_gbs = (frames * POOL_BYTES_PER_FRAME + n_words * 328) / (
         kernel_ms['pool'] * 1e-3) / 1e9
     conv_bound = 'tensor (fp32 FFMA mode)' if precision == 'fp32' else 'tensor'
+    measured = kernel_metrics()
+
+    def traffic(name, when=True):
+        entry = measured.get(name)
+        if not when or not entry or 'dram_bytes_per_frame' not in entry:
+            return None
+        return entry['dram_bytes_per_frame'] * frames
+
+    def ncu_source(name):
+        entry = measured.get(name) or {}
+        return {k: entry[k] for k in ('capture', 'commit') if k in entry}
+
+    sm_clock_hz = 1e6 * (clock_summary.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_clock_hz / 1e12          # TFLOP/s at the clock seen
+    logmel_tflops = frames * LOGMEL_FLOP_PER_FRAME / (kernel_ms['logmel'] * 1e-3) / 1e12
     candidates = {
         'logmel': {
             'kernel': 'logmel_kernel (framing + 1024-pt rFFT + mel + log)',
             'bound': 'hbm',
             'achieved': logmel_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': logmel_gbs / hbm_peak,
-            # dram read+write per frame from the ncu --set full capture in
-            # profiles/r01w_ncu.md, scaled to this launch
-            'traffic': 921.0 * frames,
-            # what actually binds it (same capture): warp-instruction issue and
-            # the shared-memory pipe, both ~64 % busy; the FP32 pipe 38 %
-            'pipes_ncu': {'issue_active': 0.636, 'smem_wavefronts': 0.644,
-                          'fma_pipe': 0.383},
-            'note': ('fp32 FFT: instruction-issue / shared-memory-pipe bound, not '
-                     'HBM bound (960 algorithmic B/frame vs ~30 kFLOP/frame), '
+            'traffic': traffic('logmel'),
+            # HBM is not what binds this kernel: the FP32 and shared-memory pipes do
+            'fp32_frac': logmel_tflops / fp32_peak,
+            'fp32_tflops': logmel_tflops, 'fp32_peak_tflops': fp32_peak,
+            'pipes_ncu': (measured.get('logmel') or {}).get('pipes'),
+            'ncu': ncu_source('logmel'),
+            'note': ('packed-fp32 FFT: bound by the shared-memory pipe and the FP32 '
+                     'pipe, not by HBM (960 algorithmic B/frame vs ~27 kFLOP/frame), '
                      'DESIGN.md 4.1')},
         'conv_frames': {
             'kernel': 'conv_stack (7 fused frame layers)',
             'bound': conv_bound,
             'achieved': conv_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s',
             'frac': conv_tflops / tensor_peak,
-            'traffic': 624.0 * frames if precision == 'bf16' else None},
+            'traffic': traffic('conv_frames', precision == 'bf16'),
+            'ncu': ncu_source('conv_frames')},
         'pool': {
             'kernel': 'pool_words_kernel',
             'bound': 'hbm',
             'achieved': pool_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-            # ncu: 209.3 MB read + 5.6 MB written per 655,899 frames (r01w_ncu.md)
-            'frac': pool_gbs / hbm_peak, 'traffic': 328.0 * frames}}
+            'frac': pool_gbs / hbm_peak, 'traffic': traffic('pool'),
+            'ncu': ncu_source('pool')}}
     for name, entry in candidates.items():
         entry['ms'] = kernel_ms[name]
         entry['share_of_step'] = kernel_ms[name] / ms_per_step
@@ -636,6 +730,39 @@ def main():
                 'port of the reference path with its bf16 autocast, serial '
                 'per-utterance loop like emphases/core.py:169-179')}
 
+    pinned = {
+        'value': audio_total / (e2e_ms * 1e-3),
+        'unit': 'audio-s/s',
+        'words_per_s': words_total / (e2e_ms * 1e-3),
+        'ms_per_step': e2e_ms,
+        'h2d_bytes_per_step': int(h2d_bytes),
+        'd2h_bytes_per_step': int(d2h_bytes),
+        'h2d_gbs_effective': h2d_bytes / (e2e_ms_rank0 * 1e-3) / 1e9,
+        'pinned_h2d_gbs_probe': pcie_gbs,
+        'gpu_local_cpus': numa_cpus,
+        'scaling': 'weak',
+        'api': ('emphases_b200.from_alignments_and_audio(alignments, PackedAudio, '
+                'model=...) -- a pre-packed pinned fp32 host buffer per rank'),
+        'note': ('PCIe-bound: one pinned H2D of the fp32 audio per '
+                 'launch, kernels overlap the next launch copy')}
+    extras = {
+        'pinned_packed': pinned,
+        'int16_pcm_upload': {
+            'value': audio_seconds / (e2e_pcm_ms * 1e-3), 'unit': 'audio-s/s',
+            'ms_per_step': e2e_pcm_ms, 'note': 'rank 0, same call, int16 host audio'},
+        'list_of_tensors': None if list_ms is None else {
+            'value': audio_seconds / (list_ms * 1e-3), 'unit': 'audio-s/s',
+            'ms_per_step': list_ms,
+            'note': ('rank 0, same call with a list of pageable per-utterance '
+                     'fp32 tensors: packing to pinned staging included')}}
+    if files_leg is not None and 'value' in files_leg:
+        # the headline: the API BASELINE.json names for this config
+        e2e = dict(files_leg)
+        e2e.update(extras)
+    else:
+        e2e = dict(pinned)
+        e2e.update({k: v for k, v in extras.items() if k != 'pinned_packed'})
+
     print(json.dumps({
         'metric': 'audio-sec/sec',
         'value': value,
@@ -656,26 +783,7 @@ def main():
         'data': 'synthetic',
         'config': workload_config(args),
         'clocks': clock_summary,
-        'e2e': {
-            'value': audio_total / (e2e_ms * 1e-3),
-            'unit': 'audio-s/s',
-            'words_per_s': words_total / (e2e_ms * 1e-3),
-            'ms_per_step': e2e_ms,
-            'h2d_bytes_per_step': int(h2d_bytes),
-            'd2h_bytes_per_step': int(d2h_bytes),
-            'h2d_gbs_effective': h2d_bytes / (e2e_ms_rank0 * 1e-3) / 1e9,
-            'pinned_h2d_gbs_probe': pcie_gbs,
-            'gpu_local_cpus': numa_cpus,
-            'int16_pcm_upload': {
-                'value': audio_seconds / (e2e_pcm_ms * 1e-3), 'unit': 'audio-s/s',
-                'ms_per_step': e2e_pcm_ms, 'note': 'rank 0, same call, int16 host audio'},
-            'list_of_tensors': None if list_ms is None else {
-                'value': audio_seconds / (list_ms * 1e-3), 'unit': 'audio-s/s',
-                'ms_per_step': list_ms,
-                'note': ('rank 0, same call with a list of pageable per-utterance '
-                         'fp32 tensors: packing to pinned staging included')},
-            'note': ('PCIe-bound: one pinned H2D of the fp32 audio per '
-                     'launch, kernels overlap the next launch copy')},
+        'e2e': e2e,
         'files_e2e': files_leg,
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,

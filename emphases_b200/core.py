@@ -89,7 +89,9 @@ def from_files_to_files(
             '.TextGrid alignments')
 
     from . import corpus
-    workers = min(32, (os.cpu_count() or 1))
+    # host threads of this process: the ranks of one box (torchrun) share its cores
+    local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+    workers = max(2, min(32, (os.cpu_count() or 1) // local_world))
     with corpus.Corpus(text_files, audio_files, workers) as parsed:
         # Fast path: 16-bit PCM wav + a parsable TextGrid go through the native
         # reader into pinned int16 / float64 buffers; files at the model rate
