@@ -437,6 +437,21 @@ def time_files_path(emphases, args, state, rank, world, local_rank, device, barr
         elapsed = (time.perf_counter() - start) / repeats
         written = len(os.listdir(os.path.join(root, 'out'))) if rank == 0 else None
         barrier()
+        # ceiling of the host side alone: the native reader decoding this
+        # rank's shard into pinned memory, all ranks at once, no GPU work
+        from emphases_b200 import corpus as corpus_module
+        mine = distributed.shard(distributed.audio_costs(audio), rank, world)
+        local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+        threads = max(2, min(32, (os.cpu_count() or 1) // local_world))
+        with corpus_module.Corpus(
+                [os.fspath(text[i]) for i in mine], [os.fspath(audio[i]) for i in mine],
+                threads) as parsed:
+            barrier()
+            t0 = time.perf_counter()
+            indices, _, packed = parsed.load(parsed.usable(None))
+            packed.ready(len(indices) - 1)
+            barrier()
+            ingest = time.perf_counter() - t0
         return {
             'value': seconds / elapsed, 'unit': 'audio-s/s',
             'words_per_s': words / elapsed,
@@ -446,12 +461,16 @@ def time_files_path(emphases, args, state, rank, world, local_rank, device, barr
             'h2d_bytes_per_step': int(samples * 2),
             'd2h_bytes_per_step': int(words * 4),
             'h2d_gbs_aggregate': samples * 2 / elapsed / 1e9,
+            'host_ingest_gbs_probe': samples * 2 / ingest / 1e9,
+            'host_ingest_ms_probe': 1e3 * ingest,
             'outputs_written': written,
             'scaling': 'strong',
             'api': 'emphases_b200.distributed.from_files_to_files (one rank per GPU, '
                    'LPT shard of one file list per rank)',
             'note': 'wav + TextGrid read, int16 H2D, inference, D2H, .pt + .TextGrid '
-                    'written; wall clock between barriers'}
+                    'written; wall clock between barriers.  Host-bound: '
+                    'host_ingest_*_probe is the native wav reader alone (headers '
+                    'already parsed) filling pinned memory on the same cores'}
     finally:
         barrier()
         if rank == 0:
