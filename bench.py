@@ -566,7 +566,7 @@ def main():
     barrier()
     elapsed_ms = start.elapsed_time(end)
     clock_summary = clocks.stop()
-    launches_per_step = len(timers[0])
+    launches_per_step = sum(entry[2] for entry in timers[0].values())
     kernel_ms = {
         name: statistics.mean(t[name][0].elapsed_time(t[name][1]) for t in timers)
         for name in timers[0]}
@@ -675,8 +675,9 @@ def main():
               'timed inside a long step)' if peaks else 'fallback')
     conv_tflops = frames * CONV_FLOP_PER_FRAME / (kernel_ms['conv_frames'] * 1e-3) / 1e12
     logmel_gbs = frames * LOGMEL_BYTES_PER_FRAME / (kernel_ms['logmel'] * 1e-3) / 1e9
+    # (absent when the pooling runs inside the conv stack's last-layer epilogue)
     pool_gbs = (frames * POOL_BYTES_PER_FRAME + n_words * 328) / (
-        kernel_ms['pool'] * 1e-3) / 1e9
+        kernel_ms['pool'] * 1e-3) / 1e9 if 'pool' in kernel_ms else None
     conv_bound = 'tensor (fp32 FFMA mode)' if precision == 'fp32' else 'tensor'
     measured = kernel_metrics()
 
@@ -709,18 +710,21 @@ def main():
                      'pipe, not by HBM (960 algorithmic B/frame vs ~27 kFLOP/frame), '
                      'DESIGN.md 4.1')},
         'conv_frames': {
-            'kernel': 'conv_stack (7 fused frame layers)',
+            'kernel': ('conv_stack (7 fused frame layers)' if 'pool' in kernel_ms else
+                       'conv_stack + word pooling (7 fused frame layers, pooling in '
+                       'the last epilogue: frame embeddings never reach HBM)'),
             'bound': conv_bound,
             'achieved': conv_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s',
             'frac': conv_tflops / tensor_peak,
-            'traffic': traffic('conv_frames', precision == 'bf16'),
-            'ncu': ncu_source('conv_frames')},
-        'pool': {
+            'traffic': traffic('conv_frames', precision == 'bf16' and 'pool' in kernel_ms),
+            'ncu': ncu_source('conv_frames')}}
+    if pool_gbs is not None:
+        candidates['pool'] = {
             'kernel': 'pool_words_kernel',
             'bound': 'hbm',
             'achieved': pool_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': pool_gbs / hbm_peak, 'traffic': traffic('pool'),
-            'ncu': ncu_source('pool')}}
+            'ncu': ncu_source('pool')}
     for name, entry in candidates.items():
         entry['ms'] = kernel_ms[name]
         entry['share_of_step'] = kernel_ms[name] / ms_per_step

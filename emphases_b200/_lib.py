@@ -30,6 +30,8 @@ SIGNATURES = {
     'emph_logmel_f32': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
     'emph_logmel_i16': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
     'emph_conv_stack': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    'emph_conv_stack_pool': [
+        _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
     'emph_pack_conv_weights': [_P, _I, _I, _I, _P, _P],
     'emph_pack_conv_weights_adjoint': [_P, _I, _I, _I, _P, _P],
     'emph_pack_conv_weights_tc': [_P, _P, _I, _I, _I, _I, _P, _P],

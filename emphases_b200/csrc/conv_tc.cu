@@ -105,6 +105,32 @@ struct Acts {
     int act[kMaxLayers];
 };
 
+// Word pooling fused into the last layer's epilogue (emphases/model/core.py:
+// 96-101: downsample at the 'intermediate' location).  row_word[g] is the word
+// row that packed frame row g belongs to, or -1.  A row of the tile is a TMEM
+// lane, 32 consecutive rows are a warp, and the rows of a word are consecutive,
+// so a warp reduces its (one to three) word segments with a segmented shuffle
+// scan and the last lane of every segment adds the segment's total to the word:
+//   kPoolSum    sums are formed in 64-bit fixed point (2^-28 units): integer
+//               addition is associative, so the result does not depend on how
+//               tiles and warps cut a word or on the order the atomics land --
+//               bit-identical run to run and for every packing of the corpus.
+//               (A variant with two 24-bit limbs reduced by redux.sync over the
+//               segment's lanes measured 2x SLOWER than the shuffle scan:
+//               3.2 vs 1.68 ms for the bf16 frame stack.)
+//   kPoolMax    maximum of non-negative values (ReLU output) as an integer
+//               atomic max on the float's bit pattern; the buffer starts at 0
+//   kPoolCenter row_word marks only the centre row of each word: a plain store
+enum { kPoolNone = 0, kPoolSum = 1, kPoolMax = 2, kPoolCenter = 3 };
+constexpr float kPoolFixedScale = 268435456.f;         // 2^28
+constexpr float kPoolFixedClamp = 524288.f;            // 2^19: 2^16 rows of it fit int64
+struct PoolArgs {
+    const int32_t* row_word;     // [total_rows]
+    long long* fixed;            // kPoolSum: [word rows][C] fixed-point sums (zeroed)
+    float* out;                  // kPoolMax / kPoolCenter: [word rows][C] (zeroed)
+    int mode;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -309,7 +335,8 @@ __global__ void __launch_bounds__(Config<PARTS>::kThreads, 1)
 conv_stack_tc_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ row_seq, int total_rows,
     const uint8_t* __restrict__ weights,   // ring entries: [tap][kg][n][8] bf16 + bias chunk
-    Acts acts, int n_layers, int tile_rows, int n_tiles, float* __restrict__ y) {
+    Acts acts, int n_layers, int tile_rows, int n_tiles, float* __restrict__ y,
+    PoolArgs pool) {
     constexpr int kSlots = Config<PARTS>::kSlots;
     constexpr int kParts = Config<PARTS>::kParts;
     constexpr int kThreads = Config<PARTS>::kThreads;
@@ -555,27 +582,85 @@ conv_stack_tc_kernel(
                     // registers here)
                     const bool store = in_range && row >= halo && row < M - halo;
                     float4* dst = reinterpret_cast<float4*>(y + (size_t)(in_range ? g : 0) * C);
+                    // fused word pooling: the segment structure of this warp's rows
+                    int wid = -1;
+                    uint32_t same = 0;          // bit d: lane - 2^d holds the same word
+                    bool tail = false;
+                    if (pool.mode != kPoolNone) {
+                        if (store) wid = __ldg(pool.row_word + g);
+#pragma unroll
+                        for (int d = 0; d < 5; ++d) {
+                            const int other = __shfl_up_sync(0xffffffffu, wid, 1 << d);
+                            if (lane >= (1 << d) && other == wid) same |= 1u << d;
+                        }
+                        const int next = __shfl_down_sync(0xffffffffu, wid, 1);
+                        tail = wid >= 0 && (lane == 31 || next != wid);
+                    }
+                    const size_t word_base = (size_t)(wid >= 0 ? wid : 0) * C;
 #pragma unroll 1
                     for (int c0 = 0; c0 < C; c0 += 16) {
                         uint32_t raw[16];
                         tmem_ld16_sum<Config<PARTS>::kClasses, Config<PARTS>::kClassStride>(
                             taddr + c0, raw);
-                        if (store) {
-                            const float4* b4 = reinterpret_cast<const float4*>(sm.bias[layer] + c0);
+                        const float4* b4 = reinterpret_cast<const float4*>(sm.bias[layer] + c0);
+                        float w[16];
 #pragma unroll
-                            for (int c4 = 0; c4 < 4; ++c4) {
-                                const float4 b = b4[c4];
-                                float w[4] = {
-                                    __uint_as_float(raw[4 * c4 + 0]) + b.x,
-                                    __uint_as_float(raw[4 * c4 + 1]) + b.y,
-                                    __uint_as_float(raw[4 * c4 + 2]) + b.z,
-                                    __uint_as_float(raw[4 * c4 + 3]) + b.w};
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float4 b = b4[c4];
+                            w[4 * c4 + 0] = __uint_as_float(raw[4 * c4 + 0]) + b.x;
+                            w[4 * c4 + 1] = __uint_as_float(raw[4 * c4 + 1]) + b.y;
+                            w[4 * c4 + 2] = __uint_as_float(raw[4 * c4 + 2]) + b.z;
+                            w[4 * c4 + 3] = __uint_as_float(raw[4 * c4 + 3]) + b.w;
+                        }
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    if (relu) w[j] = fmaxf(w[j], 0.f);
-                                    if (zero) w[j] = 0.f;
+                        for (int j = 0; j < 16; ++j) {
+                            if (relu) w[j] = fmaxf(w[j], 0.f);
+                            if (zero) w[j] = 0.f;
+                        }
+                        if (y != nullptr && store) {
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4)
+                                dst[(c0 >> 2) + c4] =
+                                    make_float4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
+                        }
+                        if (pool.mode == kPoolSum) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float clamped =
+                                    fminf(fmaxf(w[j], -kPoolFixedClamp), kPoolFixedClamp);
+                                long long q = __float2ll_rn(clamped * kPoolFixedScale);
+#pragma unroll
+                                for (int d = 0; d < 5; ++d) {
+                                    const long long other = __shfl_up_sync(0xffffffffu, q, 1 << d);
+                                    if (same & (1u << d)) q += other;
                                 }
-                                dst[(c0 >> 2) + c4] = make_float4(w[0], w[1], w[2], w[3]);
+                                if (tail)
+                                    atomicAdd(
+                                        reinterpret_cast<unsigned long long*>(
+                                            pool.fixed + word_base + c0 + j),
+                                        (unsigned long long)q);
+                            }
+                        } else if (pool.mode == kPoolMax) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float v = fmaxf(w[j], 0.f);
+#pragma unroll
+                                for (int d = 0; d < 5; ++d) {
+                                    const float other = __shfl_up_sync(0xffffffffu, v, 1 << d);
+                                    if (same & (1u << d)) v = fmaxf(v, other);
+                                }
+                                if (tail)
+                                    atomicMax(
+                                        reinterpret_cast<int*>(pool.out + word_base + c0 + j),
+                                        __float_as_int(v));
+                            }
+                        } else if (pool.mode == kPoolCenter) {
+                            if (wid >= 0) {
+                                float4* out4 = reinterpret_cast<float4*>(pool.out + word_base + c0);
+#pragma unroll
+                                for (int c4 = 0; c4 < 4; ++c4)
+                                    out4[c4] =
+                                        make_float4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
                             }
                         }
                     }
@@ -730,42 +815,11 @@ __global__ void pack_weights_tc_kernel(
 
 }  // namespace tc
 
-// conv_tc240.cu: the wide-N formulation (three taps as output columns)
-int conv_stack_bf16_tc240(
-    const float* x, const int32_t* row_seq, int32_t total_rows,
-    const float* weights, const int32_t* acts_host, int32_t n_layers, float* y,
-    cudaStream_t stream);
-int conv_weights_tc240_bytes(int n_layers);
-int pack_conv_weights_tc240(
-    const float* weights, const float* bias, int n_layers, void* packed, cudaStream_t stream);
-
-// EMPHASES_B200_TC=wide selects the experimental wide-N kernel (conv_tc240.cu:
-// numerically identical, currently epilogue-bound and slower);
-// the default is the N=80 / 16-MMA kernel in this file.  The weight blob layout
-// follows the choice, so it must not change within a process.
-static int tc_variant() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* value = getenv("EMPHASES_B200_TC");
-        cached = (value && !strcmp(value, "wide")) ? 1
-               : (value && !strcmp(value, "transposed")) ? 2 : 0;
-    }
-    return cached;
-}
-static bool use_wide() { return tc_variant() == 1; }
-// conv_tct.cu: the transposed formulation (weights in TMEM, EMPHASES_B200_TC=transposed)
-static bool use_transposed() { return tc_variant() == 2; }
-int conv_stack_bf16_tct(
-    const float* x, const int32_t* row_seq, int32_t total_rows,
-    const float* weights, const float* bias, const int32_t* acts_host, int32_t n_layers,
-    float* y, cudaStream_t stream);
-int conv_weights_tct_bytes(int n_layers);
-int pack_conv_weights_tct(const float* weights, int n_layers, void* packed, cudaStream_t stream);
-
 template <int PARTS, int KSIZE>
 static int launch_tc(
     const float* x, const int32_t* row_seq, int32_t total_rows, const float* weights,
-    const int32_t* acts_host, int32_t n_layers, float* y, cudaStream_t stream) {
+    const int32_t* acts_host, int32_t n_layers, float* y, cudaStream_t stream,
+    tc::PoolArgs pool = tc::PoolArgs{nullptr, nullptr, nullptr, tc::kPoolNone}) {
     EMPH_REQUIRE(n_layers <= tc::kMaxLayers, "emph_conv_stack(tc): too many layers");
     const int halo = n_layers * ((KSIZE - 1) / 2);
     const int tile_rows = tc::M - 2 * halo;
@@ -784,7 +838,7 @@ static int launch_tc(
     const int grid = want < sm_count() ? want : sm_count();
     tc::conv_stack_tc_kernel<PARTS, KSIZE><<<grid, tc::Config<PARTS>::kThreads, smem, stream>>>(
         x, row_seq, total_rows, reinterpret_cast<const uint8_t*>(weights), acts,
-        n_layers, tile_rows, n_tiles, y);
+        n_layers, tile_rows, n_tiles, y, pool);
     EMPH_CHECK_LAUNCH(PARTS == 1 ? "emph_conv_stack(bf16 tc)"
                       : PARTS == 2 ? "emph_conv_stack(bf16x3 tc)" : "emph_conv_stack(bf16x6 tc)");
     return EMPH_OK;
@@ -802,11 +856,6 @@ int conv_stack_bf16_tc(
     }
     if (kernel_size == 1)
         return launch_tc<1, 1>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
-    if (use_wide())
-        return conv_stack_bf16_tc240(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
-    if (use_transposed())
-        return conv_stack_bf16_tct(
-            x, row_seq, total_rows, weights, bias, acts_host, n_layers, y, stream);
     return launch_tc<1, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
@@ -840,6 +889,34 @@ int conv_stack_bf16x6_tc(
     return launch_tc<3, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream);
 }
 
+// The k = 3 tensor-core stack with word pooling fused into the last layer's
+// epilogue (see tc::PoolArgs); y may be null (frame rows are then not written)
+int conv_stack_tc_pool(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host, int32_t n_layers, int32_t channels,
+    int32_t kernel_size, int32_t precision, const int32_t* row_word, int32_t pool_mode,
+    long long* fixed, float* out, float* y, cudaStream_t stream) {
+    if (channels != tc::C || kernel_size != 3) {
+        set_error("emph_conv_stack_pool: channels=%d kernel_size=%d not compiled in",
+                  channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    const int last = acts_host[n_layers - 1];
+    if (last != EMPH_ACT_RELU && !(last == EMPH_ACT_NONE && pool_mode != tc::kPoolMax)) {
+        set_error("emph_conv_stack_pool: last activation %d is not fused", last);
+        return EMPH_ENOSYS;
+    }
+    const tc::PoolArgs pool{row_word, fixed, out, pool_mode};
+    if (precision == EMPH_PREC_BF16_TC)
+        return launch_tc<1, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream, pool);
+    if (precision == EMPH_PREC_BF16X3_TC)
+        return launch_tc<2, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream, pool);
+    if (precision == EMPH_PREC_BF16X6_TC)
+        return launch_tc<3, 3>(x, row_seq, total_rows, weights, acts_host, n_layers, y, stream, pool);
+    set_error("emph_conv_stack_pool: precision %d has no tensor-core kernel", precision);
+    return EMPH_ENOSYS;
+}
+
 }  // namespace emph
 
 #ifdef EXP_TRACE
@@ -855,8 +932,6 @@ extern "C" int emph_conv_weights_tc_bytes(
     if (precision == EMPH_PREC_BF16X3_TC) return 2 * n_layers * entry;
     if (precision == EMPH_PREC_BF16X6_TC) return 3 * n_layers * entry;
     if (precision != EMPH_PREC_BF16_TC) return 0;
-    if (kernel_size == 3 && emph::use_wide()) return emph::conv_weights_tc240_bytes(n_layers);
-    if (kernel_size == 3 && emph::use_transposed()) return emph::conv_weights_tct_bytes(n_layers);
     return n_layers * entry;
 }
 
@@ -873,10 +948,6 @@ extern "C" int emph_pack_conv_weights_tc(
                      precision == EMPH_PREC_BF16X6_TC,
                  "emph_pack_conv_weights_tc: precision %d has no tensor-core layout", precision);
     const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
-    if (parts == 1 && kernel_size == 3 && emph::use_transposed())
-        return emph::pack_conv_weights_tct(weights, n_layers, packed, (cudaStream_t)stream);
-    if (parts == 1 && kernel_size == 3 && emph::use_wide())
-        return emph::pack_conv_weights_tc240(weights, bias, n_layers, packed, (cudaStream_t)stream);
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
         weights, bias, n_layers, parts, kernel_size, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");

@@ -91,7 +91,113 @@ pool_words_kernel(
     }
 }
 
+// ---- pooling fused into the tensor-core conv stack (conv_tc.cu) ----
+int conv_stack_tc_pool(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host, int32_t n_layers, int32_t channels,
+    int32_t kernel_size, int32_t precision, const int32_t* row_word, int32_t pool_mode,
+    long long* fixed, float* out, float* y, cudaStream_t stream);
+
+// row_word[g] = the word row that frame row g belongs to (pre-set to -1): a warp
+// per word row marks [lo, hi) clipped to the sequence (or only the centre row).
+template <bool CENTER>
+__global__ void __launch_bounds__(kPoolWarps * 32)
+row_words_kernel(
+    const int32_t* __restrict__ row_start, const int32_t* __restrict__ n_rows,
+    const int32_t* __restrict__ word_seq, const int32_t* __restrict__ word_lo,
+    const int32_t* __restrict__ word_hi, int total_word_rows,
+    int32_t* __restrict__ row_word, int32_t* __restrict__ word_count) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * kPoolWarps;
+    for (int w = blockIdx.x * kPoolWarps + (threadIdx.x >> 5); w < total_word_rows;
+         w += warps_total) {
+        const int u = __ldg(word_seq + w);
+        int s = 0, e = 0;
+        if (u >= 0) {
+            const int n = __ldg(n_rows + u);
+            const int lo = __ldg(word_lo + w), hi = __ldg(word_hi + w);
+            if (CENTER) {
+                const int idx = (lo + hi) >> 1;
+                if (idx >= 0 && idx < n) { s = idx; e = idx + 1; }
+            } else {
+                s = min(max(lo, 0), n);
+                e = min(max(hi, 0), n);
+            }
+            const int base = __ldg(row_start + u);
+            for (int f = s + lane; f < e; f += 32) row_word[base + f] = w;
+        }
+        if (lane == 0) word_count[w] = u < 0 ? -1 : max(e - s, 0);
+    }
+}
+
+// fixed-point sums -> fp32 (sum) or fp32 mean (sum / count; 0 rows: NaN like
+// torch.mean of an empty slice)
+__global__ void pool_fixed_finish_kernel(
+    const long long* __restrict__ fixed, const int32_t* __restrict__ word_count,
+    long long total, int channels, int average, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double sum = (double)fixed[i] * (1.0 / 268435456.0);     // 2^-28 units
+        const int count = word_count[i / channels];               // -1: separator word row
+        out[i] = count < 0 ? 0.f : average ? (float)(sum / (double)count) : (float)sum;
+    }
+}
+
 }  // namespace emph
+
+extern "C" int emph_conv_stack_pool(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host, int32_t n_layers, int32_t channels,
+    int32_t kernel_size, int32_t precision,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* word_seq, const int32_t* word_lo, const int32_t* word_hi,
+    int32_t total_word_rows, int32_t method,
+    int32_t* row_word, int32_t* word_count, long long* fixed,
+    float* pooled, float* y, void* stream) {
+    EMPH_REQUIRE(total_rows >= 0 && total_word_rows >= 0, "emph_conv_stack_pool: negative size");
+    EMPH_REQUIRE(n_layers > 0, "emph_conv_stack_pool: no layers");
+    EMPH_REQUIRE(method == EMPH_POOL_SUM || method == EMPH_POOL_AVERAGE ||
+                     method == EMPH_POOL_MAX || method == EMPH_POOL_CENTER,
+                 "emph_conv_stack_pool: unknown method %d", method);
+    EMPH_REQUIRE(x != y, "emph_conv_stack_pool: x and y must not alias (halo rows)");
+    if (total_rows == 0 || total_word_rows == 0) return EMPH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool sums = method == EMPH_POOL_SUM || method == EMPH_POOL_AVERAGE;
+    const size_t elements = (size_t)total_word_rows * channels;
+    int s = emph::check_cuda(
+        cudaMemsetAsync(row_word, 0xFF, sizeof(int32_t) * (size_t)total_rows, st),
+        "emph_conv_stack_pool: memset");
+    if (s != EMPH_OK) return s;
+    s = emph::check_cuda(
+        sums ? cudaMemsetAsync(fixed, 0, sizeof(long long) * elements, st)
+             : cudaMemsetAsync(pooled, 0, sizeof(float) * elements, st),
+        "emph_conv_stack_pool: memset");
+    if (s != EMPH_OK) return s;
+    long want = ((long)total_word_rows + emph::kPoolWarps - 1) / emph::kPoolWarps;
+    long cap = (long)emph::sm_count() * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    if (method == EMPH_POOL_CENTER)
+        emph::row_words_kernel<true><<<grid, emph::kPoolWarps * 32, 0, st>>>(
+            row_start, n_rows, word_seq, word_lo, word_hi, total_word_rows, row_word, word_count);
+    else
+        emph::row_words_kernel<false><<<grid, emph::kPoolWarps * 32, 0, st>>>(
+            row_start, n_rows, word_seq, word_lo, word_hi, total_word_rows, row_word, word_count);
+    EMPH_CHECK_LAUNCH("emph_conv_stack_pool(row words)");
+    // tc::kPoolSum = 1, kPoolMax = 2, kPoolCenter = 3
+    const int mode = sums ? 1 : method == EMPH_POOL_MAX ? 2 : 3;
+    s = emph::conv_stack_tc_pool(
+        x, row_seq, total_rows, weights, acts_host, n_layers, channels, kernel_size, precision,
+        row_word, mode, fixed, pooled, y, st);
+    if (s != EMPH_OK) return s;
+    if (sums) {
+        const long long total = (long long)elements;
+        const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        emph::pool_fixed_finish_kernel<<<blocks, 256, 0, st>>>(
+            fixed, word_count, total, channels, method == EMPH_POOL_AVERAGE, pooled);
+        EMPH_CHECK_LAUNCH("emph_conv_stack_pool(finish)");
+    }
+    return EMPH_OK;
+}
 
 extern "C" int emph_pool_words(
     const float* x, int32_t channels,

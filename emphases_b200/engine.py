@@ -8,6 +8,7 @@ import dataclasses
 from typing import Optional, Sequence
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -177,6 +178,25 @@ class Plan:
     word_hi: np.ndarray
     audio_samples: int           # packed audio length (samples)
     audio_offsets: np.ndarray    # int64 (n_utterances,) offset of each utterance
+
+    def words_disjoint(self):
+        """True when every frame row belongs to at most one word and no word is
+        empty: the words of a sequence are in order and their clipped [lo, hi)
+        do not overlap (what an alignment produces).  The fused conv + pooling
+        kernel needs it; anything else takes the separate pooling kernel."""
+        cached = getattr(self, '_words_disjoint', None)
+        if cached is None:
+            keep = self.word_seq >= 0
+            seq = self.word_seq[keep]
+            frames = self.n_rows[seq].astype(np.int64)
+            lo = np.clip(self.word_lo[keep].astype(np.int64), 0, frames)
+            hi = np.clip(self.word_hi[keep].astype(np.int64), 0, frames)
+            same = seq[1:] == seq[:-1]
+            cached = bool(
+                np.all(hi > lo) and np.all(self.word_lo[keep] >= 0) and
+                np.all(~same | (lo[1:] >= hi[:-1])))
+            self._words_disjoint = cached
+        return cached
 
     def int32_blob(self):
         parts = [
@@ -494,6 +514,16 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
 ###############################################################################
 
 
+# Word pooling fused into the last layer of the tensor-core frame stack
+# (emph_conv_stack_pool) instead of the separate pooling kernel.  Off by
+# default: measured on a B200 (3.31 M frames, bf16) the fused epilogue's
+# segmented 64-bit shuffle scan sits in series with the slot's next tile and
+# costs more than it saves -- 1.68 ms against 1.27 + 0.24 ms for conv stack +
+# pooling kernel (profiles/r02i_fused_pooling.md).  EMPHASES_B200_FUSE_POOLING=1
+# enables it.
+FUSE_POOLING = os.environ.get('EMPHASES_B200_FUSE_POOLING', '0') == '1'
+
+
 def tensor_core_shape(stack):
     return stack.channels == KERNEL_CHANNELS and stack.kernel_size in (1, 3)
 
@@ -674,6 +704,41 @@ class Engine:
             _lib.stream_ptr())
         return y
 
+    def conv_stack_pool(self, x, row_seq, stack: ConvStack, precision, views,
+                        total_word_rows, method, ws=None, keep_frames=False):
+        """conv_stack followed by pool in ONE kernel (emph_conv_stack_pool):
+        returns (pooled, frames or None); None when the configuration is not
+        fused (the caller then runs the two kernels)"""
+        last = int(stack.acts[-1])
+        if (
+            precision == _lib.PREC_FP32 or not tensor_core_shape(stack) or
+            stack.kernel_size != 3 or x.shape[1] != stack.channels or
+            not (last == _lib.ACT_RELU or (last == _lib.ACT_NONE and method != 'max'))
+        ):
+            return None
+        rows, channels = x.shape[0], stack.channels
+        pooled = _empty(
+            ws, 'pooled', (total_word_rows, channels), torch.float32, self.device)
+        frames = _empty(ws, 'frames', (rows, channels), torch.float32, self.device) \
+            if keep_frames else None
+        row_word = _empty(ws, 'row_word', (rows,), torch.int32, self.device)
+        word_count = _empty(ws, 'word_count', (total_word_rows,), torch.int32, self.device)
+        fixed = _empty(
+            ws, 'pooled_fixed', (total_word_rows, channels), torch.int64, self.device) \
+            if method in ('sum', 'average') else None
+        acts = stack.acts.astype(np.int32)
+        _lib.call(
+            'emph_conv_stack_pool', _lib.ptr(x), _lib.ptr(row_seq), rows,
+            _lib.ptr(stack.tensor_core_weights(precision)),
+            acts.ctypes.data_as(ctypes.c_void_p), stack.n_layers, channels,
+            stack.kernel_size, precision, _lib.ptr(views['row_start']),
+            _lib.ptr(views['n_rows']), _lib.ptr(views['word_seq']),
+            _lib.ptr(views['word_lo']), _lib.ptr(views['word_hi']), total_word_rows,
+            _lib.POOL[method], _lib.ptr(row_word), _lib.ptr(word_count),
+            _lib.ptr(fixed) if fixed is not None else None, _lib.ptr(pooled),
+            _lib.ptr(frames) if frames is not None else None, _lib.stream_ptr())
+        return pooled, frames
+
     def pool(self, x, row_start, n_rows, word_seq, word_lo, word_hi, method,
              ws=None):
         total_word_rows = word_seq.shape[0]
@@ -749,8 +814,9 @@ class Engine:
         if views is None:
             views = self.upload_plan(plan)
 
-        def timed(name, launch):
-            # CUDA events on the launch stream around one kernel (bench.py)
+        def timed(name, launch, kernels=1):
+            # CUDA events on the launch stream around one stage (bench.py);
+            # `kernels` = kernel launches of ours the stage issues
             if timers is None:
                 return launch()
             start = torch.cuda.Event(enable_timing=True)
@@ -758,7 +824,7 @@ class Engine:
             start.record()
             output = launch()
             end.record()
-            timers[name] = (start, end)
+            timers[name] = (start, end, kernels)
             return output
 
         row_seq = timed('row_index_frames', lambda: self.row_index(
@@ -770,6 +836,7 @@ class Engine:
         features = timed('logmel', lambda: self.logmel(
             audio, views, plan, row_seq, normalize, ws))
         transformer_variant = hasattr(weights, 'input_layer')
+        pooled = None
         if transformer_variant:
             from . import transformer
             embedded = self.conv_stack(
@@ -779,12 +846,26 @@ class Engine:
                 self, weights.frame, embedded, views['row_start'], plan.n_rows,
                 plan.n_rows, row_seq, self.device))
         else:
-            frames = timed('conv_frames', lambda: self.conv_stack(
-                features, row_seq, weights.frame,
-                frame_precision(precision, weights.frame), ws, 'frames'))
-        pooled = timed('pool', lambda: self.pool(
-            frames, views['row_start'], views['n_rows'], views['word_seq'],
-            views['word_lo'], views['word_hi'], method, ws))
+            fused = None
+            if location == 'intermediate' and FUSE_POOLING and plan.words_disjoint():
+                # frame stack + word pooling in one kernel: the frame embeddings
+                # never travel to HBM (kept only on request)
+                # (word-of-row map, conv + pooling, fixed point -> fp32 for sums)
+                fused = timed('conv_frames', lambda: self.conv_stack_pool(
+                    features, row_seq, weights.frame,
+                    frame_precision(precision, weights.frame), views,
+                    plan.total_word_rows, method, ws, keep_frames=keep),
+                    kernels=3 if method in ('sum', 'average') else 2)
+            if fused is not None:
+                pooled, frames = fused
+            else:
+                frames = timed('conv_frames', lambda: self.conv_stack(
+                    features, row_seq, weights.frame,
+                    frame_precision(precision, weights.frame), ws, 'frames'))
+        if pooled is None:
+            pooled = timed('pool', lambda: self.pool(
+                frames, views['row_start'], views['n_rows'], views['word_seq'],
+                views['word_lo'], views['word_hi'], method, ws))
         if location == 'intermediate' and transformer_variant:
             from . import transformer
             words = timed('conv_words', lambda: transformer.run_stack(

@@ -170,6 +170,40 @@ int emph_pack_conv_weights_tc(
     const float* weights, const float* bias, int32_t n_layers, int32_t channels,
     int32_t kernel_size, int32_t precision, void* packed, void* stream);
 
+/*
+ * emph_conv_stack (tensor-core precisions, channels 80, kernel size 3) with
+ * the frame -> word pooling of emph_pool_words fused into the last layer's
+ * epilogue: emphases/model/core.py:92-101 (frame_encoder followed by
+ * downsample at the 'intermediate' location) in one pass, the frame rows never
+ * travelling to HBM unless `y` is given.
+ *
+ * Requirements (else EMPH_ENOSYS and nothing is written: call emph_conv_stack
+ * + emph_pool_words instead): the words of a sequence do not overlap (each
+ * frame row belongs to at most one word), the last activation is ReLU (or
+ * none, except for `max`).
+ *
+ *   row_word    scratch [total_rows] int32, word_count scratch
+ *               [total_word_rows] int32, fixed scratch [total_word_rows]
+ *               [channels] int64 (sum / average only; may be null otherwise)
+ *   pooled      [total_word_rows][channels] fp32, as emph_pool_words writes it
+ *               (word rows without frames: 0 for sum / max / center -- the
+ *               host raises before launching for those -- NaN for average)
+ *   y           [total_rows][channels] fp32 frame rows, or NULL
+ *
+ * Sums are formed in 64-bit fixed point (2^-28 units, values clamped to
+ * +-2^19), so the result is independent of how tiles cut a word and of the
+ * order the atomics land: bit-identical for every packing of the corpus.
+ */
+int emph_conv_stack_pool(
+    const float* x, const int32_t* row_seq, int32_t total_rows,
+    const float* weights, const int32_t* acts_host, int32_t n_layers, int32_t channels,
+    int32_t kernel_size, int32_t precision,
+    const int32_t* row_start, const int32_t* n_rows,
+    const int32_t* word_seq, const int32_t* word_lo, const int32_t* word_hi,
+    int32_t total_word_rows, int32_t method,
+    int32_t* row_word, int32_t* word_count, long long* fixed,
+    float* pooled, float* y, void* stream);
+
 /* (out, in, k) Conv1d weight -> [k][in][out] (device to device). */
 int emph_pack_conv_weights(
     const float* conv_weight, int32_t out_channels, int32_t in_channels,

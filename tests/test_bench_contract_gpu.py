@@ -26,14 +26,16 @@ def test_bench_line_contract():
         assert key in line, key
     assert line['metric'] == 'audio-sec/sec' and line['n_gpus'] == 1 and line['steps'] == 3
     assert line['vs_baseline'] is None and line['scaling'] == 'weak'
-    assert line['gpu_launches'] == 7 * 3          # seven kernels per pass
+    # kernels per pass: 2 row maps, log-mel, frame stack (+ word-of-row map and
+    # fixed-point finish when the pooling is fused, else the pooling kernel),
+    # word stack, head
+    assert line['gpu_launches'] in (7 * 3, 8 * 3)
     roofline = line['roofline']
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in roofline, key
     assert roofline['bound'] in ('hbm', 'tensor')
     assert abs(roofline['frac'] - roofline['achieved'] / roofline['peak']) < 1e-9
-    for name in ('conv_frames', 'pool'):
-        assert name in roofline['others'] or name in roofline['kernel']
+    assert 'conv_frames' in roofline['others'] or 'conv_frames' in roofline['kernel']
     e2e = line['e2e']
     assert e2e['value'] > 0 and e2e['h2d_bytes_per_step'] > 0 and e2e['d2h_bytes_per_step'] > 0
     assert e2e['value'] < line['value']           # copies inside the timed region

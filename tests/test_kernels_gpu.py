@@ -592,39 +592,113 @@ def test_forward_packed_bf16x3_golden(eng, golden, batch_size):
     assert error < 2e-5, f'bf16x3 scores max-abs {error}'
 
 
-def test_wide_n_conv_kernel_variant():
-    """EMPHASES_B200_TC=wide selects the experimental N=240 formulation
-    (csrc/conv_tc240.cu: the three taps as output columns, tap shift applied to
-    the accumulators).  The choice is read once per process, so the bf16 conv
-    parity tests are re-run in a child process with the variable set."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, EMPHASES_B200_TC='wide')
-    result = subprocess.run(
-        [sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_kernels_gpu.py'),
-         '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
-         '-k', 'test_conv_stack_bf16_tc or test_forward_packed_bf16_golden'],
-        cwd=root, env=env, capture_output=True, text=True, timeout=600)
-    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
-    assert ' passed' in result.stdout
+###############################################################################
+# Word pooling fused into the tensor-core conv stack (emph_conv_stack_pool)
+###############################################################################
 
 
-def test_transposed_conv_kernel_variant():
-    """EMPHASES_B200_TC=transposed selects the experimental transposed
-    formulation (csrc/conv_tct.cu: weights held in TMEM as the A operand,
-    written there by tcgen05.st; the activation tile is the B operand, so one
-    MMA covers 128 rows at N = 128).  Same child-process scheme as above."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, EMPHASES_B200_TC='transposed')
-    result = subprocess.run(
-        [sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_kernels_gpu.py'),
-         '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider',
-         '-k', 'test_conv_stack_bf16_tc or test_forward_packed_bf16_golden'],
-        cwd=root, env=env, capture_output=True, text=True, timeout=180)
-    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
-    assert ' passed' in result.stdout
+def _fused_corpus(seeds):
+    from emphases_b200 import engine
+    utterances = []
+    for seed in seeds:
+        times, audio = oracle.synthetic_utterance(seed)
+        utterances.append((np.asarray(times), audio.shape[-1]))
+    return utterances, engine.make_plan(utterances)
+
+
+@pytest.mark.parametrize('method', ['sum', 'average', 'max', 'center'])
+@pytest.mark.parametrize('mode', ['bf16', 'bf16x3', 'bf16x6'])
+def test_fused_pooling_matches_separate_kernels(eng, golden, mode, method):
+    """emph_conv_stack_pool == emph_conv_stack followed by emph_pool_words:
+    max / center bit for bit (the same conv rows, an exact reduction), sum /
+    average within 2e-6 of the largest value (64-bit fixed-point sums against
+    the pooling kernel's fp32 running sums)"""
+    from emphases_b200 import _lib
+    precision = {'bf16': _lib.PREC_BF16_TC, 'bf16x3': _lib.PREC_BF16X3_TC,
+                 'bf16x6': _lib.PREC_BF16X6_TC}[mode]
+    weights = default_weights(state_from_golden(golden('c1')))
+    _, plan = _fused_corpus(range(300, 309))
+    assert plan.words_disjoint()
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    generator = torch.Generator().manual_seed(3)
+    x = torch.randn(plan.total_rows, 80, generator=generator).cuda()
+    x[(row_seq < 0)] = 0
+    frames = eng.conv_stack(x, row_seq, weights.frame, precision)
+    separate = eng.pool(
+        frames, views['row_start'], views['n_rows'], views['word_seq'],
+        views['word_lo'], views['word_hi'], method)
+    fused, kept = eng.conv_stack_pool(
+        x, row_seq, weights.frame, precision, views, plan.total_word_rows, method,
+        keep_frames=True)
+    assert torch.equal(kept, frames)
+    keep = torch.from_numpy(plan.word_seq >= 0).cuda()
+    assert (fused[~keep] == 0).all()
+    if method in ('max', 'center'):
+        assert torch.equal(fused[keep], separate[keep])
+    else:
+        scale = separate[keep].abs().max().item()
+        assert (fused[keep] - separate[keep]).abs().max().item() < 2e-6 * scale
+    # and without the frame rows
+    alone, none = eng.conv_stack_pool(
+        x, row_seq, weights.frame, precision, views, plan.total_word_rows, method)
+    assert none is None and torch.equal(alone, fused)
+
+
+def test_fused_pooling_segment_assignment_bit_exact(eng):
+    """Segmentation through the fused kernel, as integers: a one-layer identity
+    stack in the exact bf16x6 mode passes frame indicators / frame indices
+    through unchanged, so pooled sums recover every word's [lo, hi) exactly"""
+    from emphases_b200 import _lib, engine
+    utterances, plan = _fused_corpus(range(200, 206))
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    weights = torch.zeros(1, 3, 80, 80)
+    weights[0, 1] = torch.eye(80)
+    stack = engine.ConvStack(
+        weights.cuda(), torch.zeros(1, 80).cuda(),
+        np.asarray([_lib.ACT_NONE], dtype=np.int32), 3, 80)
+    x = torch.zeros(plan.total_rows, 80)
+    for u in range(plan.n_seq):
+        s, n = int(plan.row_start[u]), int(plan.n_rows[u])
+        x[s:s + n, 0] = 1
+        x[s:s + n, 1] = torch.arange(n, dtype=torch.float32)
+    pooled, _ = eng.conv_stack_pool(
+        x.cuda(), row_seq, stack, _lib.PREC_BF16X6_TC, views, plan.total_word_rows, 'sum')
+    pooled = pooled.cpu()
+    center, _ = eng.conv_stack_pool(
+        x.cuda(), row_seq, stack, _lib.PREC_BF16X6_TC, views, plan.total_word_rows, 'center')
+    center = center.cpu()
+    for u in range(plan.n_seq):
+        expected = oracle.word_bounds([tuple(t) for t in utterances[u][0].tolist()])
+        s = int(plan.word_row_start[u])
+        for j, (lo, hi) in enumerate(expected):
+            hi = min(hi, int(plan.n_rows[u]))
+            assert pooled[s + j, 0].item() == hi - lo
+            assert pooled[s + j, 1].item() == (lo + hi - 1) * (hi - lo) // 2
+            assert center[s + j, 1].item() == (lo + hi) // 2
+
+
+def test_fused_pooling_is_packing_invariant(eng, golden):
+    """Fixed-point sums do not depend on how tiles and warps cut a word: the
+    same utterances packed behind a different prefix pool bit-identically"""
+    from emphases_b200 import _lib
+    weights = default_weights(state_from_golden(golden('c1')))
+    results = []
+    for seeds in ([400, 401, 402, 403], [410, 400, 401, 402, 403]):
+        _, plan = _fused_corpus(seeds)
+        views = eng.upload_plan(plan)
+        row_seq = eng.row_index(
+            views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+        x = torch.zeros(plan.total_rows, 80)
+        for u, seed in enumerate(seeds):
+            s, n = int(plan.row_start[u]), int(plan.n_rows[u])
+            generator = torch.Generator().manual_seed(seed)
+            x[s:s + n] = torch.randn(n, 80, generator=generator)
+        pooled, _ = eng.conv_stack_pool(
+            x.cuda(), row_seq, weights.frame, _lib.PREC_BF16X6_TC, views,
+            plan.total_word_rows, 'sum')
+        first = len(seeds) - 4
+        start = int(plan.word_row_start[first])
+        results.append(pooled[start:].cpu())
+    assert torch.equal(results[0], results[1])
