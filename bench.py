@@ -477,6 +477,35 @@ def time_files_path(emphases, args, state, rank, world, local_rank, device, barr
             shutil.rmtree(root, ignore_errors=True)
 
 
+def time_single_utterance(emphases, model, gpu, calls=200):
+    """configs[0] on the GPU: emphases_b200.from_alignment_and_audio on one
+    10 s utterance with a 25-word alignment (the native single-utterance call,
+    csrc/utterance.cu), pageable host audio in, scores read back to the host:
+    median wall time per call"""
+    import tempfile
+    generator = torch.Generator().manual_seed(11)
+    audio = (0.1 * torch.randn(1, 10 * SAMPLE_RATE, generator=generator)).clamp(-1, 1)
+    cuts = torch.sort(torch.rand(24, generator=generator) * 10).values.tolist()
+    edges = [0.] + cuts + [10.]
+    alignment = emphases.Alignment.from_times(list(zip(edges[:-1], edges[1:])))
+    with tempfile.TemporaryDirectory() as directory:
+        checkpoint = os.path.join(directory, 'checkpoint.pt')
+        torch.save({'model': model.state_dict()}, checkpoint)
+        samples = []
+        for index in range(calls + 20):
+            torch.cuda.synchronize()
+            start = time.perf_counter()
+            emphases.from_alignment_and_audio(
+                alignment, audio, SAMPLE_RATE, checkpoint=checkpoint, gpu=gpu).cpu()
+            if index >= 20:
+                samples.append(time.perf_counter() - start)
+    median = statistics.median(samples)
+    return {
+        'ms_per_call': 1e3 * median, 'value': 10. / median, 'unit': 'audio-s/s',
+        'calls': calls, 'workload': 'configs[0]: one 10 s utterance, 25 words',
+        'api': 'emphases_b200.from_alignment_and_audio (host audio in, scores on the host out)'}
+
+
 def workload_config(args):
     return {
         'workload': (
@@ -634,6 +663,12 @@ def main():
         del audios
     h2d_bytes = host_audio.numel() * 4 + plan.int32_blob().nbytes + plan.n_seq * 8
     d2h_bytes = plan.total_word_rows * 4
+
+    # ---- BASELINE config 1 as a latency: one 10 s utterance, 25 words, host audio
+    # in, scores on the host out, through emphases_b200.from_alignment_and_audio ----
+    single = None
+    if rank == 0:
+        single = time_single_utterance(emphases, model, local_rank)
 
     # ---- the API BASELINE.json names: from_files_to_files on one shared corpus ----
     files_leg = None
@@ -808,6 +843,7 @@ def main():
         'clocks': clock_summary,
         'e2e': e2e,
         'files_e2e': files_leg,
+        'single_utterance': single,
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,
         'cpu_baseline': cpu}))

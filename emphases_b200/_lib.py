@@ -60,6 +60,24 @@ SIGNATURES = {
         _P, _P, _P, _P, _I, _I, _I, ctypes.c_double, ctypes.c_double, _P, _P],
 }
 
+class UtteranceStack(ctypes.Structure):
+    """emph_utterance_stack"""
+    _fields_ = [
+        ('weights', _P), ('bias', _P), ('acts_host', _P), ('n_layers', _I),
+        ('channels', _I), ('kernel_size', _I), ('precision', _I)]
+
+
+class UtteranceModel(ctypes.Structure):
+    """emph_utterance_model"""
+    _fields_ = [
+        ('frame', UtteranceStack), ('word', UtteranceStack), ('has_word_stack', _I),
+        ('head_weight', _P), ('head_bias', _F), ('head_kernel', _I), ('head_mode', _I),
+        ('mel_ptr', _P), ('mel_col', _P), ('mel_val', _P), ('n_mels', _I),
+        ('normalize', _I), ('pool_method', _I)]
+
+
+ENOSYS = -38        # EMPH_ENOSYS: the configuration is not built / not handled
+
 _lib = None
 
 
@@ -106,6 +124,12 @@ def load():
     lib.emph_corpus_close.restype = None
     lib.emph_conv_weights_tc_bytes.argtypes = [_I, _I, _I, _I]
     lib.emph_conv_weights_tc_bytes.restype = ctypes.c_int
+    lib.emph_infer_utterance_workspace.argtypes = [ctypes.c_longlong, _I, _I, _I]
+    lib.emph_infer_utterance_workspace.restype = ctypes.c_longlong
+    lib.emph_infer_utterance.argtypes = [
+        ctypes.POINTER(UtteranceModel), _P, _I, _P, _I, ctypes.c_longlong, _P,
+        ctypes.c_longlong, ctypes.POINTER(_P), ctypes.POINTER(_P), _P]
+    lib.emph_infer_utterance.restype = ctypes.c_int
     _lib = lib
     return lib
 

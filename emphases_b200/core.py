@@ -187,6 +187,16 @@ def from_alignment_and_audio(
                 'reference (emphases/baselines) and is out of scope here')
         raise ValueError(
             f'Emphasis annotation method {emphases.METHOD} is not defined')
+    if batch_size is None and not isinstance(gpu, (list, tuple)):
+        # one utterance, one chunk: a single native call plans and launches
+        # the whole path (csrc/utterance.cu); None = not that case
+        from . import single
+        device = emphases.resolve_device(gpu)
+        with torch.cuda.device(device):
+            scores = single.from_alignment_and_audio(
+                load_model(checkpoint, device), alignment, audio, sample_rate, device)
+        if scores is not None:
+            return scores
     return from_alignments_and_audio(
         [alignment], [audio], sample_rate, checkpoint, batch_size, gpu,
         to_cpu=False)[0]

@@ -241,6 +241,56 @@ int emph_pool_words(
     int32_t total_word_rows, int32_t method, float* y, void* stream);
 
 /*
+ * One utterance through the whole path in one call: BASELINE config 1,
+ * emphases.from_alignment_and_audio on a single utterance with batch_size =
+ * None (emphases/core.py:223-287: preprocess -> infer -> postprocess).  The
+ * chunk plan (emphases/core.py:361-401 for an utterance that is ONE chunk) is
+ * made on the host with the same float64 operations as the batched planner,
+ * the index arrays travel in one copy, and the seven kernels
+ * (2 row maps, log-mel, frame stack, pooling, word stack, head) are launched
+ * back to back on `stream`.
+ *
+ * Returns EMPH_ENOSYS -- nothing launched -- when the utterance is not a single
+ * chunk or its bounds are ones the reference raises on: take the general path.
+ *
+ *   model       stacks as emph_conv_stack takes them (weights = the blob that
+ *               matches `precision`), head as emph_output_head, the mel basis
+ *               as emph_logmel_*; has_word_stack = 0 for the locations without
+ *               a word decoder
+ *   times       host [n_words][2] float64 word (start, end) seconds
+ *   audio       n_samples fp32 (or int16 PCM) samples, host or device memory
+ *   workspace   device scratch of emph_infer_utterance_workspace(...) bytes
+ *   logits_out, scores_out  receive device pointers INTO the workspace:
+ *               n_words values each, valid until the workspace is reused
+ */
+typedef struct {
+    const void* weights;
+    const float* bias;
+    const int32_t* acts_host;
+    int32_t n_layers, channels, kernel_size, precision;
+} emph_utterance_stack;
+
+typedef struct {
+    emph_utterance_stack frame, word;
+    int32_t has_word_stack;
+    const float* head_weight;
+    float head_bias;
+    int32_t head_kernel, head_mode;
+    const int32_t* mel_ptr;
+    const int16_t* mel_col;
+    const float* mel_val;
+    int32_t n_mels, normalize, pool_method;
+} emph_utterance_model;
+
+long long emph_infer_utterance_workspace(
+    long long n_samples, int32_t n_words, int32_t channels, int32_t n_mels);
+int emph_infer_utterance(
+    const emph_utterance_model* model, const double* times, int32_t n_words,
+    const void* audio, int32_t audio_is_int16, long long n_samples,
+    void* workspace, long long workspace_bytes,
+    float** logits_out, float** scores_out, void* stream);
+
+/*
  * Output projection Conv1d(channels -> 1, kernel_size, 'same') over packed rows
  * (emphases/model/core.py:33-37,138) + postprocess (core.py:335-342).
  *   weight [kernel_size][channels], bias_host scalar.

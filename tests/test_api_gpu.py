@@ -566,3 +566,49 @@ def test_non_16k_audio_end_to_end(emphases, golden, c1_checkpoint):
         emphases.Alignment.from_times(times), audio, 24000,
         checkpoint=c1_checkpoint, gpu=0)
     assert (scores.cpu() - expected).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize('method,location', [
+    ('sum', 'intermediate'), ('average', 'intermediate'), ('max', 'loss'),
+    ('center', 'inference')])
+def test_single_utterance_native_call_matches_batched_path(
+    emphases, golden, c1_checkpoint, method, location
+):
+    """emph_infer_utterance (one native call: C++ chunk plan + seven launches)
+    must give bit for bit what the batched scheduler gives, for host and
+    device audio; what it declines falls back to the general path"""
+    from emphases_b200 import single
+    emphases.configure(DOWNSAMPLE_METHOD=method, DOWNSAMPLE_LOCATION=location)
+    device = torch.device('cuda', 0)
+    torch.manual_seed(3)
+    model = emphases.Model().to(device).eval()
+    for seed in range(5):
+        times, audio = oracle.synthetic_utterance(900 + seed, duration=0.8 + 1.7 * seed)
+        alignment = emphases.Alignment.from_times(times)
+        forms = {'host': audio, 'device': audio.to(device), 'flat': audio[0].clone()}
+        for name, form in forms.items():
+            fast = single.from_alignment_and_audio(model, alignment, form, 16000, device)
+            assert fast is not None, name
+            slow = emphases.from_alignments_and_audio(
+                [alignment], [form.reshape(1, -1)], 16000, model=model, gpu=0,
+                to_cpu=False)[0]
+            assert fast.shape == slow.shape == (1, len(times))
+            assert torch.equal(fast, slow), (method, location, seed, name)
+    # the public entry point takes the native call ...
+    times, audio = oracle.synthetic_utterance(950)
+    alignment = emphases.Alignment.from_times(times)
+    expected = oracle.from_alignment_and_audio(
+        times, audio, {k: v.detach().cpu() for k, v in model.state_dict().items()},
+        {'DOWNSAMPLE_METHOD': method, 'DOWNSAMPLE_LOCATION': location})
+    checkpoint = c1_checkpoint.parent / f'single_{method}_{location}.pt'
+    torch.save({'model': model.state_dict()}, checkpoint)
+    got = emphases.from_alignment_and_audio(alignment, audio, 16000, checkpoint, gpu=0)
+    assert (got.cpu() - expected).abs().max() < 1e-5
+    # ... and what the native planner declines (other sample rates, chunked
+    # calls, stereo) still goes through the general path
+    assert single.from_alignment_and_audio(model, alignment, audio, 22050, device) is None
+    assert single.from_alignment_and_audio(
+        model, alignment, torch.cat([audio, audio]), 16000, device) is None
+    chunked = emphases.from_alignment_and_audio(
+        alignment, audio, 16000, checkpoint, batch_size=120, gpu=0)
+    assert chunked.shape == got.shape

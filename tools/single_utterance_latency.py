@@ -16,7 +16,7 @@ edges = [0.] + cuts + [10.]
 alignment = emphases.Alignment.from_times(list(zip(edges[:-1], edges[1:])))
 path = '/tmp/single_utterance_checkpoint.pt'
 torch.save({'model': state}, path)
-for precision in ('fp32', 'bf16'):
+for precision in ('bf16x6', 'bf16'):
     emphases.configure(PRECISION=precision)
     for _ in range(20):
         emphases.from_alignment_and_audio(alignment, audio, 16000, checkpoint=path, gpu=0).cpu()
@@ -31,4 +31,4 @@ for precision in ('fp32', 'bf16'):
 pr = cProfile.Profile(); pr.enable()
 for _ in range(50):
     emphases.from_alignment_and_audio(alignment, audio, 16000, checkpoint=path, gpu=0).cpu()
-pr.disable(); pstats.Stats(pr).sort_stats('cumulative').print_stats(16)
+pr.disable(); pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
