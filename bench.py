@@ -78,6 +78,9 @@ def parse_args():
         choices=['convolution', 'transformer'],
         help='transformer = BASELINE config 3 (informational, fp32 kernels)')
     parser.add_argument('--cpu-seconds', type=float, default=15.)
+    parser.add_argument(
+        '--transformer-steps', type=int, default=2,
+        help='timed passes of the config-3 (Transformer variant) leg; 0 skips it')
     parser.add_argument('--file-utterances', type=int, default=3000)
     parser.add_argument(
         '--corpus-copies', type=int, default=8,
@@ -477,6 +480,115 @@ def time_files_path(emphases, args, state, rank, world, local_rank, device, barr
             shutil.rmtree(root, ignore_errors=True)
 
 
+def time_transformer_variant(
+    emphases, engine, eng, device, device_audio, plan, views, audio_seconds, steps
+):
+    """configs[2]: the Transformer-layer variant (padding-masked attention over
+    frames, emphases/model/layers/transformer.py:13-52) with random-init
+    weights over the SAME packed corpus, inputs resident in HBM"""
+    emphases.configure(ARCHITECTURE='transformer')
+    torch.manual_seed(0)
+    model = emphases.Model().to(device).eval()
+    weights = model.packed_weights()
+    code = emphases.precision_code()
+
+    def step():
+        return eng.forward_packed(
+            device_audio, plan, weights, method='sum', location='intermediate',
+            precision=code, views=views)
+
+    step()
+    torch.cuda.synchronize(device)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        result = step()
+    end.record()
+    torch.cuda.synchronize(device)
+    ms = start.elapsed_time(end) / steps
+    assert torch.isfinite(result['scores']).all()
+    del model, weights, result
+    return {
+        'value': audio_seconds / (ms * 1e-3), 'unit': 'audio-s/s', 'ms_per_step': ms,
+        'steps': steps, 'utterances': int(plan.n_seq),
+        'workload': 'configs[2]: Transformer-layer variant, same corpus, kernel-only',
+        'note': ('attention is fp32 CUDA-core flash-style (csrc/attention.cu), the per-row '
+                 'linear maps run on the tensor cores (bf16x6)')}
+
+
+def synthetic_training_batch(seed, max_frames=75000):
+    """A padded batch shaped like the reference's collate (B * Tmax <=
+    MAX_TRAINING_FRAMES = 75,000 frames, emphases/config/defaults.py;
+    utterances U(2, 20) s, 2.5 words/s)"""
+    generator = np.random.default_rng(seed)
+    lengths = []
+    while True:
+        frames = int(generator.uniform(2., 20.) * 100)
+        if (len(lengths) + 1) * max(lengths + [frames]) > max_frames:
+            break
+        lengths.append(frames)
+    words = [max(2, int(2.5 * t / 100)) for t in lengths]
+    tmax, wmax = max(lengths), max(words)
+    torch_generator = torch.Generator().manual_seed(seed)
+    features = torch.zeros(len(lengths), 80, tmax)
+    bounds = torch.zeros(len(lengths), 2, wmax, dtype=torch.long)
+    for i, (t, w) in enumerate(zip(lengths, words)):
+        features[i, :, :t] = torch.randn(80, t, generator=torch_generator)
+        cuts = np.sort(generator.choice(np.arange(1, t - 1), size=w - 1, replace=False))
+        edges = np.concatenate([[0], cuts, [t]])
+        bounds[i, 0, :w] = torch.from_numpy(edges[:-1])
+        bounds[i, 1, :w] = torch.from_numpy(edges[1:])
+    targets = torch.rand(len(lengths), 1, wmax, generator=torch_generator)
+    return (features, torch.tensor(lengths), bounds, torch.tensor(words), targets)
+
+
+def time_train_step(emphases, rank, world, device, barrier, steps=20, warmup=5):
+    """configs[4]: forward + backward (BCE on word scores) + NCCL gradient
+    all-reduce + Adam on one synthetic collate-shaped batch per rank (weak
+    scaling); CUDA events, max over ranks"""
+    from emphases_b200 import training
+    saved = {key: getattr(emphases, key) for key in ('PRECISION',)}
+    torch.manual_seed(0)
+    model = emphases.Model().to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4)
+    batch = synthetic_training_batch(100 + rank)
+    batch = (batch[0].to(device),) + batch[1:4] + (batch[4].to(device),)
+    frames = int(batch[1].sum())
+    for _ in range(warmup):
+        value = training.train_step(model, optimizer, batch)
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        value = training.train_step(model, optimizer, batch)
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end) / steps
+    stats = torch.tensor([ms, frames], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        worst, total = stats.clone(), stats.clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        ms, frames_total = worst[0].item(), total[1].item()
+    else:
+        frames_total = frames
+    emphases.configure(**saved)
+    return {
+        'ms_per_step': ms, 'frames_per_s': frames_total / (ms * 1e-3),
+        'value': frames_total / 100. / (ms * 1e-3), 'unit': 'audio-s/s',
+        'scaling': 'weak', 'n_gpus': world,
+        'batch': {'utterances': int(batch[0].shape[0]), 'tmax': int(batch[0].shape[2]),
+                  'frames': frames,
+                  'padded_frames': int(batch[0].shape[0] * batch[0].shape[2])},
+        'loss': float(value),
+        'precision': (f'{training.TRAIN_PRECISION} forward / input gradients, fp32 weight '
+                      'gradients, Adam'),
+        'workload': ('configs[4]: forward + backward + BCE on word scores + NCCL gradient '
+                     'all-reduce (flat buffer, in place) + optimizer step, one '
+                     'collate-shaped batch per rank')}
+
+
 def time_single_utterance(emphases, model, gpu, calls=200):
     """configs[0] on the GPU: emphases_b200.from_alignment_and_audio on one
     10 s utterance with a 25-word alignment (the native single-utterance call,
@@ -670,6 +782,18 @@ def main():
     if rank == 0:
         single = time_single_utterance(emphases, model, local_rank)
 
+    # ---- BASELINE config 3: the Transformer-layer variant over the same corpus,
+    # kernel-only, rank 0 (informational: the conv model is the headline) ----
+    transformer_leg = None
+    if rank == 0 and args.architecture == 'convolution' and args.transformer_steps > 0:
+        transformer_leg = time_transformer_variant(
+            emphases, engine, eng, device, device_audio, plan, views, audio_seconds,
+            args.transformer_steps)
+        emphases.configure(ARCHITECTURE='convolution', PRECISION=precision)
+
+    # ---- BASELINE config 5: the data-parallel training step (every rank) ----
+    train_leg = time_train_step(emphases, rank, world, device, barrier)
+
     # ---- the API BASELINE.json names: from_files_to_files on one shared corpus ----
     files_leg = None
     if args.file_utterances > 0:
@@ -844,6 +968,8 @@ def main():
         'e2e': e2e,
         'files_e2e': files_leg,
         'single_utterance': single,
+        'train_step': train_leg,
+        'transformer_variant': transformer_leg,
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,
         'cpu_baseline': cpu}))

@@ -76,6 +76,15 @@ class UtteranceModel(ctypes.Structure):
         ('normalize', _I), ('pool_method', _I)]
 
 
+class TrainModel(ctypes.Structure):
+    """emph_train_model"""
+    _fields_ = [
+        ('n_frame_layers', _I), ('n_word_layers', _I), ('channels', _I),
+        ('kernel_size', _I), ('head_kernel', _I), ('pool_method', _I),
+        ('forward_precision', _I), ('precision', _I),
+        ('acts', _P), ('weights', _P), ('biases', _P), ('zero_bias', _P)]
+
+
 ENOSYS = -38        # EMPH_ENOSYS: the configuration is not built / not handled
 
 _lib = None
@@ -130,6 +139,14 @@ def load():
         ctypes.POINTER(UtteranceModel), _P, _I, _P, _I, ctypes.c_longlong, _P,
         ctypes.c_longlong, ctypes.POINTER(_P), ctypes.POINTER(_P), _P]
     lib.emph_infer_utterance.restype = ctypes.c_int
+    lib.emph_train_workspace.argtypes = [ctypes.POINTER(TrainModel), _I, _I, _I]
+    lib.emph_train_workspace.restype = ctypes.c_longlong
+    lib.emph_train_forward.argtypes = [
+        ctypes.POINTER(TrainModel), _P, _I, _I, _P, _P, _P, _I, _P, ctypes.c_longlong, _P, _P]
+    lib.emph_train_forward.restype = ctypes.c_int
+    lib.emph_train_backward.argtypes = [
+        ctypes.POINTER(TrainModel), _P, _I, _I, _P, _I, _P, ctypes.c_longlong, _P, _I, _P]
+    lib.emph_train_backward.restype = ctypes.c_int
     _lib = lib
     return lib
 

@@ -1,6 +1,9 @@
 // C-ABI plumbing: error string, version, small utility kernels.
 #include <stdarg.h>
 
+#include <mutex>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace emph {
@@ -148,6 +151,56 @@ __global__ void widen_rows_kernel(
         if (q < quads_in) v = reinterpret_cast<const float4*>(x)[r * quads_in + q];
         reinterpret_cast<float4*>(y)[i] = v;
     }
+}
+
+}  // namespace emph
+
+namespace emph {
+
+namespace {
+struct StagingSlot {
+    void* buffer = nullptr;
+    size_t capacity = 0;
+    cudaEvent_t consumed = nullptr;
+};
+constexpr int kStagingSlots = 8;
+constexpr int kStagingDevices = 16;        // an event belongs to the device it was made on
+StagingSlot g_staging[kStagingDevices][kStagingSlots];
+int g_staging_next[kStagingDevices] = {};
+std::mutex g_staging_mutex;
+}  // namespace
+
+int staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return EMPH_OK;
+    int device = 0;
+    cudaGetDevice(&device);
+    device = device < 0 ? 0 : device % kStagingDevices;
+    std::lock_guard<std::mutex> lock(g_staging_mutex);
+    StagingSlot& slot = g_staging[device][g_staging_next[device]];
+    g_staging_next[device] = (g_staging_next[device] + 1) % kStagingSlots;
+    if (slot.consumed == nullptr) {
+        int s = check_cuda(
+            cudaEventCreateWithFlags(&slot.consumed, cudaEventDisableTiming), "staging event");
+        if (s != EMPH_OK) return s;
+    } else {
+        // the copy that last used this slot must have been consumed by its stream
+        int s = check_cuda(cudaEventSynchronize(slot.consumed), "staging wait");
+        if (s != EMPH_OK) return s;
+    }
+    if (slot.capacity < bytes) {
+        if (slot.buffer) cudaFreeHost(slot.buffer);
+        slot.buffer = nullptr;
+        slot.capacity = 0;
+        const size_t capacity = bytes < (1u << 16) ? (1u << 16) : bytes * 2;
+        int s = check_cuda(cudaHostAlloc(&slot.buffer, capacity, cudaHostAllocDefault), "staging alloc");
+        if (s != EMPH_OK) return s;
+        slot.capacity = capacity;
+    }
+    memcpy(slot.buffer, src, bytes);
+    int s = check_cuda(
+        cudaMemcpyAsync(dst, slot.buffer, bytes, cudaMemcpyHostToDevice, stream), "staged upload");
+    if (s != EMPH_OK) return s;
+    return check_cuda(cudaEventRecord(slot.consumed, stream), "staging record");
 }
 
 }  // namespace emph

@@ -33,6 +33,12 @@ inline int check_cuda(cudaError_t status, const char* what) {
         }                                    \
     } while (0)
 
+// Host -> device copy of a small, freshly built host array through a ring of
+// page-locked staging buffers (api.cu): truly asynchronous (a cudaMemcpyAsync
+// from pageable memory synchronises the stream first), and `src` may be reused
+// as soon as the call returns.
+int staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t stream);
+
 inline int sm_count() {
     static int cached = 0;
     if (cached == 0) {

@@ -778,9 +778,13 @@ conv_stack_tc_kernel(
 // parts = 2 / 3: that many entries per layer -- (W_hi, bias chunk), (W_mid, zeros)
 // (, (W_lo, zeros)) with W_hi = bf16(W), W_mid = bf16(W - W_hi), W_lo = bf16 of
 // what is still left.
+// source: 0 = the packed fp32 layout [L][tap][in][out]; 1 = ONE Conv1d weight
+// (out, in, k) as the module holds it; 2 = the adjoint convolution of that
+// Conv1d weight (channel matrix transposed, taps flipped: the input-gradient
+// pass of the training step)
 __global__ void pack_weights_tc_kernel(
     const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int parts,
-    int ks, __nv_bfloat16* __restrict__ out) {
+    int ks, int source, __nv_bfloat16* __restrict__ out) {
     const int per_entry = layer_bytes(ks) / 2;
     const int conv = conv_bytes(ks) / 2;
     const int entries = parts;
@@ -796,7 +800,10 @@ __global__ void pack_weights_tc_kernel(
             const int kg = rest % KG;
             const int tap = rest / KG;
             const int ci = kg * 8 + e;
-            const float value = w[((size_t)(layer * ks + tap) * C + ci) * C + n];
+            const float value =
+                source == 0 ? w[((size_t)(layer * ks + tap) * C + ci) * C + n]
+                : source == 1 ? w[((size_t)n * C + ci) * ks + tap]
+                : w[((size_t)ci * C + n) * ks + (ks - 1 - tap)];
             v = value;                               // part p: rounded below after
             for (int q = 0; q < part; ++q)           // removing the earlier parts
                 v -= __bfloat162float(__float2bfloat16_rn(v));
@@ -949,7 +956,22 @@ extern "C" int emph_pack_conv_weights_tc(
                  "emph_pack_conv_weights_tc: precision %d has no tensor-core layout", precision);
     const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
     emph::tc::pack_weights_tc_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(
-        weights, bias, n_layers, parts, kernel_size, reinterpret_cast<__nv_bfloat16*>(packed));
+        weights, bias, n_layers, parts, kernel_size, 0, reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("emph_pack_conv_weights_tc");
     return EMPH_OK;
 }
+
+// One Conv1d (out, in, k) weight (or its adjoint) straight into the operand
+// blob of a one-layer stack: what the training step needs every step
+namespace emph {
+int pack_conv1d_weights_tc(
+    const float* conv_weight, const float* bias, int kernel_size, int precision, int adjoint,
+    void* packed, cudaStream_t stream) {
+    const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
+    tc::pack_weights_tc_kernel<<<64, 256, 0, stream>>>(
+        conv_weight, bias, 1, parts, kernel_size, adjoint ? 2 : 1,
+        reinterpret_cast<__nv_bfloat16*>(packed));
+    EMPH_CHECK_LAUNCH("pack_conv1d_weights_tc");
+    return EMPH_OK;
+}
+}  // namespace emph

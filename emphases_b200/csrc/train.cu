@@ -62,7 +62,9 @@ __global__ void activation_forward_kernel(
 
 // Weight / bias gradient of one conv layer.  256 threads: thread (gi, go) owns
 // a 5 x 5 block of (ci, co) for all taps (C = 80: 16 x 16 blocks).
-template <int C, int KS>
+// CONV1D: dw is addressed as the Conv1d parameter (out, in, k) instead of the
+// packed [k][in][out]
+template <int C, int KS, bool CONV1D>
 __global__ void __launch_bounds__(256)
 conv_weight_grad_kernel(
     const float* __restrict__ x, const float* __restrict__ dpre, int total_rows,
@@ -124,7 +126,10 @@ conv_weight_grad_kernel(
         for (int i = 0; i < B; ++i)
 #pragma unroll
             for (int o = 0; o < B; ++o)
-                atomicAdd(dw + ((size_t)t * C + gi * B + i) * C + go * B + o, acc[t][i][o]);
+                atomicAdd(
+                    dw + (CONV1D ? ((size_t)(go * B + o) * C + gi * B + i) * KS + t
+                                 : ((size_t)t * C + gi * B + i) * C + go * B + o),
+                    acc[t][i][o]);
     if (gi == 0) {
 #pragma unroll
         for (int o = 0; o < B; ++o) atomicAdd(db + go * B + o, bias_acc[o]);
@@ -197,24 +202,35 @@ head_backward_kernel(
         }
         dx[i] = row_seq[r] >= 0 ? acc : 0.f;
     }
-    if (blockIdx.x == 0) {
-        // dw[tap][c] = sum_r x[r + tap - half][c] dz[r];  db = sum_r dz[r]
-        for (int i = threadIdx.x; i < kernel_size * channels; i += blockDim.x) {
-            const int tap = i / channels, c = i % channels;
-            float acc = 0.f;
-            for (int r = 0; r < total_rows; ++r) {
-                const int g = r + tap - half;
-                if (row_seq[r] >= 0 && g >= 0 && g < total_rows)
-                    acc = fmaf(x[(size_t)g * channels + c], dz[r], acc);
-            }
-            dw[i] = acc;
+}
+
+// dw[tap][c] = sum_r x[r + tap - half][c] dz[r];  db = sum_r dz[r] over the rows
+// of real sequences: a CTA per chunk of rows, one thread per (tap, c), partial
+// sums added to the (zeroed) outputs
+constexpr int kHeadGradRows = 64;
+__global__ void __launch_bounds__(256)
+head_weight_grad_kernel(
+    const float* __restrict__ x, const float* __restrict__ dz,
+    const int32_t* __restrict__ row_seq, int total_rows, int channels, int kernel_size,
+    float* __restrict__ dw, float* __restrict__ db) {
+    const int half = (kernel_size - 1) / 2;
+    const int r0 = blockIdx.x * kHeadGradRows;
+    const int r1 = min(r0 + kHeadGradRows, total_rows);
+    for (int i = threadIdx.x; i < kernel_size * channels; i += blockDim.x) {
+        const int tap = i / channels, c = i % channels;
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const int g = r + tap - half;
+            if (row_seq[r] >= 0 && g >= 0 && g < total_rows)
+                acc = fmaf(x[(size_t)g * channels + c], dz[r], acc);
         }
-        if (threadIdx.x == 0) {
-            float acc = 0.f;
-            for (int r = 0; r < total_rows; ++r)
-                if (row_seq[r] >= 0) acc += dz[r];
-            db[0] = acc;
-        }
+        if (acc != 0.f) atomicAdd(dw + i, acc);
+    }
+    if (threadIdx.x == 0) {
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r)
+            if (row_seq[r] >= 0) acc += dz[r];
+        if (acc != 0.f) atomicAdd(db, acc);
     }
 }
 
@@ -304,10 +320,42 @@ int emph_conv_weight_grad(
     if (total_rows == 0) return EMPH_OK;
     int grid = (total_rows + 63) / 64;
     if (grid > emph::sm_count() * 2) grid = emph::sm_count() * 2;
-    emph::conv_weight_grad_kernel<80, 3><<<grid, 256, 0, st>>>(x, dpre, total_rows, dw, db);
+    emph::conv_weight_grad_kernel<80, 3, false><<<grid, 256, 0, st>>>(x, dpre, total_rows, dw, db);
     EMPH_CHECK_LAUNCH("emph_conv_weight_grad");
     return EMPH_OK;
 }
+}  // extern "C"
+
+// The same sums written (accumulate = 0: after zeroing) or added straight into
+// the gradient of the Conv1d parameter, (out, in, k) and (out): no layout pass
+namespace emph {
+int conv1d_weight_grad(
+    const float* x, const float* dpre, int total_rows, int channels, int kernel_size,
+    float* grad_weight, float* grad_bias, int accumulate, cudaStream_t st) {
+    if (!(channels == 80 && kernel_size == 3)) {
+        set_error("conv1d_weight_grad: channels=%d kernel_size=%d not compiled in",
+                  channels, kernel_size);
+        return EMPH_ENOSYS;
+    }
+    if (!accumulate) {
+        int s = check_cuda(
+            cudaMemsetAsync(grad_weight, 0, sizeof(float) * kernel_size * channels * channels, st),
+            "memset dw");
+        if (s != EMPH_OK) return s;
+        s = check_cuda(cudaMemsetAsync(grad_bias, 0, sizeof(float) * channels, st), "memset db");
+        if (s != EMPH_OK) return s;
+    }
+    if (total_rows == 0) return EMPH_OK;
+    int grid = (total_rows + 63) / 64;
+    if (grid > sm_count() * 2) grid = sm_count() * 2;
+    conv_weight_grad_kernel<80, 3, true><<<grid, 256, 0, st>>>(
+        x, dpre, total_rows, grad_weight, grad_bias);
+    EMPH_CHECK_LAUNCH("conv1d_weight_grad");
+    return EMPH_OK;
+}
+}  // namespace emph
+
+extern "C" {
 
 int emph_pool_words_backward(
     const float* dy, const float* x, int32_t channels,
@@ -330,11 +378,20 @@ int emph_output_head_backward(
     const float* x, const float* dz, const int32_t* row_seq, int32_t total_rows,
     int32_t channels, int32_t kernel_size, const float* weight,
     float* dx, float* dw, float* db, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int s = emph::check_cuda(
+        cudaMemsetAsync(dw, 0, sizeof(float) * kernel_size * channels, st), "memset head dw");
+    if (s != EMPH_OK) return s;
+    s = emph::check_cuda(cudaMemsetAsync(db, 0, sizeof(float), st), "memset head db");
+    if (s != EMPH_OK) return s;
     if (total_rows == 0) return EMPH_OK;
     int grid = (int)(((size_t)total_rows * channels + 255) / 256);
     if (grid > emph::sm_count() * 4) grid = emph::sm_count() * 4;
-    emph::head_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    emph::head_backward_kernel<<<grid, 256, 0, st>>>(
         x, dz, row_seq, total_rows, channels, kernel_size, weight, dx, dw, db);
+    emph::head_weight_grad_kernel<<<
+        (total_rows + emph::kHeadGradRows - 1) / emph::kHeadGradRows, 256, 0, st>>>(
+        x, dz, row_seq, total_rows, channels, kernel_size, dw, db);
     EMPH_CHECK_LAUNCH("emph_output_head_backward");
     return EMPH_OK;
 }

@@ -143,8 +143,7 @@ extern "C" int emph_infer_utterance(
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* base = static_cast<uint8_t*>(workspace);
 
-    // ---- index arrays: one blob, one copy (pageable: a copy this small is
-    // staged by the driver before the call returns, so the buffer is ours again) ----
+    // ---- index arrays: one blob, one copy through the pinned staging ring ----
     const int rows = plan.total_rows, word_rows = plan.total_word_rows;
     // [audio_off (int64: 2 words)][audio_len][chunk_start][chunk_len][row_start][n_rows]
     // [word_row_start][n_words][word_seq w][word_lo w][word_hi w]
@@ -165,9 +164,7 @@ extern "C" int emph_infer_utterance(
     memcpy(word_lo, plan.word_lo.data(), sizeof(int32_t) * word_rows);
     memcpy(word_hi, plan.word_hi.data(), sizeof(int32_t) * word_rows);
     int32_t* dev = reinterpret_cast<int32_t*>(base + l.blob);
-    int s = check_cuda(
-        cudaMemcpyAsync(dev, host, blob_words * 4, cudaMemcpyHostToDevice, st),
-        "emph_infer_utterance: index copy");
+    int s = staged_upload(dev, host, blob_words * 4, st);
     if (s != EMPH_OK) return s;
     const int64_t* audio_off = reinterpret_cast<const int64_t*>(dev);
     const int32_t *audio_len = dev + 2, *chunk_start = dev + 3, *chunk_len = dev + 4,

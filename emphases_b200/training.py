@@ -8,6 +8,9 @@ training mode goes through `forward_with_grad`: a torch.autograd.Function
 whose backward fills the `.grad` of the Model's own torch parameters, so any
 torch optimizer (the reference uses Adam, train/core.py:69-75) can step.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
@@ -260,8 +263,194 @@ class _ConvModelFunction(torch.autograd.Function):
         return (None, None, None, None, *ordered)
 
 
+###############################################################################
+# Native step: one C-ABI call for the forward, one for the backward
+###############################################################################
+
+# Precision of the convolutions of the native step, forward+backward:
+# 'bf16x6' (default): tensor cores with hi/mid/lo-split operands, fp32 grade --
+# every parameter gradient within 2e-4 of autograd, like the fp32 kernels.
+# 'bf16x3' (hi/lo split, 1e-5 class logits) leaves 2e-3 on the gradient of the
+# first layer, and so does 'bf16x3+bf16x6' (x3 forward, x6 input gradients:
+# the forward's 1e-5 is what the deep gradients amplify); 2.01 instead of
+# 2.10 ms per step.  'fp32': the FFMA kernels, 4.1 ms.  Weight gradients are
+# always fp32.
+TRAIN_PRECISION = os.environ.get('EMPHASES_B200_TRAIN_PRECISION', 'bf16x6')
+_TRAIN_PRECISIONS = {
+    'fp32': (_lib.PREC_FP32, _lib.PREC_FP32),
+    'bf16x3': (_lib.PREC_BF16X3_TC, _lib.PREC_BF16X3_TC),
+    'bf16x6': (_lib.PREC_BF16X6_TC, _lib.PREC_BF16X6_TC),
+    'bf16x3+bf16x6': (_lib.PREC_BF16X3_TC, _lib.PREC_BF16X6_TC)}
+
+
+class _NativeState:
+    """Per-model launch descriptor, flat gradient buffer and workspace of
+    csrc/train_step.cu"""
+
+    def __init__(self, model, device):
+        self.device = device
+        frame, word = _layer_list(model)
+        self.layers = frame + word
+        self.n_frame, self.n_word = len(frame), len(word)
+        # parameters in descriptor order: (weight, bias) per layer, then the head
+        self.ordered = []
+        for weight, bias, _ in self.layers:
+            self.ordered += [weight, bias]
+        self.ordered += [model.output_layer.weight, model.output_layer.bias]
+        sizes = [p.numel() for p in self.ordered]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self.flat = torch.zeros(int(self.offsets[-1]), dtype=torch.float32, device=device)
+        self.zero_bias = torch.zeros(engine.KERNEL_CHANNELS, dtype=torch.float32, device=device)
+        self.acts = np.ascontiguousarray(
+            np.asarray([act for _, _, act in self.layers], dtype=np.int32))
+        count = len(self.layers) + 1
+        self.weight_pointers = (ctypes.c_void_p * count)()
+        self.bias_pointers = (ctypes.c_void_p * count)()
+        self.grad_pointers = (ctypes.c_void_p * (2 * count))()
+        self.descriptor = _lib.TrainModel()
+        self.workspace = None
+        self.pointer_key = None
+        self.lib = _lib.load()
+
+    def refresh(self, model):
+        """Parameter storage is stable across optimizer steps; re-read the
+        pointers only when it moved (model.to(...), load_state_dict)"""
+        key = tuple(p.data_ptr() for p in self.ordered)
+        if key == self.pointer_key:
+            return
+        self.pointer_key = key
+        weights = [w for w, _, _ in self.layers] + [model.output_layer.weight]
+        biases = [b for _, b, _ in self.layers] + [model.output_layer.bias]
+        for i, (w, b) in enumerate(zip(weights, biases)):
+            self.weight_pointers[i] = w.data_ptr()
+            self.bias_pointers[i] = b.data_ptr()
+        d = self.descriptor
+        d.n_frame_layers, d.n_word_layers = self.n_frame, self.n_word
+        d.channels = engine.KERNEL_CHANNELS
+        d.kernel_size = int(model.input_layer.weight.shape[2])
+        d.head_kernel = int(model.output_layer.weight.shape[2])
+        d.acts = self.acts.ctypes.data
+        d.weights = ctypes.cast(self.weight_pointers, ctypes.c_void_p)
+        d.biases = ctypes.cast(self.bias_pointers, ctypes.c_void_p)
+        d.zero_bias = self.zero_bias.data_ptr()
+
+    def views(self, flat=None):
+        flat = self.flat if flat is None else flat
+        return [
+            flat[int(a):int(b)].view(p.shape)
+            for a, b, p in zip(self.offsets[:-1], self.offsets[1:], self.ordered)]
+
+    def aliases_flat(self, parameter, index):
+        grad = parameter.grad
+        return (
+            grad is not None and grad.dtype == torch.float32 and grad.is_contiguous() and
+            grad.data_ptr() == self.flat.data_ptr() + 4 * int(self.offsets[index]))
+
+
+def _native_state(model, device):
+    state = getattr(model, '_native_train_state', None)
+    if state is None or state.device != device:
+        state = _NativeState(model, device)
+        object.__setattr__(model, '_native_train_state', state)
+    state.refresh(model)
+    return state
+
+
+def native_step_supported(model, features):
+    """The configurations csrc/train_step.cu is built for"""
+    return (
+        model.architecture == 'convolution' and
+        model.location in ('intermediate', 'loss') and
+        emphases.CHANNELS == engine.KERNEL_CHANNELS == emphases.NUM_FEATURES and
+        int(model.input_layer.weight.shape[2]) == 3 and
+        all(int(w.shape[2]) == 3 for w, _, _ in sum(_layer_list(model), [])) and
+        emphases.DOWNSAMPLE_METHOD in _lib.POOL and
+        features.dtype == torch.float32 and features.is_cuda and
+        TRAIN_PRECISION in _TRAIN_PRECISIONS)
+
+
+class _NativeConvFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, model, features, frame_lengths, word_bounds, word_lengths, *parameters):
+        device = features.device
+        state = _native_state(model, device)
+        features = features.detach().contiguous()
+        batch, _, frames = features.shape
+        wmax = int(word_bounds.shape[2])
+        bounds = word_bounds.detach().to('cpu', torch.int64).contiguous()
+        lengths = word_lengths.detach().to('cpu', torch.int64).contiguous()
+        frame_lengths = frame_lengths.detach().to('cpu', torch.int64).contiguous()
+        descriptor = state.descriptor
+        descriptor.pool_method = _lib.POOL[emphases.DOWNSAMPLE_METHOD]
+        descriptor.forward_precision, descriptor.precision = _TRAIN_PRECISIONS[TRAIN_PRECISION]
+        need = state.lib.emph_train_workspace(ctypes.byref(descriptor), batch, frames, wmax)
+        if need < 0:
+            raise _lib.EmphasesB200Error(
+                'emph_train_workspace: ' + state.lib.emph_last_error().decode())
+        if state.workspace is None or state.workspace.numel() < need:
+            state.workspace = None
+            state.workspace = torch.empty(
+                int(need * 1.1) + 4096, dtype=torch.uint8, device=device)
+        logits = torch.empty((batch, 1, wmax), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            stream = torch._C._cuda_getCurrentRawStream(device.index)
+            status = state.lib.emph_train_forward(
+                ctypes.byref(descriptor), features.data_ptr(), batch, frames,
+                frame_lengths.data_ptr(), bounds.data_ptr(), lengths.data_ptr(), wmax,
+                state.workspace.data_ptr(), state.workspace.numel(),
+                logits.data_ptr(), stream)
+        if status != 0:
+            raise _lib.EmphasesB200Error(
+                f'emph_train_forward failed ({status}): ' +
+                state.lib.emph_last_error().decode('utf-8', 'replace'))
+        ctx.model, ctx.state = model, state
+        ctx.shape = (batch, frames, wmax)
+        ctx.frame_lengths = frame_lengths
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        model, state = ctx.model, ctx.state
+        batch, frames, wmax = ctx.shape
+        device = grad_logits.device
+        grad_logits = grad_logits.detach().to(torch.float32).contiguous()
+        # Gradients land in the flat buffer, in the parameters' own layouts.
+        # Parameters whose .grad already IS their slice of the flat buffer are
+        # accumulated into in place (nothing is returned for them); otherwise
+        # fresh views of the buffer are handed to autograd, which adopts them as
+        # .grad -- so the data-parallel all-reduce runs on the buffer itself.
+        aliased = [state.aliases_flat(p, i) for i, p in enumerate(state.ordered)]
+        in_place = all(aliased)
+        target = state.flat if (in_place or not any(aliased)) else torch.empty_like(state.flat)
+        views = state.views(target)
+        for i, view in enumerate(views):
+            state.grad_pointers[i] = view.data_ptr()
+        with torch.cuda.device(device):
+            stream = torch._C._cuda_getCurrentRawStream(device.index)
+            status = state.lib.emph_train_backward(
+                ctypes.byref(state.descriptor), grad_logits.data_ptr(), batch, frames,
+                ctx.frame_lengths.data_ptr(), wmax,
+                state.workspace.data_ptr(), state.workspace.numel(),
+                ctypes.cast(state.grad_pointers, ctypes.c_void_p), int(in_place), stream)
+        if status != 0:
+            raise _lib.EmphasesB200Error(
+                f'emph_train_backward failed ({status}): ' +
+                state.lib.emph_last_error().decode('utf-8', 'replace'))
+        by_parameter = {id(p): v for p, v in zip(state.ordered, views)}
+        del views
+        ordered = [
+            None if in_place else by_parameter.get(id(p)) for p in model.parameters()]
+        del by_parameter
+        return (None, None, None, None, None, *ordered)
+
+
 def forward_with_grad(model, features, frame_lengths, word_bounds, word_lengths):
     """Model.forward in training mode (gradients flow to model.parameters())"""
+    if native_step_supported(model, features):
+        return _NativeConvFunction.apply(
+            model, features, frame_lengths, word_bounds, word_lengths,
+            *model.parameters())
     return _ConvModelFunction.apply(
         model, features, word_bounds, word_lengths, *model.parameters())
 
@@ -291,6 +480,20 @@ class _MaskedLoss(torch.autograd.Function):
         return (grad.reshape(ctx.shape) * grad_output, None, None, None)
 
 
+def _device_mask(lengths, device):
+    """mask_from_lengths on `device` without a device -> host round trip:
+    lengths that live on the host (what the collate produces) are turned into
+    the mask there and uploaded asynchronously (torch.arange(lengths.max()) on
+    device lengths synchronises the stream: a bubble in every training step)"""
+    from . import model as model_module
+    if lengths.device.type == 'cuda':
+        return model_module.mask_from_lengths(lengths)
+    mask = model_module.mask_from_lengths(lengths)
+    if torch.cuda.is_available():
+        mask = mask.pin_memory()
+    return mask.to(device, non_blocking=True)
+
+
 def loss(
     scores, targets, frame_lengths, word_bounds, word_lengths, training=False,
     loss_fn=None
@@ -309,9 +512,9 @@ def loss(
             targets.to(scores.device), word_bounds, word_lengths, frame_lengths)
         if emphases.UPSAMPLE_METHOD == 'linear':
             targets = torch.clamp(targets, min=0., max=1.)
-        mask = model_module.mask_from_lengths(frame_lengths.to(scores.device))
+        mask = _device_mask(frame_lengths, scores.device)
     else:
-        mask = model_module.mask_from_lengths(word_lengths.to(scores.device))
+        mask = _device_mask(word_lengths, scores.device)
     return _MaskedLoss.apply(scores, targets, mask, 0 if loss_fn == 'bce' else 1)
 
 
@@ -329,6 +532,16 @@ def allreduce_gradients(model, average=True):
         return
     world = dist.get_world_size()
     if world == 1:
+        return
+    state = getattr(model, '_native_train_state', None)
+    if state is not None and all(
+        state.aliases_flat(p, i) for i, p in enumerate(state.ordered)
+    ) and len(state.ordered) == sum(1 for _ in model.parameters()):
+        # the native step wrote every gradient into one flat buffer that the
+        # .grad tensors alias: reduce it in place, no packing or copy-back
+        dist.all_reduce(state.flat, op=dist.ReduceOp.SUM)
+        if average:
+            state.flat.div_(world)
         return
     parameters = [p for p in model.parameters() if p.grad is not None]
     flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in parameters])

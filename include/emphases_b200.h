@@ -406,6 +406,60 @@ int emph_masked_loss(
     const float* logits, const float* targets, const uint8_t* valid,
     int32_t total_rows, int32_t mode, float* loss, float* dlogits, void* stream);
 /*
+ * Training-mode forward and backward of the convolution model, ONE call each
+ * (emphases/train/core.py:111-142: model(...) and backward() of one step).
+ * Built for channels = NUM_MELS = 80, kernel size 3 and the word-resolution
+ * locations ('intermediate': with word decoder, 'loss': without); other
+ * configurations use the per-kernel entry points above.
+ *
+ *   model     layers in order: input layer, frame encoder layers, word decoder
+ *             layers (n_word_layers may be 0), then the output projection.
+ *             weights[i] / biases[i] are the Conv1d parameters themselves
+ *             ((out, in, k) fp32 on the device; they change every step, so
+ *             both calls re-pack what they need); acts[i] the EMPH_ACT_* code
+ *             after layer i.  forward_precision / precision: EMPH_PREC_FP32,
+ *             EMPH_PREC_BF16X3_TC or _BF16X6_TC for the forward / the
+ *             input-gradient convolutions (weight gradients are always fp32).
+ *   features  (B, 80, T) fp32 device; word_bounds (B, 2, Wmax) / word_lengths
+ *             (B) int64 HOST arrays (emphases/data/collate.py:72-78).
+ *             frame_lengths (B) int64 host, or NULL: the reference convolves
+ *             all T padded columns of every item; rows further than one row
+ *             per frame layer beyond an item's length cannot reach a word, so
+ *             with the lengths given they are skipped (same logits, same
+ *             gradients).  Pass the same array to both calls.
+ *   workspace device scratch of emph_train_workspace(...) bytes: it carries the
+ *             kept activations from emph_train_forward to emph_train_backward
+ *   logits    (B, 1, Wmax) fp32 device out (padded slots included, as
+ *             emphases/model/core.py:138 returns them)
+ *   grads     host array of device pointers, two per layer (weight then bias)
+ *             in the order above plus the output projection's: gradients in
+ *             the parameters' own layouts, written (accumulate = 0) or added
+ */
+typedef struct {
+    int32_t n_frame_layers, n_word_layers, channels, kernel_size, head_kernel;
+    int32_t pool_method;
+    int32_t forward_precision;      /* the forward convolutions */
+    int32_t precision;              /* the input-gradient convolutions */
+    const int32_t* acts;
+    const float* const* weights;
+    const float* const* biases;
+    const float* zero_bias;         /* device [channels] zeros */
+} emph_train_model;
+
+long long emph_train_workspace(
+    const emph_train_model* model, int32_t batch, int32_t frames, int32_t wmax);
+int emph_train_forward(
+    const emph_train_model* model, const float* features, int32_t batch, int32_t frames,
+    const int64_t* frame_lengths_host,
+    const int64_t* word_bounds_host, const int64_t* word_lengths_host, int32_t wmax,
+    void* workspace, long long workspace_bytes, float* logits, void* stream);
+int emph_train_backward(
+    const emph_train_model* model, const float* grad_logits, int32_t batch, int32_t frames,
+    const int64_t* frame_lengths_host,
+    int32_t wmax, void* workspace, long long workspace_bytes, float* const* grads,
+    int32_t accumulate, void* stream);
+
+/*
  * Word -> frame interpolation (emphases/core.py:472-544 `upsample`) on the
  * reference's layouts: xs (B, C, Wmax) fp32, bounds (B, 2, Wmax) int64,
  * lengths int64 -> out (B, C, Tmax), zero past frame_lengths[b].  linear != 0:

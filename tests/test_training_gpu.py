@@ -209,3 +209,59 @@ def test_gradients_other_locations(emphases, golden, location):
         got = parameter.grad.cpu()
         scale = want.abs().max().item() + 1e-12
         assert (got - want).abs().max().item() < 2e-4 * scale + 1e-7, name
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16x6', 'bf16x3+bf16x6'])
+def test_native_step_matches_per_kernel_path(emphases, golden, precision):
+    """csrc/train_step.cu (one call per forward / backward) against the
+    per-kernel Python orchestration it replaces: same logits and gradients
+    (fp32: the same kernels in the same order; the tensor-core modes within
+    their forward tolerance), gradients land in ONE flat buffer the .grad
+    tensors alias, and a second backward without zero_grad accumulates"""
+    from emphases_b200 import training
+    state = state_from_golden(golden('sweep'))
+    batch = padded_batch(seed=5)
+    features, frame_lengths, bounds, word_lengths, targets = batch
+    results = {}
+    for name in ('native', 'kernels'):
+        model = emphases.Model()
+        model.load_state_dict({k: v for k, v in state.items() if k in model.state_dict()})
+        model = model.cuda().train()
+        if name == 'native':
+            training.TRAIN_PRECISION = precision
+            assert training.native_step_supported(model, features.cuda())
+            scores = model(features.cuda(), frame_lengths, bounds, word_lengths)
+        else:
+            scores = training._ConvModelFunction.apply(
+                model, features.cuda(), bounds, word_lengths, *model.parameters())
+        value = emphases.loss(
+            scores, targets.cuda(), frame_lengths, bounds, word_lengths, training=True)
+        value.backward()
+        results[name] = (scores.detach(), {n: p.grad.clone() for n, p in model.named_parameters()})
+        if name == 'native':
+            native = model
+    tolerance = {'fp32': 1e-6, 'bf16x3': 3e-5, 'bf16x6': 3e-6, 'bf16x3+bf16x6': 3e-5}[precision]
+    # (bf16x3's 16-bit operands: 1e-5 class logits, but up to 2 % on the gradient
+    # of the first layers after thirteen input-gradient convolutions -- which is
+    # why the default is bf16x6)
+    gradient_tolerance = {
+        'fp32': 2e-5, 'bf16x3': 5e-2, 'bf16x6': 1e-4, 'bf16x3+bf16x6': 5e-2}[precision]
+    assert (results['native'][0] - results['kernels'][0]).abs().max() < tolerance
+    for name, want in results['kernels'][1].items():
+        got = results['native'][1][name]
+        scale = want.abs().max().item() + 1e-12
+        assert (got - want).abs().max().item() < gradient_tolerance * scale + 1e-8, name
+    # every .grad is a slice of the flat buffer ...
+    flat_state = native._native_train_state
+    assert all(flat_state.aliases_flat(p, i) for i, p in enumerate(flat_state.ordered))
+    assert len(flat_state.ordered) == len(list(native.parameters()))
+    # ... and a second backward accumulates into it
+    scores = native(features.cuda(), frame_lengths, bounds, word_lengths)
+    emphases.loss(
+        scores, targets.cuda(), frame_lengths, bounds, word_lengths, training=True).backward()
+    training.TRAIN_PRECISION = 'bf16x6'
+    for name, parameter in native.named_parameters():
+        want = 2 * results['native'][1][name]
+        scale = want.abs().max().item() + 1e-12
+        # (float atomics in the weight-gradient kernel: sums agree to rounding)
+        assert (parameter.grad - want).abs().max().item() < 1e-5 * scale + 1e-9, name
