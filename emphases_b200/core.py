@@ -82,6 +82,7 @@ def from_files_to_files(
     if output_prefixes is None:
         output_prefixes = [Path(file).stem for file in text_files]
     text_files = [os.fspath(file) for file in text_files]
+    audio_files = [os.fspath(file) for file in audio_files]
     if any(file.endswith('.txt') for file in text_files):
         raise NotImplementedError(
             'Transcript (.txt) inputs need forced alignment with pyfoal/HTK '
@@ -103,6 +104,8 @@ def from_files_to_files(
             key=lambda rate: rate != emphases.SAMPLE_RATE)
         scores = [None] * len(text_files)
         failure = []
+        single_device = not (isinstance(gpu, (list, tuple)) and len(gpu) > 1)
+        flat_results = []       # (file indices, flat host scores, words per file)
 
         def write_alignments():
             try:
@@ -125,6 +128,18 @@ def from_files_to_files(
                         gpu[0] if isinstance(gpu, (list, tuple)) and gpu else gpu)
                     packed = resampling.resample_packed(
                         packed, rate, emphases.SAMPLE_RATE, device)
+                if single_device:
+                    # per launch: the words of its files in one flat host tensor
+                    # (no 24,000-way split: the native writer takes pointers)
+                    for members, flat_scores, counts in from_alignments_and_audio(
+                        times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size,
+                        gpu, flat=True
+                    ):
+                        files = indices[np.asarray(members, dtype=np.int64)]
+                        flat_results.append((files, flat_scores, counts))
+                        for index in files:
+                            scores[int(index)] = True
+                    continue
                 results = from_alignments_and_audio(
                     times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size, gpu)
                 for index, result in zip(indices, results):
@@ -137,10 +152,14 @@ def from_files_to_files(
         indices = np.nonzero(parsable)[0]
 
     # {prefix}.pt: same archives torch.save would write, from the native pool
-    done = [int(i) for i in indices]
-    corpus.write_scores(
-        [f'{output_prefixes[i]}.pt' for i in done], [scores[i] for i in done],
-        workers)
+    for files, flat_scores, counts in flat_results:
+        corpus.write_score_rows(
+            [f'{output_prefixes[int(i)]}.pt' for i in files], flat_scores, counts, workers)
+    done = [int(i) for i in indices if scores[int(i)] is not True]
+    if done:
+        corpus.write_scores(
+            [f'{output_prefixes[i]}.pt' for i in done], [scores[i] for i in done],
+            workers)
 
     # Everything else (other encodings / sample rates) goes file by file
     first_gpu = gpu[0] if isinstance(gpu, (list, tuple)) and gpu else gpu
@@ -210,14 +229,18 @@ def from_alignments_and_audio(
     batch_size=None,
     gpu=None,
     to_cpu=True,
-    model=None
+    model=None,
+    flat=False
 ):
     """Batched form of from_alignment_and_audio (extension): lists in, list
     of (1, W_i) score tensors out.  `gpu` may be a list of device indices:
     utterances are split with the length-balanced scheduler and each shard
-    runs on its own device; results are gathered on the host."""
+    runs on its own device; results are gathered on the host.  flat=True
+    (one device): scheduler.run_on_device's unsplit per-launch results."""
     from . import scheduler
     if isinstance(gpu, (list, tuple)) and len(gpu) > 1:
+        if flat:
+            raise ValueError('flat results are a single-device form')
         return scheduler.run_sharded(
             alignments, audios, sample_rate, checkpoint, batch_size, list(gpu))
     if isinstance(gpu, (list, tuple)):
@@ -227,7 +250,8 @@ def from_alignments_and_audio(
         model = load_model(checkpoint, device)
     with torch.cuda.device(device):
         return scheduler.run_on_device(
-            model, alignments, audios, sample_rate, batch_size, device, to_cpu)
+            model, alignments, audios, sample_rate, batch_size, device, to_cpu,
+            flat=flat)
 
 
 ###############################################################################

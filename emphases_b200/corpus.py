@@ -13,8 +13,16 @@ import torch
 from . import _lib, scheduler
 
 
+def _encode(path):
+    # (os.fsencode costs ~1 us per path through its fspath / type checks; a
+    # corpus has tens of thousands)
+    if type(path) is str:
+        return path.encode('utf-8', 'surrogateescape')
+    return os.fsencode(path)
+
+
 def _paths(paths):
-    encoded = [os.fsencode(path) for path in paths]
+    encoded = [_encode(path) for path in paths]
     array = (ctypes.c_char_p * len(encoded))(*encoded)
     return array, encoded          # keep `encoded` alive with the array
 
@@ -74,7 +82,7 @@ class Corpus:
             mask &= self.sample_rate == sample_rate
         return mask
 
-    def load(self, mask, pin=True, group_samples=1 << 25):
+    def load(self, mask, pin=True, group_samples=1 << 26):
         """(indices, word-time arrays, PackedAudio[int16]) of the files
         selected by `mask` (compact: entry j belongs to file indices[j]).
 
@@ -143,11 +151,34 @@ class Corpus:
 
     def write_textgrids(self, output_paths, mask):
         encoded = [
-            os.fsencode(path) if m else b''
+            _encode(path) if m else b''
             for path, m in zip(output_paths, mask)]
         array = (ctypes.c_char_p * len(encoded))(*encoded)
         if self.lib.emph_corpus_write_textgrids(self.handle, array, self.threads):
             raise OSError('could not write some TextGrid files')
+
+
+def write_score_rows(paths, flat_scores, counts, threads=None):
+    """torch.save(row_i[None], paths[i]) where row i is the next counts[i]
+    values of ONE flat fp32 host tensor: no per-file tensor objects"""
+    lib = _lib.load()
+    flat_scores = flat_scores.detach()
+    if flat_scores.device.type != 'cpu' or flat_scores.dtype != torch.float32 \
+            or not flat_scores.is_contiguous():
+        flat_scores = flat_scores.to(device='cpu', dtype=torch.float32).contiguous()
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    if int(counts.sum()) != flat_scores.numel() or len(counts) != len(paths):
+        raise ValueError('write_score_rows: counts do not match the scores')
+    starts = np.concatenate([[0], np.cumsum(counts[:-1], dtype=np.int64)]) \
+        if len(counts) else np.zeros(0, dtype=np.int64)
+    pointers = (flat_scores.data_ptr() + 4 * starts).astype(np.uint64)
+    array, keep = _paths(paths)
+    threads = threads or min(32, os.cpu_count() or 1)
+    if lib.emph_write_score_rows(
+        array, pointers.ctypes.data, counts.ctypes.data, len(paths), threads
+    ):
+        raise OSError('could not write some score files')
+    del keep
 
 
 def write_scores(paths, scores, threads=None):

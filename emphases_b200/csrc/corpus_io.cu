@@ -19,6 +19,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -345,6 +348,98 @@ bool write_score_file(const char* path, const float* values, uint32_t count) {
     return (std::fclose(f) == 0) && ok;
 }
 
+// A process-wide pool of worker threads: the corpus calls arrive in bursts of
+// hundreds (a fill per group of files, writers per launch), and spawning 24
+// threads for each costs about a millisecond.  One job runs at a time; callers
+// are serialised on `submit`.
+class WorkerPool {
+public:
+    static WorkerPool& instance() {
+        static WorkerPool pool;
+        return pool;
+    }
+    // run body(i) for i in [0, n) on up to n_threads workers (the caller helps)
+    void run(int n, int n_threads, const std::function<void(int)>& body) {
+        if (n <= 0) return;
+        std::lock_guard<std::mutex> submit_lock(submit_);
+        if (n_threads < 1) n_threads = 1;
+        if (n_threads > n) n_threads = n;
+        grow(n_threads - 1);
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            body_ = &body;
+            count_ = n;
+            next_.store(0);
+            wanted_ = n_threads - 1;
+            started_ = 0;
+            pending_ = n_threads - 1;
+            ++generation_;
+        }
+        wake_.notify_all();
+        for (int i = next_.fetch_add(1); i < n; i = next_.fetch_add(1)) body(i);
+        std::unique_lock<std::mutex> lock(mutex_);
+        done_.wait(lock, [&] { return pending_ == 0; });
+        body_ = nullptr;
+    }
+
+private:
+    WorkerPool() = default;
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            stop_ = true;
+            ++generation_;
+        }
+        wake_.notify_all();
+        for (auto& thread : threads_) thread.join();
+    }
+    void grow(int workers) {
+        while ((int)threads_.size() < workers) {
+            const int index = (int)threads_.size();
+            threads_.emplace_back([this, index] { loop(index); });
+        }
+    }
+    void loop(int index) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* body;
+            int count;
+            {
+                std::unique_lock<std::mutex> lock(mutex_);
+                wake_.wait(lock, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+                if (started_ >= wanted_) continue;     // this job needs fewer workers
+                ++started_;
+                body = body_;
+                count = count_;
+            }
+            for (int i = next_.fetch_add(1); i < count; i = next_.fetch_add(1)) (*body)(i);
+            {
+                std::lock_guard<std::mutex> lock(mutex_);
+                --pending_;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex submit_, mutex_;
+    std::condition_variable wake_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)>* body_ = nullptr;
+    std::atomic<int> next_{0};
+    int count_ = 0, wanted_ = 0, started_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+
+// many short calls (a fill per group of files, a writer per launch): the pool
+template <typename Fn>
+void pooled_for(int n, int n_threads, Fn fn) {
+    const std::function<void(int)> body = fn;
+    WorkerPool::instance().run(n, n_threads, body);
+}
+
+// one long call (it may run beside a pooled one): its own threads
 template <typename Fn>
 void parallel_for(int n, int n_threads, Fn fn) {
     if (n_threads < 1) n_threads = 1;
@@ -406,7 +501,7 @@ int emph_corpus_fill_files(
     if (!corpus || n_indices < 0 || (n_indices > 0 && !file_indices)) return EMPH_EINVAL;
     const int n_files = (int)corpus->files.size();
     std::atomic<int> failures(0);
-    parallel_for(n_indices, n_threads, [&](int k) {
+    pooled_for(n_indices, n_threads, [&](int k) {
         const int i = file_indices[k];
         if (i < 0 || i >= n_files) { ++failures; return; }
         FileEntry& e = corpus->files[i];
@@ -550,7 +645,7 @@ int emph_write_score_rows(
     int32_t n_files, int32_t n_threads) {
     if (n_files < 0 || (n_files > 0 && (!paths || !rows || !counts))) return EMPH_EINVAL;
     std::atomic<int> failures(0);
-    parallel_for(n_files, n_threads, [&](int i) {
+    pooled_for(n_files, n_threads, [&](int i) {
         if (paths[i] == nullptr || paths[i][0] == 0) return;
         if (counts[i] < 0 || (counts[i] > 0 && !rows[i]) ||
             !write_score_file(paths[i], rows[i], (uint32_t)counts[i]))

@@ -301,12 +301,15 @@ def _prepare(audios, sample_rate, device=None):
 
 def run_on_device(
     model, alignments, audios, sample_rate, batch_size, device, to_cpu=True,
-    output='scores'
+    output='scores', flat=False
 ):
     """Run a list of utterances on one device; returns a list of (1, W_i)
     score tensors (CPU when to_cpu, else on `device`).  output='logits'
     returns the network output before postprocessing (the evaluation caller,
-    emphases/evaluate/core.py:73-94)."""
+    emphases/evaluate/core.py:73-94).  flat=True (host results only) skips the
+    per-utterance split: a list of (utterance indices, flat fp32 host tensor
+    of their words in order, words per utterance), one entry per launch --
+    what the native .pt writer of from_files_to_files consumes."""
     if output not in ('scores', 'logits'):
         raise ValueError(f'output {output} is not defined')
     emphases.require_mel_features_only()
@@ -393,18 +396,22 @@ def run_on_device(
         torch.cuda.current_stream(device).synchronize()
 
     outputs = [None] * len(alignments)
+    launches_flat = []
     for members, plan, scores in pending:
         # word rows without separators are all words of all utterances in order
         keep = torch.from_numpy(np.nonzero(plan.word_seq >= 0)[0])
         # (indexing copies, so the pinned staging buffer can be reused)
-        flat = scores[keep.to(scores.device)] if len(keep) else scores[:0].clone()
+        flat_scores = scores[keep.to(scores.device)] if len(keep) else scores[:0].clone()
         per_utterance = np.bincount(
             plan.utterance, weights=plan.n_words, minlength=len(members)
         ).astype(np.int64)
-        pieces = torch.split(flat, per_utterance.tolist())
+        if flat:
+            launches_flat.append((members, flat_scores, per_utterance))
+            continue
+        pieces = torch.split(flat_scores, per_utterance.tolist())
         for index, piece in zip(members, pieces):
             outputs[index] = piece[None]
-    return outputs
+    return launches_flat if flat else outputs
 
 
 def _run_via_model(

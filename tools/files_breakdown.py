@@ -1,32 +1,38 @@
-"""Time emphases_b200.from_files_to_files on an on-disk synthetic corpus"""
-import os, sys, time, tempfile, cProfile, pstats
+"""Where the time of emphases_b200.from_files_to_files goes: wall time and a
+cProfile of one call on bench.py's on-disk corpus (files x copies)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
 import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import emphases_b200 as emphases
-from pathlib import Path
 
-count = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-lengths, times = bench.corpus_layout(count, 77)
-root = Path(tempfile.mkdtemp(dir='/dev/shm' if os.path.isdir('/dev/shm') else None))
-generator = torch.Generator().manual_seed(0)
-text_files, audio_files, prefixes = [], [], []
-t0 = time.perf_counter()
-for i, (n, t) in enumerate(zip(lengths, times)):
-    audio = (0.1 * torch.randn(1, int(n), generator=generator)).clamp(-1, 1)
-    emphases.load.save_wav(root / f'u{i}.wav', audio)
-    emphases.Alignment.from_times([tuple(x) for x in t.tolist()]).save(root / f'u{i}.TextGrid')
-    text_files.append(root / f'u{i}.TextGrid'); audio_files.append(root / f'u{i}.wav')
-    prefixes.append(root / 'out' / f'u{i}')
-(root / 'out').mkdir()
-print(f'wrote {count} files in {time.perf_counter()-t0:.1f}s, audio {lengths.sum()/16000:.0f}s')
-state = bench.random_state(); emphases.configure(PRECISION='bf16')
-ckpt = root / 'ckpt.pt'; torch.save({'model': state}, ckpt)
-for rep in range(3):
-    t0 = time.perf_counter()
-    emphases.from_files_to_files(text_files, audio_files, prefixes, checkpoint=ckpt, gpu=0)
-    dt = time.perf_counter() - t0
-    print(f'from_files_to_files: {dt*1e3:.0f} ms = {lengths.sum()/16000/dt:.0f} audio-s/s, {dt/count*1e3:.2f} ms/file')
-pr = cProfile.Profile(); pr.enable()
-emphases.from_files_to_files(text_files, audio_files, prefixes, checkpoint=ckpt, gpu=0)
-pr.disable(); pstats.Stats(pr).sort_stats('cumulative').print_stats(14)
+count = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+copies = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+state = bench.random_state()
+emphases.configure(PRECISION='bf16')
+root = bench.corpus_root() + '_breakdown'
+text, audio, prefixes, checkpoint, seconds, words, samples = bench.build_corpus(
+    emphases, root, count, copies, state)
+try:
+    for rep in range(3):
+        t0 = time.perf_counter()
+        emphases.from_files_to_files(text, audio, prefixes, checkpoint=checkpoint, gpu=0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(f'from_files_to_files: {dt * 1e3:.0f} ms = {seconds / dt:.0f} audio-s/s, '
+              f'{dt / len(text) * 1e3:.3f} ms/file')
+    profile = cProfile.Profile()
+    profile.enable()
+    emphases.from_files_to_files(text, audio, prefixes, checkpoint=checkpoint, gpu=0)
+    torch.cuda.synchronize()
+    profile.disable()
+    pstats.Stats(profile).sort_stats('cumulative').print_stats(40)
+finally:
+    import shutil
+    shutil.rmtree(root, ignore_errors=True)
