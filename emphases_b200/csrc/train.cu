@@ -346,8 +346,11 @@ int conv1d_weight_grad(
         if (s != EMPH_OK) return s;
     }
     if (total_rows == 0) return EMPH_OK;
+    // one CTA per SM: every CTA ends with 19,280 atomics on the same addresses,
+    // and halving their number beats the second CTA's latency hiding (measured:
+    // 2.015 / 2.049 / 2.20 / 2.36 ms per training step at 1 / 2 / 3 / 4 CTAs per SM)
     int grid = (total_rows + 63) / 64;
-    if (grid > sm_count() * 2) grid = sm_count() * 2;
+    if (grid > sm_count()) grid = sm_count();
     conv_weight_grad_kernel<80, 3, true><<<grid, 256, 0, st>>>(
         x, dpre, total_rows, grad_weight, grad_bias);
     EMPH_CHECK_LAUNCH("conv1d_weight_grad");
