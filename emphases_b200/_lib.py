@@ -29,6 +29,10 @@ SIGNATURES = {
     'emph_row_index': [_P, _P, _I, _P, _I, _P],
     'emph_logmel_f32': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
     'emph_logmel_i16': [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P],
+    'emph_logmel_resampled_f32': [
+        _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P],
+    'emph_logmel_resampled_i16': [
+        _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P],
     'emph_conv_stack': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'emph_conv_stack_pool': [
         _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],

@@ -123,7 +123,11 @@ def from_files_to_files(
             for rate in rates:
                 indices, times, packed = parsed.load(
                     parsable & (parsed.sample_rate == rate))
-                if rate != emphases.SAMPLE_RATE:
+                if rate != emphases.SAMPLE_RATE and single_device:
+                    # converted inside the log-mel kernel, launch by launch
+                    from . import scheduler
+                    packed = scheduler.ResampledSource(packed, rate)
+                elif rate != emphases.SAMPLE_RATE:
                     device = emphases.resolve_device(
                         gpu[0] if isinstance(gpu, (list, tuple)) and gpu else gpu)
                     packed = resampling.resample_packed(

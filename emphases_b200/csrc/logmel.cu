@@ -249,19 +249,53 @@ __device__ __forceinline__ float to_float<int16_t>(int16_t v) {
     return (float)v * (1.f / 32768.f);
 }
 
+// Sample-rate conversion fused into the front end (emphases/core.py:613-619:
+// the reference resamples with torchaudio.transforms.Resample before anything
+// else).  With it the packed `audio` is at the SOURCE rate and sample n of an
+// utterance at the model rate is the polyphase windowed-sinc sum
+//   y[q * fresh + p] = sum_k filter[p][k] * x[q * orig - width + k]
+// over the taps whose filter value is not zero (tap_lo[p] .. tap_hi[p]), the
+// same sum in the same order as csrc/resample.cu -- bit-identical samples,
+// which then never exist in HBM.
+struct Resampler {
+    const float* filter;          // [fresh][taps], resampling.filter_bank
+    const int32_t* tap_lo;        // [fresh] first tap with a non-zero value
+    const int32_t* tap_hi;        // [fresh] one past the last one
+    const int32_t* source_len;    // [n_seq] samples of the sequence's utterance at the source rate
+    int orig, fresh, width, taps;
+};
+
+template <typename T>
+__device__ __forceinline__ float resampled_sample(
+    const Resampler& rs, const T* __restrict__ src, int src_len, int n) {
+    const int q = n / rs.fresh, p = n - q * rs.fresh;
+    const float* __restrict__ w = rs.filter + (size_t)p * rs.taps;
+    const long long first = (long long)q * rs.orig - rs.width;      // source index of tap 0
+    long long k0 = __ldg(rs.tap_lo + p), k1 = __ldg(rs.tap_hi + p);
+    if (-first > k0) k0 = -first;
+    if ((long long)src_len - first < k1) k1 = (long long)src_len - first;
+    float acc = 0.f;
+    for (long long k = k0; k < k1; ++k)
+        acc = fmaf(__ldg(w + k), to_float<T>(__ldg(src + first + k)), acc);
+    return acc;
+}
+
 // Sample q of the reflect-padded chunk, through the whole index map
 // (SURVEY.md A.2): chunk[j] = P[s + j], P = zeros(432) ++ audio ++ zeros(432)
-template <typename T>
+template <typename T, bool RESAMPLE>
 __device__ __forceinline__ float chunk_sample(
-    const T* __restrict__ audio, int T_len, int s, int L, int q) {
+    const T* __restrict__ audio, int T_len, int s, int L, int q, const Resampler& rs,
+    int src_len) {
     int j = q - kPad;
     if (j < 0) j = -j;
     if (j >= L) j = 2 * (L - 1) - j;
     int a = s + j - kPad;
-    return (a >= 0 && a < T_len) ? to_float<T>(audio[a]) : 0.f;
+    if (!(a >= 0 && a < T_len)) return 0.f;
+    if constexpr (RESAMPLE) return resampled_sample<T>(rs, audio, src_len, a);
+    else return to_float<T>(audio[a]);
 }
 
-template <typename T>
+template <typename T, bool RESAMPLE>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 logmel_kernel(
     const T* __restrict__ audio,
@@ -271,7 +305,7 @@ logmel_kernel(
     const int32_t* __restrict__ row_seq, int total_rows,
     const int32_t* __restrict__ mel_ptr, const int16_t* __restrict__ mel_col,
     const float* __restrict__ mel_val, int n_mels, int normalize,
-    float* __restrict__ out) {
+    float* __restrict__ out, Resampler rs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LogmelSmem& sm = *reinterpret_cast<LogmelSmem*>(smem_raw);
 
@@ -432,8 +466,10 @@ logmel_kernel(
                 const bool ok =
                     q0 >= kPad && q0 + kSpan - kPad <= __ldg(chunk_len + u) &&
                     a0 >= 0 && a0 + kSpan <= __ldg(audio_len + u) &&
-                    (reinterpret_cast<uintptr_t>(audio + index) & 15) == 0;
-                if (ok) desc = index;
+                    (RESAMPLE || (reinterpret_cast<uintptr_t>(audio + index) & 15) == 0);
+                // (resampling variant: the tile's samples are computed, not copied:
+                // sequence and first model-rate sample)
+                if (ok) desc = RESAMPLE ? ((long long)u << 32) | (unsigned)a0 : index;
             }
         }
         if (tid < kRound) sm.tile_src[tid] = desc;
@@ -441,7 +477,7 @@ logmel_kernel(
     if (tid == 0) mbar_init(&sm.bar, 1);
     describe_round(0);
     __syncthreads();
-    if (tid == 0 && sm.tile_src[0] >= 0)
+    if (!RESAMPLE && tid == 0 && sm.tile_src[0] >= 0)
         bulk_fetch(sm.stage, audio + sm.tile_src[0], kSpan * sizeof(T), &sm.bar);
     uint32_t parity = 0;
     int it = 0;
@@ -450,8 +486,21 @@ logmel_kernel(
         const int row0 = tile * kTile;
         const bool staged = sm.tile_src[it & (kRound - 1)] >= 0;
         if (staged) {
-            mbar_wait(&sm.bar, parity);
-            parity ^= 1;
+            if constexpr (RESAMPLE) {
+                // the tile's 3424 model-rate samples, resampled cooperatively into
+                // the stage (the previous tile's FFT phase is long over)
+                const long long desc = sm.tile_src[it & (kRound - 1)];
+                const int u = (int)(desc >> 32), a0 = (int)(desc & 0xffffffffLL);
+                const T* src = audio + __ldg(audio_off + u);
+                const int src_len = __ldg(rs.source_len + u);
+                float* stage = reinterpret_cast<float*>(sm.stage);
+                for (int i = tid; i < kSpan; i += blockDim.x)
+                    stage[i] = resampled_sample<T>(rs, src, src_len, a0 + i);
+                __syncthreads();
+            } else {
+                mbar_wait(&sm.bar, parity);
+                parity ^= 1;
+            }
         }
 
         // ======================= phase 1: FFT + magnitude =======================
@@ -461,11 +510,11 @@ logmel_kernel(
             // pass 1: lane handles butterflies j = 2 lane (v0) and 2 lane + 1 (v1);
             // inputs z[j + 64 r], so one 16-byte load brings both butterflies' inputs
             C2 v0[8], v1[8];
-            auto load_run = [&](const T* p) {    // 1024 contiguous samples
+            auto load_run = [&](auto* p) {    // 1024 contiguous samples
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int n = 4 * lane + 128 * r;
-                    if constexpr (sizeof(T) == 4) {
+                    if constexpr (sizeof(*p) == 4) {
                         const float4 x = *reinterpret_cast<const float4*>(p + n);
                         v0[r] = C2{x.x, x.y};
                         v1[r] = C2{x.z, x.w};
@@ -477,7 +526,10 @@ logmel_kernel(
                 }
             };
             if (staged) {
-                load_run(reinterpret_cast<const T*>(sm.stage) + f * kHop);
+                if constexpr (RESAMPLE)
+                    load_run(reinterpret_cast<const float*>(sm.stage) + f * kHop);
+                else
+                    load_run(reinterpret_cast<const T*>(sm.stage) + f * kHop);
             } else {
                 const int row = row0 + f;
                 if (row >= total_rows) break;
@@ -490,8 +542,9 @@ logmel_kernel(
                 const T* src = audio + __ldg(audio_off + u);
                 const int q0 = frame * kHop;            // first sample in reflect-padded coords
                 const int a0 = s + q0 - 2 * kPad;       // audio index of sample q0
-                const bool interior = (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
+                const bool interior = !RESAMPLE && (q0 >= kPad) && (q0 + kFft - kPad <= L) &&
                                       (a0 >= 0) && (a0 + kFft <= T_len);
+                const int src_len = RESAMPLE ? __ldg(rs.source_len + u) : 0;
                 if (interior) {
                     load_run(src + a0);
                 } else {
@@ -499,11 +552,11 @@ logmel_kernel(
                     for (int r = 0; r < 8; ++r) {
                         const int n = q0 + 4 * lane + 128 * r;
                         v0[r] = C2{
-                            chunk_sample<T>(src, T_len, s, L, n),
-                            chunk_sample<T>(src, T_len, s, L, n + 1)};
+                            chunk_sample<T, RESAMPLE>(src, T_len, s, L, n, rs, src_len),
+                            chunk_sample<T, RESAMPLE>(src, T_len, s, L, n + 1, rs, src_len)};
                         v1[r] = C2{
-                            chunk_sample<T>(src, T_len, s, L, n + 2),
-                            chunk_sample<T>(src, T_len, s, L, n + 3)};
+                            chunk_sample<T, RESAMPLE>(src, T_len, s, L, n + 2, rs, src_len),
+                            chunk_sample<T, RESAMPLE>(src, T_len, s, L, n + 3, rs, src_len)};
                     }
                 }
             }
@@ -625,7 +678,7 @@ logmel_kernel(
             describe_round(it + 1);
             __syncthreads();
         }
-        if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
+        if (!RESAMPLE && tid == 0 && tile + (int)gridDim.x < n_tiles) {
             const long long next = sm.tile_src[(it + 1) & (kRound - 1)];
             if (next >= 0) bulk_fetch(sm.stage, audio + next, kSpan * sizeof(T), &sm.bar);
         }
@@ -705,7 +758,7 @@ logmel_kernel(
     }
 }
 
-template <typename T>
+template <typename T, bool RESAMPLE>
 int launch_logmel(
     const T* audio,
     const int64_t* audio_off, const int32_t* audio_len,
@@ -713,23 +766,42 @@ int launch_logmel(
     const int32_t* row_start, int32_t n_seq,
     const int32_t* row_seq, int32_t total_rows,
     const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
-    int32_t n_mels, int32_t normalize, float* out, void* stream) {
+    int32_t n_mels, int32_t normalize, float* out, void* stream,
+    Resampler rs = Resampler{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0}) {
     EMPH_REQUIRE(n_seq >= 0 && total_rows >= 0, "emph_logmel: negative size");
     EMPH_REQUIRE(n_mels > 0 && n_mels <= kMaxMels, "emph_logmel: n_mels %d out of range", n_mels);
     if (total_rows == 0) return EMPH_OK;
     const size_t smem = sizeof(LogmelSmem);
     int s = check_cuda(
         cudaFuncSetAttribute(
-            logmel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            logmel_kernel<T, RESAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
         "logmel smem attribute");
     if (s != EMPH_OK) return s;
     const int n_tiles = (total_rows + kTile - 1) / kTile;
     const int grid = n_tiles < 2 * sm_count() ? n_tiles : 2 * sm_count();
-    logmel_kernel<T><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
+    logmel_kernel<T, RESAMPLE><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(
         audio, audio_off, audio_len, chunk_start, chunk_len, row_start,
-        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out);
+        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out, rs);
     EMPH_CHECK_LAUNCH("emph_logmel");
     return EMPH_OK;
+}
+
+template <typename T>
+int launch_logmel_resampled(
+    const T* audio, const int64_t* audio_off, const int32_t* source_len,
+    const int32_t* audio_len, const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    const float* filter, const int32_t* tap_lo, const int32_t* tap_hi,
+    int32_t orig_freq, int32_t new_freq, int32_t width, float* out, void* stream) {
+    EMPH_REQUIRE(filter && tap_lo && tap_hi && source_len, "emph_logmel_resampled: null filter");
+    EMPH_REQUIRE(orig_freq > 0 && new_freq > 0 && width >= 0, "emph_logmel_resampled: bad filter");
+    const Resampler rs{filter, tap_lo, tap_hi, source_len, orig_freq, new_freq, width,
+                       2 * width + orig_freq};
+    return launch_logmel<T, true>(
+        audio, audio_off, audio_len, chunk_start, chunk_len, row_start, n_seq, row_seq,
+        total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out, stream, rs);
 }
 
 }  // namespace emph
@@ -744,7 +816,7 @@ int emph_logmel_f32(
     const int32_t* row_seq, int32_t total_rows,
     const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
     int32_t n_mels, int32_t normalize, float* out, void* stream) {
-    return emph::launch_logmel<float>(
+    return emph::launch_logmel<float, false>(
         audio, audio_off, audio_len, chunk_start, chunk_len, row_start, n_seq,
         row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out, stream);
 }
@@ -757,9 +829,37 @@ int emph_logmel_i16(
     const int32_t* row_seq, int32_t total_rows,
     const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
     int32_t n_mels, int32_t normalize, float* out, void* stream) {
-    return emph::launch_logmel<int16_t>(
+    return emph::launch_logmel<int16_t, false>(
         audio, audio_off, audio_len, chunk_start, chunk_len, row_start, n_seq,
         row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, out, stream);
+}
+
+int emph_logmel_resampled_f32(
+    const float* audio, const int64_t* audio_off, const int32_t* source_len,
+    const int32_t* audio_len, const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    const float* filter, const int32_t* tap_lo, const int32_t* tap_hi,
+    int32_t orig_freq, int32_t new_freq, int32_t width, float* out, void* stream) {
+    return emph::launch_logmel_resampled<float>(
+        audio, audio_off, source_len, audio_len, chunk_start, chunk_len, row_start, n_seq,
+        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, filter, tap_lo,
+        tap_hi, orig_freq, new_freq, width, out, stream);
+}
+
+int emph_logmel_resampled_i16(
+    const int16_t* audio, const int64_t* audio_off, const int32_t* source_len,
+    const int32_t* audio_len, const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    const float* filter, const int32_t* tap_lo, const int32_t* tap_hi,
+    int32_t orig_freq, int32_t new_freq, int32_t width, float* out, void* stream) {
+    return emph::launch_logmel_resampled<int16_t>(
+        audio, audio_off, source_len, audio_len, chunk_start, chunk_len, row_start, n_seq,
+        row_seq, total_rows, mel_ptr, mel_col, mel_val, n_mels, normalize, filter, tap_lo,
+        tap_hi, orig_freq, new_freq, width, out, stream);
 }
 
 }  // extern "C"

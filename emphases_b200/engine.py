@@ -663,10 +663,30 @@ class Engine:
             _lib.ptr(row_seq), total_rows, _lib.stream_ptr())
         return row_seq
 
-    def logmel(self, audio, views, plan, row_seq, normalize=False, ws=None):
+    def logmel(self, audio, views, plan, row_seq, normalize=False, ws=None,
+               resample=None):
+        """resample: None, or the fused sample-rate conversion -- `audio` is then
+        packed at the source rate and `resample` holds the device filter bank
+        (resampling.device_bank) plus per-sequence `source_off` (int64) and
+        `source_len` (int32) in source samples; the plan stays in 16 kHz samples"""
         out = _empty(
             ws, 'features', (plan.total_rows, self.n_mels), torch.float32,
             self.device)
+        if resample is not None:
+            name = {torch.float32: 'emph_logmel_resampled_f32',
+                    torch.int16: 'emph_logmel_resampled_i16'}[audio.dtype]
+            bank = resample['bank']
+            _lib.call(
+                name, _lib.ptr(audio), _lib.ptr(resample['source_off']),
+                _lib.ptr(resample['source_len']), _lib.ptr(views['audio_len']),
+                _lib.ptr(views['chunk_start']), _lib.ptr(views['chunk_len']),
+                _lib.ptr(views['row_start']), plan.n_seq, _lib.ptr(row_seq),
+                plan.total_rows, _lib.ptr(self.mel_ptr), _lib.ptr(self.mel_col),
+                _lib.ptr(self.mel_val), self.n_mels, int(bool(normalize)),
+                _lib.ptr(bank['filter']), _lib.ptr(bank['tap_lo']),
+                _lib.ptr(bank['tap_hi']), bank['orig'], bank['new'], bank['width'],
+                _lib.ptr(out), _lib.stream_ptr())
+            return out
         name = {torch.float32: 'emph_logmel_f32', torch.int16: 'emph_logmel_i16'}[
             audio.dtype]
         _lib.call(
@@ -795,21 +815,23 @@ class Engine:
         views=None,
         keep=False,
         timers=None,
-        ws=None
+        ws=None,
+        resample=None
     ):
         """audio: packed device tensor (fp32 or int16).  Returns dict with
-        `scores` and `logits` per packed word row (device tensors)."""
+        `scores` and `logits` per packed word row (device tensors).
+        resample: see Engine.logmel."""
         if location not in ('intermediate', 'loss', 'inference'):
             raise ValueError(
                 f'Downsample location {location} not handled by the packed path')
         with _lib.same_stream():
             return self._forward_packed(
                 audio, plan, weights, method, location, precision, head_mode,
-                normalize, views, keep, timers, ws)
+                normalize, views, keep, timers, ws, resample)
 
     def _forward_packed(
         self, audio, plan, weights, method, location, precision, head_mode,
-        normalize, views, keep, timers, ws
+        normalize, views, keep, timers, ws, resample=None
     ):
         if views is None:
             views = self.upload_plan(plan)
@@ -834,7 +856,7 @@ class Engine:
             views['word_row_start'], views['n_words'], plan.n_seq,
             plan.total_word_rows, ws, 'word_row_seq'))
         features = timed('logmel', lambda: self.logmel(
-            audio, views, plan, row_seq, normalize, ws))
+            audio, views, plan, row_seq, normalize, ws, resample))
         transformer_variant = hasattr(weights, 'input_layer')
         pooled = None
         if transformer_variant:

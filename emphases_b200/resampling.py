@@ -42,6 +42,35 @@ def filter_bank(orig_freq, new_freq):
 
 
 _device_banks = {}
+_fused_banks = {}
+
+
+def device_bank(sample_rate, target_rate, device):
+    """The filter bank on `device` in the form the fused log-mel front end
+    takes (csrc/logmel.cu, emph_logmel_resampled_*): the kernels plus, per
+    output phase, the range of taps that are not exactly zero (the Hann window
+    of torchaudio's kernel is zero outside 6 zero crossings, so of the
+    2 * width + orig taps only ~2 * width carry weight)"""
+    key = (int(sample_rate), int(target_rate), torch.device(device))
+    if key not in _fused_banks:
+        kernels, width, orig, new = filter_bank(int(sample_rate), int(target_rate))
+        nonzero = kernels != 0
+        tap_lo = np.where(nonzero.any(1), nonzero.argmax(1), 0).astype(np.int32)
+        tap_hi = np.where(
+            nonzero.any(1), kernels.shape[1] - nonzero[:, ::-1].argmax(1), 0).astype(np.int32)
+        _fused_banks[key] = {
+            'filter': torch.from_numpy(kernels).to(device),
+            'tap_lo': torch.from_numpy(tap_lo).to(device),
+            'tap_hi': torch.from_numpy(tap_hi).to(device),
+            'orig': orig, 'new': new, 'width': width}
+    return _fused_banks[key]
+
+
+def resampled_lengths(lengths, sample_rate, target_rate):
+    """ceil(new * T / orig): the lengths torchaudio's Resample produces"""
+    gcd = math.gcd(int(sample_rate), int(target_rate))
+    orig, new = int(sample_rate) // gcd, int(target_rate) // gcd
+    return -(-(new * np.asarray(lengths, dtype=np.int64)) // orig)
 
 
 def resample(audio, sample_rate, target_rate, device):

@@ -218,6 +218,50 @@ def pack_audio(audios, dtype=torch.float32, pin=True):
     return PackedAudio(buffer, offsets, lengths)
 
 
+class ResampledSource:
+    """A packed corpus at another sample rate, converted on the fly: planning
+    sees the model-rate lengths, every launch uploads the SOURCE samples of its
+    utterances and the log-mel kernel resamples them tile by tile in shared
+    memory (emph_logmel_resampled_*) -- the 16 kHz audio never exists in HBM
+    (the reference resamples utterance by utterance first, core.py:613-619)."""
+
+    def __init__(self, source, sample_rate):
+        from . import resampling
+        self.source = source              # PackedAudio / StreamedPack at `sample_rate`
+        self.sample_rate = int(sample_rate)
+        self.lengths = resampling.resampled_lengths(
+            source.lengths, sample_rate, emphases.SAMPLE_RATE)
+
+    def __len__(self):
+        return len(self.lengths)
+
+    def start(self, launches):
+        if isinstance(self.source, StreamedPack):
+            self.source.start(launches)
+
+    def finish(self):
+        if isinstance(self.source, StreamedPack):
+            self.source.finish()
+
+    def launch_source(self, number, first, last):
+        return self.source.launch_source(number, first, last)
+
+    def launch_resampling(self, members, plan, device):
+        """Per-sequence source offsets (relative to the launch's slice) and
+        lengths for emph_logmel_resampled_*"""
+        from . import resampling
+        first = members[0]
+        base = int(self.source.offsets[first])
+        utterances = np.asarray(members, dtype=np.int64)[plan.utterance]
+        source_off = torch.from_numpy(
+            (self.source.offsets[utterances] - base).astype(np.int64))
+        source_len = torch.from_numpy(self.source.lengths[utterances].astype(np.int32))
+        return {
+            'bank': resampling.device_bank(self.sample_rate, emphases.SAMPLE_RATE, device),
+            'source_off': source_off.to(device, non_blocking=True),
+            'source_len': source_len.to(device, non_blocking=True)}
+
+
 ###############################################################################
 # Length-balanced scheduling
 ###############################################################################
@@ -279,9 +323,11 @@ def bucket_launches(frames: Sequence[int], max_rows: int) -> List[List[int]]:
 
 def _prepare(audios, sample_rate, device=None):
     """A PackedAudio for a list of utterances"""
+    if isinstance(audios, ResampledSource):
+        return audios
     if isinstance(audios, PackedAudio):
         if sample_rate != emphases.SAMPLE_RATE:
-            raise ValueError('PackedAudio must already be at 16 kHz')
+            return ResampledSource(audios, sample_rate)
         return audios
     cuda = [audio for audio in audios if audio.device.type == 'cuda']
     if sample_rate != emphases.SAMPLE_RATE and (cuda or len(audios) < 2):
@@ -290,10 +336,8 @@ def _prepare(audios, sample_rate, device=None):
     if cuda:
         audios = [audio.cpu() for audio in audios]
     if sample_rate != emphases.SAMPLE_RATE:
-        # one packed resampling launch for the whole list
-        from . import resampling
-        return resampling.resample_packed(
-            StreamedPack(audios), sample_rate, emphases.SAMPLE_RATE, device)
+        # resampled inside the log-mel kernel, launch by launch
+        return ResampledSource(StreamedPack(audios), sample_rate)
     if len(audios) > 1:
         return StreamedPack(audios)
     return pack_audio(audios, pin=False)
@@ -337,7 +381,7 @@ def run_on_device(
 
     frames = (packed.lengths + 2 * engine.PADDING) // engine.HOPSIZE
     launches = bucket_launches(frames, emphases.MAX_ROWS_PER_LAUNCH)
-    if isinstance(packed, StreamedPack):
+    if isinstance(packed, (StreamedPack, ResampledSource)):
         packed.start(launches)
     streams = [torch.cuda.current_stream(device)]
     if len(launches) > 1:
@@ -365,11 +409,14 @@ def run_on_device(
                 batch_size,
                 validate_method=method)
             with torch.cuda.stream(stream):
+                resample = packed.launch_resampling(members, plan, device) \
+                    if isinstance(packed, ResampledSource) else None
                 result = eng.forward_packed(
                     device_audio, plan, weights, method=method,
                     location=model.location, precision=precision,
                     head_mode=head_mode, normalize=emphases.NORMALIZE,
-                    views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws)
+                    views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws,
+                    resample=resample)
                 scores = result[output]
                 if not to_cpu:
                     scores = scores.clone()       # the workspace is reused
@@ -382,13 +429,13 @@ def run_on_device(
     except BaseException:
         # an error (e.g. a word without frames) must not leave the background
         # packer writing into staging buffers the next call reuses
-        if isinstance(packed, StreamedPack):
+        if isinstance(packed, (StreamedPack, ResampledSource)):
             packed.finish()
         torch.cuda.synchronize(device)
         raise
     for stream in streams:
         torch.cuda.current_stream(device).wait_stream(stream)
-    if isinstance(packed, StreamedPack):
+    if isinstance(packed, (StreamedPack, ResampledSource)):
         packed.finish()
         # the staging buffers are reused by this thread's next call
         torch.cuda.current_stream(device).synchronize()

@@ -133,6 +133,38 @@ int emph_logmel_i16(
     float* out, void* stream);
 
 /*
+ * emph_logmel_* with the sample-rate conversion of emphases.resample
+ * (emphases/core.py:613-619 -> torchaudio.transforms.Resample) fused into the
+ * front end: `audio` is packed at the SOURCE rate (audio_off / source_len in
+ * source samples per sequence) while audio_len, chunk_start and chunk_len stay
+ * in model-rate (16 kHz) samples, audio_len[u] = ceil(new * source_len / orig).
+ * Every model-rate sample the frames need is the polyphase windowed-sinc sum
+ * of csrc/resample.cu (emph_resample_*: same filter bank, same order, so the
+ * features equal those of resampling first, bit for bit) -- computed tile by
+ * tile in shared memory, never written to HBM.
+ *
+ *   filter      [new_freq][2 * width + orig_freq] fp32 (rates divided by their
+ *               gcd), tap_lo / tap_hi [new_freq]: the range of taps of each
+ *               phase that are not exactly zero
+ */
+int emph_logmel_resampled_f32(
+    const float* audio, const int64_t* audio_off, const int32_t* source_len,
+    const int32_t* audio_len, const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    const float* filter, const int32_t* tap_lo, const int32_t* tap_hi,
+    int32_t orig_freq, int32_t new_freq, int32_t width, float* out, void* stream);
+int emph_logmel_resampled_i16(
+    const int16_t* audio, const int64_t* audio_off, const int32_t* source_len,
+    const int32_t* audio_len, const int32_t* chunk_start, const int32_t* chunk_len,
+    const int32_t* row_start, int32_t n_seq, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* mel_ptr, const int16_t* mel_col, const float* mel_val,
+    int32_t n_mels, int32_t normalize,
+    const float* filter, const int32_t* tap_lo, const int32_t* tap_hi,
+    int32_t orig_freq, int32_t new_freq, int32_t width, float* out, void* stream);
+
+/*
  * A stack of n_layers Conv1d(channels -> channels, kernel_size,
  * padding='same') layers, each followed by its activation, over the packed row
  * axis (emphases/model/core.py:17-20 input_layer + emphases/model/layers/

@@ -702,3 +702,53 @@ def test_fused_pooling_is_packing_invariant(eng, golden):
         start = int(plan.word_row_start[first])
         results.append(pooled[start:].cpu())
     assert torch.equal(results[0], results[1])
+
+
+###############################################################################
+# Sample-rate conversion fused into the log-mel front end
+###############################################################################
+
+
+@pytest.mark.parametrize('dtype', ['f32', 'i16'])
+@pytest.mark.parametrize('rate', [44100, 24000, 8000, 22050])
+def test_logmel_with_fused_resampling_equals_resampling_first(eng, rate, dtype):
+    """emph_logmel_resampled_* on source-rate audio == emph_resample_* followed
+    by emph_logmel_* (bit for bit: same filter bank, same summation order), on
+    a ragged packed corpus with chunk edges, for fp32 and int16 PCM sources"""
+    from emphases_b200 import engine, resampling, scheduler
+    device = torch.device('cuda', 0)
+    generator = torch.Generator().manual_seed(rate)
+    sources, audios, utterances = [], [], []
+    for index, seconds in enumerate([0.37, 1.93, 0.8, 2.71, 0.05]):
+        samples = int(seconds * rate) + index
+        source = (0.1 * torch.randn(1, samples, generator=generator)).clamp(-1, 1)
+        if dtype == 'i16':
+            source = (source * 32768.).round().clamp(-32768, 32767).to(torch.int16)
+        as_float = source.float() / 32768. if dtype == 'i16' else source
+        audio = resampling.resample(as_float, rate, 16000, device).cpu()
+        duration = audio.shape[-1] / 16000.
+        words = max(1, int(3 * duration))
+        edges = np.linspace(0., duration, words + 1)
+        utterances.append((np.stack([edges[:-1], edges[1:]], 1), audio.shape[-1]))
+        sources.append(source)
+        audios.append(audio)
+    plan = engine.make_plan(utterances)
+    views = eng.upload_plan(plan)
+    row_seq = eng.row_index(views['row_start'], views['n_rows'], plan.n_seq, plan.total_rows)
+    packed16 = torch.zeros(plan.audio_samples)
+    for offset, audio in zip(plan.audio_offsets, audios):
+        packed16[offset:offset + audio.shape[-1]] = audio[0]
+    expected = eng.logmel(packed16.cuda(), views, plan, row_seq).clone()
+
+    packed_source = scheduler.pack_audio(sources, dtype=sources[0].dtype, pin=False)
+    lengths16 = resampling.resampled_lengths(packed_source.lengths, rate, 16000)
+    assert [int(n) for n in lengths16] == [a.shape[-1] for a in audios]
+    resample = {
+        'bank': resampling.device_bank(rate, 16000, device),
+        'source_off': torch.from_numpy(
+            packed_source.offsets[plan.utterance].astype(np.int64)).cuda(),
+        'source_len': torch.from_numpy(
+            packed_source.lengths[plan.utterance].astype(np.int32)).cuda()}
+    fused = eng.logmel(
+        packed_source.buffer.cuda(), views, plan, row_seq, resample=resample)
+    assert torch.equal(fused, expected)
