@@ -125,6 +125,12 @@ def load():
     lib.emph_write_score_files.restype = ctypes.c_int
     lib.emph_corpus_open.argtypes = [_P, _P, _I, _I]
     lib.emph_corpus_open.restype = ctypes.c_void_p
+    lib.emph_corpus_open_blob.argtypes = [ctypes.c_char_p, ctypes.c_char_p, _I, _I]
+    lib.emph_corpus_open_blob.restype = ctypes.c_void_p
+    lib.emph_corpus_write_textgrids_blob.argtypes = [_P, ctypes.c_char_p, _P, _I]
+    lib.emph_corpus_write_textgrids_blob.restype = ctypes.c_int
+    lib.emph_write_score_rows_blob.argtypes = [ctypes.c_char_p, _P, _P, _P, _I, _I]
+    lib.emph_write_score_rows_blob.restype = ctypes.c_int
     lib.emph_corpus_info.argtypes = [_P, _P, _P, _P, _P, _P]
     lib.emph_corpus_info.restype = ctypes.c_int
     lib.emph_corpus_error.argtypes = [_P, _I]

@@ -83,6 +83,7 @@ def from_files_to_files(
         output_prefixes = [Path(file).stem for file in text_files]
     text_files = [os.fspath(file) for file in text_files]
     audio_files = [os.fspath(file) for file in audio_files]
+    output_prefixes = [os.fspath(prefix) for prefix in output_prefixes]
     if any(file.endswith('.txt') for file in text_files):
         raise NotImplementedError(
             'Transcript (.txt) inputs need forced alignment with pyfoal/HTK '
@@ -109,8 +110,7 @@ def from_files_to_files(
 
         def write_alignments():
             try:
-                parsed.write_textgrids(
-                    [f'{prefix}.TextGrid' for prefix in output_prefixes], parsable)
+                parsed.write_textgrids_to_prefixes(output_prefixes, parsable)
             except Exception as error:      # re-raised on the caller's thread
                 failure.append(error)
 
@@ -158,7 +158,8 @@ def from_files_to_files(
     # {prefix}.pt: same archives torch.save would write, from the native pool
     for files, flat_scores, counts in flat_results:
         corpus.write_score_rows(
-            [f'{output_prefixes[int(i)]}.pt' for i in files], flat_scores, counts, workers)
+            [output_prefixes[i] for i in files.tolist()], flat_scores, counts, workers,
+            suffix='.pt')
     done = [int(i) for i in indices if scores[int(i)] is not True]
     if done:
         corpus.write_scores(

@@ -21,6 +21,14 @@ def _encode(path):
     return os.fsencode(path)
 
 
+def _blob(paths, suffix=''):
+    """All paths (str) + suffix as one buffer of NUL-terminated strings"""
+    if not paths:
+        return b''
+    separator = suffix + '\0'
+    return (separator.join(paths) + separator).encode('utf-8', 'surrogateescape')
+
+
 def _paths(paths):
     encoded = [_encode(path) for path in paths]
     array = (ctypes.c_char_p * len(encoded))(*encoded)
@@ -39,10 +47,15 @@ class Corpus:
         self.lib = lib
         self.count = len(text_files)
         self.threads = threads or min(32, os.cpu_count() or 1)
-        text_array, self._text_keep = _paths(text_files)
-        audio_array, self._audio_keep = _paths(audio_files)
-        self.handle = lib.emph_corpus_open(
-            text_array, audio_array, self.count, self.threads)
+        if all(type(path) is str for path in text_files) and \
+                all(type(path) is str for path in audio_files):
+            self.handle = lib.emph_corpus_open_blob(
+                _blob(text_files), _blob(audio_files), self.count, self.threads)
+        else:
+            text_array, self._text_keep = _paths(text_files)
+            audio_array, self._audio_keep = _paths(audio_files)
+            self.handle = lib.emph_corpus_open(
+                text_array, audio_array, self.count, self.threads)
         n = max(self.count, 1)
         self.status = np.zeros(n, dtype=np.int32)
         self.sample_rate = np.zeros(n, dtype=np.int32)
@@ -149,6 +162,15 @@ class Corpus:
         packed.ready = ready
         return indices, per_file, packed
 
+    def write_textgrids_to_prefixes(self, prefixes, mask):
+        """`{prefix}.TextGrid` for the files selected by `mask` (str prefixes)"""
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        chosen = [prefix for prefix, m in zip(prefixes, mask) if m]
+        if self.lib.emph_corpus_write_textgrids_blob(
+            self.handle, _blob(chosen, '.TextGrid'), mask.ctypes.data, self.threads
+        ):
+            raise OSError('could not write some TextGrid files')
+
     def write_textgrids(self, output_paths, mask):
         encoded = [
             _encode(path) if m else b''
@@ -158,9 +180,9 @@ class Corpus:
             raise OSError('could not write some TextGrid files')
 
 
-def write_score_rows(paths, flat_scores, counts, threads=None):
-    """torch.save(row_i[None], paths[i]) where row i is the next counts[i]
-    values of ONE flat fp32 host tensor: no per-file tensor objects"""
+def write_score_rows(paths, flat_scores, counts, threads=None, suffix=''):
+    """torch.save(row_i[None], paths[i] + suffix) where row i is the next
+    counts[i] values of ONE flat fp32 host tensor: no per-file tensor objects"""
     lib = _lib.load()
     flat_scores = flat_scores.detach()
     if flat_scores.device.type != 'cpu' or flat_scores.dtype != torch.float32 \
@@ -171,14 +193,20 @@ def write_score_rows(paths, flat_scores, counts, threads=None):
         raise ValueError('write_score_rows: counts do not match the scores')
     starts = np.concatenate([[0], np.cumsum(counts[:-1], dtype=np.int64)]) \
         if len(counts) else np.zeros(0, dtype=np.int64)
-    pointers = (flat_scores.data_ptr() + 4 * starts).astype(np.uint64)
-    array, keep = _paths(paths)
     threads = threads or min(32, os.cpu_count() or 1)
-    if lib.emph_write_score_rows(
-        array, pointers.ctypes.data, counts.ctypes.data, len(paths), threads
-    ):
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    if all(type(path) is str for path in paths):
+        status = lib.emph_write_score_rows_blob(
+            _blob(paths, suffix), flat_scores.data_ptr(), starts.ctypes.data,
+            counts.ctypes.data, len(paths), threads)
+    else:
+        pointers = (flat_scores.data_ptr() + 4 * starts).astype(np.uint64)
+        array, keep = _paths([f'{path}{suffix}' for path in paths])
+        status = lib.emph_write_score_rows(
+            array, pointers.ctypes.data, counts.ctypes.data, len(paths), threads)
+        del keep
+    if status:
         raise OSError('could not write some score files')
-    del keep
 
 
 def write_scores(paths, scores, threads=None):

@@ -656,4 +656,50 @@ int emph_write_score_rows(
 
 void emph_corpus_close(emph_corpus* corpus) { delete corpus; }
 
+// ---- the same entry points with the paths as ONE buffer of NUL-terminated
+// strings (n of them, back to back): building a char*[] of tens of thousands
+// of Python strings costs more than parsing the files ----
+static std::vector<const char*> split_blob(const char* blob, int32_t n) {
+    std::vector<const char*> out((size_t)(n > 0 ? n : 0));
+    const char* cursor = blob;
+    for (int32_t i = 0; i < n; ++i) {
+        out[i] = cursor;
+        cursor += std::strlen(cursor) + 1;
+    }
+    return out;
+}
+
+emph_corpus* emph_corpus_open_blob(
+    const char* text_blob, const char* audio_blob, int32_t n_files, int32_t n_threads) {
+    const std::vector<const char*> text = split_blob(text_blob, n_files);
+    const std::vector<const char*> audio = split_blob(audio_blob, n_files);
+    return emph_corpus_open(text.data(), audio.data(), n_files, n_threads);
+}
+
+/* paths of the files with mask[i] != 0 only, in file order */
+int emph_corpus_write_textgrids_blob(
+    const emph_corpus* corpus, const char* path_blob, const uint8_t* mask, int32_t n_threads) {
+    if (!corpus || !mask) return EMPH_EINVAL;
+    const int32_t n = (int32_t)corpus->files.size();
+    std::vector<const char*> paths((size_t)n, nullptr);
+    const char* cursor = path_blob;
+    for (int32_t i = 0; i < n; ++i) {
+        if (!mask[i]) continue;
+        paths[i] = cursor;
+        cursor += std::strlen(cursor) + 1;
+    }
+    return emph_corpus_write_textgrids(corpus, paths.data(), n_threads);
+}
+
+/* file i holds counts[i] values starting at base[starts[i]] */
+int emph_write_score_rows_blob(
+    const char* path_blob, const float* base, const int64_t* starts, const int32_t* counts,
+    int32_t n_files, int32_t n_threads) {
+    if (n_files < 0 || (n_files > 0 && (!path_blob || !base || !starts || !counts))) return EMPH_EINVAL;
+    const std::vector<const char*> paths = split_blob(path_blob, n_files);
+    std::vector<const float*> rows((size_t)n_files);
+    for (int32_t i = 0; i < n_files; ++i) rows[i] = base + starts[i];
+    return emph_write_score_rows(paths.data(), rows.data(), counts, n_files, n_threads);
+}
+
 }  // extern "C"

@@ -616,6 +616,19 @@ int emph_write_score_rows(
     const char* const* paths, const float* const* rows, const int32_t* counts,
     int32_t n_files, int32_t n_threads);
 
+/* The same three entry points with the paths as ONE buffer of NUL-terminated
+ * strings, back to back (a char*[] of tens of thousands of strings costs the
+ * Python binding more than parsing the files does).  write_textgrids_blob:
+ * only the paths of the files with mask[i] != 0, in file order;
+ * write_score_rows_blob: file i holds counts[i] values from base[starts[i]]. */
+emph_corpus* emph_corpus_open_blob(
+    const char* text_blob, const char* audio_blob, int32_t n_files, int32_t n_threads);
+int emph_corpus_write_textgrids_blob(
+    const emph_corpus* corpus, const char* path_blob, const uint8_t* mask, int32_t n_threads);
+int emph_write_score_rows_blob(
+    const char* path_blob, const float* base, const int64_t* starts, const int32_t* counts,
+    int32_t n_files, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif
