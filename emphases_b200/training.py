@@ -309,6 +309,7 @@ class _NativeState:
         self.grad_pointers = (ctypes.c_void_p * (2 * count))()
         self.descriptor = _lib.TrainModel()
         self.workspace = None
+        self.generation = 0           # forward calls so far: the workspace holds the last one
         self.pointer_key = None
         self.lib = _lib.load()
 
@@ -359,6 +360,7 @@ def _native_state(model, device):
 def native_step_supported(model, features):
     """The configurations csrc/train_step.cu is built for"""
     return (
+        os.environ.get('EMPHASES_B200_TRAIN_NATIVE', '1') != '0' and
         model.architecture == 'convolution' and
         model.location in ('intermediate', 'loss') and
         emphases.CHANNELS == engine.KERNEL_CHANNELS == emphases.NUM_FEATURES and
@@ -404,7 +406,9 @@ class _NativeConvFunction(torch.autograd.Function):
             raise _lib.EmphasesB200Error(
                 f'emph_train_forward failed ({status}): ' +
                 state.lib.emph_last_error().decode('utf-8', 'replace'))
+        state.generation += 1
         ctx.model, ctx.state = model, state
+        ctx.generation = state.generation
         ctx.shape = (batch, frames, wmax)
         ctx.frame_lengths = frame_lengths
         return logits
@@ -412,6 +416,12 @@ class _NativeConvFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_logits):
         model, state = ctx.model, ctx.state
+        if ctx.generation != state.generation:
+            raise RuntimeError(
+                'the native training step keeps ONE forward pass of a model alive (its '
+                'activations live in a per-model workspace): call backward() before the '
+                "next training-mode forward, or set EMPHASES_B200_TRAIN_NATIVE=0 for the "
+                'per-kernel path')
         batch, frames, wmax = ctx.shape
         device = grad_logits.device
         grad_logits = grad_logits.detach().to(torch.float32).contiguous()
