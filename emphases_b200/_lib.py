@@ -131,6 +131,8 @@ def load():
     lib.emph_corpus_write_textgrids_blob.restype = ctypes.c_int
     lib.emph_write_score_rows_blob.argtypes = [ctypes.c_char_p, _P, _P, _P, _I, _I]
     lib.emph_write_score_rows_blob.restype = ctypes.c_int
+    lib.emph_file_sizes.argtypes = [ctypes.c_char_p, _I, _I, _P]
+    lib.emph_file_sizes.restype = ctypes.c_int
     lib.emph_corpus_info.argtypes = [_P, _P, _P, _P, _P, _P]
     lib.emph_corpus_info.restype = ctypes.c_int
     lib.emph_corpus_error.argtypes = [_P, _I]

@@ -22,17 +22,35 @@ def rank_and_world():
 
 
 def shard(costs, rank=None, world=None):
-    """Indices of this rank's utterances: deterministic LPT split by cost
-    (frames; frames**2 for the transformer variant) -- identical on every
-    rank, so no communication is needed to agree on it."""
+    """Indices of this rank's utterances: deterministic length-balanced split
+    by cost (frames; frames**2 for the transformer variant) -- identical on
+    every rank, so no communication is needed to agree on it.  LPT for short
+    lists, its vectorised snake form for long ones."""
     if rank is None or world is None:
         rank, world = rank_and_world()
+    if world == 1:
+        return list(range(len(costs)))
+    if len(costs) > 2048:
+        return scheduler.snake_assign(costs, world)[rank]
     return scheduler.lpt_assign(list(costs), world)[rank]
 
 
 def audio_costs(audio_files):
-    """Cost proxy without decoding: file size in bytes ~ samples"""
-    return [os.path.getsize(file) for file in audio_files]
+    """Cost proxy without decoding: file size in bytes ~ samples (native stat
+    on the worker pool: every rank looks at the whole list)"""
+    import ctypes
+    import numpy as np
+    from . import _lib, corpus
+    files = [os.fspath(file) for file in audio_files]
+    sizes = np.zeros(max(len(files), 1), dtype=np.int64)
+    local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+    threads = max(2, min(32, (os.cpu_count() or 1) // local_world))
+    _lib.load().emph_file_sizes(
+        corpus._blob(files), len(files), threads, sizes.ctypes.data_as(ctypes.c_void_p))
+    sizes = sizes[:len(files)]
+    if np.any(sizes < 0):
+        raise FileNotFoundError(files[int(np.nonzero(sizes < 0)[0][0])])
+    return sizes
 
 
 def from_files_to_files(
@@ -48,7 +66,8 @@ def from_files_to_files(
     rank, world = rank_and_world()
     if output_prefixes is None:
         output_prefixes = [os.path.splitext(str(f))[0] for f in text_files]
-    mine = shard(audio_costs(audio_files), rank, world)
+    mine = list(range(len(audio_files))) if world == 1 else \
+        shard(audio_costs(audio_files), rank, world)
     if gpu is None:
         gpu = int(os.environ.get('LOCAL_RANK', 0))
     if mine:

@@ -282,6 +282,19 @@ def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
     return [sorted(shard) for shard in shards]
 
 
+def snake_assign(costs, workers: int) -> List[List[int]]:
+    """Length-balanced split for LONG lists (tens of thousands of files): items
+    sorted by cost, dealt to the workers in a snake (0 .. W-1, W-1 .. 0, ...).
+    Within a fraction of a percent of lpt_assign's balance at these sizes, but
+    vectorised: lpt_assign's heap costs ~2 us per item on every rank."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind='stable')
+    position = np.arange(len(order))
+    lap, slot = position // workers, position % workers
+    worker = np.where(lap % 2 == 0, slot, workers - 1 - slot)
+    return [np.sort(order[worker == w]).tolist() for w in range(workers)]
+
+
 def contiguous_assign(costs, workers: int) -> List[List[int]]:
     """Cut the item list into `workers` contiguous ranges of (nearly) equal
     total cost; returns, per worker, the item indices (possibly empty)"""

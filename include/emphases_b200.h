@@ -628,6 +628,10 @@ int emph_corpus_write_textgrids_blob(
 int emph_write_score_rows_blob(
     const char* path_blob, const float* base, const int64_t* starts, const int32_t* counts,
     int32_t n_files, int32_t n_threads);
+/* sizes[i] = bytes of file i of a NUL-separated path buffer, -1 if it cannot
+ * be stat'ed: the cost proxy of the length-balanced sharding of a file list
+ * (emphases/core.py:169-179 walks the files in order on one device). */
+int emph_file_sizes(const char* path_blob, int32_t n_files, int32_t n_threads, int64_t* sizes);
 
 #ifdef __cplusplus
 }
