@@ -215,6 +215,29 @@ def test_scheduler_lpt_and_buckets():
     assert all(o % engine.AUDIO_ALIGN == 0 for o in offsets)
 
 
+def test_snake_split_and_native_file_sizes(tmp_path):
+    """Long file lists: the vectorised split is a balanced partition, identical
+    on every rank, and its cost proxy is the native stat of every file"""
+    from emphases_b200 import distributed, scheduler
+    rng = np.random.default_rng(3)
+    costs = rng.integers(16000, 400000, 5000)
+    for world in (2, 3, 8):
+        shards = scheduler.snake_assign(costs, world)
+        assert sorted(i for shard in shards for i in shard) == list(range(5000))
+        assert all(shard == sorted(shard) for shard in shards)
+        loads = np.array([costs[shard].sum() for shard in shards], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.002
+        assert [distributed.shard(costs, rank, world) for rank in range(world)] == shards
+    assert distributed.shard(costs, 0, 1) == list(range(5000))
+    files = []
+    for index, size in enumerate([0, 1, 44, 100000]):
+        files.append(tmp_path / f'{index}.wav')
+        files[-1].write_bytes(b'x' * size)
+    assert distributed.audio_costs(files).tolist() == [0, 1, 44, 100000]
+    with pytest.raises(FileNotFoundError):
+        distributed.audio_costs(files + [tmp_path / 'missing.wav'])
+
+
 def test_vectorised_plan_matches_scalar_chunker():
     """The whole-corpus fast path must equal the per-utterance chunker"""
     import bench
