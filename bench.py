@@ -512,8 +512,9 @@ def time_transformer_variant(
         'value': audio_seconds / (ms * 1e-3), 'unit': 'audio-s/s', 'ms_per_step': ms,
         'steps': steps, 'utterances': int(plan.n_seq),
         'workload': 'configs[2]: Transformer-layer variant, same corpus, kernel-only',
-        'note': ('attention is fp32 CUDA-core flash-style (csrc/attention.cu), the per-row '
-                 'linear maps run on the tensor cores (bf16x6)')}
+        'note': ('attention on the tensor cores (csrc/attention_tc.cu: mma.sync, fp16 operands '
+                 'in the bf16 mode, split bf16 in the fp32-grade modes), the per-row linear '
+                 'maps on tcgen05 (bf16x6)')}
 
 
 def synthetic_training_batch(seed, max_frames=75000):

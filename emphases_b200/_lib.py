@@ -47,6 +47,8 @@ SIGNATURES = {
     'emph_segment_rows': [_P, _I, _P, _P, _P, _I, _P, _I, _P, _P],
     'emph_add_positional': [_P, _P, _P, _I, _I, _P, _I, _P, _P],
     'emph_attention_rows': [_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _I, _F, _P, _P],
+    'emph_attention_rows_tc': [
+        _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _I, _F, _I, _P, ctypes.c_int64, _P, _P],
     'emph_add_layernorm': [_P, _P, _P, _P, _F, _P, _I, _I, _P, _P],
     'emph_resample_f32': [_P, ctypes.c_int64, _P, _I, _I, _I, _P, ctypes.c_int64, _P],
     'emph_resample_packed_i16': [
@@ -145,6 +147,8 @@ def load():
     lib.emph_corpus_close.restype = None
     lib.emph_conv_weights_tc_bytes.argtypes = [_I, _I, _I, _I]
     lib.emph_conv_weights_tc_bytes.restype = ctypes.c_int
+    lib.emph_attention_tc_workspace.argtypes = [_I, _I, _I, _I]
+    lib.emph_attention_tc_workspace.restype = ctypes.c_int64
     lib.emph_infer_utterance_workspace.argtypes = [ctypes.c_longlong, _I, _I, _I]
     lib.emph_infer_utterance_workspace.restype = ctypes.c_longlong
     lib.emph_infer_utterance.argtypes = [

@@ -1,0 +1,491 @@
+// Tensor-core form of the Transformer variant's attention
+// (emphases/model/layers/transformer.py:18-30: nn.TransformerEncoder with
+// src_key_padding_mask; 2 heads of 40 dims at the default 80 channels), sm_100a.
+//
+// Same contract as emph_attention_rows (attention.cu): block-diagonal attention
+// over packed rows, keys >= n_keys[u] masked, every row of a sequence computed
+// as a query.  Two kernels:
+//
+//   attention_stage_kernel  K and V rows fp32 -> 16-bit operands, once per call,
+//       in the layout the main kernel wants in shared memory: per head, one
+//       record per row [K parts | V parts | pad], the record length chosen so
+//       that the eight 16-byte rows of an ldmatrix fall on distinct banks
+//       (length = 16 mod 32 bytes).  A tile of 64 keys is then ONE contiguous
+//       range and moves with one cp.async.bulk.
+//   attention_rows_tc_kernel  FlashAttention-2 register flow on mma.sync
+//       m16n8k16 (fp32 accumulators).  A CTA of 8 warps owns one block of 128
+//       queries, 16 per warp, Q fragments in registers; key tiles arrive in a
+//       two-stage ring (mbarrier + bulk copy issued one tile ahead).  Per tile
+//       and warp: S = Q K^T (B = K records through ldmatrix), online softmax on
+//       the accumulator fragments in the log2 domain, and the S fragments ARE
+//       the A fragments of O += P V (B = V records through ldmatrix.trans).
+//
+// Operand modes:
+//   kPlainFp16  one fp16 per operand (2^-11; activations of this model sit far
+//               inside fp16's range, and the reference itself runs attention in
+//               fp16 under torch.autocast on CUDA, emphases/core.py:606).  One
+//               bf16 per operand runs at the same speed and is 4x less exact
+//               (4.6e-3 on the scores of bench.py's corpus, over the 2e-3 bar;
+//               fp16: 3.2e-4), so it is not built.
+//   kSplitBf16  every operand a bf16 (hi, lo) pair, hi*hi + hi*lo + lo*hi: three
+//               MMAs per product, 2^-17 of the product -- the fp32-grade mode
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace emph {
+namespace attn_tc {
+
+constexpr int kThreads = 256;
+constexpr int kQueries = 128;      // per CTA = the host's query block
+constexpr int kKeys = 64;          // per shared-memory tile
+enum { kPlainFp16 = 0, kSplitBf16 = 1 };
+
+template <int D, int MODE>
+struct Layout {
+    static constexpr int DP = (D + 15) / 16 * 16;          // K dims padded to whole k-steps
+    static constexpr int NP = MODE == kSplitBf16 ? 2 : 1;  // operand parts
+    static constexpr int kOffV = NP * DP;                   // in 16-bit elements
+    static constexpr int kContent = NP * (DP + D) * 2;      // bytes
+    static constexpr int kRecord = kContent % 32 == 16 ? kContent : kContent + 16;
+    static constexpr int kTileBytes = kKeys * kRecord;
+    static constexpr int kSmemBytes = 2 * kTileBytes + 16;  // + two mbarriers
+    static_assert(D % 8 == 0, "head dim must be a multiple of 8");
+    static_assert(kRecord % 32 == 16, "ldmatrix rows must land on distinct banks");
+};
+
+__device__ __forceinline__ float exp2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// {lo -> bits 0..15, hi -> bits 16..31}
+template <int MODE>
+__device__ __forceinline__ uint32_t pack_pair(float lo, float hi) {
+    uint32_t r;
+    if (MODE == kPlainFp16)
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// what the rounding to bf16 dropped, as a second bf16 pair
+__device__ __forceinline__ uint32_t pack_residual(float lo, float hi, uint32_t rounded) {
+    return pack_pair<kSplitBf16>(
+        lo - __uint_as_float(rounded << 16), hi - __uint_as_float(rounded & 0xffff0000u));
+}
+
+template <int MODE>
+__device__ __forceinline__ void mma_16816(
+    float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (MODE == kPlainFp16)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 "
+            "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
+            "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t address) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(address));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t address) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(address));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t address) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(address));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t address) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(address));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// one thread: expect `bytes` on the barrier and start the bulk copy
+__device__ __forceinline__ void bulk_fetch(
+    uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b64 state;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 state, [%0], %1;\n\t}"
+        ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// K, V rows -> staged 16-bit records.  One thread per (row, 8-dim chunk, head);
+// rows [total_rows, padded_rows) and K's padded dims are zeros, so a key tile
+// may always be fetched whole (its tail past the sequence is masked in S and
+// meets finite V values).
+// ---------------------------------------------------------------------------
+template <int D, int MODE>
+__global__ void __launch_bounds__(256)
+attention_stage_kernel(
+    const float* __restrict__ k, const float* __restrict__ v, int channels,
+    int total_rows, int padded_rows, unsigned char* __restrict__ staged) {
+    using L = Layout<D, MODE>;
+    constexpr int kChunks = L::DP / 8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(i / kChunks), chunk = (int)(i % kChunks);
+    const int head = blockIdx.y;
+    if (row >= padded_rows) return;
+    const bool real = 8 * chunk < D;                         // else: K's zero padding
+    float4 ka = make_float4(0.f, 0.f, 0.f, 0.f), kb = ka, va = ka, vb = ka;
+    if (real && row < total_rows) {
+        const size_t src = (size_t)row * channels + (size_t)head * D + 8 * chunk;
+        ka = *reinterpret_cast<const float4*>(k + src);
+        kb = *reinterpret_cast<const float4*>(k + src + 4);
+        va = *reinterpret_cast<const float4*>(v + src);
+        vb = *reinterpret_cast<const float4*>(v + src + 4);
+    }
+    unsigned char* record = staged + ((size_t)head * padded_rows + row) * L::kRecord;
+    uint4 kh, vh;
+    kh.x = pack_pair<MODE>(ka.x, ka.y); kh.y = pack_pair<MODE>(ka.z, ka.w);
+    kh.z = pack_pair<MODE>(kb.x, kb.y); kh.w = pack_pair<MODE>(kb.z, kb.w);
+    vh.x = pack_pair<MODE>(va.x, va.y); vh.y = pack_pair<MODE>(va.z, va.w);
+    vh.z = pack_pair<MODE>(vb.x, vb.y); vh.w = pack_pair<MODE>(vb.z, vb.w);
+    *reinterpret_cast<uint4*>(record + 2 * (8 * chunk)) = kh;
+    if (real) *reinterpret_cast<uint4*>(record + 2 * (L::kOffV + 8 * chunk)) = vh;
+    if (MODE == kSplitBf16) {
+        uint4 kl, vl;
+        kl.x = pack_residual(ka.x, ka.y, kh.x); kl.y = pack_residual(ka.z, ka.w, kh.y);
+        kl.z = pack_residual(kb.x, kb.y, kh.z); kl.w = pack_residual(kb.z, kb.w, kh.w);
+        vl.x = pack_residual(va.x, va.y, vh.x); vl.y = pack_residual(va.z, va.w, vh.y);
+        vl.z = pack_residual(vb.x, vb.y, vh.z); vl.w = pack_residual(vb.z, vb.w, vh.w);
+        *reinterpret_cast<uint4*>(record + 2 * (L::DP + 8 * chunk)) = kl;
+        if (real) *reinterpret_cast<uint4*>(record + 2 * (L::kOffV + D + 8 * chunk)) = vl;
+    }
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+attention_rows_tc_kernel(
+    const float* __restrict__ q, const unsigned char* __restrict__ staged, int padded_rows,
+    int channels, const int32_t* __restrict__ row_start, const int32_t* __restrict__ n_queries,
+    const int32_t* __restrict__ n_keys,
+    const int32_t* __restrict__ block_seq, const int32_t* __restrict__ block_q0,
+    float scale, float* __restrict__ out) {
+    using L = Layout<D, MODE>;
+    constexpr int DP = L::DP;
+    constexpr int KS = DP / 16;                // k-steps of Q K^T
+    constexpr int NT = D / 8;                  // n-tiles of P V
+    constexpr int NP = L::NP;
+    constexpr bool SPLIT = MODE == kSplitBf16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t tiles = smem_u32(smem);
+    const uint32_t bars = tiles + 2 * L::kTileBytes;
+
+    const int u = block_seq[blockIdx.x];
+    const int q0 = block_q0[blockIdx.x];
+    const int head = blockIdx.y;
+    const int base = row_start[u];
+    const int nk = n_keys[u];
+    const int nq = n_queries[u];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int row[2] = {q0 + 16 * warp + g, q0 + 16 * warp + g + 8};
+    const size_t column = (size_t)head * D;
+    const float scale2 = scale * 1.4426950408889634f;      // scores in the log2 domain
+    const int n_tiles = (nk + kKeys - 1) / kKeys;
+    const unsigned char* source =
+        staged + ((size_t)head * padded_rows + base) * L::kRecord;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (n_tiles > 0) bulk_fetch(tiles, source, L::kTileBytes, bars);
+    }
+
+    // A fragments of Q (m16 x k16 per k-step): a0 (g, 2t) a1 (g+8, 2t) a2 (g, 2t+8) a3 (g+8, 2t+8)
+    uint32_t qf[NP][KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = row[i & 1], c = 16 * s + 8 * (i >> 1) + 2 * t;
+            float2 x = make_float2(0.f, 0.f);
+            if (r < nq && c < D)
+                x = *reinterpret_cast<const float2*>(q + (size_t)(base + r) * channels + column + c);
+            qf[0][s][i] = pack_pair<MODE>(x.x, x.y);
+            if (SPLIT) qf[NP - 1][s][i] = pack_residual(x.x, x.y, qf[0][s][i]);
+        }
+
+    float o[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
+
+    // per-lane byte offsets of the ldmatrix rows inside a tile
+    const uint32_t k_lane = (uint32_t)(lane & 7) * L::kRecord + 16u * (lane >> 3);
+    const uint32_t k_lane_tail = (uint32_t)(lane & 7) * L::kRecord + 16u * ((lane >> 3) & 1);
+    const uint32_t v_lane =
+        (uint32_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * L::kRecord + 2u * L::kOffV;
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int count = min(kKeys, nk - tile * kKeys);
+        const uint32_t stage = tiles + (tile & 1) * L::kTileBytes;
+        // every warp is done with tile - 1: its stage may take tile + 1
+        __syncthreads();
+        if (threadIdx.x == 0 && tile + 1 < n_tiles)
+            bulk_fetch(tiles + ((tile + 1) & 1) * L::kTileBytes,
+                       source + (size_t)(tile + 1) * L::kTileBytes, L::kTileBytes,
+                       bars + 8 * ((tile + 1) & 1));
+        mbar_wait(bars + 8 * (tile & 1), (tile >> 1) & 1);
+
+        // ---- S = Q K^T: 8 n-tiles of 8 keys ----
+        float s[kKeys / 8][4];
+#pragma unroll
+        for (int j = 0; j < kKeys / 8; ++j) {
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                // B fragments of this key tile: b0 = dims 16s + 2t.., b1 = 16s + 8 + 2t..
+                const uint32_t rows = stage + 8 * j * L::kRecord + 2 * part * DP;
+                uint32_t b[KS][2];
+#pragma unroll
+                for (int s2 = 0; s2 < KS / 2; ++s2) {
+                    uint32_t r4[4];
+                    ldmatrix_x4(r4, rows + k_lane + 64 * s2);
+                    b[2 * s2][0] = r4[0]; b[2 * s2][1] = r4[1];
+                    b[2 * s2 + 1][0] = r4[2]; b[2 * s2 + 1][1] = r4[3];
+                }
+                if (KS & 1) ldmatrix_x2(b[KS - 1], rows + k_lane_tail + 32 * (KS - 1));
+#pragma unroll
+                for (int step = 0; step < KS; ++step) {
+                    mma_16816<MODE>(s[j], qf[0][step], b[step][0], b[step][1]);
+                    if (SPLIT && part == 0)
+                        mma_16816<MODE>(s[j], qf[NP - 1][step], b[step][0], b[step][1]);
+                }
+            }
+        }
+        if (count < kKeys) {
+#pragma unroll
+            for (int j = 0; j < kKeys / 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (8 * j + 2 * t + (i & 1) >= count) s[j][i] = -CUDART_INF_F;
+        }
+
+        // ---- online softmax: rows g (values 0, 1 of a tile) and g + 8 (2, 3) ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float peak = s[0][2 * r];
+#pragma unroll
+            for (int j = 0; j < kKeys / 8; ++j)
+                peak = fmaxf(peak, fmaxf(s[j][2 * r], s[j][2 * r + 1]));
+            peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, 1));
+            peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, 2));
+            const float updated = fmaxf(m[r], peak);   // finite: every tile has a valid key
+            const float correction = exp2_fast((m[r] - updated) * scale2);
+            const float shift = -updated * scale2;
+            m[r] = updated;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < kKeys / 8; ++j) {
+                s[j][2 * r] = exp2_fast(fmaf(s[j][2 * r], scale2, shift));
+                s[j][2 * r + 1] = exp2_fast(fmaf(s[j][2 * r + 1], scale2, shift));
+                sum += s[j][2 * r] + s[j][2 * r + 1];
+            }
+            l[r] = fmaf(l[r], correction, sum);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                o[n][2 * r] *= correction;
+                o[n][2 * r + 1] *= correction;
+            }
+        }
+
+        // ---- O += P V: accumulator tiles 2kk, 2kk+1 of S are the A fragment of step kk ----
+#pragma unroll
+        for (int kk = 0; kk < kKeys / 16; ++kk) {
+            uint32_t pf[NP][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float lo = s[2 * kk + (i >> 1)][2 * (i & 1)];
+                const float hi = s[2 * kk + (i >> 1)][2 * (i & 1) + 1];
+                pf[0][i] = pack_pair<MODE>(lo, hi);
+                if (SPLIT) pf[NP - 1][i] = pack_residual(lo, hi, pf[0][i]);
+            }
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                const uint32_t rows = stage + 16 * kk * L::kRecord + v_lane + 2 * part * D;
+#pragma unroll
+                for (int n2 = 0; n2 < NT / 2; ++n2) {
+                    uint32_t r4[4];
+                    ldmatrix_x4_trans(r4, rows + 16 * (2 * n2 + (lane >> 4)));
+                    mma_16816<MODE>(o[2 * n2], pf[0], r4[0], r4[1]);
+                    mma_16816<MODE>(o[2 * n2 + 1], pf[0], r4[2], r4[3]);
+                    if (SPLIT && part == 0) {
+                        mma_16816<MODE>(o[2 * n2], pf[NP - 1], r4[0], r4[1]);
+                        mma_16816<MODE>(o[2 * n2 + 1], pf[NP - 1], r4[2], r4[3]);
+                    }
+                }
+                if (NT & 1) {
+                    uint32_t r2[2];
+                    ldmatrix_x2_trans(r2, rows + 16 * (NT - 1));
+                    mma_16816<MODE>(o[NT - 1], pf[0], r2[0], r2[1]);
+                    if (SPLIT && part == 0) mma_16816<MODE>(o[NT - 1], pf[NP - 1], r2[0], r2[1]);
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float total = l[r];
+        total += __shfl_xor_sync(0xffffffffu, total, 1);
+        total += __shfl_xor_sync(0xffffffffu, total, 2);
+        if (row[r] >= nq) continue;
+        const float inv = 1.f / total;
+        float* dst = out + (size_t)(base + row[r]) * channels + column + 2 * t;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+            *reinterpret_cast<float2*>(dst + 8 * n) =
+                make_float2(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+    }
+}
+
+struct Call {
+    const float *q, *k, *v;
+    int channels, heads;
+    const int32_t *row_start, *n_queries, *n_keys;
+    int total_rows;
+    const int32_t *block_seq, *block_q0;
+    int n_blocks;
+    float scale;
+    unsigned char* workspace;
+    size_t workspace_bytes;
+    float* out;
+    cudaStream_t stream;
+};
+
+inline int padded_rows(int total_rows) { return total_rows + kKeys; }
+
+template <int D, int MODE>
+size_t workspace_bytes(int total_rows, int heads) {
+    return (size_t)heads * padded_rows(total_rows) * Layout<D, MODE>::kRecord;
+}
+
+template <int D, int MODE>
+int run(const Call& c) {
+    using L = Layout<D, MODE>;
+    const int rows = padded_rows(c.total_rows);
+    const size_t needed = workspace_bytes<D, MODE>(c.total_rows, c.heads);
+    EMPH_REQUIRE(c.workspace_bytes >= needed,
+                 "emph_attention_rows_tc: workspace of %zu bytes is too small", c.workspace_bytes);
+    const long long items = (long long)rows * (L::DP / 8);
+    attention_stage_kernel<D, MODE><<<dim3((unsigned)((items + 255) / 256), c.heads), 256, 0,
+                                      c.stream>>>(
+        c.k, c.v, c.channels, c.total_rows, rows, c.workspace);
+    EMPH_CHECK_LAUNCH("emph_attention_rows_tc(stage)");
+    const int status = check_cuda(
+        cudaFuncSetAttribute(attention_rows_tc_kernel<D, MODE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes),
+        "emph_attention_rows_tc(shared memory)");
+    if (status != EMPH_OK) return status;
+    attention_rows_tc_kernel<D, MODE><<<dim3(c.n_blocks, c.heads), kThreads, L::kSmemBytes,
+                                        c.stream>>>(
+        c.q, c.workspace, rows, c.channels, c.row_start, c.n_queries, c.n_keys, c.block_seq,
+        c.block_q0, c.scale, c.out);
+    EMPH_CHECK_LAUNCH("emph_attention_rows_tc");
+    return EMPH_OK;
+}
+
+template <int D>
+int run_mode(int mode, const Call& c) {
+    switch (mode) {
+        case kPlainFp16: return run<D, kPlainFp16>(c);
+        case kSplitBf16: return run<D, kSplitBf16>(c);
+    }
+    set_error("emph_attention_rows_tc: unknown operand mode %d", mode);
+    return EMPH_EINVAL;
+}
+
+template <int D>
+size_t workspace_mode(int mode, int total_rows, int heads) {
+    return mode == kSplitBf16 ? workspace_bytes<D, kSplitBf16>(total_rows, heads)
+                              : workspace_bytes<D, kPlainFp16>(total_rows, heads);
+}
+
+// separator rows are zero
+__global__ void clear_separators_kernel(
+    const int32_t* __restrict__ row_seq, int total_rows, int channels, float* __restrict__ out) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= total_rows) return;
+    if (row_seq[r] >= 0) return;
+    for (int c = threadIdx.x & 31; c < channels; c += 32) out[(size_t)r * channels + c] = 0.f;
+}
+
+}  // namespace attn_tc
+}  // namespace emph
+
+extern "C" {
+
+int64_t emph_attention_tc_workspace(
+    int32_t total_rows, int32_t channels, int32_t heads, int32_t mode) {
+    if (total_rows < 0 || heads <= 0 || channels % heads != 0) return -1;
+    switch (channels / heads) {
+        case 40: return (int64_t)emph::attn_tc::workspace_mode<40>(mode, total_rows, heads);
+        case 32: return (int64_t)emph::attn_tc::workspace_mode<32>(mode, total_rows, heads);
+        case 64: return (int64_t)emph::attn_tc::workspace_mode<64>(mode, total_rows, heads);
+    }
+    return -1;
+}
+
+int emph_attention_rows_tc(
+    const float* q, const float* k, const float* v, int32_t channels, int32_t heads,
+    const int32_t* row_start, const int32_t* n_queries, const int32_t* n_keys,
+    const int32_t* row_seq, int32_t total_rows,
+    const int32_t* block_seq, const int32_t* block_q0, int32_t n_blocks,
+    float scale, int32_t mode, void* workspace, int64_t workspace_bytes, float* out,
+    void* stream) {
+    EMPH_REQUIRE(heads > 0 && channels % heads == 0, "emph_attention_rows_tc: bad head count");
+    const int head_dim = channels / heads;
+    if (total_rows == 0) return EMPH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    emph::attn_tc::clear_separators_kernel<<<(total_rows + 7) / 8, 256, 0, st>>>(
+        row_seq, total_rows, channels, out);
+    EMPH_CHECK_LAUNCH("emph_attention_rows_tc(clear)");
+    if (n_blocks == 0) return EMPH_OK;
+    EMPH_REQUIRE(workspace != nullptr && workspace_bytes >= 0,
+                 "emph_attention_rows_tc: no workspace");
+    const emph::attn_tc::Call call{
+        q, k, v, channels, heads, row_start, n_queries, n_keys, total_rows, block_seq, block_q0,
+        n_blocks, scale, (unsigned char*)workspace, (size_t)workspace_bytes, out, st};
+    switch (head_dim) {
+        case 40: return emph::attn_tc::run_mode<40>(mode, call);
+        case 32: return emph::attn_tc::run_mode<32>(mode, call);
+        case 64: return emph::attn_tc::run_mode<64>(mode, call);
+    }
+    emph::set_error("emph_attention_rows_tc: head_dim %d not compiled in", head_dim);
+    return EMPH_ENOSYS;
+}
+
+}  // extern "C"

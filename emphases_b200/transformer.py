@@ -158,6 +158,34 @@ def pack_weights(model, device):
 ###############################################################################
 
 
+ATTENTION_MODES = {'fp16': 0, 'bf16x3': 1}     # operand modes of csrc/attention_tc.cu
+
+
+def attention_mode():
+    """How attention runs for the configured PRECISION: None = the fp32
+    CUDA-core kernel (emph_attention_rows), else the operand mode of the
+    tensor-core kernel (emph_attention_rows_tc): fp16 operands in the 2e-3
+    'bf16' mode (3e-4 on the scores of bench.py's corpus), split bf16 in the
+    fp32-grade modes (3e-6).  EMPHASES_B200_ATTENTION = fp32 | fp16 | bf16x3
+    overrides."""
+    import os
+    choice = os.environ.get('EMPHASES_B200_ATTENTION') or {
+        'fp32': 'fp32', 'bf16': 'fp16', 'bf16x3': 'bf16x3', 'bf16x6': 'bf16x3',
+    }[emphases.PRECISION]
+    if choice != 'fp32' and choice not in ATTENTION_MODES:
+        raise ValueError(f'EMPHASES_B200_ATTENTION={choice} is not defined')
+    return ATTENTION_MODES.get(choice)
+
+
+def attention_workspace(total_rows, channels, mode, device):
+    """Device buffer for the 16-bit K / V records of one attention call"""
+    size = _lib.load().emph_attention_tc_workspace(total_rows, channels, HEADS, mode)
+    if size < 0:
+        raise NotImplementedError(
+            f'tensor-core attention is not compiled for {channels // HEADS}-dim heads')
+    return torch.empty(max(size, 1), dtype=torch.uint8, device=device)
+
+
 def query_blocks(n_keys, block=128):
     """(block_seq, block_q0): 128-query blocks (kAttnQ of csrc/attention.cu)
     that never cross a sequence"""
@@ -189,6 +217,9 @@ def run_stack(
     d_block_seq = meta[2 * n_seq:2 * n_seq + len(block_seq)]
     d_block_q0 = meta[2 * n_seq + len(block_seq):]
     scale = 1.0 / math.sqrt(channels // HEADS)
+    mode = attention_mode()
+    workspace = None if mode is None else attention_workspace(
+        total_rows, channels, mode, device)
 
     h = torch.empty_like(x)
     _lib.call(
@@ -200,12 +231,20 @@ def run_stack(
             eng.conv_stack(h, row_seq, part, engine.linear_precision(part))
             for part in layer.qkv)
         context = torch.empty_like(h)
-        _lib.call(
-            'emph_attention_rows', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v),
-            channels, HEADS, _lib.ptr(row_start), _lib.ptr(n_queries),
-            _lib.ptr(n_keys), _lib.ptr(row_seq), total_rows, _lib.ptr(d_block_seq),
-            _lib.ptr(d_block_q0), len(block_seq), scale, _lib.ptr(context),
-            _lib.stream_ptr())
+        if mode is None:
+            _lib.call(
+                'emph_attention_rows', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v),
+                channels, HEADS, _lib.ptr(row_start), _lib.ptr(n_queries),
+                _lib.ptr(n_keys), _lib.ptr(row_seq), total_rows, _lib.ptr(d_block_seq),
+                _lib.ptr(d_block_q0), len(block_seq), scale, _lib.ptr(context),
+                _lib.stream_ptr())
+        else:
+            _lib.call(
+                'emph_attention_rows_tc', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v),
+                channels, HEADS, _lib.ptr(row_start), _lib.ptr(n_queries),
+                _lib.ptr(n_keys), _lib.ptr(row_seq), total_rows, _lib.ptr(d_block_seq),
+                _lib.ptr(d_block_q0), len(block_seq), scale, mode, _lib.ptr(workspace),
+                workspace.numel(), _lib.ptr(context), _lib.stream_ptr())
         attended = eng.conv_stack(
             context, row_seq, layer.out_proj, engine.linear_precision(layer.out_proj))
         normed = torch.empty_like(h)

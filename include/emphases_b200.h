@@ -381,6 +381,14 @@ int emph_segment_rows(
  *   nn.TransformerEncoder does (their values reach valid words through the
  *   k=3 output conv).  The caller supplies the query blocks (block_seq[b],
  *   block_q0[b]): 128 queries each, never crossing a sequence.
+ * emph_attention_rows_tc: the same attention on the tensor cores (mma.sync
+ *   m16n8k16, fp32 accumulation and softmax; csrc/attention_tc.cu).  `mode`:
+ *   0 = one fp16 per operand (the reference itself runs attention in half
+ *   precision under torch.autocast, core.py:606), 1 = every operand a bf16
+ *   (hi, lo) pair, three MMAs per product (fp32 grade: scores within 1e-5 of
+ *   the fp32 path).  K and V are first converted into `workspace`
+ *   (emph_attention_tc_workspace bytes, 256-byte aligned; -1 = unsupported
+ *   head dim), which a later call may reuse.
  * emph_add_layernorm: y = LayerNorm(x + residual; gamma, beta, eps).
  */
 int emph_add_positional(
@@ -394,6 +402,15 @@ int emph_attention_rows(
     const int32_t* block_seq,
     const int32_t* block_q0, int32_t n_blocks, float scale, float* out,
     void* stream);
+int emph_attention_rows_tc(
+    const float* q, const float* k, const float* v, int32_t channels,
+    int32_t heads, const int32_t* row_start, const int32_t* n_queries,
+    const int32_t* n_keys, const int32_t* row_seq, int32_t total_rows,
+    const int32_t* block_seq,
+    const int32_t* block_q0, int32_t n_blocks, float scale, int32_t mode,
+    void* workspace, int64_t workspace_bytes, float* out, void* stream);
+int64_t emph_attention_tc_workspace(
+    int32_t total_rows, int32_t channels, int32_t heads, int32_t mode);
 int emph_add_layernorm(
     const float* x, const float* residual, const float* gamma,
     const float* beta, float eps, const int32_t* row_seq, int32_t total_rows,

@@ -421,10 +421,10 @@ def test_transformer_variant_input_location(emphases, golden):
 def test_transformer_variant_linear_maps_on_tensor_cores(emphases, golden):
     """With a tensor-core PRECISION the Transformer variant's per-row linear
     maps (kernel-size-1 stacks: QKV, output projection, feed-forward) run in
-    the fp32-grade bf16x6 tcgen05 mode; attention stays fp32.  Same parity bar
-    as the all-fp32 path."""
+    the fp32-grade bf16x6 tcgen05 mode and attention in the split-bf16
+    tensor-core form.  Same parity bar as the all-fp32 path."""
     data = golden('transformer')
-    emphases.configure(ARCHITECTURE='transformer', PRECISION='bf16')
+    emphases.configure(ARCHITECTURE='transformer', PRECISION='bf16x6')
     model = emphases.Model()
     model.load_state_dict(state_from_golden(data), strict=False)
     model = model.cuda().eval()
@@ -437,6 +437,35 @@ def test_transformer_variant_linear_maps_on_tensor_cores(emphases, golden):
             np.testing.assert_allclose(
                 logits[i, :, :words], data['b2.logits'][i, :, :words],
                 rtol=0, atol=3e-5)
+
+
+# logits; the 'bf16' bar is the 2e-3 score tolerance (sigmoid slope <= 1/4)
+TRANSFORMER_TC_TOLERANCE = {'bf16': 8e-3, 'bf16x3': 1e-4}
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('location', ['intermediate', 'input'])
+def test_transformer_variant_tensor_core_attention(emphases, golden, precision, location):
+    """PRECISION 'bf16' / 'bf16x3': attention itself runs on the tensor cores
+    (fp16 / split-bf16 operands, csrc/attention_tc.cu), vs the reference logits"""
+    from emphases_b200 import transformer
+    data = golden('transformer' if location == 'intermediate' else 'transformer_input')
+    emphases.configure(
+        ARCHITECTURE='transformer', PRECISION=precision, DOWNSAMPLE_LOCATION=location)
+    expected_mode = {'bf16': 'fp16', 'bf16x3': 'bf16x3'}[precision]
+    assert transformer.attention_mode() == transformer.ATTENTION_MODES[expected_mode]
+    model = emphases.Model()
+    model.load_state_dict(state_from_golden(data), strict=False)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        batch = [torch.from_numpy(data[f'b2.{name}']) for name in (
+            'features', 'frame_lengths', 'bounds', 'word_lengths')]
+        batch[0] = batch[0].cuda()
+        logits = model(*batch).cpu().numpy()
+        for i, words in enumerate(batch[3].tolist()):
+            error = np.abs(logits[i, :, :words] - data['b2.logits'][i, :, :words]).max()
+            print(f'{precision} {location} utterance {i}: max |logit error| {error:.3e}')
+            assert error < TRANSFORMER_TC_TOLERANCE[precision]
 
 
 def test_transformer_end_to_end(emphases, golden, tmp_path):

@@ -752,3 +752,99 @@ def test_logmel_with_fused_resampling_equals_resampling_first(eng, rate, dtype):
     fused = eng.logmel(
         packed_source.buffer.cuda(), views, plan, row_seq, resample=resample)
     assert torch.equal(fused, expected)
+
+
+def _attention_case(seed, lengths, keys, channels=80, spread=1.0):
+    """Packed q, k, v rows of ragged sequences (with padded, key-masked tails)
+    and the fp64 attention of every head computed with torch"""
+    from emphases_b200 import transformer
+    heads = transformer.HEADS
+    rng = np.random.default_rng(seed)
+    row_start, n_rows, total = make_rows(lengths)
+    q, k, v = (
+        torch.from_numpy(rng.standard_normal((total, channels)).astype(np.float32) * scale)
+        for scale in (spread, spread, 1.0))
+    head_dim = channels // heads
+    expected = torch.zeros(total, channels, dtype=torch.float64)
+    for start, length, valid in zip(row_start.tolist(), lengths, keys):
+        for head in range(heads):
+            columns = slice(head * head_dim, (head + 1) * head_dim)
+            logits = q[start:start + length, columns].double() @ \
+                k[start:start + valid, columns].double().T / np.sqrt(head_dim)
+            expected[start:start + length, columns] = \
+                torch.softmax(logits, dim=1) @ v[start:start + valid, columns].double()
+    return row_start, n_rows, total, q, k, v, expected
+
+
+def _run_attention(eng, row_start, n_rows, total, q, k, v, lengths, keys, mode):
+    from emphases_b200 import _lib, transformer
+    channels = q.shape[1]
+    block_seq, block_q0 = transformer.query_blocks(np.asarray(lengths))
+    device = torch.device('cuda:0')
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total)
+    n_keys = torch.tensor(keys, dtype=torch.int32, device=device)
+    d_seq = torch.from_numpy(block_seq).to(device)
+    d_q0 = torch.from_numpy(block_q0).to(device)
+    q, k, v = q.to(device), k.to(device), v.to(device)
+    out = torch.full((total, channels), float('nan'), device=device)
+    scale = 1.0 / np.sqrt(channels // transformer.HEADS)
+    if mode is None:
+        _lib.call(
+            'emph_attention_rows', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), channels,
+            transformer.HEADS, _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(n_keys),
+            _lib.ptr(row_seq), total, _lib.ptr(d_seq), _lib.ptr(d_q0), len(block_seq),
+            scale, _lib.ptr(out), _lib.stream_ptr())
+    else:
+        workspace = transformer.attention_workspace(total, channels, mode, device)
+        workspace.fill_(0xff)                  # NaN patterns wherever staging skips a byte
+        _lib.call(
+            'emph_attention_rows_tc', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), channels,
+            transformer.HEADS, _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(n_keys),
+            _lib.ptr(row_seq), total, _lib.ptr(d_seq), _lib.ptr(d_q0), len(block_seq),
+            scale, mode, _lib.ptr(workspace), workspace.numel(), _lib.ptr(out),
+            _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+# max-abs error of the attention output (unit-variance q, k, v: logits far
+# larger than the model's) vs fp64, per form: fp32 CUDA cores, split bf16, fp16
+ATTENTION_TOLERANCE = {None: 2e-6, 1: 3e-5, 0: 4e-3}
+
+
+@pytest.mark.parametrize('channels', [80, 64, 128])
+@pytest.mark.parametrize('mode', [None, 1, 0], ids=['fp32', 'bf16x3', 'fp16'])
+def test_attention_rows_all_forms(eng, mode, channels):
+    """Block-diagonal, key-masked attention over ragged packed sequences: the
+    CUDA-core kernel and the tensor-core forms against fp64 torch; sequence
+    lengths around the 64-key tile and the 128-query block, single rows, padded
+    (masked) tails, head dims 40 / 32 / 64"""
+    lengths = [1, 7, 63, 64, 65, 127, 128, 129, 200, 333, 700]
+    keys = [1, 3, 63, 64, 60, 127, 128, 1, 137, 333, 641]
+    row_start, n_rows, total, q, k, v, expected = _attention_case(
+        5, lengths, keys, channels)
+    got = _run_attention(eng, row_start, n_rows, total, q, k, v, lengths, keys, mode)
+    rows = torch.cat([
+        torch.arange(start, start + length)
+        for start, length in zip(row_start.tolist(), lengths)])
+    separators = torch.ones(total, dtype=torch.bool)
+    separators[rows] = False
+    assert torch.all(got[separators] == 0)
+    error = (got[rows].double() - expected[rows]).abs().max().item()
+    print(f'attention mode {mode}, {channels} channels: max error {error:.3e}')
+    assert error < ATTENTION_TOLERANCE[mode], error
+
+
+def test_attention_tensor_core_peaked_softmax(eng):
+    """Large logits (|q.k|/sqrt(d) up to ~40: one key dominates each row): the
+    split form still follows fp64 to 3e-4 where 16-bit logits would not"""
+    lengths, keys = [300, 90], [300, 77]
+    row_start, n_rows, total, q, k, v, expected = _attention_case(
+        9, lengths, keys, spread=2.5)
+    rows = torch.cat([
+        torch.arange(start, start + length)
+        for start, length in zip(row_start.tolist(), lengths)])
+    exact = _run_attention(eng, row_start, n_rows, total, q, k, v, lengths, keys, None)
+    split = _run_attention(eng, row_start, n_rows, total, q, k, v, lengths, keys, 1)
+    assert (exact[rows].double() - expected[rows]).abs().max() < 2e-5
+    assert (split[rows].double() - expected[rows]).abs().max() < 3e-4
