@@ -15,7 +15,10 @@
 //   attention_rows_tc_kernel  FlashAttention-2 register flow on mma.sync
 //       m16n8k16 (fp32 accumulators).  A CTA of 8 warps owns one block of 128
 //       queries, 16 per warp, Q fragments in registers; key tiles arrive in a
-//       two-stage ring (mbarrier + bulk copy issued one tile ahead).  Per tile
+//       three-stage ring of bulk copies issued two tiles ahead.  The ring runs
+//       on mbarriers alone ("full": the copy landed; "empty": all 8 warps have
+//       read the stage), so the warps of a CTA never wait for each other --
+//       while one is in its softmax another keeps the tensor pipe busy.  Per tile
 //       and warp: S = Q K^T (B = K records through ldmatrix), online softmax on
 //       the accumulator fragments in the log2 domain, and the S fragments ARE
 //       the A fragments of O += P V (B = V records through ldmatrix.trans).
@@ -41,6 +44,7 @@ namespace attn_tc {
 constexpr int kThreads = 256;
 constexpr int kQueries = 128;      // per CTA = the host's query block
 constexpr int kKeys = 64;          // per shared-memory tile
+constexpr int kStages = 3;         // key tiles in flight
 enum { kPlainFp16 = 0, kSplitBf16 = 1 };
 
 template <int D, int MODE>
@@ -51,7 +55,7 @@ struct Layout {
     static constexpr int kContent = NP * (DP + D) * 2;      // bytes
     static constexpr int kRecord = kContent % 32 == 16 ? kContent : kContent + 16;
     static constexpr int kTileBytes = kKeys * kRecord;
-    static constexpr int kSmemBytes = 2 * kTileBytes + 16;  // + two mbarriers
+    static constexpr int kSmemBytes = kStages * kTileBytes + 16 * kStages;  // + mbarriers
     static_assert(D % 8 == 0, "head dim must be a multiple of 8");
     static_assert(kRecord % 32 == 16, "ldmatrix rows must land on distinct banks");
 };
@@ -116,6 +120,11 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t add
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b64 state;\n\t"
+        "mbarrier.arrive.shared::cta.b64 state, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -200,7 +209,8 @@ attention_rows_tc_kernel(
     constexpr bool SPLIT = MODE == kSplitBf16;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tiles = smem_u32(smem);
-    const uint32_t bars = tiles + 2 * L::kTileBytes;
+    const uint32_t full = tiles + kStages * L::kTileBytes;   // one 8-byte barrier per stage
+    const uint32_t empty = full + 8 * kStages;
 
     const int u = block_seq[blockIdx.x];
     const int q0 = block_q0[blockIdx.x];
@@ -218,11 +228,19 @@ attention_rows_tc_kernel(
         staged + ((size_t)head * padded_rows + base) * L::kRecord;
 
     if (threadIdx.x == 0) {
-        mbar_init(bars, 1);
-        mbar_init(bars + 8, 1);
+#pragma unroll
+        for (int stage = 0; stage < kStages; ++stage) {
+            mbar_init(full + 8 * stage, 1);
+            mbar_init(empty + 8 * stage, kThreads / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (n_tiles > 0) bulk_fetch(tiles, source, L::kTileBytes, bars);
+#pragma unroll
+        for (int ahead = 0; ahead < kStages - 1; ++ahead)
+            if (ahead < n_tiles)
+                bulk_fetch(tiles + ahead * L::kTileBytes, source + (size_t)ahead * L::kTileBytes,
+                           L::kTileBytes, full + 8 * ahead);
     }
+    __syncthreads();                           // the barriers exist for everyone
 
     // A fragments of Q (m16 x k16 per k-step): a0 (g, 2t) a1 (g+8, 2t) a2 (g, 2t+8) a3 (g+8, 2t+8)
     uint32_t qf[NP][KS][4];
@@ -249,16 +267,20 @@ attention_rows_tc_kernel(
     const uint32_t v_lane =
         (uint32_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * L::kRecord + 2u * L::kOffV;
 
+    // ring position of `tile` and of the tile fetched now (kStages - 1 ahead)
+    int slot = 0, use = 0, next_slot = kStages - 1, next_use = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
         const int count = min(kKeys, nk - tile * kKeys);
-        const uint32_t stage = tiles + (tile & 1) * L::kTileBytes;
-        // every warp is done with tile - 1: its stage may take tile + 1
-        __syncthreads();
-        if (threadIdx.x == 0 && tile + 1 < n_tiles)
-            bulk_fetch(tiles + ((tile + 1) & 1) * L::kTileBytes,
-                       source + (size_t)(tile + 1) * L::kTileBytes, L::kTileBytes,
-                       bars + 8 * ((tile + 1) & 1));
-        mbar_wait(bars + 8 * (tile & 1), (tile >> 1) & 1);
+        const uint32_t stage = tiles + slot * L::kTileBytes;
+        if (threadIdx.x == 0 && tile + kStages - 1 < n_tiles) {
+            // tile - 1 lived in that stage: wait until all warps have read it
+            if (next_use > 0) mbar_wait(empty + 8 * next_slot, (next_use - 1) & 1);
+            bulk_fetch(tiles + next_slot * L::kTileBytes,
+                       source + (size_t)(tile + kStages - 1) * L::kTileBytes, L::kTileBytes,
+                       full + 8 * next_slot);
+        }
+        __syncwarp();
+        mbar_wait(full + 8 * slot, use & 1);
 
         // ---- S = Q K^T: 8 n-tiles of 8 keys ----
         float s[kKeys / 8][4];
@@ -355,6 +377,11 @@ attention_rows_tc_kernel(
                 }
             }
         }
+        // this warp's last read of the stage is done (ldmatrix is synchronous)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8 * slot);
+        if (++slot == kStages) { slot = 0; ++use; }
+        if (++next_slot == kStages) { next_slot = 0; ++next_use; }
     }
 
 #pragma unroll
