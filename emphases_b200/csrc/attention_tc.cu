@@ -152,13 +152,15 @@ __device__ __forceinline__ void bulk_fetch(
 // K, V rows -> staged 16-bit records.  One thread per (row, 8-dim chunk, head);
 // rows [total_rows, padded_rows) and K's padded dims are zeros, so a key tile
 // may always be fetched whole (its tail past the sequence is masked in S and
-// meets finite V values).
+// meets finite V values).  The same threads zero the separator rows of the
+// attention output (no query block covers them).
 // ---------------------------------------------------------------------------
 template <int D, int MODE>
 __global__ void __launch_bounds__(256)
 attention_stage_kernel(
     const float* __restrict__ k, const float* __restrict__ v, int channels,
-    int total_rows, int padded_rows, unsigned char* __restrict__ staged) {
+    int total_rows, int padded_rows, unsigned char* __restrict__ staged,
+    const int32_t* __restrict__ row_seq, float* __restrict__ out) {
     using L = Layout<D, MODE>;
     constexpr int kChunks = L::DP / 8;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,6 +175,11 @@ attention_stage_kernel(
         kb = *reinterpret_cast<const float4*>(k + src + 4);
         va = *reinterpret_cast<const float4*>(v + src);
         vb = *reinterpret_cast<const float4*>(v + src + 4);
+        if (row_seq[row] < 0) {
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(out + src) = zero;
+            *reinterpret_cast<float4*>(out + src + 4) = zero;
+        }
     }
     unsigned char* record = staged + ((size_t)head * padded_rows + row) * L::kRecord;
     uint4 kh, vh;
@@ -272,6 +279,12 @@ attention_rows_tc_kernel(
     for (int tile = 0; tile < n_tiles; ++tile) {
         const int count = min(kKeys, nk - tile * kKeys);
         const uint32_t stage = tiles + slot * L::kTileBytes;
+#ifdef EMPH_ATTENTION_CTA_BARRIER
+        // sanitizer builds only: racecheck does not see the ordering that the
+        // "empty" mbarriers give (ldmatrix reads -> refill of the stage by the
+        // async proxy); with a CTA barrier here it can check everything else
+        __syncthreads();
+#endif
         if (threadIdx.x == 0 && tile + kStages - 1 < n_tiles) {
             // tile - 1 lived in that stage: wait until all warps have read it
             if (next_use > 0) mbar_wait(empty + 8 * next_slot, (next_use - 1) & 1);
@@ -299,6 +312,8 @@ attention_rows_tc_kernel(
                     b[2 * s2][0] = r4[0]; b[2 * s2][1] = r4[1];
                     b[2 * s2 + 1][0] = r4[2]; b[2 * s2 + 1][1] = r4[3];
                 }
+                // (head dim 40: the third k-step is half padding, but an m16n8k8
+                // costs the same 8 clk as an m16n8k16, profiles/r02x_mma_sync_microbench.txt)
                 if (KS & 1) ldmatrix_x2(b[KS - 1], rows + k_lane_tail + 32 * (KS - 1));
 #pragma unroll
                 for (int step = 0; step < KS; ++step) {
@@ -402,7 +417,7 @@ attention_rows_tc_kernel(
 struct Call {
     const float *q, *k, *v;
     int channels, heads;
-    const int32_t *row_start, *n_queries, *n_keys;
+    const int32_t *row_start, *n_queries, *n_keys, *row_seq;
     int total_rows;
     const int32_t *block_seq, *block_q0;
     int n_blocks;
@@ -430,8 +445,9 @@ int run(const Call& c) {
     const long long items = (long long)rows * (L::DP / 8);
     attention_stage_kernel<D, MODE><<<dim3((unsigned)((items + 255) / 256), c.heads), 256, 0,
                                       c.stream>>>(
-        c.k, c.v, c.channels, c.total_rows, rows, c.workspace);
+        c.k, c.v, c.channels, c.total_rows, rows, c.workspace, c.row_seq, c.out);
     EMPH_CHECK_LAUNCH("emph_attention_rows_tc(stage)");
+    if (c.n_blocks == 0) return EMPH_OK;
     const int status = check_cuda(
         cudaFuncSetAttribute(attention_rows_tc_kernel<D, MODE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes),
@@ -461,15 +477,6 @@ size_t workspace_mode(int mode, int total_rows, int heads) {
                               : workspace_bytes<D, kPlainFp16>(total_rows, heads);
 }
 
-// separator rows are zero
-__global__ void clear_separators_kernel(
-    const int32_t* __restrict__ row_seq, int total_rows, int channels, float* __restrict__ out) {
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= total_rows) return;
-    if (row_seq[r] >= 0) return;
-    for (int c = threadIdx.x & 31; c < channels; c += 32) out[(size_t)r * channels + c] = 0.f;
-}
-
 }  // namespace attn_tc
 }  // namespace emph
 
@@ -497,14 +504,11 @@ int emph_attention_rows_tc(
     const int head_dim = channels / heads;
     if (total_rows == 0) return EMPH_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    emph::attn_tc::clear_separators_kernel<<<(total_rows + 7) / 8, 256, 0, st>>>(
-        row_seq, total_rows, channels, out);
-    EMPH_CHECK_LAUNCH("emph_attention_rows_tc(clear)");
-    if (n_blocks == 0) return EMPH_OK;
     EMPH_REQUIRE(workspace != nullptr && workspace_bytes >= 0,
                  "emph_attention_rows_tc: no workspace");
     const emph::attn_tc::Call call{
-        q, k, v, channels, heads, row_start, n_queries, n_keys, total_rows, block_seq, block_q0,
+        q, k, v, channels, heads, row_start, n_queries, n_keys, row_seq, total_rows, block_seq,
+        block_q0,
         n_blocks, scale, (unsigned char*)workspace, (size_t)workspace_bytes, out, st};
     switch (head_dim) {
         case 40: return emph::attn_tc::run_mode<40>(mode, call);
