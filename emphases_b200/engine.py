@@ -529,12 +529,15 @@ def tensor_core_shape(stack):
 
 
 def linear_precision(stack):
-    """Per-row linear maps of the Transformer variant (kernel-size-1 stacks):
-    the fp32-grade tensor-core mode whenever a tensor-core PRECISION is
-    selected (attention, LayerNorm and the residual path stay fp32, so the
-    variant keeps its fp32-grade parity), else the FFMA kernel"""
-    if emphases_precision() != _lib.PREC_FP32 and tensor_core_shape(stack):
-        return _lib.PREC_BF16X6_TC
+    """Per-row linear maps of the Transformer variant (kernel-size-1 stacks) run
+    at fp32 grade on the tensor cores whenever a tensor-core PRECISION is
+    selected: split-bf16 `bf16x6` in the 1e-5 mode, `bf16x3` in the 'bf16x3'
+    and 'bf16' modes (scores of bench.py's corpus within 9e-6 of the fp32 mode
+    with x3 maps and split-bf16 attention, 2.8e-4 with fp16 attention); else
+    the FFMA kernel.  LayerNorm and the residual path stay fp32."""
+    precision = emphases_precision()
+    if precision != _lib.PREC_FP32 and tensor_core_shape(stack):
+        return _lib.PREC_BF16X6_TC if precision == _lib.PREC_BF16X6_TC else _lib.PREC_BF16X3_TC
     return _lib.PREC_FP32
 
 

@@ -61,12 +61,62 @@ class Transformer(torch.nn.Module):
 
 
 @dataclasses.dataclass
+class FusedLayer:
+    """Operands of csrc/transformer_tc.cu: bf16 weight parts
+    [matrix][part][out][in + 8] and fp32 biases"""
+    qkv_weight: torch.Tensor
+    qkv_bias: torch.Tensor
+    out_weight: torch.Tensor
+    out_bias: torch.Tensor
+    ffn_weight: torch.Tensor
+    ffn_bias: torch.Tensor
+
+
+def split_parts(matrices, parts, device):
+    """[(out, in) fp32] -> bf16 (matrices, parts, out, in + 8): part p is the
+    bf16 rounding of what parts < p left over (round to nearest even, like
+    cvt.rn.bf16x2.f32 on the activation side)"""
+    blob = torch.zeros(
+        (len(matrices), parts) + (matrices[0].shape[0], matrices[0].shape[1] + 8),
+        dtype=torch.bfloat16, device=device)
+    for index, matrix in enumerate(matrices):
+        rest = matrix.detach().to(device, torch.float32).clone()
+        for part in range(parts):
+            rounded = rest.to(torch.bfloat16)
+            blob[index, part, :, :matrix.shape[1]] = rounded
+            rest -= rounded.float()
+    return blob.contiguous()
+
+
+@dataclasses.dataclass
 class EncoderLayer:
     qkv: List[engine.ConvStack]          # three 1-layer, kernel-1 stacks
     out_proj: engine.ConvStack
     feedforward: engine.ConvStack        # linear1 + ReLU + linear2, fused
     norm1: tuple
     norm2: tuple
+    raw: dict = None                     # the module's fp32 tensors (fused path)
+    packs: dict = dataclasses.field(default_factory=dict)
+
+    def fused(self, parts, device) -> FusedLayer:
+        if parts not in self.packs:
+            raw, channels = self.raw, self.norm1[0].shape[0]
+            in_proj = raw['in_proj_weight']
+
+            def vector(*names):
+                return torch.cat([
+                    raw[name].detach().to(device, torch.float32).reshape(-1)
+                    for name in names]).contiguous()
+            self.packs[parts] = FusedLayer(
+                split_parts(
+                    [in_proj[i * channels:(i + 1) * channels] for i in range(3)],
+                    parts, device),
+                vector('in_proj_bias'),
+                split_parts([raw['out_proj.weight']], parts, device),
+                vector('out_proj.bias'),
+                split_parts([raw['linear1.weight'], raw['linear2.weight']], parts, device),
+                vector('linear1.bias', 'linear2.bias'))
+        return self.packs[parts]
 
 
 @dataclasses.dataclass
@@ -113,8 +163,16 @@ def pack_stack(state, prefix, layers, channels, device):
             return (
                 state[f'{p}.{name}.weight'].detach().to(device, torch.float32).contiguous(),
                 state[f'{p}.{name}.bias'].detach().to(device, torch.float32).contiguous())
+        raw = {
+            'in_proj_weight': w, 'in_proj_bias': b,
+            'out_proj.weight': state[f'{p}.self_attn.out_proj.weight'],
+            'out_proj.bias': state[f'{p}.self_attn.out_proj.bias'],
+            'linear1.weight': state[f'{p}.linear1.weight'],
+            'linear1.bias': state[f'{p}.linear1.bias'],
+            'linear2.weight': state[f'{p}.linear2.weight'],
+            'linear2.bias': state[f'{p}.linear2.bias']}
         encoder_layers.append(EncoderLayer(
-            qkv, out_proj, feedforward, norm('norm1'), norm('norm2')))
+            qkv, out_proj, feedforward, norm('norm1'), norm('norm2'), raw))
     table = state[f'{prefix}.position.encoding'].detach().to(
         device, torch.float32)[:, 0, :].contiguous()
     return TransformerStack(table, encoder_layers, channels)
@@ -177,13 +235,64 @@ def attention_mode():
     return ATTENTION_MODES.get(choice)
 
 
-def attention_workspace(total_rows, channels, mode, device):
-    """Device buffer for the 16-bit K / V records of one attention call"""
+def attention_workspace(total_rows, channels, mode, device, zero=False):
+    """Device buffer for the 16-bit K / V records of one attention call
+    (`zero`: the fused layer kernels write only the live elements of a record)"""
     size = _lib.load().emph_attention_tc_workspace(total_rows, channels, HEADS, mode)
     if size < 0:
         raise NotImplementedError(
             f'tensor-core attention is not compiled for {channels // HEADS}-dim heads')
-    return torch.empty(max(size, 1), dtype=torch.uint8, device=device)
+    make = torch.zeros if zero else torch.empty
+    return make(max(size, 1), dtype=torch.uint8, device=device)
+
+
+FUSED_CHANNELS = 80                # csrc/transformer_tc.cu is compiled for d_model 80
+
+
+def fused_layers(channels, mode):
+    """The fused per-row passes (emph_transformer_qkv / _proj_norm / _ffn_norm)
+    serve the default width whenever attention runs on the tensor cores;
+    EMPHASES_B200_FUSED_LAYERS=0 keeps the per-op launches"""
+    import os
+    return (
+        mode is not None and channels == FUSED_CHANNELS
+        and os.environ.get('EMPHASES_B200_FUSED_LAYERS', '1') != '0')
+
+
+def run_fused_layers(
+    stack, h, mode, row_start, n_queries, n_keys, row_seq, d_block_seq, d_block_q0,
+    n_blocks, scale, device
+):
+    """Every encoder layer as qkv -> attention -> out_proj + LayerNorm ->
+    feed-forward + LayerNorm: four launches, five row buffers for the stack"""
+    total_rows, channels = h.shape
+    parts = 3 if emphases.PRECISION == 'bf16x6' else 2
+    records = attention_workspace(total_rows, channels, mode, device, zero=True)
+    q, context, normed, spare = (torch.empty_like(h) for _ in range(4))
+    stream = _lib.stream_ptr()
+    for layer in stack.layers:
+        pack = layer.fused(parts, device)
+        _lib.call(
+            'emph_transformer_qkv', _lib.ptr(h), total_rows, channels,
+            _lib.ptr(pack.qkv_weight), _lib.ptr(pack.qkv_bias), parts, mode, _lib.ptr(q),
+            _lib.ptr(records), records.numel(), stream)
+        _lib.call(
+            'emph_attention_rows_staged', _lib.ptr(q), _lib.ptr(records), records.numel(),
+            channels, HEADS, _lib.ptr(row_start), _lib.ptr(n_queries), _lib.ptr(n_keys),
+            total_rows, _lib.ptr(d_block_seq), _lib.ptr(d_block_q0), n_blocks, scale, mode,
+            _lib.ptr(context), stream)
+        _lib.call(
+            'emph_transformer_proj_norm', _lib.ptr(context), _lib.ptr(h), total_rows, channels,
+            _lib.ptr(pack.out_weight), _lib.ptr(pack.out_bias), parts,
+            _lib.ptr(layer.norm1[0]), _lib.ptr(layer.norm1[1]), 1e-5, _lib.ptr(row_seq),
+            _lib.ptr(normed), stream)
+        _lib.call(
+            'emph_transformer_ffn_norm', _lib.ptr(normed), total_rows, channels,
+            _lib.ptr(pack.ffn_weight), _lib.ptr(pack.ffn_bias), parts,
+            _lib.ptr(layer.norm2[0]), _lib.ptr(layer.norm2[1]), 1e-5, _lib.ptr(row_seq),
+            _lib.ptr(spare), stream)
+        h, spare = spare, h
+    return h
 
 
 def query_blocks(n_keys, block=128):
@@ -218,7 +327,8 @@ def run_stack(
     d_block_q0 = meta[2 * n_seq + len(block_seq):]
     scale = 1.0 / math.sqrt(channels // HEADS)
     mode = attention_mode()
-    workspace = None if mode is None else attention_workspace(
+    fused = fused_layers(channels, mode)
+    workspace = None if mode is None or fused else attention_workspace(
         total_rows, channels, mode, device)
 
     h = torch.empty_like(x)
@@ -226,6 +336,10 @@ def run_stack(
         'emph_add_positional', _lib.ptr(x), _lib.ptr(row_start),
         _lib.ptr(row_seq), total_rows, channels, _lib.ptr(stack.table),
         stack.table.shape[0], _lib.ptr(h), _lib.stream_ptr())
+    if fused:
+        return run_fused_layers(
+            stack, h, mode, row_start, n_queries, n_keys, row_seq, d_block_seq, d_block_q0,
+            len(block_seq), scale, device)
     for layer in stack.layers:
         q, k, v = (
             eng.conv_stack(h, row_seq, part, engine.linear_precision(part))

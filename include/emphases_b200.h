@@ -411,6 +411,44 @@ int emph_attention_rows_tc(
     void* workspace, int64_t workspace_bytes, float* out, void* stream);
 int64_t emph_attention_tc_workspace(
     int32_t total_rows, int32_t channels, int32_t heads, int32_t mode);
+
+/*
+ * One Transformer encoder layer (transformer.py:18-23: post-norm
+ * nn.TransformerEncoderLayer, ReLU, dim_feedforward = channels = 80) as three
+ * fused per-row passes around the attention kernel (csrc/transformer_tc.cu),
+ * fp32 grade on mma.sync: activations and weights split into `parts` bf16
+ * parts (2: three products, 3: six products).  Weight blobs are bf16
+ * [matrix][part][out][in + 8] (part p = bf16 of what parts < p left over).
+ *
+ * emph_transformer_qkv: q = x Wq^T + bq as fp32 rows; k and v are written
+ *   directly as the 16-bit records emph_attention_rows_staged reads
+ *   (`attention_mode` as in emph_attention_rows_tc; the buffer has
+ *   emph_attention_tc_workspace bytes and must have been zeroed once).
+ *   weights: 3 matrices (rows 0..79 / 80..159 / 160..239 of in_proj_weight).
+ * emph_attention_rows_staged: emph_attention_rows_tc without the staging pass.
+ * emph_transformer_proj_norm: y = LayerNorm(residual + x W^T + b).
+ * emph_transformer_ffn_norm: y = LayerNorm(x + relu(x W1^T + b1) W2^T + b2)
+ *   (weights: 2 matrices, bias: b1 then b2).  Separator rows of y are zero.
+ */
+int emph_transformer_qkv(
+    const float* x, int32_t total_rows, int32_t channels, const void* weights,
+    const float* bias, int32_t parts, int32_t attention_mode, float* q,
+    void* staged, int64_t staged_bytes, void* stream);
+int emph_attention_rows_staged(
+    const float* q, const void* staged, int64_t staged_bytes, int32_t channels,
+    int32_t heads, const int32_t* row_start, const int32_t* n_queries,
+    const int32_t* n_keys, int32_t total_rows, const int32_t* block_seq,
+    const int32_t* block_q0, int32_t n_blocks, float scale, int32_t mode,
+    float* out, void* stream);
+int emph_transformer_proj_norm(
+    const float* x, const float* residual, int32_t total_rows, int32_t channels,
+    const void* weights, const float* bias, int32_t parts, const float* gamma,
+    const float* beta, float eps, const int32_t* row_seq, float* y,
+    void* stream);
+int emph_transformer_ffn_norm(
+    const float* x, int32_t total_rows, int32_t channels, const void* weights,
+    const float* bias, int32_t parts, const float* gamma, const float* beta,
+    float eps, const int32_t* row_seq, float* y, void* stream);
 int emph_add_layernorm(
     const float* x, const float* residual, const float* gamma,
     const float* beta, float eps, const int32_t* row_seq, int32_t total_rows,

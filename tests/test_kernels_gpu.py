@@ -848,3 +848,102 @@ def test_attention_tensor_core_peaked_softmax(eng):
     split = _run_attention(eng, row_start, n_rows, total, q, k, v, lengths, keys, 1)
     assert (exact[rows].double() - expected[rows]).abs().max() < 2e-5
     assert (split[rows].double() - expected[rows]).abs().max() < 3e-4
+
+
+@pytest.mark.parametrize('parts', [2, 3])
+def test_transformer_fused_passes(eng, parts):
+    """csrc/transformer_tc.cu against fp64 torch on ragged packed rows: the
+    out-projection + residual + LayerNorm pass, the feed-forward + residual +
+    LayerNorm pass, and the q / k / v pass whose k / v records feed
+    emph_attention_rows_staged (checked through the attention output)"""
+    from emphases_b200 import _lib, transformer
+    device = torch.device('cuda:0')
+    lengths, keys = [1, 37, 128, 130, 261], [1, 30, 128, 97, 261]
+    row_start, n_rows, total = make_rows(lengths)
+    row_seq = eng.row_index(row_start, n_rows, len(lengths), total)
+    rows = torch.cat([
+        torch.arange(start, start + length)
+        for start, length in zip(row_start.tolist(), lengths)])
+    generator = torch.Generator().manual_seed(7)
+    channels = 80
+
+    def normal(*shape, scale=1.0):
+        return torch.randn(*shape, generator=generator) * scale
+
+    x, residual = normal(total, channels), normal(total, channels)
+    weight = [normal(channels, channels, scale=channels ** -.5) for _ in range(5)]
+    bias = [normal(channels, scale=.1) for _ in range(5)]
+    gamma, beta = 1 + normal(channels, scale=.1), normal(channels, scale=.1)
+    tolerance = {2: 3e-5, 3: 2e-6}[parts]
+
+    def layernorm(value):
+        return torch.nn.functional.layer_norm(
+            value, (channels,), gamma.double(), beta.double(), 1e-5)
+
+    def check(got, want):
+        got = got.cpu()
+        separators = torch.ones(total, dtype=torch.bool)
+        separators[rows] = False
+        assert torch.all(got[separators] == 0)
+        error = (got[rows].double() - want[rows]).abs().max().item()
+        assert error < tolerance, error
+
+    dx, dres = x.to(device), residual.to(device)
+    dgamma, dbeta = gamma.to(device), beta.to(device)
+    stream = _lib.stream_ptr()
+
+    # y = LayerNorm(residual + x W^T + b)
+    blob = transformer.split_parts([weight[0]], parts, device)
+    dbias = bias[0].to(device)
+    y = torch.full_like(dx, float('nan'))
+    _lib.call(
+        'emph_transformer_proj_norm', _lib.ptr(dx), _lib.ptr(dres), total, channels,
+        _lib.ptr(blob), _lib.ptr(dbias), parts, _lib.ptr(dgamma), _lib.ptr(dbeta), 1e-5,
+        _lib.ptr(row_seq), _lib.ptr(y), stream)
+    check(y, layernorm(residual.double() + x.double() @ weight[0].double().T + bias[0].double()))
+
+    # y = LayerNorm(x + relu(x W1^T + b1) W2^T + b2)
+    blob = transformer.split_parts(weight[:2], parts, device)
+    dbias = torch.cat(bias[:2]).to(device)
+    y = torch.full_like(dx, float('nan'))
+    _lib.call(
+        'emph_transformer_ffn_norm', _lib.ptr(dx), total, channels, _lib.ptr(blob),
+        _lib.ptr(dbias), parts, _lib.ptr(dgamma), _lib.ptr(dbeta), 1e-5, _lib.ptr(row_seq),
+        _lib.ptr(y), stream)
+    hidden = torch.relu(x.double() @ weight[0].double().T + bias[0].double())
+    check(y, layernorm(x.double() + hidden @ weight[1].double().T + bias[1].double()))
+
+    # q rows + k / v records -> attention
+    q64, k64, v64 = (
+        x.double() @ weight[2 + i].double().T + bias[2 + i].double() for i in range(3))
+    blob = transformer.split_parts(weight[2:], parts, device)
+    dbias = torch.cat(bias[2:]).to(device)
+    heads, head_dim = transformer.HEADS, channels // transformer.HEADS
+    expected = torch.zeros(total, channels, dtype=torch.float64)
+    for start, length, valid in zip(row_start.tolist(), lengths, keys):
+        for head in range(heads):
+            columns = slice(head * head_dim, (head + 1) * head_dim)
+            logits = q64[start:start + length, columns] @ \
+                k64[start:start + valid, columns].T / np.sqrt(head_dim)
+            expected[start:start + length, columns] = \
+                torch.softmax(logits, dim=1) @ v64[start:start + valid, columns]
+    block_seq, block_q0 = transformer.query_blocks(np.asarray(lengths))
+    d_seq, d_q0 = torch.from_numpy(block_seq).to(device), torch.from_numpy(block_q0).to(device)
+    n_keys = torch.tensor(keys, dtype=torch.int32, device=device)
+    for mode, bound in ((1, 2e-4), (0, 2e-2)):
+        records = transformer.attention_workspace(total, channels, mode, device, zero=True)
+        q = torch.full_like(dx, float('nan'))
+        out = torch.zeros_like(dx)
+        _lib.call(
+            'emph_transformer_qkv', _lib.ptr(dx), total, channels, _lib.ptr(blob),
+            _lib.ptr(dbias), parts, mode, _lib.ptr(q), _lib.ptr(records), records.numel(),
+            stream)
+        _lib.call(
+            'emph_attention_rows_staged', _lib.ptr(q), _lib.ptr(records), records.numel(),
+            channels, heads, _lib.ptr(row_start), _lib.ptr(n_rows), _lib.ptr(n_keys), total,
+            _lib.ptr(d_seq), _lib.ptr(d_q0), len(block_seq), 1.0 / np.sqrt(head_dim), mode,
+            _lib.ptr(out), stream)
+        torch.cuda.synchronize()
+        assert (q.cpu()[rows].double() - q64[rows]).abs().max() < tolerance
+        error = (out.cpu()[rows].double() - expected[rows]).abs().max().item()
+        assert error < bound, (mode, error)
