@@ -512,9 +512,10 @@ def time_transformer_variant(
         'value': audio_seconds / (ms * 1e-3), 'unit': 'audio-s/s', 'ms_per_step': ms,
         'steps': steps, 'utterances': int(plan.n_seq),
         'workload': 'configs[2]: Transformer-layer variant, same corpus, kernel-only',
-        'note': ('attention on the tensor cores (csrc/attention_tc.cu: mma.sync, fp16 operands '
-                 'in the bf16 mode, split bf16 in the fp32-grade modes), the per-row linear '
-                 'maps on tcgen05 (bf16x6)')}
+        'note': ('per layer: fused q/k/v, out-projection + LayerNorm and feed-forward + '
+                 'LayerNorm passes (csrc/transformer_tc.cu, split-bf16 mma.sync) around '
+                 'tensor-core attention (csrc/attention_tc.cu: fp16 operands in the bf16 mode, '
+                 'split bf16 in the fp32-grade modes)')}
 
 
 def synthetic_training_batch(seed, max_frames=75000):
