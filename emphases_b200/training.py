@@ -549,6 +549,9 @@ def allreduce_gradients(model, average=True):
     ) and len(state.ordered) == sum(1 for _ in model.parameters()):
         # the native step wrote every gradient into one flat buffer that the
         # .grad tensors alias: reduce it in place, no packing or copy-back
+        if average and dist.get_backend() == 'nccl':
+            dist.all_reduce(state.flat, op=dist.ReduceOp.AVG)     # no separate scaling launch
+            return
         dist.all_reduce(state.flat, op=dist.ReduceOp.SUM)
         if average:
             state.flat.div_(world)
