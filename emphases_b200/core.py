@@ -68,6 +68,12 @@ def from_file_to_file(
     torch.save(results.cpu(), f'{output_prefix}.pt')
 
 
+# from_files_to_files: write a launch's .pt files while later launches run
+# (EMPHASES_B200_OVERLAP_SCORE_WRITES=0: all of them after the last launch)
+OVERLAP_SCORE_WRITES = os.environ.get('EMPHASES_B200_OVERLAP_SCORE_WRITES', '1') != '0'
+SCORE_WRITER_THREADS = 8
+
+
 def from_files_to_files(
     text_files,
     audio_files,
@@ -134,7 +140,24 @@ def from_files_to_files(
                         packed, rate, emphases.SAMPLE_RATE, device)
                 if single_device:
                     # per launch: the words of its files in one flat host tensor
-                    # (no 24,000-way split: the native writer takes pointers)
+                    # (no 24,000-way split: the native writer takes pointers),
+                    # written as {prefix}.pt -- the archives torch.save would
+                    # write -- on a background thread while later launches are
+                    # decoded and run; on its own few threads (negative count),
+                    # beside the decode that owns the worker pool
+                    def write_launch(members, flat_scores, counts, indices=indices):
+                        files = indices[np.asarray(members, dtype=np.int64)]
+                        corpus.write_score_rows(
+                            [output_prefixes[i] for i in files.tolist()], flat_scores,
+                            counts, -SCORE_WRITER_THREADS, suffix='.pt')
+                        for index in files:
+                            scores[int(index)] = True
+
+                    if OVERLAP_SCORE_WRITES:
+                        from_alignments_and_audio(
+                            times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size,
+                            gpu, flat=True, sink=write_launch)
+                        continue
                     for members, flat_scores, counts in from_alignments_and_audio(
                         times, packed, emphases.SAMPLE_RATE, checkpoint, batch_size,
                         gpu, flat=True
@@ -235,13 +258,15 @@ def from_alignments_and_audio(
     gpu=None,
     to_cpu=True,
     model=None,
-    flat=False
+    flat=False,
+    sink=None
 ):
     """Batched form of from_alignment_and_audio (extension): lists in, list
     of (1, W_i) score tensors out.  `gpu` may be a list of device indices:
     utterances are split with the length-balanced scheduler and each shard
     runs on its own device; results are gathered on the host.  flat=True
-    (one device): scheduler.run_on_device's unsplit per-launch results."""
+    (one device): scheduler.run_on_device's unsplit per-launch results, handed
+    to `sink` launch by launch on a background thread when one is given."""
     from . import scheduler
     if isinstance(gpu, (list, tuple)) and len(gpu) > 1:
         if flat:
@@ -256,7 +281,7 @@ def from_alignments_and_audio(
     with torch.cuda.device(device):
         return scheduler.run_on_device(
             model, alignments, audios, sample_rate, batch_size, device, to_cpu,
-            flat=flat)
+            flat=flat, sink=sink)
 
 
 ###############################################################################

@@ -182,7 +182,9 @@ class Corpus:
 
 def write_score_rows(paths, flat_scores, counts, threads=None, suffix=''):
     """torch.save(row_i[None], paths[i] + suffix) where row i is the next
-    counts[i] values of ONE flat fp32 host tensor: no per-file tensor objects"""
+    counts[i] values of ONE flat fp32 host tensor: no per-file tensor objects.
+    threads < 0: that many threads of the call's own instead of the shared
+    worker pool (a writer running beside a decode that occupies the pool)"""
     lib = _lib.load()
     flat_scores = flat_scores.detach()
     if flat_scores.device.type != 'cpu' or flat_scores.dtype != torch.float32 \

@@ -647,12 +647,16 @@ int emph_write_score_rows(
     int32_t n_files, int32_t n_threads) {
     if (n_files < 0 || (n_files > 0 && (!paths || !rows || !counts))) return EMPH_EINVAL;
     std::atomic<int> failures(0);
-    pooled_for(n_files, n_threads, [&](int i) {
+    auto write = [&](int i) {
         if (paths[i] == nullptr || paths[i][0] == 0) return;
         if (counts[i] < 0 || (counts[i] > 0 && !rows[i]) ||
             !write_score_file(paths[i], rows[i], (uint32_t)counts[i]))
             ++failures;
-    });
+    };
+    // n_threads < 0: -n_threads threads of this call's own (it runs beside a
+    // decode that occupies the shared pool)
+    if (n_threads < 0) parallel_for(n_files, -n_threads, write);
+    else pooled_for(n_files, n_threads, write);
     return failures.load() == 0 ? EMPH_OK : EMPH_EINVAL;
 }
 

@@ -356,9 +356,63 @@ def _prepare(audios, sample_rate, device=None):
     return pack_audio(audios, pin=False)
 
 
+def _flat_result(members, plan, scores):
+    """(utterance indices, their words' values in order as one flat tensor,
+    words per utterance) of one launch"""
+    # word rows without separators are all words of all utterances in order
+    keep = torch.from_numpy(np.nonzero(plan.word_seq >= 0)[0])
+    # (indexing copies, so the pinned staging buffer can be reused)
+    flat_scores = scores[keep.to(scores.device)] if len(keep) else scores[:0].clone()
+    per_utterance = np.bincount(
+        plan.utterance, weights=plan.n_words, minlength=len(members)
+    ).astype(np.int64)
+    return members, flat_scores, per_utterance
+
+
+class _LaunchSink:
+    """Hands every launch's flat host result to `consume` on a background
+    thread as soon as its device -> host copy has landed, while later launches
+    are still being decoded, uploaded and run (from_files_to_files writes the
+    .pt files of launch i under the decode of launch i + k)."""
+
+    def __init__(self, consume):
+        import queue
+        import threading
+        self.consume = consume
+        self.queue = queue.Queue()
+        self.failure = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            item = self.queue.get()
+            if item is None:
+                return
+            if self.failure is not None:
+                continue                      # drain
+            members, plan, scores, event = item
+            try:
+                event.synchronize()
+                self.consume(*_flat_result(members, plan, scores))
+            except BaseException as error:    # re-raised on the caller's thread
+                self.failure = error
+
+    def put(self, members, plan, scores, stream):
+        event = torch.cuda.Event()
+        event.record(stream)
+        self.queue.put((members, plan, scores, event))
+
+    def close(self):
+        self.queue.put(None)
+        self.thread.join()
+        if self.failure is not None:
+            raise self.failure
+
+
 def run_on_device(
     model, alignments, audios, sample_rate, batch_size, device, to_cpu=True,
-    output='scores', flat=False
+    output='scores', flat=False, sink=None
 ):
     """Run a list of utterances on one device; returns a list of (1, W_i)
     score tensors (CPU when to_cpu, else on `device`).  output='logits'
@@ -366,7 +420,11 @@ def run_on_device(
     emphases/evaluate/core.py:73-94).  flat=True (host results only) skips the
     per-utterance split: a list of (utterance indices, flat fp32 host tensor
     of their words in order, words per utterance), one entry per launch --
-    what the native .pt writer of from_files_to_files consumes."""
+    what the native .pt writer of from_files_to_files consumes.  `sink`
+    (with flat=True): a callable taking such an entry, called on a background
+    thread launch by launch while later launches run; nothing is returned."""
+    if sink is not None and not (flat and to_cpu):
+        raise ValueError('a sink takes flat host results')
     if output not in ('scores', 'logits'):
         raise ValueError(f'output {output} is not defined')
     emphases.require_mel_features_only()
@@ -402,6 +460,7 @@ def run_on_device(
         for stream in streams:
             stream.wait_stream(torch.cuda.current_stream(device))
     pending = []
+    consumer = _LaunchSink(sink) if sink is not None else None
     try:
         for number, members in enumerate(launches):
             first, last = members[0], members[-1]
@@ -438,13 +497,21 @@ def run_on_device(
                         ('scores', number), scores.numel(), scores.dtype)
                     host.copy_(scores, non_blocking=True)
                     scores = host
-            pending.append((members, plan, scores))
+            if consumer is not None:
+                consumer.put(members, plan, scores, stream)
+            else:
+                pending.append((members, plan, scores))
     except BaseException:
         # an error (e.g. a word without frames) must not leave the background
         # packer writing into staging buffers the next call reuses
         if isinstance(packed, (StreamedPack, ResampledSource)):
             packed.finish()
         torch.cuda.synchronize(device)
+        if consumer is not None:
+            try:
+                consumer.close()
+            except BaseException:
+                pass
         raise
     for stream in streams:
         torch.cuda.current_stream(device).wait_stream(stream)
@@ -455,16 +522,13 @@ def run_on_device(
     elif to_cpu:
         torch.cuda.current_stream(device).synchronize()
 
+    if consumer is not None:
+        consumer.close()
+        return []
     outputs = [None] * len(alignments)
     launches_flat = []
     for members, plan, scores in pending:
-        # word rows without separators are all words of all utterances in order
-        keep = torch.from_numpy(np.nonzero(plan.word_seq >= 0)[0])
-        # (indexing copies, so the pinned staging buffer can be reused)
-        flat_scores = scores[keep.to(scores.device)] if len(keep) else scores[:0].clone()
-        per_utterance = np.bincount(
-            plan.utterance, weights=plan.n_words, minlength=len(members)
-        ).astype(np.int64)
+        members, flat_scores, per_utterance = _flat_result(members, plan, scores)
         if flat:
             launches_flat.append((members, flat_scores, per_utterance))
             continue

@@ -666,7 +666,9 @@ int emph_pack_audio_f32(
 int emph_write_score_files(
     const char* const* paths, const float* scores, const int64_t* offsets,
     const int32_t* counts, int32_t n_files, int32_t n_threads);
-/* The same with one HOST pointer per file (rows[i] holds counts[i] floats). */
+/* The same with one HOST pointer per file (rows[i] holds counts[i] floats).
+ * n_threads < 0: -n_threads threads of the call's own instead of the shared
+ * worker pool (a writer that runs beside a decode occupying the pool). */
 int emph_write_score_rows(
     const char* const* paths, const float* const* rows, const int32_t* counts,
     int32_t n_files, int32_t n_threads);
