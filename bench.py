@@ -493,9 +493,11 @@ def time_transformer_variant(
     code = emphases.precision_code()
 
     def step():
+        # (the launch workspace the product path uses, scheduler.run_on_device:
+        # no gigabyte allocations per pass)
         return eng.forward_packed(
             device_audio, plan, weights, method='sum', location='intermediate',
-            precision=code, views=views)
+            precision=code, views=views, ws=eng.workspace('bench_transformer'))
 
     step()
     torch.cuda.synchronize(device)
@@ -714,6 +716,24 @@ def main():
         name: statistics.mean(t[name][0].elapsed_time(t[name][1]) for t in timers)
         for name in timers[0]}
 
+    # ---- when the pooling runs inside the conv stack's epilogue: the two
+    # kernels on their own, for the conv stack's stand-alone tensor fraction ----
+    unfused_ms = None
+    if rank == 0 and 'pool' not in kernel_ms:
+        saved = engine.FUSE_POOLING
+        engine.FUSE_POOLING = '0'
+        try:
+            step()
+            samples = [{} for _ in range(3)]
+            for sample in samples:
+                step(sample)
+            torch.cuda.synchronize(device)
+            unfused_ms = {
+                name: statistics.mean(t[name][0].elapsed_time(t[name][1]) for t in samples)
+                for name in ('conv_frames', 'pool')}
+        finally:
+            engine.FUSE_POOLING = saved
+
     # ---- the same step in the product's default precision (bf16x6: fp32-grade on
     # the tensor cores); the headline stays the reference's own bf16 class ----
     default_leg = None
@@ -916,6 +936,13 @@ def main():
             'achieved': pool_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': pool_gbs / hbm_peak, 'traffic': traffic('pool'),
             'ncu': ncu_source('pool')}
+    if unfused_ms is not None:
+        alone = frames * CONV_FLOP_PER_FRAME / (unfused_ms['conv_frames'] * 1e-3) / 1e12
+        candidates['conv_frames']['separate_kernels'] = {
+            'conv_frames_ms': unfused_ms['conv_frames'], 'pool_ms': unfused_ms['pool'],
+            'conv_tflops': alone, 'conv_frac': alone / tensor_peak,
+            'note': ('the same stage as conv stack + pooling kernel '
+                     '(EMPHASES_B200_FUSE_POOLING=0), 3 launches outside the timed region')}
     for name, entry in candidates.items():
         entry['ms'] = kernel_ms[name]
         entry['share_of_step'] = kernel_ms[name] / ms_per_step

@@ -109,15 +109,19 @@ struct Acts {
 // 96-101: downsample at the 'intermediate' location).  row_word[g] is the word
 // row that packed frame row g belongs to, or -1.  A row of the tile is a TMEM
 // lane, 32 consecutive rows are a warp, and the rows of a word are consecutive,
-// so a warp reduces its (one to three) word segments with a segmented shuffle
-// scan and the last lane of every segment adds the segment's total to the word:
-//   kPoolSum    sums are formed in 64-bit fixed point (2^-28 units): integer
-//               addition is associative, so the result does not depend on how
-//               tiles and warps cut a word or on the order the atomics land --
-//               bit-identical run to run and for every packing of the corpus.
-//               (A variant with two 24-bit limbs reduced by redux.sync over the
-//               segment's lanes measured 2x SLOWER than the shuffle scan:
-//               3.2 vs 1.68 ms for the bf16 frame stack.)
+// so a warp reduces its (one to three) word runs itself: the 16 columns of an
+// epilogue chunk are transposed through a warp-private piece of the slot's idle
+// operand buffer (lane = row writes, lane = (row parity, column) reads), every
+// lane adds the consecutive rows of its column and parity and flushes one value
+// per run end:
+//   kPoolSum    pieces of <= 16 rows are summed in fp32 in row order, converted
+//               to 64-bit fixed point (2^-28 units) and added to the word with
+//               an integer atomic: integer addition is associative, so the
+//               result does not depend on the order the atomics land (bit-
+//               identical run to run).  (The first version summed every element
+//               in fixed point with a segmented shuffle scan -- 800 shuffles per
+//               warp and tile, 1.68 ms against 1.27 + 0.24 unfused; a variant
+//               with redux.sync over the segment's lanes measured 3.2 ms.)
 //   kPoolMax    maximum of non-negative values (ReLU output) as an integer
 //               atomic max on the float's bit pattern; the buffer starts at 0
 //   kPoolCenter row_word marks only the centre row of each word: a plain store
@@ -582,20 +586,24 @@ conv_stack_tc_kernel(
                     // registers here)
                     const bool store = in_range && row >= halo && row < M - halo;
                     float4* dst = reinterpret_cast<float4*>(y + (size_t)(in_range ? g : 0) * C);
-                    // fused word pooling: the segment structure of this warp's rows
+                    // fused word pooling: the run structure of this warp's rows.  Each
+                    // half-warp reduces the rows of one parity (half h: rows h, h + 2,
+                    // ...), so bit r of `starts` / `ends` says that row r opens / closes
+                    // a run of equal words in ITS parity sequence
                     int wid = -1;
-                    uint32_t same = 0;          // bit d: lane - 2^d holds the same word
-                    bool tail = false;
+                    uint32_t starts = 0, ends = 0;
                     if (pool.mode != kPoolNone) {
                         if (store) wid = __ldg(pool.row_word + g);
-#pragma unroll
-                        for (int d = 0; d < 5; ++d) {
-                            const int other = __shfl_up_sync(0xffffffffu, wid, 1 << d);
-                            if (lane >= (1 << d) && other == wid) same |= 1u << d;
-                        }
-                        const int next = __shfl_down_sync(0xffffffffu, wid, 1);
-                        tail = wid >= 0 && (lane == 31 || next != wid);
+                        const int before = __shfl_up_sync(0xffffffffu, wid, 2);
+                        const int after = __shfl_down_sync(0xffffffffu, wid, 2);
+                        starts = __ballot_sync(0xffffffffu, lane < 2 || before != wid);
+                        ends = __ballot_sync(0xffffffffu, lane >= 30 || after != wid);
                     }
+                    // scratch of this warp: the interior (rows 1 .. 128) of k-group
+                    // `quad` of the slot's operand buffer = 2048 contiguous bytes =
+                    // [32 rows][16 floats]; the last layer's MMAs are done with it, and
+                    // the slot's warps meet at a barrier before the next tile is stored
+                    float* scratch = reinterpret_cast<float*>(act + (quad * RB + 1) * 16);
                     const size_t word_base = (size_t)(wid >= 0 ? wid : 0) * C;
 #pragma unroll 1
                     for (int c0 = 0; c0 < C; c0 += 16) {
@@ -623,36 +631,49 @@ conv_stack_tc_kernel(
                                 dst[(c0 >> 2) + c4] =
                                     make_float4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
                         }
-                        if (pool.mode == kPoolSum) {
+                        if (pool.mode == kPoolSum || pool.mode == kPoolMax) {
+                            // transpose through shared memory: lane = row writes its 16
+                            // values (float4 slot q of row r at q ^ ((r & 7) >> 1):
+                            // conflict-free both ways), then lane = (parity, column)
+                            // walks its 16 rows and keeps one running value per run
+                            const bool is_sum = pool.mode == kPoolSum;
+                            __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float clamped =
-                                    fminf(fmaxf(w[j], -kPoolFixedClamp), kPoolFixedClamp);
-                                long long q = __float2ll_rn(clamped * kPoolFixedScale);
-#pragma unroll
-                                for (int d = 0; d < 5; ++d) {
-                                    const long long other = __shfl_up_sync(0xffffffffu, q, 1 << d);
-                                    if (same & (1u << d)) q += other;
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<float4*>(
+                                    scratch + lane * 16 + 4 * (q ^ ((lane & 7) >> 1))) =
+                                    make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                            __syncwarp();
+                            const int parity = lane >> 4, column = lane & 15;
+                            float run = 0.f;
+#pragma unroll 4
+                            for (int k = 0; k < 16; ++k) {
+                                const int r = 2 * k + parity;
+                                const float v = scratch[r * 16 + 4 * ((column >> 2) ^ ((r & 7) >> 1)) +
+                                                        (column & 3)];
+                                const bool opens = (starts >> r) & 1u;
+                                run = is_sum ? (opens ? v : run + v)
+                                             : (opens ? fmaxf(v, 0.f) : fmaxf(run, v));
+                                if ((ends >> (2 * k)) & 3u) {          // warp-uniform
+                                    const int word = __shfl_sync(0xffffffffu, wid, r);
+                                    if (((ends >> r) & 1u) && word >= 0) {
+                                        const size_t at = (size_t)word * C + c0 + column;
+                                        if (is_sum) {
+                                            // <= 16 rows per piece: 2^23 * 2^28 = 2^51, and
+                                            // 2^12 pieces of it fit int64
+                                            const float clamped = fminf(
+                                                fmaxf(run, -16.f * kPoolFixedClamp),
+                                                16.f * kPoolFixedClamp);
+                                            atomicAdd(
+                                                reinterpret_cast<unsigned long long*>(pool.fixed + at),
+                                                (unsigned long long)__float2ll_rn(
+                                                    clamped * kPoolFixedScale));
+                                        } else {
+                                            atomicMax(reinterpret_cast<int*>(pool.out + at),
+                                                      __float_as_int(run));
+                                        }
+                                    }
                                 }
-                                if (tail)
-                                    atomicAdd(
-                                        reinterpret_cast<unsigned long long*>(
-                                            pool.fixed + word_base + c0 + j),
-                                        (unsigned long long)q);
-                            }
-                        } else if (pool.mode == kPoolMax) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float v = fmaxf(w[j], 0.f);
-#pragma unroll
-                                for (int d = 0; d < 5; ++d) {
-                                    const float other = __shfl_up_sync(0xffffffffu, v, 1 << d);
-                                    if (same & (1u << d)) v = fmaxf(v, other);
-                                }
-                                if (tail)
-                                    atomicMax(
-                                        reinterpret_cast<int*>(pool.out + word_base + c0 + j),
-                                        __float_as_int(v));
                             }
                         } else if (pool.mode == kPoolCenter) {
                             if (wid >= 0) {
@@ -664,6 +685,10 @@ conv_stack_tc_kernel(
                             }
                         }
                     }
+                    // the scratch lives in the operand buffer the slot's four warps
+                    // fill together for the next tile: nobody stores before all are done
+                    if (pool.mode == kPoolSum || pool.mode == kPoolMax)
+                        asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory");
                 } else {
                     epilogue_generic<PARTS>(
                         taddr, act, row, a, valid, true,

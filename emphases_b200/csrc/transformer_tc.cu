@@ -199,7 +199,9 @@ __device__ __forceinline__ void layernorm_store(
 // ---------------------------------------------------------------------------
 // q, k, v projections of one layer.  weights: [3][NP][80][88] bf16 (q, k, v),
 // bias [240].  q goes out as fp32 rows; k and v as the attention kernel's
-// records (attention_tc.cuh Layout<40, ATT>), so no staging pass follows.
+// records (attention_tc.cuh Layout<40, ATT>), so no staging pass follows.  Every
+// byte of a row's records that the attention kernel reads is written here; the
+// caller keeps the 64 records of slack behind each head's rows zero.
 // ---------------------------------------------------------------------------
 template <int NP, int ATT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -255,6 +257,19 @@ qkv_kernel(
                     if (ATT == kSplitBf16)
                         *reinterpret_cast<uint32_t*>(record + 2 * (first + next_part + dim)) =
                             attn_tc::pack_residual(acc[j][2 * r], acc[j][2 * r + 1], hi);
+                }
+                // K's padded dims [D, DP) are zeros in every part (the lane quad
+                // of a row covers the 8 of them)
+                if (matrix == 1 && L::DP - D == 8) {
+#pragma unroll
+                    for (int head = 0; head < 2; ++head) {
+                        unsigned char* record =
+                            staged + ((size_t)head * padded_rows + row) * L::kRecord;
+#pragma unroll
+                        for (int part = 0; part < L::NP; ++part)
+                            *reinterpret_cast<uint32_t*>(
+                                record + 2 * (part * L::DP + D + 2 * t)) = 0u;
+                    }
                 }
             }
         }

@@ -514,14 +514,21 @@ def pack_weights(state, device, layers, activation, dropout, has_decoder):
 ###############################################################################
 
 
-# Word pooling fused into the last layer of the tensor-core frame stack
-# (emph_conv_stack_pool) instead of the separate pooling kernel.  Off by
-# default: measured on a B200 (3.31 M frames, bf16) the fused epilogue's
-# segmented 64-bit shuffle scan sits in series with the slot's next tile and
-# costs more than it saves -- 1.68 ms against 1.27 + 0.24 ms for conv stack +
-# pooling kernel (profiles/r02i_fused_pooling.md).  EMPHASES_B200_FUSE_POOLING=1
-# enables it.
-FUSE_POOLING = os.environ.get('EMPHASES_B200_FUSE_POOLING', '0') == '1'
+# Frame stack + word pooling as ONE kernel at the 'intermediate' location (the
+# frame embeddings never travel to HBM).  Measured on a B200 (3.31 M frames):
+# in the plain bf16 mode (4 tile slots) the fused stage takes 1.42 ms against
+# 1.25 + 0.25 ms for conv stack + pooling kernel; in the split modes (2 slots:
+# the longer last-layer epilogue sits in series with the slot's next tile) it
+# loses, 9.88 against 9.53 ms per step in bf16x6
+# (profiles/r02i_fused_pooling.md).  Default: fused in the bf16 mode only;
+# EMPHASES_B200_FUSE_POOLING=1 / 0 forces it on (where applicable) / off.
+FUSE_POOLING = os.environ.get('EMPHASES_B200_FUSE_POOLING', 'auto')
+
+
+def fuse_pooling(precision):
+    if FUSE_POOLING in ('0', '1'):
+        return FUSE_POOLING == '1'
+    return precision == _lib.PREC_BF16_TC
 
 
 def tensor_core_shape(stack):
@@ -869,10 +876,11 @@ class Engine:
                 linear_precision(weights.input_layer))
             frames = timed('conv_frames', lambda: transformer.run_stack(
                 self, weights.frame, embedded, views['row_start'], plan.n_rows,
-                plan.n_rows, row_seq, self.device))
+                plan.n_rows, row_seq, self.device, ws, 'frame_'))
         else:
             fused = None
-            if location == 'intermediate' and FUSE_POOLING and plan.words_disjoint():
+            if location == 'intermediate' and plan.words_disjoint() and fuse_pooling(
+                    frame_precision(precision, weights.frame)):
                 # frame stack + word pooling in one kernel: the frame embeddings
                 # never travel to HBM (kept only on request)
                 # (word-of-row map, conv + pooling, fixed point -> fp32 for sums)
@@ -895,7 +903,7 @@ class Engine:
             from . import transformer
             words = timed('conv_words', lambda: transformer.run_stack(
                 self, weights.word, pooled, views['word_row_start'],
-                plan.n_words, plan.n_words, word_row_seq, self.device))
+                plan.n_words, plan.n_words, word_row_seq, self.device, ws, 'word_'))
         elif location == 'intermediate':
             words = timed('conv_words', lambda: self.conv_stack(
                 pooled, word_row_seq, weights.word,

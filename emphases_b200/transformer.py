@@ -235,15 +235,22 @@ def attention_mode():
     return ATTENTION_MODES.get(choice)
 
 
-def attention_workspace(total_rows, channels, mode, device, zero=False):
-    """Device buffer for the 16-bit K / V records of one attention call
-    (`zero`: the fused layer kernels write only the live elements of a record)"""
+def attention_workspace(total_rows, channels, mode, device, zero=False, ws=None, tag=''):
+    """Device buffer for the 16-bit K / V records of one attention call: heads x
+    (total_rows + 64) records, head-major.  `zero`: the 64 records of slack
+    behind each head's rows are cleared (the fused q / k / v pass writes the
+    records of the rows only; emph_attention_rows_tc's staging pass writes all)"""
     size = _lib.load().emph_attention_tc_workspace(total_rows, channels, HEADS, mode)
     if size < 0:
         raise NotImplementedError(
             f'tensor-core attention is not compiled for {channels // HEADS}-dim heads')
-    make = torch.zeros if zero else torch.empty
-    return make(max(size, 1), dtype=torch.uint8, device=device)
+    records = engine._empty(ws, f'{tag}records', (max(size, 1),), torch.uint8, device)
+    if zero and size:
+        per_head = size // HEADS
+        record = per_head // (total_rows + 64)
+        for head in range(HEADS):
+            records[head * per_head + total_rows * record:(head + 1) * per_head].zero_()
+    return records
 
 
 FUSED_CHANNELS = 80                # csrc/transformer_tc.cu is compiled for d_model 80
@@ -261,14 +268,20 @@ def fused_layers(channels, mode):
 
 def run_fused_layers(
     stack, h, mode, row_start, n_queries, n_keys, row_seq, d_block_seq, d_block_q0,
-    n_blocks, scale, device
+    n_blocks, scale, device, ws=None, tag='frame_'
 ):
     """Every encoder layer as qkv -> attention -> out_proj + LayerNorm ->
-    feed-forward + LayerNorm: four launches, five row buffers for the stack"""
+    feed-forward + LayerNorm: four launches, five row buffers for the stack.
+    With a launch workspace `ws` all buffers are grow-only views of it (fresh
+    gigabyte allocations per call make the caching allocator fall back to
+    cudaMalloc / cudaFree: 30-40 ms stalls)"""
     total_rows, channels = h.shape
     parts = 3 if emphases.PRECISION == 'bf16x6' else 2
-    records = attention_workspace(total_rows, channels, mode, device, zero=True)
-    q, context, normed, spare = (torch.empty_like(h) for _ in range(4))
+    records = attention_workspace(
+        total_rows, channels, mode, device, zero=True, ws=ws, tag=tag)
+    q, context, normed, spare = (
+        engine._empty(ws, f'{tag}{name}', tuple(h.shape), torch.float32, device)
+        for name in ('q', 'context', 'normed', 'spare'))
     stream = _lib.stream_ptr()
     for layer in stack.layers:
         pack = layer.fused(parts, device)
@@ -307,10 +320,13 @@ def query_blocks(n_keys, block=128):
 
 
 def run_stack(
-    eng, stack, x, row_start, n_rows_host, n_keys_host, row_seq, device
+    eng, stack, x, row_start, n_rows_host, n_keys_host, row_seq, device, ws=None,
+    tag='frame_'
 ):
     """x: packed rows (total_rows, C); sequence u has n_rows[u] rows (all are
-    queries) of which the first n_keys[u] are valid keys"""
+    queries) of which the first n_keys[u] are valid keys.  `ws`: the launch's
+    grow-only engine workspace (buffers named with `tag`; the result then lives
+    there until the next stack with the same tag runs on it)"""
     if int(np.max(n_rows_host, initial=0)) > stack.table.shape[0]:
         raise RuntimeError(
             f'The size of tensor a ({int(np.max(n_rows_host))}) must match the '
@@ -331,15 +347,15 @@ def run_stack(
     workspace = None if mode is None or fused else attention_workspace(
         total_rows, channels, mode, device)
 
-    h = torch.empty_like(x)
+    h = engine._empty(ws, f'{tag}positional', tuple(x.shape), torch.float32, device)
     _lib.call(
         'emph_add_positional', _lib.ptr(x), _lib.ptr(row_start),
         _lib.ptr(row_seq), total_rows, channels, _lib.ptr(stack.table),
         stack.table.shape[0], _lib.ptr(h), _lib.stream_ptr())
     if fused:
         return run_fused_layers(
-            stack, h, mode, row_start, n_queries, n_keys, row_seq, d_block_seq, d_block_q0,
-            len(block_seq), scale, device)
+            stack, h, mode, row_start, n_queries, n_keys, row_seq, d_block_seq,
+            d_block_q0, len(block_seq), scale, device, ws, tag)
     for layer in stack.layers:
         q, k, v = (
             eng.conv_stack(h, row_seq, part, engine.linear_precision(part))
@@ -402,7 +418,7 @@ def run_forward(
         def decode(pooled, word_row_seq, word_start, wmax, lengths):
             return run_stack(
                 eng, weights.word, pooled, word_start,
-                np.full(len(lengths), wmax), lengths, word_row_seq, device)
+                np.full(len(lengths), wmax), lengths, word_row_seq, device, tag='word_')
 
         return segments.run_forward_input(
             model, eng, weights, features, word_bounds, word_lengths, method,
@@ -451,7 +467,7 @@ def run_forward(
     if model.location == 'intermediate':
         pooled = run_stack(
             eng, weights.word, pooled, views['word_row_start'],
-            np.full(batch, wmax), lengths, word_row_seq, device)
+            np.full(batch, wmax), lengths, word_row_seq, device, tag='word_')
     logits, _ = eng.head(
         pooled, word_row_seq, weights, _lib.HEAD_LOGITS, want_scores=False)
     index = torch.from_numpy(

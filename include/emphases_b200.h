@@ -423,7 +423,8 @@ int64_t emph_attention_tc_workspace(
  * emph_transformer_qkv: q = x Wq^T + bq as fp32 rows; k and v are written
  *   directly as the 16-bit records emph_attention_rows_staged reads
  *   (`attention_mode` as in emph_attention_rows_tc; the buffer has
- *   emph_attention_tc_workspace bytes and must have been zeroed once).
+ *   emph_attention_tc_workspace bytes = heads x (total_rows + 64) records,
+ *   head-major; the caller zeroes the 64 records behind each head's rows).
  *   weights: 3 matrices (rows 0..79 / 80..159 / 160..239 of in_proj_weight).
  * emph_attention_rows_staged: emph_attention_rows_tc without the staging pass.
  * emph_transformer_proj_norm: y = LayerNorm(residual + x W^T + b).

@@ -679,13 +679,15 @@ def test_fused_pooling_segment_assignment_bit_exact(eng):
             assert center[s + j, 1].item() == (lo + hi) // 2
 
 
-def test_fused_pooling_is_packing_invariant(eng, golden):
-    """Fixed-point sums do not depend on how tiles and warps cut a word: the
-    same utterances packed behind a different prefix pool bit-identically"""
+def test_fused_pooling_is_deterministic_and_packing_stable(eng, golden):
+    """The integer atomics make the fused sums bit-identical run to run whatever
+    order the partial sums land in; packing the same utterances behind a
+    different prefix moves the cuts between the <= 16-row fp32 partial sums, so
+    those results agree to fp32 rounding of the sums (not bit for bit)"""
     from emphases_b200 import _lib
     weights = default_weights(state_from_golden(golden('c1')))
     results = []
-    for seeds in ([400, 401, 402, 403], [410, 400, 401, 402, 403]):
+    for seeds in ([400, 401, 402, 403], [400, 401, 402, 403], [410, 400, 401, 402, 403]):
         _, plan = _fused_corpus(seeds)
         views = eng.upload_plan(plan)
         row_seq = eng.row_index(
@@ -702,6 +704,8 @@ def test_fused_pooling_is_packing_invariant(eng, golden):
         start = int(plan.word_row_start[first])
         results.append(pooled[start:].cpu())
     assert torch.equal(results[0], results[1])
+    scale = results[0].abs().max().item()
+    assert (results[0] - results[2]).abs().max().item() < 1e-6 * max(scale, 1.0)
 
 
 ###############################################################################
