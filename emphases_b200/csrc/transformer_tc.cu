@@ -14,7 +14,8 @@
 // m16n8k16 with fp32 accumulators, at fp32 grade: activations and weights are
 // split into NP bf16 parts (NP = 2: hi*hi + hi*lo + lo*hi, 2^-17 per product;
 // NP = 3: six products, 2^-24) exactly like the tcgen05 conv stack's bf16x3 /
-// bf16x6 modes.  The activation fragments are built in registers from fp32 row
+// bf16x6 modes.  NP = 1 is one fp16 value per operand (2^-12, like the
+// attention kernel's fp16 form): the 2e-3 'bf16' mode, bound by HBM alone.  The activation fragments are built in registers from fp32 row
 // loads (an A fragment's elements are the thread's own (row, column) pairs, the
 // same positions the accumulators use, so the feed-forward block chains its two
 // products without leaving registers and the residual lines up with the
@@ -38,26 +39,23 @@ constexpr int kWPartBytes = C * kWStride * 2;          // 14,080
 constexpr int kThreads = 256;
 constexpr int kRowsPerCta = 16 * (kThreads / 32);      // 128
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ void mma_bf16(
-    float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
-        "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
+// operand type of the NP-part form: one fp16, or NP bf16 parts
+template <int NP>
+struct Operand {
+    static constexpr int kMode = NP == 1 ? kPlainFp16 : kSplitBf16;
+};
 
 // (lo, hi) fp32 pair -> NP bf16 pairs whose sum is the pair to 2^-(8 NP + 1)
+// (NP = 1: one fp16 pair)
 template <int NP>
 __device__ __forceinline__ void split_pair(float lo, float hi, uint32_t (&parts)[NP]) {
+    if (NP == 1) {
+        parts[0] = attn_tc::pack_pair<kPlainFp16>(lo, hi);
+        return;
+    }
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        parts[p] = pack_bf16(lo, hi);
+        parts[p] = attn_tc::pack_pair<kSplitBf16>(lo, hi);
         lo -= __uint_as_float(parts[p] << 16);
         hi -= __uint_as_float(parts[p] & 0xffff0000u);
     }
@@ -126,7 +124,8 @@ __device__ __forceinline__ void product(
                 }
                 if (KS & 1) attn_tc::ldmatrix_x2(b[KS - 1], rows + lane_tail + 32 * (KS - 1));
 #pragma unroll
-                for (int s = 0; s < KS; ++s) mma_bf16(acc[j], a[pa][s], b[s][0], b[s][1]);
+                for (int s = 0; s < KS; ++s)
+                    attn_tc::mma_16816<Operand<NP>::kMode>(acc[j], a[pa][s], b[s][0], b[s][1]);
             }
         }
     }
@@ -204,7 +203,7 @@ __device__ __forceinline__ void layernorm_store(
 // caller keeps the 64 records of slack behind each head's rows zero.
 // ---------------------------------------------------------------------------
 template <int NP, int ATT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, NP == 1 ? 2 : 1)
 qkv_kernel(
     const float* __restrict__ x, int total_rows, const unsigned char* __restrict__ weights,
     const float* __restrict__ bias, float* __restrict__ q, unsigned char* __restrict__ staged,
@@ -370,7 +369,7 @@ extern "C" {
 #define EMPH_XF_REQUIRE_SHAPE(name)                                                      \
     EMPH_REQUIRE(channels == emph::xf_tc::C, name ": compiled for 80 channels, got %d",  \
                  channels);                                                              \
-    EMPH_REQUIRE(parts == 2 || parts == 3, name ": parts must be 2 or 3, got %d", parts)
+    EMPH_REQUIRE(parts >= 1 && parts <= 3, name ": parts must be 1, 2 or 3, got %d", parts)
 
 int emph_transformer_qkv(
     const float* x, int32_t total_rows, int32_t channels, const void* weights, const float* bias,
@@ -390,7 +389,7 @@ int emph_transformer_qkv(
                  (long long)staged_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = 3 * parts * kWPartBytes;
-    const int grid = grid_for(total_rows, 1);
+    const int grid = grid_for(total_rows, parts == 1 ? 2 : 1);
 #define EMPH_XF_QKV(NP, ATT)                                                              \
     do {                                                                                  \
         const int status = configure(qkv_kernel<NP, ATT>, smem, "emph_transformer_qkv"); \
@@ -399,7 +398,9 @@ int emph_transformer_qkv(
             x, total_rows, (const unsigned char*)weights, bias, q, (unsigned char*)staged, \
             padded_rows);                                                                 \
     } while (0)
-    if (parts == 2 && attention_mode == kPlainFp16) EMPH_XF_QKV(2, kPlainFp16);
+    if (parts == 1 && attention_mode == kPlainFp16) EMPH_XF_QKV(1, kPlainFp16);
+    else if (parts == 1) EMPH_XF_QKV(1, kSplitBf16);
+    else if (parts == 2 && attention_mode == kPlainFp16) EMPH_XF_QKV(2, kPlainFp16);
     else if (parts == 2) EMPH_XF_QKV(2, kSplitBf16);
     else if (attention_mode == kPlainFp16) EMPH_XF_QKV(3, kPlainFp16);
     else EMPH_XF_QKV(3, kSplitBf16);
@@ -418,7 +419,13 @@ int emph_transformer_proj_norm(
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = parts * kWPartBytes;
     const int grid = grid_for(total_rows, 2);
-    if (parts == 2) {
+    if (parts == 1) {
+        const int status = configure(proj_norm_kernel<1>, smem, "emph_transformer_proj_norm");
+        if (status != EMPH_OK) return status;
+        proj_norm_kernel<1><<<grid, kThreads, smem, st>>>(
+            x, residual, total_rows, (const unsigned char*)weights, bias, gamma, beta, eps,
+            row_seq, y);
+    } else if (parts == 2) {
         const int status = configure(proj_norm_kernel<2>, smem, "emph_transformer_proj_norm");
         if (status != EMPH_OK) return status;
         proj_norm_kernel<2><<<grid, kThreads, smem, st>>>(
@@ -445,7 +452,12 @@ int emph_transformer_ffn_norm(
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = 2 * parts * kWPartBytes;
     const int grid = grid_for(total_rows, 2);
-    if (parts == 2) {
+    if (parts == 1) {
+        const int status = configure(ffn_norm_kernel<1>, smem, "emph_transformer_ffn_norm");
+        if (status != EMPH_OK) return status;
+        ffn_norm_kernel<1><<<grid, kThreads, smem, st>>>(
+            x, total_rows, (const unsigned char*)weights, bias, gamma, beta, eps, row_seq, y);
+    } else if (parts == 2) {
         const int status = configure(ffn_norm_kernel<2>, smem, "emph_transformer_ffn_norm");
         if (status != EMPH_OK) return status;
         ffn_norm_kernel<2><<<grid, kThreads, smem, st>>>(

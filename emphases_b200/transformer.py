@@ -76,13 +76,14 @@ def split_parts(matrices, parts, device):
     """[(out, in) fp32] -> bf16 (matrices, parts, out, in + 8): part p is the
     bf16 rounding of what parts < p left over (round to nearest even, like
     cvt.rn.bf16x2.f32 on the activation side)"""
+    dtype = torch.float16 if parts == 1 else torch.bfloat16      # one fp16 value, or bf16 parts
     blob = torch.zeros(
         (len(matrices), parts) + (matrices[0].shape[0], matrices[0].shape[1] + 8),
-        dtype=torch.bfloat16, device=device)
+        dtype=dtype, device=device)
     for index, matrix in enumerate(matrices):
         rest = matrix.detach().to(device, torch.float32).clone()
         for part in range(parts):
-            rounded = rest.to(torch.bfloat16)
+            rounded = rest.to(dtype)
             blob[index, part, :, :matrix.shape[1]] = rounded
             rest -= rounded.float()
     return blob.contiguous()
@@ -266,6 +267,19 @@ def fused_layers(channels, mode):
         and os.environ.get('EMPHASES_B200_FUSED_LAYERS', '1') != '0')
 
 
+def fused_parts():
+    """Operand parts of the fused per-row passes: 3 bf16 parts in 'bf16x6', 2 in
+    'bf16x3' and 'bf16'.  EMPHASES_B200_LINEAR_PARTS=1 selects one fp16 value
+    per operand: on bench.py's corpus 48.3 instead of 52.7 ms per pass in the
+    'bf16' mode at 1.1e-3 instead of 3.0e-4 on the scores -- inside the 2e-3
+    bar, but with half the margin, so it is not the default"""
+    import os
+    override = os.environ.get('EMPHASES_B200_LINEAR_PARTS')
+    if override:
+        return int(override)
+    return 3 if emphases.PRECISION == 'bf16x6' else 2
+
+
 def run_fused_layers(
     stack, h, mode, row_start, n_queries, n_keys, row_seq, d_block_seq, d_block_q0,
     n_blocks, scale, device, ws=None, tag='frame_'
@@ -276,7 +290,7 @@ def run_fused_layers(
     gigabyte allocations per call make the caching allocator fall back to
     cudaMalloc / cudaFree: 30-40 ms stalls)"""
     total_rows, channels = h.shape
-    parts = 3 if emphases.PRECISION == 'bf16x6' else 2
+    parts = fused_parts()
     records = attention_workspace(
         total_rows, channels, mode, device, zero=True, ws=ws, tag=tag)
     q, context, normed, spare = (

@@ -416,9 +416,10 @@ int64_t emph_attention_tc_workspace(
  * One Transformer encoder layer (transformer.py:18-23: post-norm
  * nn.TransformerEncoderLayer, ReLU, dim_feedforward = channels = 80) as three
  * fused per-row passes around the attention kernel (csrc/transformer_tc.cu),
- * fp32 grade on mma.sync: activations and weights split into `parts` bf16
- * parts (2: three products, 3: six products).  Weight blobs are bf16
- * [matrix][part][out][in + 8] (part p = bf16 of what parts < p left over).
+ * on mma.sync: activations and weights split into `parts` bf16 parts (2: three
+ * products, 3: six products: fp32 grade) or, parts = 1, rounded to one fp16
+ * value (the 2e-3 mode).  Weight blobs are 16-bit [matrix][part][out][in + 8]
+ * (part p = bf16 of what parts < p left over; parts = 1: fp16).
  *
  * emph_transformer_qkv: q = x Wq^T + bq as fp32 rows; k and v are written
  *   directly as the 16-bit records emph_attention_rows_staged reads

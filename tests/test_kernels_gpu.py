@@ -854,7 +854,7 @@ def test_attention_tensor_core_peaked_softmax(eng):
     assert (split[rows].double() - expected[rows]).abs().max() < 3e-4
 
 
-@pytest.mark.parametrize('parts', [2, 3])
+@pytest.mark.parametrize('parts', [1, 2, 3])
 def test_transformer_fused_passes(eng, parts):
     """csrc/transformer_tc.cu against fp64 torch on ragged packed rows: the
     out-projection + residual + LayerNorm pass, the feed-forward + residual +
@@ -878,7 +878,7 @@ def test_transformer_fused_passes(eng, parts):
     weight = [normal(channels, channels, scale=channels ** -.5) for _ in range(5)]
     bias = [normal(channels, scale=.1) for _ in range(5)]
     gamma, beta = 1 + normal(channels, scale=.1), normal(channels, scale=.1)
-    tolerance = {2: 3e-5, 3: 2e-6}[parts]
+    tolerance = {1: 4e-3, 2: 3e-5, 3: 2e-6}[parts]      # one fp16 value / 2 / 3 bf16 parts
 
     def layernorm(value):
         return torch.nn.functional.layer_norm(
@@ -934,7 +934,7 @@ def test_transformer_fused_passes(eng, parts):
     block_seq, block_q0 = transformer.query_blocks(np.asarray(lengths))
     d_seq, d_q0 = torch.from_numpy(block_seq).to(device), torch.from_numpy(block_q0).to(device)
     n_keys = torch.tensor(keys, dtype=torch.int32, device=device)
-    for mode, bound in ((1, 2e-4), (0, 2e-2)):
+    for mode, bound in ((1, 2e-4 if parts > 1 else 2e-2), (0, 2e-2)):
         records = transformer.attention_workspace(total, channels, mode, device, zero=True)
         q = torch.full_like(dx, float('nan'))
         out = torch.zeros_like(dx)
