@@ -927,8 +927,10 @@ def main():
             'bound': conv_bound,
             'achieved': conv_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s',
             'frac': conv_tflops / tensor_peak,
-            'traffic': traffic('conv_frames', precision == 'bf16' and 'pool' in kernel_ms),
-            'ncu': ncu_source('conv_frames')}}
+            'traffic': traffic(
+                'conv_frames' if 'pool' in kernel_ms else 'conv_frames_fused',
+                precision == 'bf16'),
+            'ncu': ncu_source('conv_frames' if 'pool' in kernel_ms else 'conv_frames_fused')}}
     if pool_gbs is not None:
         candidates['pool'] = {
             'kernel': 'pool_words_kernel',
