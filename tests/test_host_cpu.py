@@ -414,3 +414,44 @@ def test_native_audio_packer_and_lossless_narrowing():
     assert lib.emph_pack_audio_f32(
         pointers.ctypes.data, lengths.ctypes.data, offsets.ctypes.data, 4,
         ctypes.c_void_p(dst.data_ptr()), None, None, 2) == 0
+
+
+def test_transformer_operand_policy_and_weight_parts(monkeypatch):
+    """Host side of the tensor-core Transformer path: which attention form and
+    how many operand parts each PRECISION selects, and that the bf16 weight
+    parts of csrc/transformer_tc.cu add up to the fp32 weight"""
+    import emphases_b200 as emphases
+    from emphases_b200 import transformer
+    monkeypatch.delenv('EMPHASES_B200_ATTENTION', raising=False)
+    monkeypatch.delenv('EMPHASES_B200_LINEAR_PARTS', raising=False)
+    monkeypatch.delenv('EMPHASES_B200_FUSED_LAYERS', raising=False)
+    expected = {        # PRECISION -> (attention operand mode, parts of the per-row passes)
+        'fp32': (None, None), 'bf16': ('fp16', 2), 'bf16x3': ('bf16x3', 2), 'bf16x6': ('bf16x3', 3)}
+    try:
+        for precision, (attention, parts) in expected.items():
+            emphases.configure(PRECISION=precision)
+            mode = transformer.attention_mode()
+            assert mode == (None if attention is None else transformer.ATTENTION_MODES[attention])
+            assert transformer.fused_layers(80, mode) == (attention is not None)
+            assert not transformer.fused_layers(64, mode)
+            if parts is not None:
+                assert transformer.fused_parts() == parts
+        monkeypatch.setenv('EMPHASES_B200_ATTENTION', 'fp32')
+        assert transformer.attention_mode() is None
+        monkeypatch.setenv('EMPHASES_B200_ATTENTION', 'int8')
+        with pytest.raises(ValueError):
+            transformer.attention_mode()
+    finally:
+        emphases.reset_configuration()
+    generator = torch.Generator().manual_seed(2)
+    weight = torch.randn(80, 80, generator=generator) * 0.3
+    for parts, bound in ((1, 2.0 ** -11), (2, 2.0 ** -16), (3, 2.0 ** -24)):
+        blob = transformer.split_parts([weight, -weight], parts, torch.device('cpu'))
+        assert blob.shape == (2, parts, 80, 88)
+        assert blob.dtype == (torch.float16 if parts == 1 else torch.bfloat16)
+        assert torch.all(blob[..., 80:] == 0)              # the row padding
+        total = blob[0, :, :, :80].float().sum(0)
+        assert (total - weight).abs().max() <= bound * weight.abs().max()
+        assert torch.equal(blob[1], -blob[0])
+    assert transformer.query_blocks([1, 128, 129])[0].tolist() == [0, 1, 2, 2]
+    assert transformer.query_blocks([1, 128, 129])[1].tolist() == [0, 0, 0, 128]
