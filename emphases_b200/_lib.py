@@ -52,6 +52,8 @@ SIGNATURES = {
         _P, _P, ctypes.c_int64, _I, _I, _P, _P, _P, _I, _P, _P, _I, _F, _I, _P, _P],
     'emph_transformer_proj_norm': [_P, _P, _I, _I, _P, _P, _I, _P, _P, _F, _P, _P, _P],
     'emph_transformer_ffn_norm': [_P, _I, _I, _P, _P, _I, _P, _P, _F, _P, _P, _P],
+    'emph_transformer_layer_tail': [
+        _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _F, _P, _P, _P],
     'emph_attention_rows_tc': [
         _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _I, _F, _I, _P, ctypes.c_int64, _P, _P],
     'emph_add_layernorm': [_P, _P, _P, _P, _F, _P, _I, _I, _P, _P],

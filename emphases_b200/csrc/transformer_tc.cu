@@ -155,12 +155,12 @@ __device__ __forceinline__ void load_weights(
     __syncthreads();
 }
 
-// y = LayerNorm(v) * gamma + beta for the warp's 16 rows; zeros on separator rows
-__device__ __forceinline__ void layernorm_store(
+// v <- LayerNorm(v) * gamma + beta for the warp's 16 rows (a row's 80 values sit
+// in one lane quad)
+__device__ __forceinline__ void layernorm_values(
     float (&v)[NT][4], const float* __restrict__ gamma, const float* __restrict__ beta,
-    float eps, const int32_t* __restrict__ row_seq, int row0, int total_rows, int lane,
-    float* __restrict__ y) {
-    const int g = lane >> 2, t = lane & 3;
+    float eps, int lane) {
+    const int t = lane & 3;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         float sum = 0.f;
@@ -179,20 +179,40 @@ __device__ __forceinline__ void layernorm_store(
         square += __shfl_xor_sync(0xffffffffu, square, 1);
         square += __shfl_xor_sync(0xffffffffu, square, 2);
         const float inv = rsqrtf(square * (1.f / C) + eps);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + 8 * j + 2 * t));
+            const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + 8 * j + 2 * t));
+            v[j][2 * r] = (v[j][2 * r] - mean) * inv * gm.x + bt.x;
+            v[j][2 * r + 1] = (v[j][2 * r + 1] - mean) * inv * gm.y + bt.y;
+        }
+    }
+}
+
+// the warp's 16 rows to y; zeros on separator rows
+__device__ __forceinline__ void store_rows(
+    const float (&v)[NT][4], const int32_t* __restrict__ row_seq, int row0, int total_rows,
+    int lane, float* __restrict__ y) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
         const int row = row0 + g + 8 * r;
         if (row >= total_rows) continue;
         const bool separator = row_seq[row] < 0;
         float* dst = y + (size_t)row * C + 2 * t;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + 8 * j + 2 * t));
-            const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + 8 * j + 2 * t));
-            float2 out;
-            out.x = separator ? 0.f : (v[j][2 * r] - mean) * inv * gm.x + bt.x;
-            out.y = separator ? 0.f : (v[j][2 * r + 1] - mean) * inv * gm.y + bt.y;
-            *reinterpret_cast<float2*>(dst + 8 * j) = out;
-        }
+        for (int j = 0; j < NT; ++j)
+            *reinterpret_cast<float2*>(dst + 8 * j) = make_float2(
+                separator ? 0.f : v[j][2 * r], separator ? 0.f : v[j][2 * r + 1]);
     }
+}
+
+__device__ __forceinline__ void layernorm_store(
+    float (&v)[NT][4], const float* __restrict__ gamma, const float* __restrict__ beta,
+    float eps, const int32_t* __restrict__ row_seq, int row0, int total_rows, int lane,
+    float* __restrict__ y) {
+    layernorm_values(v, gamma, beta, eps, lane);
+    store_rows(v, row_seq, row0, total_rows, lane, y);
 }
 
 // ---------------------------------------------------------------------------
@@ -349,6 +369,63 @@ ffn_norm_kernel(
     }
 }
 
+// Everything of a layer behind the attention in one pass:
+//   n = LayerNorm1(residual + x Wo^T + bo);  y = LayerNorm2(n + relu(n W1^T + b1) W2^T + b2)
+// weights: [3][NP][80][88] (out-projection, linear1, linear2), bias [240]; the
+// intermediate n never leaves registers
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+layer_tail_kernel(
+    const float* __restrict__ x, const float* __restrict__ residual, int total_rows,
+    const unsigned char* __restrict__ weights, const float* __restrict__ bias,
+    const float* __restrict__ gamma1, const float* __restrict__ beta1,
+    const float* __restrict__ gamma2, const float* __restrict__ beta2, float eps,
+    const int32_t* __restrict__ row_seq, float* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    load_weights(smem, weights, 3 * NP * kWPartBytes);
+    const uint32_t w = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int tile = blockIdx.x; tile * kRowsPerCta < total_rows; tile += gridDim.x) {
+        const int row0 = tile * kRowsPerCta + 16 * warp;
+        if (row0 >= total_rows) continue;
+        uint32_t a[NP][KS][4];
+        float normed[NT][4];
+        {
+            float v[NT][4];
+            load_tiles(x, row0, total_rows, lane, v);
+            fragments_from_tiles<NP>(v, a);
+            clear(normed);
+            product<NP>(normed, a, w, lane);
+            add_bias(normed, bias, lane);
+            load_tiles(residual, row0, total_rows, lane, v);
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) normed[j][i] += v[j][i];
+        }
+        layernorm_values(normed, gamma1, beta1, eps, lane);
+        fragments_from_tiles<NP>(normed, a);
+        float acc[NT][4];
+        clear(acc);
+        product<NP>(acc, a, w + NP * kWPartBytes, lane);
+        add_bias(acc, bias + C, lane);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = fmaxf(acc[j][i], 0.f);
+        fragments_from_tiles<NP>(acc, a);
+        clear(acc);
+        product<NP>(acc, a, w + 2 * NP * kWPartBytes, lane);
+        add_bias(acc, bias + 2 * C, lane);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] += normed[j][i];
+        layernorm_store(acc, gamma2, beta2, eps, row_seq, row0, total_rows, lane, y);
+    }
+}
+
 template <typename Kernel>
 int configure(Kernel kernel, int smem_bytes, const char* what) {
     return check_cuda(
@@ -469,6 +546,34 @@ int emph_transformer_ffn_norm(
             x, total_rows, (const unsigned char*)weights, bias, gamma, beta, eps, row_seq, y);
     }
     EMPH_CHECK_LAUNCH("emph_transformer_ffn_norm");
+    return EMPH_OK;
+}
+
+int emph_transformer_layer_tail(
+    const float* x, const float* residual, int32_t total_rows, int32_t channels,
+    const void* weights, const float* bias, int32_t parts, const float* gamma1,
+    const float* beta1, const float* gamma2, const float* beta2, float eps,
+    const int32_t* row_seq, float* y, void* stream) {
+    using namespace emph::xf_tc;
+    EMPH_XF_REQUIRE_SHAPE("emph_transformer_layer_tail");
+    if (total_rows <= 0) return EMPH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = 3 * parts * kWPartBytes;
+    const int grid = grid_for(total_rows, 1);
+#define EMPH_XF_TAIL(NP)                                                                  \
+    do {                                                                                  \
+        const int status =                                                                \
+            configure(layer_tail_kernel<NP>, smem, "emph_transformer_layer_tail");        \
+        if (status != EMPH_OK) return status;                                             \
+        layer_tail_kernel<NP><<<grid, kThreads, smem, st>>>(                              \
+            x, residual, total_rows, (const unsigned char*)weights, bias, gamma1, beta1,  \
+            gamma2, beta2, eps, row_seq, y);                                              \
+    } while (0)
+    if (parts == 1) EMPH_XF_TAIL(1);
+    else if (parts == 2) EMPH_XF_TAIL(2);
+    else EMPH_XF_TAIL(3);
+#undef EMPH_XF_TAIL
+    EMPH_CHECK_LAUNCH("emph_transformer_layer_tail");
     return EMPH_OK;
 }
 

@@ -70,6 +70,8 @@ class FusedLayer:
     out_bias: torch.Tensor
     ffn_weight: torch.Tensor
     ffn_bias: torch.Tensor
+    tail_weight: torch.Tensor        # out-projection, linear1, linear2 in one blob
+    tail_bias: torch.Tensor
 
 
 def split_parts(matrices, parts, device):
@@ -116,7 +118,11 @@ class EncoderLayer:
                 split_parts([raw['out_proj.weight']], parts, device),
                 vector('out_proj.bias'),
                 split_parts([raw['linear1.weight'], raw['linear2.weight']], parts, device),
-                vector('linear1.bias', 'linear2.bias'))
+                vector('linear1.bias', 'linear2.bias'),
+                split_parts(
+                    [raw['out_proj.weight'], raw['linear1.weight'], raw['linear2.weight']],
+                    parts, device),
+                vector('out_proj.bias', 'linear1.bias', 'linear2.bias'))
         return self.packs[parts]
 
 
@@ -255,6 +261,10 @@ def attention_workspace(total_rows, channels, mode, device, zero=False, ws=None,
 
 
 FUSED_CHANNELS = 80                # csrc/transformer_tc.cu is compiled for d_model 80
+# out-projection + LayerNorm + feed-forward + LayerNorm as ONE pass
+# (emph_transformer_layer_tail) instead of two
+import os as _os
+FUSED_TAIL = _os.environ.get('EMPHASES_B200_FUSED_TAIL', '1') != '0'
 
 
 def fused_layers(channels, mode):
@@ -308,6 +318,17 @@ def run_fused_layers(
             channels, HEADS, _lib.ptr(row_start), _lib.ptr(n_queries), _lib.ptr(n_keys),
             total_rows, _lib.ptr(d_block_seq), _lib.ptr(d_block_q0), n_blocks, scale, mode,
             _lib.ptr(context), stream)
+        if FUSED_TAIL and parts <= 2:
+            # (with three parts the pass is bound by its 18 products per
+            # element, not by the row traffic it saves: no gain measured)
+            _lib.call(
+                'emph_transformer_layer_tail', _lib.ptr(context), _lib.ptr(h), total_rows,
+                channels, _lib.ptr(pack.tail_weight), _lib.ptr(pack.tail_bias), parts,
+                _lib.ptr(layer.norm1[0]), _lib.ptr(layer.norm1[1]),
+                _lib.ptr(layer.norm2[0]), _lib.ptr(layer.norm2[1]), 1e-5, _lib.ptr(row_seq),
+                _lib.ptr(spare), stream)
+            h, spare = spare, h
+            continue
         _lib.call(
             'emph_transformer_proj_norm', _lib.ptr(context), _lib.ptr(h), total_rows, channels,
             _lib.ptr(pack.out_weight), _lib.ptr(pack.out_bias), parts,

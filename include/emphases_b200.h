@@ -451,6 +451,13 @@ int emph_transformer_ffn_norm(
     const float* x, int32_t total_rows, int32_t channels, const void* weights,
     const float* bias, int32_t parts, const float* gamma, const float* beta,
     float eps, const int32_t* row_seq, float* y, void* stream);
+/* Both of the above in one pass (weights: out-projection, linear1, linear2;
+ * bias: bo, b1, b2): the LayerNorm1 output never leaves registers. */
+int emph_transformer_layer_tail(
+    const float* x, const float* residual, int32_t total_rows, int32_t channels,
+    const void* weights, const float* bias, int32_t parts, const float* gamma1,
+    const float* beta1, const float* gamma2, const float* beta2, float eps,
+    const int32_t* row_seq, float* y, void* stream);
 int emph_add_layernorm(
     const float* x, const float* residual, const float* gamma,
     const float* beta, float eps, const int32_t* row_seq, int32_t total_rows,

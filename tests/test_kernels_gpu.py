@@ -917,6 +917,22 @@ def test_transformer_fused_passes(eng, parts):
     hidden = torch.relu(x.double() @ weight[0].double().T + bias[0].double())
     check(y, layernorm(x.double() + hidden @ weight[1].double().T + bias[1].double()))
 
+    # the two passes above as one: LayerNorm(n + relu(n W1^T + b1) W2^T + b2) with
+    # n = LayerNorm(residual + x W0^T + b0) (second LayerNorm with swapped vectors)
+    blob = transformer.split_parts(weight[:3], parts, device)
+    dbias = torch.cat(bias[:3]).to(device)
+    y = torch.full_like(dx, float('nan'))
+    _lib.call(
+        'emph_transformer_layer_tail', _lib.ptr(dx), _lib.ptr(dres), total, channels,
+        _lib.ptr(blob), _lib.ptr(dbias), parts, _lib.ptr(dgamma), _lib.ptr(dbeta),
+        _lib.ptr(dbeta), _lib.ptr(dgamma), 1e-5, _lib.ptr(row_seq), _lib.ptr(y), stream)
+    first = layernorm(residual.double() + x.double() @ weight[0].double().T + bias[0].double())
+    hidden = torch.relu(first @ weight[1].double().T + bias[1].double())
+    second = torch.nn.functional.layer_norm(
+        first + hidden @ weight[2].double().T + bias[2].double(), (channels,),
+        beta.double(), gamma.double(), 1e-5)
+    check(y, second)
+
     # q rows + k / v records -> attention
     q64, k64, v64 = (
         x.double() @ weight[2 + i].double().T + bias[2 + i].double() for i in range(3))
