@@ -440,7 +440,23 @@ def time_files_path(emphases, args, state, rank, world, local_rank, device, barr
         elapsed = (time.perf_counter() - start) / repeats
         written = len(os.listdir(os.path.join(root, 'out'))) if rank == 0 else None
         barrier()
-        # ceiling of the host side alone: the native reader decoding this
+        # the host side of the same call on its own: everything but the kernels
+        # (file reads, parsing, planning, uploads, score download, both writers)
+        from emphases_b200 import scheduler as scheduler_module
+        scheduler_module.HOST_PATH_PROBE = True
+        try:
+            run()
+            barrier()
+            start = time.perf_counter()
+            for _ in range(2):
+                run()
+                barrier()
+            host_path = (time.perf_counter() - start) / 2
+        finally:
+            scheduler_module.HOST_PATH_PROBE = False
+        run()                               # the outputs left behind are real scores
+        barrier()
+        # ceiling of the reader alone: the native reader decoding this
         # rank's shard into pinned memory, all ranks at once, no GPU work
         from emphases_b200 import corpus as corpus_module
         mine = distributed.shard(distributed.audio_costs(audio), rank, world)
@@ -466,12 +482,16 @@ def time_files_path(emphases, args, state, rank, world, local_rank, device, barr
             'h2d_gbs_aggregate': samples * 2 / elapsed / 1e9,
             'host_ingest_gbs_probe': samples * 2 / ingest / 1e9,
             'host_ingest_ms_probe': 1e3 * ingest,
+            'host_path_ms_probe': 1e3 * host_path,
+            'host_bound_fraction': host_path / elapsed,
             'outputs_written': written,
             'scaling': 'strong',
             'api': 'emphases_b200.distributed.from_files_to_files (one rank per GPU, '
                    'LPT shard of one file list per rank)',
             'note': 'wav + TextGrid read, int16 H2D, inference, D2H, .pt + .TextGrid '
                     'written; wall clock between barriers.  Host-bound: '
+                    'host_path_ms_probe is the same call with the kernels skipped '
+                    '(reads, parsing, planning, copies, writers), '
                     'host_ingest_*_probe is the native wav reader alone (headers '
                     'already parsed) filling pinned memory on the same cores'}
     finally:

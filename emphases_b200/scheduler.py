@@ -369,6 +369,12 @@ def _flat_result(members, plan, scores):
     return members, flat_scores, per_utterance
 
 
+# bench.py's host-path probe: run_on_device with everything but the kernels
+# (decode, planning, uploads, score download, result hand-off): the time the
+# host side of the files path needs on its own
+HOST_PATH_PROBE = False
+
+
 class _LaunchSink:
     """Hands every launch's flat host result to `consume` on a background
     thread as soon as its device -> host copy has landed, while later launches
@@ -483,13 +489,17 @@ def run_on_device(
             with torch.cuda.stream(stream):
                 resample = packed.launch_resampling(members, plan, device) \
                     if isinstance(packed, ResampledSource) else None
-                result = eng.forward_packed(
-                    device_audio, plan, weights, method=method,
-                    location=model.location, precision=precision,
-                    head_mode=head_mode, normalize=emphases.NORMALIZE,
-                    views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws,
-                    resample=resample)
-                scores = result[output]
+                if HOST_PATH_PROBE:
+                    eng.upload_plan(plan, slot=number, ws=ws)
+                    scores = ws.get('probe_scores', (plan.total_word_rows,), torch.float32)
+                else:
+                    result = eng.forward_packed(
+                        device_audio, plan, weights, method=method,
+                        location=model.location, precision=precision,
+                        head_mode=head_mode, normalize=emphases.NORMALIZE,
+                        views=eng.upload_plan(plan, slot=number, ws=ws), ws=ws,
+                        resample=resample)
+                    scores = result[output]
                 if not to_cpu:
                     scores = scores.clone()       # the workspace is reused
                 if to_cpu:
