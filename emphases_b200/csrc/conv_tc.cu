@@ -807,7 +807,7 @@ conv_stack_tc_kernel(
 // (out, in, k) as the module holds it; 2 = the adjoint convolution of that
 // Conv1d weight (channel matrix transposed, taps flipped: the input-gradient
 // pass of the training step)
-__global__ void pack_weights_tc_kernel(
+__device__ __forceinline__ void pack_weights_tc_body(
     const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int parts,
     int ks, int source, __nv_bfloat16* __restrict__ out) {
     const int per_entry = layer_bytes(ks) / 2;
@@ -843,6 +843,25 @@ __global__ void pack_weights_tc_kernel(
         }
         out[i] = __float2bfloat16_rn(v);
     }
+}
+
+__global__ void pack_weights_tc_kernel(
+    const float* __restrict__ w, const float* __restrict__ bias, int n_layers, int parts,
+    int ks, int source, __nv_bfloat16* __restrict__ out) {
+    pack_weights_tc_body(w, bias, n_layers, parts, ks, source, out);
+}
+
+// the Conv1d weights of up to 32 layers, each into its own blob (blockIdx.y =
+// layer): the training step packs a whole direction in one launch
+struct PackBatch {
+    const float* weight[32];
+    const float* bias[32];
+};
+__global__ void pack_conv1d_batch_kernel(
+    PackBatch batch, int parts, int ks, int source, size_t blob_elements,
+    __nv_bfloat16* __restrict__ out) {
+    pack_weights_tc_body(batch.weight[blockIdx.y], batch.bias[blockIdx.y], 1, parts, ks, source,
+                         out + blockIdx.y * blob_elements);
 }
 
 }  // namespace tc
@@ -997,6 +1016,31 @@ int pack_conv1d_weights_tc(
         conv_weight, bias, 1, parts, kernel_size, adjoint ? 2 : 1,
         reinterpret_cast<__nv_bfloat16*>(packed));
     EMPH_CHECK_LAUNCH("pack_conv1d_weights_tc");
+    return EMPH_OK;
+}
+
+// bytes of one layer's operand blob in the given tensor-core precision
+size_t conv1d_blob_bytes(int kernel_size, int precision) {
+    const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
+    return (size_t)parts * tc::layer_bytes(kernel_size);
+}
+
+// n Conv1d weights -> n blobs `stride` bytes apart, one launch
+int pack_conv1d_weights_tc_batch(
+    const float* const* conv_weights, const float* const* biases, int n, int kernel_size,
+    int precision, int adjoint, void* packed, size_t stride, cudaStream_t stream) {
+    EMPH_REQUIRE(n >= 0 && n <= 32 && stride % 2 == 0, "pack_conv1d_weights_tc_batch: bad batch");
+    if (n == 0) return EMPH_OK;
+    const int parts = precision == EMPH_PREC_BF16X6_TC ? 3 : precision == EMPH_PREC_BF16X3_TC ? 2 : 1;
+    tc::PackBatch batch;
+    for (int i = 0; i < n; ++i) {
+        batch.weight[i] = conv_weights[i];
+        batch.bias[i] = biases[i];
+    }
+    tc::pack_conv1d_batch_kernel<<<dim3(16, n), 256, 0, stream>>>(
+        batch, parts, kernel_size, adjoint ? 2 : 1, stride / 2,
+        reinterpret_cast<__nv_bfloat16*>(packed));
+    EMPH_CHECK_LAUNCH("pack_conv1d_weights_tc_batch");
     return EMPH_OK;
 }
 }  // namespace emph

@@ -20,6 +20,10 @@ namespace emph {
 int pack_conv1d_weights_tc(
     const float* conv_weight, const float* bias, int kernel_size, int precision, int adjoint,
     void* packed, cudaStream_t stream);
+size_t conv1d_blob_bytes(int kernel_size, int precision);
+int pack_conv1d_weights_tc_batch(
+    const float* const* conv_weights, const float* const* biases, int n, int kernel_size,
+    int precision, int adjoint, void* packed, size_t stride, cudaStream_t stream);
 int conv1d_weight_grad(
     const float* x, const float* dpre, int total_rows, int channels, int kernel_size,
     float* grad_weight, float* grad_bias, int accumulate, cudaStream_t st);
@@ -77,7 +81,7 @@ struct TrainLayout {
     std::vector<size_t> frame_out, frame_pre, word_out, word_pre;
     size_t pooled, logits_rows;
     // per-call scratch
-    size_t packed_w, adjoint_w, tc_w, dw, db, dz, grad_a, grad_b, head_w, head_dw, head_db;
+    size_t packed_w, adjoint_w, tc_w, tc_stride, dw, db, dz, grad_a, grad_b, head_w, head_dw, head_db;
     size_t total_bytes;
 };
 
@@ -135,7 +139,9 @@ static TrainLayout make_layout(
     const size_t weight_bytes = sizeof(float) * kTrainKernel * kTrainChannels * kTrainChannels;
     l.packed_w = take(weight_bytes);
     l.adjoint_w = take(weight_bytes);
-    l.tc_w = take(3 * (kTrainKernel * kTrainChannels * kTrainChannels * 2 + 2 * kTrainChannels * 16) + 1024);
+    // one operand blob per layer: a whole direction is packed by one launch
+    l.tc_stride = up(3 * (kTrainKernel * kTrainChannels * kTrainChannels * 2 + 2 * kTrainChannels * 16) + 1024);
+    l.tc_w = take(l.tc_stride * (size_t)(l.n_frame + l.n_word));
     l.dw = take(weight_bytes);
     l.db = take(sizeof(float) * kTrainChannels);
     l.dz = take(sizeof(float) * (size_t)l.total_words);
@@ -164,10 +170,12 @@ static int check_model(const emph_train_model& m) {
 }
 
 // one conv layer y = act(conv(x, W) + b) with W in the Conv1d (out, in, k) layout
+// (tensor-core modes: layer `index`'s blob was packed by pack_direction)
 static int conv_layer(
     const emph_train_model& m, const TrainLayout& l, uint8_t* base, const float* x,
-    const int32_t* row_seq, int rows, const float* weight, const float* bias, int act,
+    const int32_t* row_seq, int rows, int index, const float* bias, int act,
     bool adjoint, float* y, void* stream) {
+    const float* weight = m.weights[index];
     const int32_t acts[1] = {act};
     const int precision = adjoint ? m.precision : m.forward_precision;
     if (precision == EMPH_PREC_FP32) {
@@ -179,13 +187,24 @@ static int conv_layer(
         return emph_conv_stack(x, row_seq, rows, packed, bias, acts, 1, kTrainChannels,
                                kTrainKernel, EMPH_PREC_FP32, y, stream);
     }
-    // tensor-core modes: the Conv1d weight goes straight into the operand blob
-    void* blob = base + l.tc_w;
-    int s = pack_conv1d_weights_tc(weight, bias, kTrainKernel, precision, adjoint, blob,
-                                   (cudaStream_t)stream);
-    if (s != EMPH_OK) return s;
+    const void* blob = base + l.tc_w + l.tc_stride * (size_t)index;
     return emph_conv_stack(x, row_seq, rows, static_cast<const float*>(blob), bias, acts, 1,
                            kTrainChannels, kTrainKernel, precision, y, stream);
+}
+
+// tensor-core modes: the Conv1d weights of all layers go straight into their
+// operand blobs (forward: with the biases; adjoint: transposed, taps flipped,
+// zero bias) in ONE launch
+static int pack_direction(
+    const emph_train_model& m, const TrainLayout& l, uint8_t* base, bool adjoint, void* stream) {
+    const int precision = adjoint ? m.precision : m.forward_precision;
+    if (precision == EMPH_PREC_FP32) return EMPH_OK;
+    const int n = l.n_frame + l.n_word;
+    const float* biases[32];
+    for (int i = 0; i < n; ++i) biases[i] = adjoint ? m.zero_bias : m.biases[i];
+    return pack_conv1d_weights_tc_batch(
+        m.weights, biases, n, kTrainKernel, precision, adjoint, base + l.tc_w, l.tc_stride,
+        (cudaStream_t)stream);
 }
 
 }  // namespace emph
@@ -248,6 +267,7 @@ extern "C" int emph_train_forward(
                             ints(l.row_seq), l.total, floats(l.rows), stream))) return s;
 
     // ---- layers, every output kept ----
+    if ((s = pack_direction(m, l, base, false, stream))) return s;
     auto run_stack = [&](int first, int count, const float* input, const int32_t* seq, int rows,
                          const std::vector<size_t>& out, const std::vector<size_t>& pre) -> int {
         const float* x = input;
@@ -255,13 +275,13 @@ extern "C" int emph_train_forward(
             const int act = m.acts[first + i];
             int status;
             if (keeps_pre(act)) {
-                status = conv_layer(m, l, base, x, seq, rows, m.weights[first + i], m.biases[first + i],
+                status = conv_layer(m, l, base, x, seq, rows, first + i, m.biases[first + i],
                                     EMPH_ACT_NONE, false, floats(pre[i]), stream);
                 if (status == EMPH_OK)
                     status = emph_activation_forward(floats(pre[i]), seq, rows, kTrainChannels, act,
                                                      floats(out[i]), stream);
             } else {
-                status = conv_layer(m, l, base, x, seq, rows, m.weights[first + i], m.biases[first + i],
+                status = conv_layer(m, l, base, x, seq, rows, first + i, m.biases[first + i],
                                     act, false, floats(out[i]), stream);
             }
             if (status != EMPH_OK) return status;
@@ -331,6 +351,7 @@ extern "C" int emph_train_backward(
     EMPH_CHECK_LAUNCH("emph_train_backward(head)");
 
     // conv stacks, last layer first; dy in `dx`, result back in `dx`
+    if ((s = pack_direction(m, l, base, true, stream))) return s;
     auto stack_backward = [&](int first, int count, const float* input, const int32_t* seq, int rows,
                               const std::vector<size_t>& out, const std::vector<size_t>& pre) -> int {
         for (int i = count - 1; i >= 0; --i) {
@@ -346,7 +367,7 @@ extern "C" int emph_train_backward(
             if (status != EMPH_OK) return status;
             if (first + i == 0) break;          // the features need no gradient
             // dx = conv(dpre, W flipped and transposed), zero bias, no activation
-            status = conv_layer(m, l, base, other, seq, rows, m.weights[first + i], m.zero_bias,
+            status = conv_layer(m, l, base, other, seq, rows, first + i, m.zero_bias,
                                 EMPH_ACT_NONE, true, dx, stream);
             if (status != EMPH_OK) return status;
         }
